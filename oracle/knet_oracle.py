@@ -1,0 +1,395 @@
+"""TEST INFRASTRUCTURE ONLY -- the CPU oracle for the KernelUpdateHead hot path.
+
+A plain-torch (CPU) restatement of the reference algorithm, written as explicit
+math on a `state_dict`, with every function citing the reference lines it
+follows.  It is the CHECKER for the CUDA path: only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import it.  The product
+package (video-k-net_b200/vknet) never imports anything from oracle/.
+
+Pinning: the reference ships no tests or golden vectors for this path
+(SURVEY.md section 8c), so this restatement is pinned against the reference
+code ITSELF, imported verbatim through oracle/ref_shim.py:
+  * tests/test_oracle_vs_reference.py (CPU, this container) runs both on the same
+    seeded inputs and demands agreement to fp32 round-off;
+  * oracle/make_golden.py stores reference outputs as fixtures under
+    tests/golden/, which travel to the GPU box where /root/reference is absent.
+
+All tensors keep the reference layouts: x [B,C,H,W], proposal_feat [B,N,C,K,K],
+mask_preds [B,N,H,W].  Computation dtype follows the input dtype (fp32 or fp64;
+fp64 gives a "truth" to separate our error from the reference's own round-off).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------
+# primitives (third-party semantics restated)
+# ----------------------------------------------------------------------------------------
+def linear(x, w, b=None):
+    y = x.matmul(w.t().to(x.dtype))
+    return y if b is None else y + b.to(x.dtype)
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    """nn.LayerNorm(C), eps 1e-5, biased variance (mmcv build_norm_layer(dict(type='LN')))."""
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w.to(x.dtype) + b.to(x.dtype)
+
+
+def mha_core(query, key, value, sd, prefix, num_heads):
+    """torch nn.MultiheadAttention forward, seq-first [L,B,E], dropout 0, no masks.
+    Packed in_proj [3E,E]; q scaled by 1/sqrt(head_dim); softmax over keys; out_proj.
+    (the math mmcv MultiheadAttention delegates to: knet/det/kernel_update_head.py:100-101, 206)"""
+    L, B, E = query.shape
+    S = key.shape[0]
+    hd = E // num_heads
+    w = sd[prefix + 'attn.in_proj_weight']
+    b = sd[prefix + 'attn.in_proj_bias']
+    q = linear(query, w[:E], b[:E])
+    k = linear(key, w[E:2 * E], b[E:2 * E])
+    v = linear(value, w[2 * E:], b[2 * E:])
+    q = q.reshape(L, B * num_heads, hd).transpose(0, 1) * (1.0 / math.sqrt(hd))
+    k = k.reshape(S, B * num_heads, hd).transpose(0, 1)
+    v = v.reshape(S, B * num_heads, hd).transpose(0, 1)
+    att = torch.softmax(q.bmm(k.transpose(1, 2)), dim=-1)
+    out = att.bmm(v).transpose(0, 1).reshape(L, B, E)
+    return linear(out, sd[prefix + 'attn.out_proj.weight'], sd[prefix + 'attn.out_proj.bias'])
+
+
+def mha_block(query, key, value, identity, sd, prefix, num_heads):
+    """mmcv MultiheadAttention wrapper: identity + attn(q,k,v) (Appendix B)."""
+    return identity + mha_core(query, key, value, sd, prefix, num_heads)
+
+
+def ffn_block(x, sd, prefix):
+    """mmcv FFN(num_fcs=2, ReLU, add_identity=True): x + W2 relu(W1 x + b1) + b2
+    (knet/det/kernel_update_head.py:119-126, 214-215)."""
+    h = torch.relu(linear(x, sd[prefix + 'layers.0.0.weight'], sd[prefix + 'layers.0.0.bias']))
+    return x + linear(h, sd[prefix + 'layers.1.weight'], sd[prefix + 'layers.1.bias'])
+
+
+# ----------------------------------------------------------------------------------------
+# KernelUpdator  (knet/kernel_updator.py:56-94)
+# ----------------------------------------------------------------------------------------
+def kernel_updator(sd, prefix, update_feature, input_feature, in_channels, feat_channels,
+                   gate_sigmoid=True, gate_norm_act=False, activate_out=False):
+    p = prefix
+    update_feature = update_feature.reshape(-1, in_channels)                       # :57
+    num_proposals = update_feature.shape[0]
+    parameters = linear(update_feature, sd[p + 'dynamic_layer.weight'], sd[p + 'dynamic_layer.bias'])  # :59
+    param_in = parameters[:, :feat_channels]                                       # :60-61
+    param_out = parameters[:, -feat_channels:]                                     # :62-63
+    input_feats = linear(input_feature.reshape(num_proposals, -1, feat_channels),  # :65-66
+                         sd[p + 'input_layer.weight'], sd[p + 'input_layer.bias'])
+    input_in = input_feats[..., :feat_channels]                                    # :67
+    input_out = input_feats[..., -feat_channels:]                                  # :68
+    gate_feats = input_in * param_in.unsqueeze(-2)                                 # :70
+    if gate_norm_act:                                                              # :71-72
+        gate_feats = torch.relu(layer_norm(gate_feats, sd[p + 'gate_norm.weight'], sd[p + 'gate_norm.bias']))
+    input_gate = layer_norm(linear(gate_feats, sd[p + 'input_gate.weight'], sd[p + 'input_gate.bias']),
+                            sd[p + 'input_norm_in.weight'], sd[p + 'input_norm_in.bias'])   # :74
+    update_gate = layer_norm(linear(gate_feats, sd[p + 'update_gate.weight'], sd[p + 'update_gate.bias']),
+                             sd[p + 'norm_in.weight'], sd[p + 'norm_in.bias'])               # :75
+    if gate_sigmoid:                                                               # :76-78
+        input_gate = torch.sigmoid(input_gate)
+        update_gate = torch.sigmoid(update_gate)
+    param_out = layer_norm(param_out, sd[p + 'norm_out.weight'], sd[p + 'norm_out.bias'])            # :79
+    input_out = layer_norm(input_out, sd[p + 'input_norm_out.weight'], sd[p + 'input_norm_out.bias'])  # :80
+    if activate_out:                                                               # :82-84
+        param_out = torch.relu(param_out)
+        input_out = torch.relu(input_out)
+    features = update_gate * param_out.unsqueeze(-2) + input_gate * input_out      # :87-88
+    features = linear(features, sd[p + 'fc_layer.weight'], sd[p + 'fc_layer.bias'])  # :90
+    features = layer_norm(features, sd[p + 'fc_norm.weight'], sd[p + 'fc_norm.bias'])  # :91
+    return torch.relu(features)                                                    # :92
+
+
+# ----------------------------------------------------------------------------------------
+# shared pieces of the stage
+# ----------------------------------------------------------------------------------------
+def hard_mask(mask_preds, thr=0.5):
+    """knet/det/kernel_update_head.py:190-192 -- 1[sigmoid(m) > thr] as float."""
+    return (torch.sigmoid(mask_preds) > thr).to(mask_preds.dtype)
+
+
+def _feat_transform(sd, x):
+    """ConvModule 1x1 + bias, no norm/act (knet/det/kernel_update_head.py:107-117, 179-180)."""
+    if 'feat_transform.conv.weight' not in sd:
+        return x
+    w = sd['feat_transform.conv.weight'].to(x.dtype)
+    assert w.shape[-1] == 1 and w.shape[-2] == 1, 'only the 1x1 feat_transform is on the shipped path'
+    B, C, H, W = x.shape
+    y = torch.einsum('oc,bcp->bop', w[:, :, 0, 0], x.reshape(B, C, H * W))
+    y = y + sd['feat_transform.conv.bias'].to(x.dtype)[None, :, None]
+    return y.reshape(B, -1, H, W)
+
+
+def _heads_and_conv(sd, cfg, obj_feat, x, B, N):
+    """cls/mask FC stacks + dynamic mask conv (knet/det/kernel_update_head.py:217-260)."""
+    C = cfg['in_channels']
+    K = cfg.get('conv_kernel_size', 1)
+    cls_feat = obj_feat.sum(-2)                                                    # :217
+    mask_feat = obj_feat                                                           # :218
+    for i in range(cfg.get('num_cls_fcs', 1)):                                     # :220-221
+        cls_feat = torch.relu(layer_norm(linear(cls_feat, sd['cls_fcs.%d.weight' % (3 * i)]),
+                                         sd['cls_fcs.%d.weight' % (3 * i + 1)], sd['cls_fcs.%d.bias' % (3 * i + 1)]))
+    for i in range(cfg.get('num_mask_fcs', 1)):                                    # :222-223
+        mask_feat = torch.relu(layer_norm(linear(mask_feat, sd['mask_fcs.%d.weight' % (3 * i)]),
+                                          sd['mask_fcs.%d.weight' % (3 * i + 1)], sd['mask_fcs.%d.bias' % (3 * i + 1)]))
+    cls_score = linear(cls_feat, sd['fc_cls.weight'], sd['fc_cls.bias']).view(B, N, -1)  # :225
+    mask_feat = linear(mask_feat, sd['fc_mask.weight'], sd['fc_mask.bias']).permute(0, 1, 3, 2)  # :227
+    H, W = x.shape[-2:]
+    mask_feat = mask_feat.reshape(B, N, C, K, K)                                   # :244-246
+    new_mask_preds = torch.cat([F.conv2d(x[i:i + 1], mask_feat[i], padding=K // 2)  # :251-259
+                                for i in range(B)], dim=0).reshape(B, N, H, W)
+    return cls_score, new_mask_preds
+
+
+def _pool(sd, cfg, x, proposal_feat, mask_preds):
+    """feat_transform, hard mask, einsum pooling, proposal reshape
+    (knet/det/kernel_update_head.py:178-200)."""
+    B, N = proposal_feat.shape[:2]
+    C = cfg['in_channels']
+    x = _feat_transform(sd, x)
+    H, W = x.shape[-2:]
+    if mask_preds.shape[-2:] != (H, W):                                            # :183-188
+        gather_mask = F.interpolate(mask_preds, (H, W), align_corners=False, mode='bilinear')
+    else:
+        gather_mask = mask_preds
+    m = hard_mask(gather_mask, cfg.get('hard_mask_thr', 0.5))
+    x_feat = torch.einsum('bnhw,bchw->bnc', m.to(x.dtype), x)                      # :195
+    proposal_feat = proposal_feat.reshape(B, N, C, -1).permute(0, 1, 3, 2)         # :198-200
+    return x, x_feat, proposal_feat
+
+
+def _update_attend_ffn(sd, cfg, x_feat, proposal_feat, B, N):
+    """KernelUpdator -> MHSA+LN -> FFN+LN (knet/det/kernel_update_head.py:201-215)."""
+    C = cfg['in_channels']
+    ku = cfg['kernel_updator_cfg']
+    obj_feat = kernel_updator(sd, 'kernel_update_conv.', x_feat, proposal_feat,
+                              ku.get('in_channels', 256), ku.get('feat_channels', 64),
+                              ku.get('gate_sigmoid', True), ku.get('gate_norm_act', False),
+                              ku.get('activate_out', False))                       # :201
+    obj_feat = obj_feat.reshape(B, N, -1).permute(1, 0, 2)                         # :204-205
+    obj_feat = layer_norm(mha_block(obj_feat, obj_feat, obj_feat, obj_feat, sd, 'attention.',
+                                    cfg.get('num_heads', 8)),
+                          sd['attention_norm.weight'], sd['attention_norm.bias'])  # :206
+    obj_feat = obj_feat.permute(1, 0, 2).reshape(B, N, -1, C)                      # :208-211
+    if cfg.get('with_ffn', True):                                                  # :214-215
+        obj_feat = layer_norm(ffn_block(obj_feat, sd, 'ffn.'), sd['ffn_norm.weight'], sd['ffn_norm.bias'])
+    return obj_feat
+
+
+# ----------------------------------------------------------------------------------------
+# KernelUpdateHead.forward  (knet/det/kernel_update_head.py:170-277)
+# ----------------------------------------------------------------------------------------
+def kernel_update_head_forward(sd, cfg, x, proposal_feat, mask_preds):
+    B, N = proposal_feat.shape[:2]
+    C = cfg['in_channels']
+    K = cfg.get('conv_kernel_size', 1)
+    x, x_feat, pf = _pool(sd, cfg, x, proposal_feat, mask_preds)
+    obj_feat = _update_attend_ffn(sd, cfg, x_feat, pf, B, N)
+    cls_score, new_mask_preds = _heads_and_conv(sd, cfg, obj_feat, x, B, N)
+    return cls_score, new_mask_preds, obj_feat.permute(0, 1, 3, 2).reshape(B, N, C, K, K)  # :275-277
+
+
+# ----------------------------------------------------------------------------------------
+# VideoKernelUpdateHead.forward  (knet/video/kernel_update_head.py:281-541)
+# ----------------------------------------------------------------------------------------
+def _cross_link(sd, cfg, cur, prev, attn_prefix, norm_prefix, ffn_prefix, ffn_norm_prefix, B, N):
+    """LN(cur + MHA(q=cur, k=v=prev)) then LN(FFN(.)) -- the block shared by the three link
+    variants (knet/video/kernel_update_head.py:337-348, 404-415, 432-444)."""
+    C = cfg['in_channels']
+    q = cur.reshape(B, N, -1).permute(1, 0, 2)
+    kv = prev.reshape(B, N, -1).permute(1, 0, 2)
+    t = layer_norm(mha_block(q, kv, kv, q, sd, attn_prefix, 8), sd[norm_prefix + 'weight'], sd[norm_prefix + 'bias'])
+    t = t.permute(1, 0, 2).reshape(B, N, -1, C)
+    return layer_norm(ffn_block(t, sd, ffn_prefix), sd[ffn_norm_prefix + 'weight'], sd[ffn_norm_prefix + 'bias'])
+
+
+def video_kernel_update_head_forward(sd, cfg, x, proposal_feat, mask_preds, previous_obj_feats=None):
+    """Returns the reference 5-tuple (cls_score, new_mask_preds, obj_feat, x_feat, obj_feat_track|None).
+    Link variants restated: previous_link='update_dynamic_cov' (:324-348),
+    previous_type='ffn' (:394-415), previous_type='update' (:417-444)."""
+    B, N = proposal_feat.shape[:2]
+    C = cfg['in_channels']
+    K = cfg.get('conv_kernel_size', 1)
+    ku = cfg['kernel_updator_cfg']
+    ku_args = (ku.get('in_channels', 256), ku.get('feat_channels', 64))
+    x, x_feat, pf = _pool(sd, cfg, x, proposal_feat, mask_preds)                   # :293-317
+    prev = None
+    if previous_obj_feats is not None:
+        prev = previous_obj_feats.reshape(B, N, C, -1).permute(0, 1, 3, 2)
+    if prev is not None and cfg.get('previous_link') == 'update_dynamic_cov':      # :324-348
+        prev_upd = kernel_updator(sd, 'attention_previous_update_link.', x_feat, prev, *ku_args)
+        pf = _cross_link(sd, cfg, pf, prev_upd, 'attention_previous_link.', 'attention_previous_norm_link.',
+                         'link_ffn_link.', 'link_ffn_norm_link.', B, N)
+    obj_feat = _update_attend_ffn(sd, cfg, x_feat, pf, B, N)                       # :372-386
+    track = None
+    if prev is not None:
+        if cfg.get('previous_type') == 'ffn':                                      # :394-415
+            track = _cross_link(sd, cfg, obj_feat, prev, 'attention_previous.', 'attention_previous_norm.',
+                                'link_ffn.', 'link_ffn_norm.', B, N)
+        elif cfg.get('previous_type') == 'update':                                 # :417-444
+            prev_trk = kernel_updator(sd, 'attention_previous_update_track.', x_feat, prev, *ku_args)
+            # the reference reshapes [B*N,1,C] -> [B,N,C,-1] -> permute(0,1,3,2) -> [B,N,C] (:422-429): a
+            # no-op relabelling for K=1, reproduced literally here.
+            prev_trk = prev_trk.reshape(B, N, C, -1).permute(0, 1, 3, 2)
+            track = _cross_link(sd, cfg, obj_feat, prev_trk, 'attention_previous_track.',
+                                'attention_previous_norm_track.', 'link_ffn_track.', 'link_ffn_norm_track.', B, N)
+    cls_score, new_mask_preds = _heads_and_conv(sd, cfg, obj_feat, x, B, N)        # :477-532
+    obj_out = obj_feat.permute(0, 1, 3, 2).reshape(B, N, C, K, K)
+    if track is not None:
+        track = track.permute(0, 1, 3, 2).reshape(B, N, C, K, K)
+    return cls_score, new_mask_preds, obj_out, x_feat, track                       # :534-541
+
+
+# ----------------------------------------------------------------------------------------
+# the S-stage loop  (knet/det/kernel_iter_head.py:118-137, 246-253; forward_dummy :317-330)
+# ----------------------------------------------------------------------------------------
+def iter_forward(sds, cfgs, x, proposal_feat, mask_preds, mask_round=None):
+    """Chains the stages exactly as KernelIterHead.simple_test does.  `mask_round`, when given, is
+    applied to each stage's new_mask_preds (e.g. a bf16 round-trip: what a bf16 module would hand
+    to the next stage); returns the per-stage outputs."""
+    outs = []
+    obj = proposal_feat
+    for sd, cfg in zip(sds, cfgs):
+        cls_score, mask_preds, obj = kernel_update_head_forward(sd, cfg, x, obj, mask_preds)
+        if mask_round is not None:
+            mask_preds = mask_round(mask_preds)
+        outs.append((cls_score, mask_preds, obj))
+    return outs
+
+
+def dummy_inputs(B, N, C, H, W, seed=1, dtype=torch.float32):
+    """forward_dummy recipe (knet/det/kernel_iter_head.py:317-330): x, proposal_feats ~ N(0,1),
+    mask_preds = proposal_feats @ x."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float32)
+    pf = torch.randn(B, N, C, 1, 1, generator=g, dtype=torch.float32)
+    mask = pf.view(B, N, C).bmm(x.view(B, C, -1)).view(B, N, H, W)
+    return x.to(dtype), pf.to(dtype), mask.to(dtype)
+
+
+# ----------------------------------------------------------------------------------------
+# weights: same shapes / init as the reference modules (kernel_update_head.py:151-168)
+# ----------------------------------------------------------------------------------------
+def default_cfg(num_classes=19, in_channels=256, feedforward_channels=2048, num_heads=8, **over):
+    """The mask_head block of configs/det/_base_/models/knet_kitti_step_s3_r50_fpn.py:88-136."""
+    cfg = dict(num_classes=num_classes, num_ffn_fcs=2, num_heads=num_heads, num_cls_fcs=1, num_mask_fcs=1,
+               feedforward_channels=feedforward_channels, in_channels=in_channels, out_channels=in_channels,
+               dropout=0.0, mask_thr=0.5, conv_kernel_size=1, mask_upsample_stride=2,
+               ffn_act_cfg=dict(type='ReLU', inplace=True), with_ffn=True,
+               feat_transform_cfg=dict(conv_cfg=dict(type='Conv2d'), act_cfg=None),
+               kernel_updator_cfg=dict(type='KernelUpdator', in_channels=in_channels, feat_channels=in_channels,
+                                       out_channels=in_channels, input_feat_shape=3,
+                                       act_cfg=dict(type='ReLU', inplace=True), norm_cfg=dict(type='LN')),
+               loss_rank=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=0.1),
+               loss_mask=dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0),
+               loss_dice=dict(type='DiceLoss', loss_weight=4.0),
+               loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0))
+    cfg.update(over)
+    return cfg
+
+
+def _xavier(g, *shape):
+    fan_out, fan_in = shape[0], shape[1]
+    rf = 1
+    for s in shape[2:]:
+        rf *= s
+    a = math.sqrt(6.0 / ((fan_in + fan_out) * rf))
+    return (torch.rand(*shape, generator=g) * 2 - 1) * a
+
+
+def _updator_params(g, sd, p, C, Fc, out):
+    sd[p + 'dynamic_layer.weight'] = _xavier(g, 2 * Fc, C)
+    sd[p + 'dynamic_layer.bias'] = torch.randn(2 * Fc, generator=g) * 0.05
+    sd[p + 'input_layer.weight'] = _xavier(g, 2 * Fc, C)
+    sd[p + 'input_layer.bias'] = torch.randn(2 * Fc, generator=g) * 0.05
+    for nm in ('input_gate', 'update_gate'):
+        sd[p + nm + '.weight'] = _xavier(g, Fc, C)
+        sd[p + nm + '.bias'] = torch.randn(Fc, generator=g) * 0.05
+    for nm in ('norm_in', 'norm_out', 'input_norm_in', 'input_norm_out'):
+        sd[p + nm + '.weight'] = 1 + 0.1 * torch.randn(Fc, generator=g)
+        sd[p + nm + '.bias'] = 0.1 * torch.randn(Fc, generator=g)
+    sd[p + 'fc_layer.weight'] = _xavier(g, out, Fc)
+    sd[p + 'fc_layer.bias'] = torch.randn(out, generator=g) * 0.05
+    sd[p + 'fc_norm.weight'] = 1 + 0.1 * torch.randn(out, generator=g)
+    sd[p + 'fc_norm.bias'] = 0.1 * torch.randn(out, generator=g)
+
+
+def _mha_params(g, sd, p, E):
+    sd[p + 'attn.in_proj_weight'] = _xavier(g, 3 * E, E)
+    sd[p + 'attn.in_proj_bias'] = torch.randn(3 * E, generator=g) * 0.05
+    sd[p + 'attn.out_proj.weight'] = _xavier(g, E, E)
+    sd[p + 'attn.out_proj.bias'] = torch.randn(E, generator=g) * 0.05
+
+
+def _ln_params(g, sd, p, C):
+    sd[p + 'weight'] = 1 + 0.1 * torch.randn(C, generator=g)
+    sd[p + 'bias'] = 0.1 * torch.randn(C, generator=g)
+
+
+def _ffn_params(g, sd, p, C, Fh):
+    sd[p + 'layers.0.0.weight'] = _xavier(g, Fh, C)
+    sd[p + 'layers.0.0.bias'] = torch.randn(Fh, generator=g) * 0.05
+    sd[p + 'layers.1.weight'] = _xavier(g, C, Fh)
+    sd[p + 'layers.1.bias'] = torch.randn(C, generator=g) * 0.05
+
+
+def random_state_dict(cfg, seed=0):
+    """A state_dict with the reference's keys and shapes.  Matrices are
+    xavier-uniform like init_weights (:151-168); biases / LN affine are perturbed away from the
+    0 / 1 defaults so that parity tests exercise every term (a freshly initialised reference
+    module has all-zero biases, which would hide a dropped bias)."""
+    g = torch.Generator().manual_seed(seed)
+    C = cfg['in_channels']
+    Fh = cfg['feedforward_channels']
+    ku = cfg['kernel_updator_cfg']
+    sd = {}
+    _mha_params(g, sd, 'attention.', C)
+    _ln_params(g, sd, 'attention_norm.', C)
+    _updator_params(g, sd, 'kernel_update_conv.', ku['in_channels'], ku['feat_channels'], ku['out_channels'])
+    if cfg.get('feat_transform_cfg') is not None:
+        sd['feat_transform.conv.weight'] = _xavier(g, C, C, 1, 1)
+        sd['feat_transform.conv.bias'] = torch.randn(C, generator=g) * 0.05
+    _ffn_params(g, sd, 'ffn.', C, Fh)
+    _ln_params(g, sd, 'ffn_norm.', C)
+    sd['cls_fcs.0.weight'] = _xavier(g, C, C)
+    _ln_params(g, sd, 'cls_fcs.1.', C)
+    sd['fc_cls.weight'] = _xavier(g, cfg['num_classes'], C)
+    sd['fc_cls.bias'] = torch.full((cfg['num_classes'],), -math.log(99.0)) + 0.05 * torch.randn(cfg['num_classes'], generator=g)
+    sd['mask_fcs.0.weight'] = _xavier(g, C, C)
+    _ln_params(g, sd, 'mask_fcs.1.', C)
+    sd['fc_mask.weight'] = _xavier(g, cfg['out_channels'], C)
+    sd['fc_mask.bias'] = torch.randn(cfg['out_channels'], generator=g) * 0.05
+    if cfg.get('previous') is not None:
+        if cfg.get('previous_type') == 'ffn':
+            _mha_params(g, sd, 'attention_previous.', C)
+            _ln_params(g, sd, 'attention_previous_norm.', C)
+            _ffn_params(g, sd, 'link_ffn.', C, Fh)
+            _ln_params(g, sd, 'link_ffn_norm.', C)
+        elif cfg.get('previous_type') == 'update':
+            _updator_params(g, sd, 'attention_previous_update_track.', ku['in_channels'], ku['feat_channels'], ku['out_channels'])
+            _mha_params(g, sd, 'attention_previous_track.', C)
+            _ln_params(g, sd, 'attention_previous_norm_track.', C)
+            _ffn_params(g, sd, 'link_ffn_track.', C, Fh)
+            _ln_params(g, sd, 'link_ffn_norm_track.', C)
+        if cfg.get('previous_link') == 'update_dynamic_cov':
+            _updator_params(g, sd, 'attention_previous_update_link.', ku['in_channels'], ku['feat_channels'], ku['out_channels'])
+            _mha_params(g, sd, 'attention_previous_link.', C)
+            _ln_params(g, sd, 'attention_previous_norm_link.', C)
+            _ffn_params(g, sd, 'link_ffn_link.', C, Fh)
+            _ln_params(g, sd, 'link_ffn_norm_link.', C)
+    return sd
+
+
+def round_bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def round_state_dict_bf16(sd):
+    return {k: round_bf16(v) for k, v in sd.items()}

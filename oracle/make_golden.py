@@ -1,0 +1,92 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+modules (imported from /root/reference through oracle/ref_shim.py) on seeded inputs.
+
+Run in the build container (the only place /root/reference exists):
+    python oracle/make_golden.py
+The fixtures travel to the GPU box; tests compare both the oracle restatement (CPU) and the
+CUDA path (GPU) against them.  Each .npz stores the inputs, the full state_dict (so the fixture
+does not depend on RNG reproducibility) and the reference outputs.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import knet_oracle as ko  # noqa: E402
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+
+def _pack(prefix, sd):
+    return {prefix + k: v.numpy() for k, v in sd.items()}
+
+
+def case_det(name, B, N, C, H, W, S, Fh, ncls, seed):
+    ref = ref_shim.load('knet')
+    cfg = ko.default_cfg(num_classes=ncls, in_channels=C, feedforward_channels=Fh)
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=seed)
+    blob = dict(x=x.numpy(), proposal_feat=pf.numpy(), mask_preds=mask.numpy(),
+                meta=np.array([B, N, C, H, W, S, Fh, ncls], dtype=np.int64))
+    obj = pf
+    with torch.no_grad():
+        for s in range(S):
+            sd = ko.random_state_dict(cfg, seed=100 * seed + s)
+            head = ref.KernelUpdateHead(**copy.deepcopy(cfg))
+            head.load_state_dict(sd, strict=True)
+            head.eval()
+            cls, mask, obj = head(x, obj, mask)     # knet/det/kernel_iter_head.py:246-253 chaining
+            blob.update(_pack('s%d.w.' % s, sd))
+            blob['s%d.cls_score' % s] = cls.numpy()
+            blob['s%d.mask_preds' % s] = mask.numpy()
+            blob['s%d.obj_feat' % s] = obj.numpy()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **blob)
+    print(name, 'ok', {k: v.shape for k, v in blob.items() if not k.split('.')[-2:][0] == 'w'} if False else '')
+
+
+def case_video(name, B, N, C, H, W, Fh, ncls, seed, previous_type, previous_link):
+    ref = ref_shim.load('knet')
+    cfg = ko.default_cfg(num_classes=ncls, in_channels=C, feedforward_channels=Fh,
+                         previous='placeholder', previous_type=previous_type, previous_link=previous_link)
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    prev = torch.randn(B, N, C, 1, 1, generator=g)
+    sd = ko.random_state_dict(cfg, seed=100 * seed)
+    head = ref.VideoKernelUpdateHead(**copy.deepcopy(cfg))
+    head.load_state_dict(sd, strict=True)
+    head.eval()
+    blob = dict(x=x.numpy(), proposal_feat=pf.numpy(), mask_preds=mask.numpy(), previous_obj_feats=prev.numpy(),
+                meta=np.array([B, N, C, H, W, 1, Fh, ncls], dtype=np.int64))
+    blob.update(_pack('s0.w.', sd))
+    with torch.no_grad():
+        cls, nm, obj, x_feat, track = head(x, pf, mask, previous_obj_feats=prev)
+        cls0, nm0, obj0, x_feat0, track0 = head(x, pf, mask)       # no previous -> 5th is None
+    assert track0 is None
+    blob.update({'s0.cls_score': cls.numpy(), 's0.mask_preds': nm.numpy(), 's0.obj_feat': obj.numpy(),
+                 's0.x_feat': x_feat.numpy(), 's0.obj_feat_track': track.numpy(),
+                 'noprev.cls_score': cls0.numpy(), 'noprev.mask_preds': nm0.numpy(), 'noprev.obj_feat': obj0.numpy()})
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **blob)
+    print(name, 'ok')
+
+
+def main():
+    assert ref_shim.available(), '/root/reference is required to (re)generate the fixtures'
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(4)
+    # BASELINE.json configs[0]: single 64x64 frame, N=10, C=64, S=1 (reference CPU case)
+    case_det('det_cfg0_b1_n10_c64_64x64_s1', 1, 10, 64, 64, 64, 1, 2048, 19, seed=1)
+    # ragged: odd H x W (HW not a multiple of any tile), B=2, two chained stages
+    case_det('det_b2_n12_c64_13x17_s2', 2, 12, 64, 13, 17, 2, 128, 5, seed=2)
+    # N above one 128-row tile is exercised at C=64 as well (N=130), 3 chained stages
+    case_det('det_b1_n130_c64_9x31_s3', 1, 130, 64, 9, 31, 3, 64, 3, seed=3)
+    case_video('video_link_ffn_b2_n12_c64_9x11', 2, 12, 64, 9, 11, 128, 5, 4, 'ffn', None)
+    case_video('video_link_update_b2_n12_c64_9x11', 2, 12, 64, 9, 11, 128, 5, 5, 'update', 'update_dynamic_cov')
+    case_video('video_link_cov_ffn_b1_n12_c64_9x11', 1, 12, 64, 9, 11, 128, 5, 6, 'ffn', 'update_dynamic_cov')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,242 @@
+"""TEST INFRASTRUCTURE ONLY -- not part of the product path.
+
+mmcv / mmdet stand-ins that let the reference's hot-path files import UNMODIFIED
+from /root/reference (they `import mmcv`, `import mmdet` at module top;
+neither wheel exists in this image and there is no network).
+
+Used only by oracle/make_golden.py and by the CPU tests that cross-check the
+restatement in oracle/knet_oracle.py against the live reference.  The GPU box
+has no /root/reference, so nothing under `-m gpu`, smoke() or bench.py touches
+this file.
+
+What is restated here is third-party behaviour:
+  * mmcv.cnn.ConvModule(norm_cfg=None, act_cfg=None)  -> nn.Conv2d(bias=True) as `.conv`
+  * mmcv.cnn.build_norm_layer(dict(type='LN'), n)    -> ('ln', nn.LayerNorm(n))
+  * mmcv.cnn.build_activation_layer(dict(type='ReLU', inplace=True))
+  * mmcv.cnn.bias_init_with_prob(p) = -log((1-p)/p)
+  * mmcv.cnn.bricks.transformer.FFN / MultiheadAttention / registries
+  * mmdet registries (HEADS), build_loss (only `.use_sigmoid` is read on the path)
+Reference call sites: knet/det/kernel_update_head.py:100-126,
+knet/kernel_updator.py:3-4, knet/video/kernel_update_head.py:108-260.
+"""
+import importlib
+import math
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = '/root/reference'
+
+
+class Registry:
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def deco(cls):
+            self.module_dict[name or cls.__name__] = cls
+            return cls
+        if module is not None:
+            return deco(module)
+        return deco
+
+    def build(self, cfg, **default):
+        cfg = dict(cfg)
+        typ = cfg.pop('type')
+        cls = self.module_dict[typ] if isinstance(typ, str) else typ
+        for k, v in default.items():
+            cfg.setdefault(k, v)
+        return cls(**cfg)
+
+
+class ConvModule(nn.Module):
+    """mmcv ConvModule restricted to what the hot path uses (no norm, no act)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0,
+                 conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU'), bias='auto', **kw):
+        super().__init__()
+        assert norm_cfg is None, 'shim: only the norm-free ConvModule is on the hot path'
+        assert act_cfg is None, 'shim: only the activation-free ConvModule is on the hot path'
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride,
+                              padding=padding, bias=True)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+def build_norm_layer(cfg, num_features, postfix=''):
+    assert cfg['type'] == 'LN'
+    return 'ln' + str(postfix), nn.LayerNorm(num_features)
+
+
+def build_activation_layer(cfg):
+    cfg = dict(cfg)
+    typ = cfg.pop('type')
+    assert typ == 'ReLU'
+    return nn.ReLU(**cfg)
+
+
+def bias_init_with_prob(prior_prob):
+    return float(-math.log((1 - prior_prob) / prior_prob))
+
+
+class FFN(nn.Module):
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                 act_cfg=dict(type='ReLU', inplace=True), ffn_drop=0., dropout_layer=None,
+                 add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        if 'dropout' in kwargs:  # deprecated alias kept by mmcv
+            ffn_drop = kwargs['dropout']
+        self.embed_dims = embed_dims
+        layers = []
+        in_channels = embed_dims
+        for _ in range(num_fcs - 1):
+            layers.append(nn.Sequential(nn.Linear(in_channels, feedforward_channels),
+                                        build_activation_layer(act_cfg), nn.Dropout(ffn_drop)))
+            in_channels = feedforward_channels
+        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(nn.Dropout(ffn_drop))
+        self.layers = nn.Sequential(*layers)
+        self.add_identity = add_identity
+
+    def forward(self, x, identity=None):
+        out = self.layers(x)
+        if not self.add_identity:
+            return out
+        if identity is None:
+            identity = x
+        return identity + out
+
+
+class MultiheadAttention(nn.Module):
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0.,
+                 dropout_layer=dict(type='Dropout', drop_prob=0.), init_cfg=None,
+                 batch_first=False, **kwargs):
+        super().__init__()
+        if 'dropout' in kwargs:
+            attn_drop = kwargs['dropout']
+        self.embed_dims = embed_dims
+        self.num_heads = num_heads
+        self.batch_first = batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.dropout_layer = nn.Identity()
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None,
+                key_pos=None, attn_mask=None, key_padding_mask=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        if query_pos is not None:
+            query = query + query_pos
+        if key_pos is not None:
+            key = key + key_pos
+        if self.batch_first:
+            query, key, value = (t.transpose(0, 1) for t in (query, key, value))
+        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
+                        key_padding_mask=key_padding_mask)[0]
+        if self.batch_first:
+            out = out.transpose(0, 1)
+        return identity + self.dropout_layer(self.proj_drop(out))
+
+
+class _FakeLoss(nn.Module):
+    def __init__(self, use_sigmoid=False, **kw):
+        super().__init__()
+        self.use_sigmoid = use_sigmoid
+
+    def forward(self, *a, **k):
+        raise NotImplementedError('losses are outside the hot path')
+
+
+def _mod(name):
+    m = types.ModuleType(name)
+    m.__path__ = []
+    sys.modules[name] = m
+    return m
+
+
+_installed = False
+
+
+def install():
+    """Put the stand-ins into sys.modules and /root/reference on sys.path."""
+    global _installed
+    if _installed:
+        return
+    names = ['mmcv', 'mmcv.cnn', 'mmcv.cnn.bricks', 'mmcv.cnn.bricks.transformer', 'mmcv.runner',
+             'mmdet', 'mmdet.core', 'mmdet.models', 'mmdet.models.builder',
+             'mmdet.models.dense_heads', 'mmdet.models.dense_heads.atss_head',
+             'mmdet.models.losses', 'mmdet.utils', 'unitrack', 'unitrack.mask']
+    mods = {n: _mod(n) for n in names}
+    for n, m in mods.items():
+        if '.' in n:
+            parent, child = n.rsplit('.', 1)
+            setattr(mods[parent], child, m)
+    cnn = mods['mmcv.cnn']
+    cnn.ConvModule = ConvModule
+    cnn.bias_init_with_prob = bias_init_with_prob
+    cnn.build_activation_layer = build_activation_layer
+    cnn.build_norm_layer = build_norm_layer
+    tr = mods['mmcv.cnn.bricks.transformer']
+    tr.TRANSFORMER_LAYER = Registry('transformer_layer')
+    tr.FFN = FFN
+    tr.MultiheadAttention = MultiheadAttention
+    tr.build_transformer_layer = lambda cfg, default_args=None: tr.TRANSFORMER_LAYER.build(cfg)
+    mods['mmcv.runner'].force_fp32 = lambda *a, **k: (lambda f: f)
+    mods['mmcv.runner'].auto_fp16 = lambda *a, **k: (lambda f: f)
+    core = mods['mmdet.core']
+    core.multi_apply = lambda func, *args, **kw: tuple(map(list, zip(*map(
+        lambda *a: func(*a, **kw), *args))))
+    core.bbox2result = lambda *a, **k: None
+    core.mask_matrix_nms = lambda *a, **k: None
+    bld = mods['mmdet.models.builder']
+    bld.HEADS = Registry('head')
+    bld.build_loss = lambda cfg: _FakeLoss(**{k: v for k, v in cfg.items() if k == 'use_sigmoid'})
+    bld.build_head = lambda cfg: bld.HEADS.build(cfg)
+    mods['mmdet.models.dense_heads.atss_head'].reduce_mean = lambda t: t
+    mods['mmdet.models.losses'].accuracy = lambda *a, **k: None
+    mods['mmdet.utils'].get_root_logger = lambda *a, **k: __import__('logging').getLogger('ref')
+    mods['unitrack.mask'].tensor_mask2box = lambda *a, **k: None
+    mods['unitrack.mask'].mask2box = lambda *a, **k: None
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _installed = True
+
+
+def available():
+    import os
+    return os.path.isdir(REFERENCE_ROOT + '/knet')
+
+
+def load(tree='knet'):
+    """Import the reference hot-path modules verbatim.  `tree` is 'knet' or 'knet_vis'
+    (they register the same registry keys, so use one per process)."""
+    install()
+    out = types.SimpleNamespace()
+    if tree == 'knet':
+        out.kernel_updator = importlib.import_module('knet.kernel_updator')
+        out.det_head = importlib.import_module('knet.det.kernel_update_head')
+        out.video_head = importlib.import_module('knet.video.kernel_update_head')
+        out.KernelUpdator = out.kernel_updator.KernelUpdator
+        out.KernelUpdateHead = out.det_head.KernelUpdateHead
+        out.VideoKernelUpdateHead = out.video_head.VideoKernelUpdateHead
+    else:
+        out.kernel_updator = importlib.import_module('knet_vis.kernel_updator')
+        out.det_head = importlib.import_module('knet_vis.det.kernel_update_head')
+        out.KernelUpdator = out.kernel_updator.KernelUpdator
+        out.KernelUpdateHead = out.det_head.KernelUpdateHead
+        try:
+            out.tracker_head = importlib.import_module('knet_vis.tracker.kernel_update_head')
+            out.KernelUpdateHeadVideo = out.tracker_head.KernelUpdateHeadVideo
+        except Exception as e:  # pragma: no cover - informational
+            out.tracker_head_error = repr(e)
+    return out
