@@ -1,0 +1,198 @@
+/*
+ * vknet.h -- C ABI of libvknet.so: the B200 (sm_100a) implementation of Video K-Net's
+ * KernelUpdateHead hot path.  Plain C: raw device pointers, POD structs, an explicit
+ * cudaStream_t (passed as void*).  No torch types cross this boundary.
+ *
+ * Each entry point names the reference code it replaces (paths under lxtGH/Video-K-Net):
+ *   knet/det/kernel_update_head.py   KernelUpdateHead.forward        :170-277
+ *   knet/kernel_updator.py           KernelUpdator.forward           :56-94
+ *   knet/video/kernel_update_head.py VideoKernelUpdateHead.forward   :281-541
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VKN_E_* code; vkn_last_error() returns a
+ *     thread-local message.  No exceptions cross the boundary.
+ *   - the CALLER owns every buffer (inputs, outputs, workspace).  The library never allocates or
+ *     frees device memory.  All work is enqueued on `stream`; nothing synchronises the device, so
+ *     every call is CUDA-graph capturable.
+ *   - layouts are the reference's: x [B,C,H,W] (NCHW, contiguous), mask_preds / new_mask_preds
+ *     [B,N,H,W], proposal_feat / obj_feat [B,N,C] (the reference's [B,N,C,1,1]; conv_kernel_size
+ *     is 1 in every shipped config and is the only size supported), cls_score [B,N,num_classes].
+ *   - x_dtype selects the storage type of x and of the mask tensors (VKN_F32 or VKN_BF16).
+ *     Kernel-side tensors (proposal_feat, obj_feat, cls_score, x_feat) are always fp32.
+ *   - w_dtype selects the storage type of weight MATRICES (VKN_F32 or VKN_BF16); bias and
+ *     LayerNorm vectors are always fp32.  Arithmetic is fp32 throughout (bf16 products are
+ *     exact in the fp32 accumulators), so VKN_BF16 changes bytes moved, not the math.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     VKN_E_CUDA.
+ */
+#ifndef VKNET_H_
+#define VKNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKN_VERSION 100
+
+enum { VKN_F32 = 0, VKN_BF16 = 1 };
+
+enum {
+  VKN_OK = 0,
+  VKN_E_INVALID = -1,     /* bad argument / inconsistent shape */
+  VKN_E_UNSUPPORTED = -2, /* a configuration outside the shipped path (e.g. conv_kernel_size != 1) */
+  VKN_E_CUDA = -3,        /* a CUDA runtime/driver call failed (message has the detail) */
+  VKN_E_WORKSPACE = -4    /* workspace too small or misaligned */
+};
+
+/* GEMM engine selection for the two big contractions (mask pooling and dynamic mask conv). */
+enum {
+  VKN_ENGINE_AUTO = 0,  /* tcgen05/TMA when x_dtype == VKN_BF16 and the shape qualifies, else SIMT fp32 */
+  VKN_ENGINE_SIMT = 1,  /* CUDA-core fp32 kernels (also the only engine for VKN_F32 storage) */
+  VKN_ENGINE_TC = 2     /* force tcgen05 (fails with VKN_E_UNSUPPORTED if the shape does not qualify) */
+};
+
+typedef struct VknShape {
+  int32_t B;            /* frames in this call */
+  int32_t N;            /* kernels (proposals) per frame: 100 / 117 / 166 in the shipped configs */
+  int32_t C;            /* channels (in_channels == feat_channels == out_channels); multiple of 64, <= 256 */
+  int32_t H, W;         /* feature-map size; HW arbitrary */
+  int32_t ffn_dim;      /* feedforward_channels (2048) */
+  int32_t num_classes;  /* fc_cls rows */
+  int32_t num_heads;    /* 8 */
+  int32_t x_dtype;      /* VKN_F32 | VKN_BF16: storage of x, mask_preds, new_mask_preds */
+  int32_t w_dtype;      /* VKN_F32 | VKN_BF16: storage of weight matrices */
+  int32_t with_ffn;     /* KernelUpdateHead(with_ffn=...) */
+  int32_t engine;       /* VKN_ENGINE_* */
+  float mask_thr_logit; /* logit(hard_mask_thr): sigmoid(m) > thr  <=>  m > mask_thr_logit (0 for thr=0.5) */
+} VknShape;
+
+/* KernelUpdator parameters (knet/kernel_updator.py:36-54).  *_w are [out,in] row-major like nn.Linear. */
+typedef struct VknUpdatorW {
+  const void *dyn_w;  const float *dyn_b;   /* dynamic_layer  [2C,C] */
+  const void *inp_w;  const float *inp_b;   /* input_layer    [2C,C] */
+  const void *ig_w;   const float *ig_b;    /* input_gate     [C,C]  */
+  const void *ug_w;   const float *ug_b;    /* update_gate    [C,C]  */
+  const float *norm_in_g, *norm_in_b;       /* norm_in        (update gate LN) */
+  const float *norm_out_g, *norm_out_b;     /* norm_out       (param_out LN)   */
+  const float *inorm_in_g, *inorm_in_b;     /* input_norm_in  (input gate LN)  */
+  const float *inorm_out_g, *inorm_out_b;   /* input_norm_out (input_out LN)   */
+  const void *fc_w;   const float *fc_b;    /* fc_layer       [C,C]  */
+  const float *fc_norm_g, *fc_norm_b;       /* fc_norm */
+} VknUpdatorW;
+
+/* mmcv MultiheadAttention (nn.MultiheadAttention packed in_proj) + the LayerNorm that follows it. */
+typedef struct VknAttnW {
+  const void *in_w;  const float *in_b;     /* in_proj  [3C,C] */
+  const void *out_w; const float *out_b;    /* out_proj [C,C]  */
+  const float *norm_g, *norm_b;
+} VknAttnW;
+
+/* mmcv FFN(num_fcs=2) + the LayerNorm that follows it. */
+typedef struct VknFfnW {
+  const void *w1; const float *b1;          /* layers.0.0 [F,C] */
+  const void *w2; const float *b2;          /* layers.1   [C,F] */
+  const float *norm_g, *norm_b;
+} VknFfnW;
+
+#define VKN_MAX_FCS 4
+
+/* One KernelUpdateHead stage (state_dict contract: SURVEY.md Appendix C). */
+typedef struct VknHeadW {
+  const void *ft_w;        /* feat_transform.conv.weight [C,C] (identity when feat_transform_cfg is None) */
+  const float *ft_b;       /* feat_transform.conv.bias   [C]   */
+  const void *ft_wt_ext;   /* [C+1,C]: rows 0..C-1 = ft_w^T, row C = ft_b  (host-prepared fold operand) */
+  VknUpdatorW upd;         /* kernel_update_conv.* */
+  VknAttnW attn;           /* attention.attn.*, attention_norm.* */
+  VknFfnW ffn;             /* ffn.*, ffn_norm.* (ignored when with_ffn == 0) */
+  int32_t num_cls_fcs, num_mask_fcs;
+  const void *cls_fc_w[VKN_MAX_FCS];  const float *cls_ln_g[VKN_MAX_FCS], *cls_ln_b[VKN_MAX_FCS];
+  const void *fc_cls_w;  const float *fc_cls_b;     /* [num_classes,C] */
+  const void *mask_fc_w[VKN_MAX_FCS]; const float *mask_ln_g[VKN_MAX_FCS], *mask_ln_b[VKN_MAX_FCS];
+  const void *fc_mask_w; const float *fc_mask_b;    /* [C,C] */
+} VknHeadW;
+
+/* One cross-frame link block of VideoKernelUpdateHead (knet/video/kernel_update_head.py:167-260):
+ * optional KernelUpdator on the previous kernels, cross attention + LN, FFN + LN. */
+typedef struct VknLinkW {
+  int32_t has_updator;     /* 1: prev' = KernelUpdator(x_feat, prev) first ('update', 'update_dynamic_cov') */
+  VknUpdatorW upd;
+  VknAttnW attn;
+  VknFfnW ffn;
+} VknLinkW;
+
+int vkn_version(void);
+const char *vkn_last_error(void);
+
+/* Names of the device kernels this library launches, '\n' separated (for the bench's launch audit). */
+const char *vkn_kernel_names(void);
+
+/* Bytes of caller-provided scratch needed by the stage / link / iter entry points for `shape`. */
+int vkn_workspace_bytes(const VknShape *shape, size_t *bytes);
+
+/* ---- individual operators (each is also a step of vkn_stage_forward) ------------------------- */
+
+/* a3+a4 with the feat_transform folded out: knet/det/kernel_update_head.py:179-195.
+ *   x_feat[b,n,:] = sum_p 1[mask[b,n,p] > thr] * (ft_w x[b,:,p] + ft_b)      -> fp32 [B,N,C]  */
+int vkn_mask_pool(const VknShape *s, const VknHeadW *w, const void *x, const void *mask_preds,
+                  float *x_feat, void *workspace, size_t workspace_bytes, void *stream);
+
+/* a5: KernelUpdator.forward, knet/kernel_updator.py:56-94.  update_feature = x_feat [P,C],
+ * input_feature = proposal_feat [P,C] (K=1), out [P,C];  P = B*N rows. */
+int vkn_kernel_update(const VknShape *s, const VknUpdatorW *w, const float *x_feat,
+                      const float *proposal_feat, float *out, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* a6: LN(q_in + MHA(q_in, kv_in, kv_in)), attention across the N kernels of each frame
+ * (knet/det/kernel_update_head.py:204-208; cross form: knet/video/kernel_update_head.py:337-345). */
+int vkn_mhsa_ln(const VknShape *s, const VknAttnW *w, const float *q_in, const float *kv_in, float *out,
+                void *workspace, size_t workspace_bytes, void *stream);
+
+/* a7: LN(in + W2 relu(W1 in + b1) + b2), knet/det/kernel_update_head.py:214-215. */
+int vkn_ffn_ln(const VknShape *s, const VknFfnW *w, const float *in, float *out, void *workspace,
+               size_t workspace_bytes, void *stream);
+
+/* a8 + the fold operand for a9: cls/mask FC stacks (knet/det/kernel_update_head.py:217-227).
+ *   cls_score [P,num_classes]; mask_kernel [P,C] = fc_mask(...) (the reference's mask_feat). */
+int vkn_heads(const VknShape *s, const VknHeadW *w, const float *obj_feat, float *cls_score,
+              float *mask_kernel, void *workspace, size_t workspace_bytes, void *stream);
+
+/* a9: dynamic 1x1 mask convolution with feat_transform folded in
+ * (knet/det/kernel_update_head.py:179-180 + :247-260):
+ *   new_mask[b,n,p] = sum_c mask_kernel[b,n,c] * (ft_w x[b,:,p] + ft_b)[c]                         */
+int vkn_mask_gemm(const VknShape *s, const VknHeadW *w, const void *x, const float *mask_kernel,
+                  void *new_mask_preds, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- whole stage / loop ----------------------------------------------------------------------- */
+
+/* KernelUpdateHead.forward (knet/det/kernel_update_head.py:170-277) for conv_kernel_size == 1.
+ * Outputs: cls_score [B,N,num_classes] fp32, new_mask_preds [B,N,H,W] x_dtype, obj_feat [B,N,C] fp32,
+ * x_feat_out [B,N,C] fp32 or NULL (the pooled feature VideoKernelUpdateHead also returns).
+ * x_feat_in, when not NULL, is a pooled feature already computed by vkn_mask_pool for these
+ * mask_preds (the video head pools once, runs its link block, then the stage): pooling is skipped
+ * and mask_preds may be NULL.  new_mask_preds may be NULL (skip a9: callers that only need kernels). */
+int vkn_stage_forward(const VknShape *s, const VknHeadW *w, const void *x, const float *proposal_feat,
+                      const void *mask_preds, const float *x_feat_in, float *cls_score, void *new_mask_preds,
+                      float *obj_feat, float *x_feat_out, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* The S-stage loop of KernelIterHead.simple_test (knet/det/kernel_iter_head.py:246-253):
+ * stage s consumes stage s-1's obj_feat and mask logits.  Only the last stage's outputs are
+ * returned (that is all simple_test reads); intermediate masks live in the workspace. */
+int vkn_iter_forward(const VknShape *s, const VknHeadW *stages, int num_stages, const void *x,
+                     const float *proposal_feat, const void *mask_preds, float *cls_score,
+                     void *new_mask_preds, float *obj_feat, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* Cross-frame link block of VideoKernelUpdateHead (knet/video/kernel_update_head.py:324-348,
+ * :394-415, :417-444):  prev' = has_updator ? KernelUpdator(x_feat, prev) : prev;
+ *   t = LN(cur + MHA(q=cur, k=v=prev'));  out = LN(FFN(t)).   cur, prev, out: [B,N,C] fp32. */
+int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, const float *prev,
+                    const float *x_feat, float *out, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKNET_H_ */

@@ -207,8 +207,6 @@ def install():
     mods['mmdet.utils'].get_root_logger = lambda *a, **k: __import__('logging').getLogger('ref')
     mods['unitrack.mask'].tensor_mask2box = lambda *a, **k: None
     mods['unitrack.mask'].mask2box = lambda *a, **k: None
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
     _installed = True
 
 
@@ -217,26 +215,36 @@ def available():
     return os.path.isdir(REFERENCE_ROOT + '/knet')
 
 
+def _load_file(modname, relpath):
+    """Import one reference file by PATH under a private module name.  (The product ships alias
+    packages named `knet` / `knet_vis` for the configs' custom_imports; importing by path guarantees
+    the oracle side really is the reference's source, whatever sys.path says.)"""
+    import importlib.util
+    import os
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    assert os.path.realpath(mod.__file__).startswith(REFERENCE_ROOT)
+    return mod
+
+
 def load(tree='knet'):
     """Import the reference hot-path modules verbatim.  `tree` is 'knet' or 'knet_vis'
     (they register the same registry keys, so use one per process)."""
     install()
     out = types.SimpleNamespace()
     if tree == 'knet':
-        out.kernel_updator = importlib.import_module('knet.kernel_updator')
-        out.det_head = importlib.import_module('knet.det.kernel_update_head')
-        out.video_head = importlib.import_module('knet.video.kernel_update_head')
+        out.kernel_updator = _load_file('_ref_knet.kernel_updator', 'knet/kernel_updator.py')
+        out.det_head = _load_file('_ref_knet.det.kernel_update_head', 'knet/det/kernel_update_head.py')
+        out.video_head = _load_file('_ref_knet.video.kernel_update_head', 'knet/video/kernel_update_head.py')
         out.KernelUpdator = out.kernel_updator.KernelUpdator
         out.KernelUpdateHead = out.det_head.KernelUpdateHead
         out.VideoKernelUpdateHead = out.video_head.VideoKernelUpdateHead
     else:
-        out.kernel_updator = importlib.import_module('knet_vis.kernel_updator')
-        out.det_head = importlib.import_module('knet_vis.det.kernel_update_head')
+        out.kernel_updator = _load_file('_ref_knet_vis.kernel_updator', 'knet_vis/kernel_updator.py')
+        out.det_head = _load_file('_ref_knet_vis.det.kernel_update_head', 'knet_vis/det/kernel_update_head.py')
         out.KernelUpdator = out.kernel_updator.KernelUpdator
         out.KernelUpdateHead = out.det_head.KernelUpdateHead
-        try:
-            out.tracker_head = importlib.import_module('knet_vis.tracker.kernel_update_head')
-            out.KernelUpdateHeadVideo = out.tracker_head.KernelUpdateHeadVideo
-        except Exception as e:  # pragma: no cover - informational
-            out.tracker_head_error = repr(e)
     return out

@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libvknet.so), against
+(a) the golden fixtures produced by the UNMODIFIED reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): kernel tensors (obj_feat, cls_score, x_feat, link outputs)
+within 1e-3 in fp32 / 1e-2 in bf16 storage; mask argmax over the N kernels identical to the
+oracle's.  Logit maps are additionally checked to 1e-3 * max|logit| (they feed the next stage's
+hard threshold).
+"""
+import pytest
+import torch
+
+import knet_oracle as ko
+from helpers import build_heads, golden_files, load_golden, maxabs, top2_gap
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-3
+TOL_BF16 = 1e-2
+
+
+@pytest.fixture(scope='module')
+def dev(built_lib):
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+def assert_masks(got, ref, what, rel=1e-3):
+    """logits close AND argmax over kernels identical (ties: pixels whose oracle top-2 gap is below the
+    logit tolerance may legitimately resolve either way; they are counted and must stay rare)."""
+    got = got.float().cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= rel * scale, '%s: mask logits max-abs err %g (scale %g)' % (what, err, scale)
+    if ref.shape[1] > 1:
+        a, b = got.argmax(1), ref.argmax(1)
+        bad = a != b
+        if bad.any():
+            gap = top2_gap(ref)[bad]
+            assert gap.max().item() <= 2 * err + 1e-6 * scale, \
+                '%s: %d argmax mismatches at non-tied pixels (max gap %g, logit err %g)' % (
+                    what, int(bad.sum()), gap.max().item(), err)
+            assert bad.float().mean().item() < 1e-3, '%s: too many tied-pixel argmax flips' % what
+
+
+# ---- golden fixtures (outputs of the unmodified reference) ---------------------------------------
+@pytest.mark.parametrize('path', golden_files('det_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_golden_det_chain(dev, path):
+    g = load_golden(path)
+    t = g['t']
+    heads = build_heads('KernelUpdateHead', g['cfg'], g['sds'], dev)
+    x, obj, m = t['x'].to(dev), t['proposal_feat'].to(dev), t['mask_preds'].to(dev)
+    for s, h in enumerate(heads):
+        cls, m, obj = h(x, obj, m)
+        assert obj.shape == t['s%d.obj_feat' % s].shape and cls.shape == t['s%d.cls_score' % s].shape
+        assert maxabs(cls, t['s%d.cls_score' % s]) < TOL_F32, 'stage %d cls_score' % s
+        assert maxabs(obj, t['s%d.obj_feat' % s]) < TOL_F32, 'stage %d obj_feat' % s
+        assert_masks(m, t['s%d.mask_preds' % s], 'stage %d' % s)
+
+
+@pytest.mark.parametrize('path', golden_files('det_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_golden_det_stagewise(dev, path):
+    """Each stage fed the REFERENCE's inputs for that stage (no error carry-over)."""
+    g = load_golden(path)
+    t = g['t']
+    heads = build_heads('KernelUpdateHead', g['cfg'], g['sds'], dev)
+    x = t['x'].to(dev)
+    for s, h in enumerate(heads):
+        obj_in = t['proposal_feat'] if s == 0 else t['s%d.obj_feat' % (s - 1)]
+        m_in = t['mask_preds'] if s == 0 else t['s%d.mask_preds' % (s - 1)]
+        cls, m, obj = h(x, obj_in.to(dev), m_in.to(dev))
+        assert maxabs(cls, t['s%d.cls_score' % s]) < TOL_F32
+        assert maxabs(obj, t['s%d.obj_feat' % s]) < TOL_F32
+        assert_masks(m, t['s%d.mask_preds' % s], 'stage %d' % s)
+
+
+@pytest.mark.parametrize('path', golden_files('video_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_golden_video_links(dev, path):
+    g = load_golden(path)
+    t = g['t']
+    h = build_heads('VideoKernelUpdateHead', g['cfg'], g['sds'], dev)[0]
+    x, pf, m, prev = (t[k].to(dev) for k in ('x', 'proposal_feat', 'mask_preds', 'previous_obj_feats'))
+    cls, nm, obj, x_feat, track = h(x, pf, m, previous_obj_feats=prev)
+    assert maxabs(x_feat, t['s0.x_feat']) < 1e-3 * max(1.0, t['s0.x_feat'].abs().max().item())
+    assert maxabs(cls, t['s0.cls_score']) < TOL_F32
+    assert maxabs(obj, t['s0.obj_feat']) < TOL_F32
+    assert track is not None and track.shape == t['s0.obj_feat_track'].shape
+    assert maxabs(track, t['s0.obj_feat_track']) < TOL_F32
+    assert_masks(nm, t['s0.mask_preds'], 'linked stage')
+    cls, nm, obj, x_feat, track = h(x, pf, m)          # no previous -> 5th output None (:540-541)
+    assert track is None
+    assert maxabs(cls, t['noprev.cls_score']) < TOL_F32
+    assert maxabs(obj, t['noprev.obj_feat']) < TOL_F32
+    assert_masks(nm, t['noprev.mask_preds'], 'unlinked stage')
+
+
+# ---- individual operators against the oracle ------------------------------------------------------
+@pytest.mark.parametrize('B,N,C,H,W,Fh', [(1, 10, 64, 8, 8, 64), (2, 37, 128, 7, 19, 96), (1, 100, 256, 24, 40, 2048)])
+def test_operators(dev, B, N, C, H, W, Fh):
+    from vknet import ops
+    cfg = ko.default_cfg(num_classes=11, in_channels=C, feedforward_channels=Fh)
+    sd = ko.random_state_dict(cfg, seed=5)
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=9)
+    g = torch.Generator().manual_seed(4)
+    rows = torch.randn(B, N, C, generator=g)
+    # a3+a4 pooling (with feat_transform)
+    xt, x_feat, pf_r = ko._pool(sd, cfg, x, pf, mask)
+    got = ops.mask_pool(h, x.to(dev), mask.to(dev))
+    assert maxabs(got, x_feat) < 1e-4 * x_feat.abs().max().item(), 'mask_pool'
+    # a5 KernelUpdator
+    want = ko.kernel_updator(sd, 'kernel_update_conv.', x_feat, pf_r, C, C).reshape(B, N, C)
+    assert maxabs(ops.kernel_update(h, x_feat.to(dev), pf.to(dev)), want) < 1e-4, 'kernel_update'
+    # a6 MHSA + LN
+    seq = rows.permute(1, 0, 2)
+    want = ko.layer_norm(ko.mha_block(seq, seq, seq, seq, sd, 'attention.', 8), sd['attention_norm.weight'],
+                         sd['attention_norm.bias']).permute(1, 0, 2)
+    assert maxabs(ops.mhsa_ln(h, rows.to(dev)), want) < 1e-4, 'mhsa_ln'
+    # a7 FFN + LN
+    want = ko.layer_norm(ko.ffn_block(rows, sd, 'ffn.'), sd['ffn_norm.weight'], sd['ffn_norm.bias'])
+    assert maxabs(ops.ffn_ln(h, rows.to(dev)), want) < 1e-4, 'ffn_ln'
+    # a8 heads
+    cls_f = torch.relu(ko.layer_norm(ko.linear(rows, sd['cls_fcs.0.weight']), sd['cls_fcs.1.weight'], sd['cls_fcs.1.bias']))
+    mk_f = torch.relu(ko.layer_norm(ko.linear(rows, sd['mask_fcs.0.weight']), sd['mask_fcs.1.weight'], sd['mask_fcs.1.bias']))
+    want_cls = ko.linear(cls_f, sd['fc_cls.weight'], sd['fc_cls.bias'])
+    want_mk = ko.linear(mk_f, sd['fc_mask.weight'], sd['fc_mask.bias'])
+    cls, mk = ops.heads(h, rows.to(dev))
+    assert maxabs(cls, want_cls) < 1e-4 and maxabs(mk, want_mk) < 1e-4, 'heads'
+    # a9 dynamic mask conv (with feat_transform folded in)
+    want = torch.einsum('bnc,bchw->bnhw', want_mk, xt)
+    assert_masks(ops.mask_gemm(h, x.to(dev), want_mk.to(dev)), want, 'mask_gemm', rel=1e-5)
+
+
+# ---- shape sweep: real kernel counts, ragged H*W, frame batches ------------------------------------
+@pytest.mark.parametrize('B,N,C,H,W', [(1, 10, 64, 64, 64), (3, 117, 64, 5, 13), (2, 166, 128, 11, 9),
+                                       (1, 100, 256, 33, 17), (4, 100, 256, 12, 20)])
+def test_stage_shapes(dev, B, N, C, H, W):
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
+    sd = ko.random_state_dict(cfg, seed=B * 1000 + N)
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=N)
+    want = ko.kernel_update_head_forward(sd, cfg, x, pf, mask)
+    cls, nm, obj = h(x.to(dev), pf.to(dev), mask.to(dev))
+    assert cls.shape == want[0].shape and nm.shape == want[1].shape and obj.shape == want[2].shape
+    assert maxabs(cls, want[0]) < TOL_F32 and maxabs(obj, want[2]) < TOL_F32
+    assert_masks(nm, want[1], 'stage')
+
+
+def test_variants_no_ffn_no_transform_more_fcs(dev):
+    """with_ffn=False, feat_transform_cfg=None, num_mask_fcs=3 (the class default) and a non-default threshold."""
+    cfg = ko.default_cfg(num_classes=5, in_channels=64, feedforward_channels=64, with_ffn=False,
+                         feat_transform_cfg=None, num_mask_fcs=3, num_cls_fcs=2, hard_mask_thr=0.7)
+    sd = ko.random_state_dict(cfg, seed=1)
+    g = torch.Generator().manual_seed(8)
+    for i in (1, 2):   # extra FC layers
+        sd['mask_fcs.%d.weight' % (3 * i)] = ko._xavier(g, 64, 64)
+        ko._ln_params(g, sd, 'mask_fcs.%d.' % (3 * i + 1), 64)
+    sd['cls_fcs.3.weight'] = ko._xavier(g, 64, 64)
+    ko._ln_params(g, sd, 'cls_fcs.4.', 64)
+    for k in [k for k in sd if k.startswith('ffn')]:
+        del sd[k]
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev)[0]
+    x, pf, mask = ko.dummy_inputs(2, 14, 64, 9, 10, seed=2)
+    want = ko.kernel_update_head_forward(sd, cfg, x, pf, mask)
+    cls, nm, obj = h(x.to(dev), pf.to(dev), mask.to(dev))
+    assert maxabs(cls, want[0]) < TOL_F32 and maxabs(obj, want[2]) < TOL_F32
+    assert_masks(nm, want[1], 'variant stage')
+
+
+# ---- bf16 storage: oracle = fp32 math on bf16-rounded x / masks / weights, masks rounded on output ----
+@pytest.mark.parametrize('B,N,C,H,W,S', [(1, 20, 64, 16, 24, 2), (2, 100, 256, 40, 24, 2)])
+def test_bf16_storage(dev, B, N, C, H, W, S):
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=512)
+    sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=70 + s)) for s in range(S)]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=6)
+    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
+    want = ko.iter_forward(sds, [cfg] * S, x, pf, mask, mask_round=ko.round_bf16)
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
+    obj, m = pf.to(dev), mask.to(dev).bfloat16()
+    xb = x.to(dev).bfloat16()
+    for s, h in enumerate(heads):
+        cls, m, obj = h(xb, obj, m)
+        assert m.dtype == torch.bfloat16 and obj.dtype == torch.float32
+        assert maxabs(cls, want[s][0]) < TOL_BF16, 'bf16 stage %d cls' % s
+        assert maxabs(obj, want[s][2]) < TOL_BF16, 'bf16 stage %d obj' % s
+        ref = want[s][1]
+        # bf16 output rounding: 1 ulp = 2^-8 relative
+        assert (m.float().cpu() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+        mism = (m.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item()
+        assert mism < 2e-3, 'bf16 stage %d: argmax mismatch rate %g' % (s, mism)
+
+
+# ---- BASELINE.json cfg1 at full size: N=100, C=256, 200x88, S=3 -------------------------------------
+def test_cfg1_full_size_loop(dev):
+    import vknet
+    B, N, C, H, W, S = 1, 100, 256, 200, 88, 3
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=2048)
+    sds = [ko.random_state_dict(cfg, seed=s) for s in range(S)]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=1)
+    want = ko.iter_forward(sds, [cfg] * S, x, pf, mask)
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev)
+    # stage-wise with the oracle's inputs: isolates each stage from threshold flips upstream
+    for s, h in enumerate(heads):
+        obj_in = pf if s == 0 else want[s - 1][2]
+        m_in = mask if s == 0 else want[s - 1][1]
+        cls, m, obj = h(x.to(dev), obj_in.to(dev), m_in.to(dev))
+        assert maxabs(cls, want[s][0]) < TOL_F32 and maxabs(obj, want[s][2]) < TOL_F32
+        assert_masks(m, want[s][1], 'cfg1 stage %d' % s)
+    # chained loop in one call == chained modules (same kernels, bit-identical)
+    loop = vknet.KernelIterLoop(heads)
+    cls_l, m_l, obj_l = loop(x.to(dev), pf.to(dev), mask.to(dev))
+    obj_c, m_c = pf.to(dev), mask.to(dev)
+    flips = []
+    for s, h in enumerate(heads):
+        cls_c, m_c, obj_c = h(x.to(dev), obj_c, m_c)
+        flips.append(int(((m_c.float().cpu() > 0) != (want[s][1] > 0)).sum()))
+    assert torch.equal(m_l, m_c) and torch.equal(obj_l, obj_c) and torch.equal(cls_l, cls_c)
+    # end of the loop vs the oracle: threshold disagreements upstream are counted, not assumed zero
+    print('cfg1 threshold disagreements per stage vs oracle:', flips)
+    assert sum(flips[:-1]) <= 8, 'too many hard-mask disagreements feeding later stages: %s' % flips
+    if sum(flips[:-1]) == 0:
+        assert maxabs(obj_l, want[-1][2]) < TOL_F32 and maxabs(cls_l, want[-1][0]) < TOL_F32
+        assert_masks(m_l, want[-1][1], 'cfg1 loop end')
+
+
+def test_graph_replay_matches_eager_and_is_deterministic(dev):
+    import vknet
+    cfg = ko.default_cfg(num_classes=19, in_channels=64, feedforward_channels=128)
+    sds = [ko.random_state_dict(cfg, seed=s) for s in range(3)]
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev)
+    x, pf, mask = (t.to(dev) for t in ko.dummy_inputs(2, 30, 64, 20, 28, seed=3))
+    loop = vknet.KernelIterLoop(heads)
+    a = [t.clone() for t in loop(x, pf, mask)]
+    b = [t.clone() for t in loop(x, pf, mask)]
+    assert all(torch.equal(u, v) for u, v in zip(a, b)), 'two eager runs differ bitwise'
+    loop.capture(x, pf, mask)
+    c = [t.clone() for t in loop.replay(x, pf, mask)]
+    assert all(torch.equal(u, v) for u, v in zip(a, c)), 'graph replay differs from the eager run'
+    x2, pf2, mask2 = (t.to(dev) for t in ko.dummy_inputs(2, 30, 64, 20, 28, seed=4))
+    d = [t.clone() for t in loop.replay(x2, pf2, mask2)]
+    e = loop(x2, pf2, mask2)
+    assert all(torch.equal(u, v) for u, v in zip(d, e))
+
+
+# ---- size-independent properties at full size ---------------------------------------------------------
+def test_properties_full_size(dev):
+    from vknet import ops
+    B, N, C, H, W = 1, 100, 256, 200, 88
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=2048)
+    sd = ko.random_state_dict(cfg, seed=2)
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev)[0]
+    x, pf, mask = (t.to(dev) for t in ko.dummy_inputs(B, N, C, H, W, seed=5))
+    # pooling is additive over disjoint pixel sets: pool(mask) = pool(mask on left half) + pool(right half)
+    neg = torch.full_like(mask, -1.0)
+    left, right = neg.clone(), neg.clone()
+    left[..., : W // 2] = mask[..., : W // 2]
+    right[..., W // 2:] = mask[..., W // 2:]
+    full = ops.mask_pool(h, x, mask)
+    parts = ops.mask_pool(h, x, left) + ops.mask_pool(h, x, right)
+    assert maxabs(full, parts) < 1e-4 * full.abs().max().item()
+    # an all-negative mask pools to exactly zero; an all-positive mask row equals the feature sum
+    assert ops.mask_pool(h, x, neg).abs().max().item() == 0.0
+    # mask conv is linear in the kernels
+    g = torch.Generator().manual_seed(0)
+    k1 = torch.randn(B, N, C, generator=g).to(dev)
+    k2 = torch.randn(B, N, C, generator=g).to(dev)
+    m12 = ops.mask_gemm(h, x, k1 + k2)
+    m1, m2 = ops.mask_gemm(h, x, k1), ops.mask_gemm(h, x, k2)
+    assert maxabs(m12, m1 + m2) < 1e-4 * m12.abs().max().item()
+    # permuting the kernels permutes the outputs (attention is permutation equivariant over N)
+    perm = torch.randperm(N, generator=g).to(dev)
+    cls, nm, obj = h(x, pf, mask)
+    cls_p, nm_p, obj_p = h(x, pf[:, perm], mask[:, perm])
+    assert maxabs(obj[:, perm], obj_p) < 1e-4 and maxabs(cls[:, perm], cls_p) < 1e-4
+    assert maxabs(nm[:, perm], nm_p) < 1e-4 * nm.abs().max().item()
+
+
+def test_error_behaviour(dev):
+    import vknet
+    cfg = ko.default_cfg(num_classes=3, in_channels=64, feedforward_channels=64)
+    h = build_heads('KernelUpdateHead', cfg, [ko.random_state_dict(cfg)], dev)[0]
+    x, pf, mask = (t.to(dev) for t in ko.dummy_inputs(1, 6, 64, 4, 4))
+    with pytest.raises(vknet.VknError):
+        h(x.cpu(), pf.cpu(), mask.cpu())                       # no CPU path
+    with pytest.raises(vknet.VknError):
+        h(x[:, :32], pf, mask)                                 # channel mismatch
+    with pytest.raises(vknet.VknError):
+        h(x.double(), pf, mask)                                # unsupported dtype
+    bad = vknet.build_head(dict(type='KernelUpdateHead', **ko.default_cfg(in_channels=64, conv_kernel_size=3)))
+    with pytest.raises(NotImplementedError):
+        bad.to(dev)(x, torch.zeros(1, 6, 64, 3, 3, device=dev), mask)

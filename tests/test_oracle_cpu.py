@@ -1,0 +1,95 @@
+"""CPU: pins the oracle (oracle/knet_oracle.py) against the reference.
+ (1) golden fixtures written by the unmodified reference (tests/golden, made by oracle/make_golden.py);
+ (2) when /root/reference is present (build container only), the live reference on fresh seeds."""
+import copy
+
+import pytest
+import torch
+
+import knet_oracle as ko
+from helpers import golden_files, load_golden, maxabs
+
+
+@pytest.mark.parametrize('path', golden_files('det_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_oracle_matches_reference_fixtures_det(path):
+    g = load_golden(path)
+    t = g['t']
+    outs = ko.iter_forward(g['sds'], [g['cfg']] * g['S'], t['x'], t['proposal_feat'], t['mask_preds'])
+    for s, (cls, m, obj) in enumerate(outs):
+        assert maxabs(cls, t['s%d.cls_score' % s]) < 2e-5
+        assert maxabs(obj, t['s%d.obj_feat' % s]) < 2e-5
+        assert maxabs(m, t['s%d.mask_preds' % s]) < 2e-4
+        assert torch.equal(m.argmax(1), t['s%d.mask_preds' % s].argmax(1))
+
+
+@pytest.mark.parametrize('path', golden_files('video_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_oracle_matches_reference_fixtures_video(path):
+    g = load_golden(path)
+    t = g['t']
+    out = ko.video_kernel_update_head_forward(g['sds'][0], g['cfg'], t['x'], t['proposal_feat'], t['mask_preds'],
+                                              t['previous_obj_feats'])
+    for name, got in zip(('cls_score', 'mask_preds', 'obj_feat', 'x_feat', 'obj_feat_track'), out):
+        ref = t['s0.' + name]
+        assert maxabs(got, ref) < 2e-5 * max(1.0, ref.abs().max().item()), name
+    out = ko.video_kernel_update_head_forward(g['sds'][0], g['cfg'], t['x'], t['proposal_feat'], t['mask_preds'], None)
+    assert out[4] is None
+    assert maxabs(out[2], t['noprev.obj_feat']) < 2e-5
+
+
+def test_fixture_generator_is_committed_and_fixtures_exist():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert os.path.exists(os.path.join(root, 'oracle', 'make_golden.py'))
+    assert len(golden_files('det_')) >= 3 and len(golden_files('video_')) >= 3
+
+
+def _live_reference():
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip('/root/reference not present (GPU box): fixtures cover this')
+    return ref_shim.load('knet')
+
+
+@pytest.mark.parametrize('B,N,C,H,W', [(1, 100, 256, 25, 11), (2, 17, 64, 7, 9)])
+def test_oracle_matches_live_reference_det(B, N, C, H, W):
+    ref = _live_reference()
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
+    sd = ko.random_state_dict(cfg, seed=42)
+    head = ref.KernelUpdateHead(**copy.deepcopy(cfg))
+    head.load_state_dict(sd, strict=True)
+    head.eval()
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=11)
+    with torch.no_grad():
+        want = head(x, pf, mask)
+    got = ko.kernel_update_head_forward(sd, cfg, x, pf, mask)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert maxabs(a, b) < 2e-5 * max(1.0, b.abs().max().item())
+
+
+def test_oracle_init_matches_reference_init():
+    """init_weights semantics (kernel_update_head.py:151-168): fc_cls.bias = -log(99), LN defaults."""
+    ref = _live_reference()
+    cfg = ko.default_cfg(num_classes=19)
+    torch.manual_seed(0)
+    head = ref.KernelUpdateHead(**copy.deepcopy(cfg))
+    head.init_weights()
+    import vknet
+    torch.manual_seed(0)
+    mine = vknet.build_head(dict(type='KernelUpdateHead', **cfg))
+    mine.init_weights()
+    sd_r, sd_m = head.state_dict(), mine.state_dict()
+    assert list(sd_r.keys()) == list(sd_m.keys())
+    for k in sd_r:
+        assert sd_r[k].shape == sd_m[k].shape, k
+    assert torch.allclose(sd_m['fc_cls.bias'], sd_r['fc_cls.bias'])
+    assert torch.equal(sd_m['attention_norm.weight'], sd_r['attention_norm.weight'])
+
+
+def test_threshold_sliver_is_documented_behaviour():
+    """sigmoid(m) > 0.5 vs m > 0 differ only for 0 < m < ~6e-8 in fp32."""
+    m = torch.tensor([-1.0, -1e-30, 0.0, 1e-30, 1e-8, 1e-6, 1.0])
+    ref = (torch.sigmoid(m) > 0.5)
+    ours = m > 0.0
+    assert torch.equal(ref[[0, 1, 2, 5, 6]], ours[[0, 1, 2, 5, 6]])
+    assert not ref[3] and ours[3]      # the sliver

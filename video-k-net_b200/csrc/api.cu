@@ -1,0 +1,459 @@
+// C-ABI entry points of libvknet.so and the host-side orchestration of one KernelUpdateHead stage.
+// Everything here only enqueues kernels on the caller's stream: no allocation, no synchronisation.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vkn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int FFN_KSPLIT = 8;   // K-slices of the second FFN Linear (K = ffn_dim)
+constexpr int A_EXT_PAD = 8;    // a_ext row = C folded channels + bias column, padded to C + 8
+
+// ---- workspace ----------------------------------------------------------------------------------
+struct Layout {
+  // pooling
+  float *pool_part, *cnt_part, *xp0, *cnt, *xp;
+  // rows
+  float *dyn, *inp, *igp, *ugp, *fc, *o, *qkv, *att, *y, *o2, *h, *zpart, *pre_c[2], *pre_m[2], *mk, *a_ext;
+  float *link_fc, *link_cur;
+  void *a_split;     // tcgen05 engine: bf16 hi/mid/lo planes of a_ext
+  // iter loop
+  void *mask_pp[2];
+  float *obj_pp[2], *cls_tmp;
+  size_t total;
+};
+
+static int pool_chunks_max(const VknShape &s) {
+  int a = pool_simt_chunks(s);
+  int b = pool_tc_chunks(s);
+  return a > b ? a : b;
+}
+
+static void carve(const VknShape &s, char *base, Layout &L) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void * {
+    off = align_up(off, 256);
+    void *p = base ? (void *)(base + off) : nullptr;
+    off += bytes;
+    return p;
+  };
+  const size_t P = (size_t)s.B * s.N, C = s.C, F = s.ffn_dim, HW = (size_t)s.H * s.W;
+  const size_t f = sizeof(float);
+  const int nch = pool_chunks_max(s);
+  L.pool_part = (float *)take((size_t)nch * P * C * f);
+  L.cnt_part = (float *)take((size_t)nch * P * f);
+  L.xp0 = (float *)take(P * C * f);
+  L.cnt = (float *)take(P * f);
+  L.xp = (float *)take(P * C * f);
+  L.dyn = (float *)take(P * 2 * C * f);
+  L.inp = (float *)take(P * 2 * C * f);
+  L.igp = (float *)take(P * C * f);
+  L.ugp = (float *)take(P * C * f);
+  L.fc = (float *)take(P * C * f);
+  L.o = (float *)take(P * C * f);
+  L.qkv = (float *)take(P * 3 * C * f);
+  L.att = (float *)take(P * C * f);
+  L.y = (float *)take(P * C * f);
+  L.o2 = (float *)take(P * C * f);
+  L.h = (float *)take(P * F * f);
+  L.zpart = (float *)take((size_t)FFN_KSPLIT * P * C * f);
+  for (int i = 0; i < 2; ++i) {
+    L.pre_c[i] = (float *)take(P * C * f);
+    L.pre_m[i] = (float *)take(P * C * f);
+  }
+  L.mk = (float *)take(P * C * f);
+  L.a_ext = (float *)take(P * (C + A_EXT_PAD) * f);
+  L.link_fc = (float *)take(P * C * f);
+  L.link_cur = (float *)take(P * C * f);
+  const size_t npad = (size_t)ceil_div(s.N, 128) * 128;
+  L.a_split = take((size_t)3 * s.B * npad * C * 2);
+  const size_t esz = s.x_dtype == VKN_BF16 ? 2 : 4;
+  for (int i = 0; i < 2; ++i) L.mask_pp[i] = take((size_t)s.B * s.N * HW * esz);
+  for (int i = 0; i < 2; ++i) L.obj_pp[i] = (float *)take(P * C * f);
+  L.cls_tmp = (float *)take(P * (size_t)s.num_classes * f);
+  L.total = align_up(off, 256);
+}
+
+static int check_shape(const VknShape *s) {
+  if (!s) VKN_FAIL(VKN_E_INVALID, "null shape");
+  if (s->B < 1 || s->N < 1 || s->H < 1 || s->W < 1) VKN_FAIL(VKN_E_INVALID, "B/N/H/W must be positive");
+  if (s->C < 64 || s->C > 256 || s->C % 64 != 0)
+    VKN_FAIL(VKN_E_UNSUPPORTED, "C = %d: channels must be a multiple of 64 in [64, 256]", s->C);
+  if (s->num_heads < 1 || s->C % s->num_heads != 0 || s->C / s->num_heads > 32)
+    VKN_FAIL(VKN_E_UNSUPPORTED, "num_heads %d does not give head_dim <= 32 for C %d", s->num_heads, s->C);
+  if (s->with_ffn && (s->ffn_dim < 32 || s->ffn_dim % 32 != 0))
+    VKN_FAIL(VKN_E_UNSUPPORTED, "ffn_dim %d must be a positive multiple of 32", s->ffn_dim);
+  if (s->num_classes < 1) VKN_FAIL(VKN_E_INVALID, "num_classes must be positive");
+  if ((s->x_dtype != VKN_F32 && s->x_dtype != VKN_BF16) || (s->w_dtype != VKN_F32 && s->w_dtype != VKN_BF16))
+    VKN_FAIL(VKN_E_INVALID, "bad dtype code");
+  if (s->engine < VKN_ENGINE_AUTO || s->engine > VKN_ENGINE_TC) VKN_FAIL(VKN_E_INVALID, "bad engine code");
+  if (s->N > 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "N = %d kernels per frame exceeds 1024", s->N);
+  return VKN_OK;
+}
+
+struct Ctx {
+  VknShape s;
+  Layout L;
+  cudaStream_t st;
+  int P;
+  bool use_tc;
+};
+
+static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, Ctx &c) {
+  VKN_TRY(check_shape(s));
+  c.s = *s;
+  if (!ws) VKN_FAIL(VKN_E_WORKSPACE, "null workspace");
+  if (reinterpret_cast<uintptr_t>(ws) & 255) VKN_FAIL(VKN_E_WORKSPACE, "workspace must be 256-byte aligned");
+  carve(c.s, (char *)ws, c.L);
+  if (c.L.total > ws_bytes)
+    VKN_FAIL(VKN_E_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", ws_bytes, c.L.total);
+  c.st = (cudaStream_t)stream;
+  c.P = s->B * s->N;
+  const bool can = tc_supported(c.s);
+  if (s->engine == VKN_ENGINE_TC && !can)
+    VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 engine requested but the shape/dtype does not qualify");
+  c.use_tc = (s->engine != VKN_ENGINE_SIMT) && can;
+  return VKN_OK;
+}
+
+// ---- RowSrc builders ------------------------------------------------------------------------------
+static RowSrc src_copy(const float *a, int lda) {
+  RowSrc r;
+  memset(&r, 0, sizeof(r));
+  r.a[0] = a;
+  r.lda[0] = lda;
+  r.pro = PRO_COPY;
+  r.nsum = 1;
+  return r;
+}
+static RowSrc src_ln(const float *a, int lda, const float *g, const float *b, bool relu) {
+  RowSrc r = src_copy(a, lda);
+  r.pro = relu ? PRO_LN_RELU : PRO_LN;
+  r.ln_g[0] = g;
+  r.ln_b[0] = b;
+  return r;
+}
+static LinArgs lin(const RowSrc &src, const void *w, int ldw, const float *bias, float *out, int ldo, int M,
+                   int N, int K, int epi) {
+  LinArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = src;
+  a.w = w;
+  a.ldw = ldw;
+  a.bias = bias;
+  a.out = out;
+  a.ldo = ldo;
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.epi = epi | (bias ? EPI_BIAS : 0);
+  a.ksplit = 1;
+  return a;
+}
+static const void *wrow(const Ctx &c, const void *w, size_t row, size_t ld) {
+  const size_t esz = c.s.w_dtype == VKN_BF16 ? 2 : 4;
+  return (const char *)w + row * ld * esz;
+}
+
+// ---- building blocks --------------------------------------------------------------------------------
+// a3+a4: pooled feature with the feat_transform folded out -> xp [P,C]
+static int k_pool(Ctx &c, const VknHeadW &w, const void *x, const void *mask, float *xp) {
+  int nch = 0;
+  if (c.use_tc) VKN_TRY(launch_pool_tc(c.s, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+  else VKN_TRY(launch_pool_simt(c.s, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+  VKN_TRY(launch_pool_reduce(c.s, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st));
+  // x_feat = xp0 . ft_w^T + cnt (x) ft_b      (sum_p M (W x + b) = W (sum_p M x) + (sum_p M) b)
+  LinArgs a = lin(src_copy(c.L.xp0, c.s.C), w.ft_w, c.s.C, w.ft_b, xp, c.s.C, c.P, c.s.C, c.s.C, EPI_ROWSCALE);
+  a.rowscale = c.L.cnt;
+  return launch_linear(&a, 1, c.s.w_dtype, c.st);
+}
+
+// a5: KernelUpdator up to the pre-LayerNorm fc_layer output (consumer applies relu(LN_fc_norm(.)))
+static int k_update(Ctx &c, const VknUpdatorW &w, const float *xp, const RowSrc &input_src, float *fc_out) {
+  const int C = c.s.C, P = c.P;
+  LinArgs two[2];
+  two[0] = lin(src_copy(xp, C), w.dyn_w, C, w.dyn_b, c.L.dyn, 2 * C, P, 2 * C, C, 0);   // kernel_updator.py:59
+  two[1] = lin(input_src, w.inp_w, C, w.inp_b, c.L.inp, 2 * C, P, 2 * C, C, 0);         // :65-66
+  VKN_TRY(launch_linear(two, 2, c.s.w_dtype, c.st));
+  RowSrc g;
+  memset(&g, 0, sizeof(g));
+  g.pro = PRO_MUL;                                                                        // :70
+  g.nsum = 1;
+  g.a[0] = c.L.inp;  g.lda[0] = 2 * C;
+  g.a[1] = c.L.dyn;  g.lda[1] = 2 * C;
+  two[0] = lin(g, w.ig_w, C, w.ig_b, c.L.igp, C, P, C, C, 0);                             // :74
+  two[1] = lin(g, w.ug_w, C, w.ug_b, c.L.ugp, C, P, C, C, 0);                             // :75
+  VKN_TRY(launch_linear(two, 2, c.s.w_dtype, c.st));
+  RowSrc gt;
+  memset(&gt, 0, sizeof(gt));
+  gt.pro = PRO_GATE;                                                                      // :76-88
+  gt.nsum = 1;
+  gt.a[0] = c.L.ugp;       gt.lda[0] = C;      gt.ln_g[0] = w.norm_in_g;    gt.ln_b[0] = w.norm_in_b;
+  gt.a[1] = c.L.dyn + C;   gt.lda[1] = 2 * C;  gt.ln_g[1] = w.norm_out_g;   gt.ln_b[1] = w.norm_out_b;
+  gt.a[2] = c.L.igp;       gt.lda[2] = C;      gt.ln_g[2] = w.inorm_in_g;   gt.ln_b[2] = w.inorm_in_b;
+  gt.a[3] = c.L.inp + C;   gt.lda[3] = 2 * C;  gt.ln_g[3] = w.inorm_out_g;  gt.ln_b[3] = w.inorm_out_b;
+  LinArgs f = lin(gt, w.fc_w, C, w.fc_b, fc_out, C, P, C, C, 0);                          // :90
+  return launch_linear(&f, 1, c.s.w_dtype, c.st);
+}
+
+// a6: y = identity + out_proj(MHA(q, kv, kv)); consumer applies LN(norm).  `identity` must be the
+// materialised q input; if null it is written to c.L.o as a side output of the q/k/v projection.
+static int k_attn(Ctx &c, const VknAttnW &w, const RowSrc &qsrc, const float *identity, const RowSrc *kvsrc,
+                  float *y_out) {
+  const int C = c.s.C, P = c.P;
+  if (kvsrc == nullptr) {
+    LinArgs a = lin(qsrc, w.in_w, C, w.in_b, c.L.qkv, 3 * C, P, 3 * C, C, 0);
+    if (identity == nullptr) {
+      a.side = c.L.o;
+      a.ldside = C;
+      identity = c.L.o;
+    }
+    VKN_TRY(launch_linear(&a, 1, c.s.w_dtype, c.st));
+  } else {
+    LinArgs two[2];
+    two[0] = lin(qsrc, w.in_w, C, w.in_b, c.L.qkv, 3 * C, P, C, C, 0);
+    if (identity == nullptr) {
+      two[0].side = c.L.o;
+      two[0].ldside = C;
+      identity = c.L.o;
+    }
+    two[1] = lin(*kvsrc, wrow(c, w.in_w, C, C), C, w.in_b + C, c.L.qkv + C, 3 * C, P, 2 * C, C, 0);
+    VKN_TRY(launch_linear(two, 2, c.s.w_dtype, c.st));
+  }
+  VKN_TRY(launch_attention(c.L.qkv, 3 * C, c.L.qkv + C, 3 * C, c.L.qkv + 2 * C, 3 * C, c.L.att, C, c.s.B, c.s.N,
+                           C, c.s.num_heads, c.st));
+  LinArgs o = lin(src_copy(c.L.att, C), w.out_w, C, w.out_b, y_out, C, P, C, C, EPI_RES);
+  o.res = identity;
+  o.ldres = C;
+  return launch_linear(&o, 1, c.s.w_dtype, c.st);
+}
+
+// a7: FFN.  in_src is the (unmaterialised) input; it is written to c.L.o2 for the residual.
+// Returns the pending source: LN_ffn(o2 + b2 + sum_k zpart_k).
+static int k_ffn(Ctx &c, const VknFfnW &w, const RowSrc &in_src, RowSrc *pending) {
+  const int C = c.s.C, P = c.P, F = c.s.ffn_dim;
+  LinArgs a = lin(in_src, w.w1, C, w.b1, c.L.h, F, P, F, C, EPI_RELU);
+  a.side = c.L.o2;
+  a.ldside = C;
+  VKN_TRY(launch_linear(&a, 1, c.s.w_dtype, c.st));
+  LinArgs b = lin(src_copy(c.L.h, F), w.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
+  b.ksplit = FFN_KSPLIT;
+  b.out_split_stride = (long long)P * C;
+  VKN_TRY(launch_linear(&b, 1, c.s.w_dtype, c.st));
+  RowSrc r = src_ln(c.L.zpart, C, w.norm_g, w.norm_b, false);
+  r.nsum = FFN_KSPLIT;
+  r.sum_stride = (long long)P * C;
+  r.pbias = w.b2;
+  r.pres = c.L.o2;
+  r.ldpres = C;
+  *pending = r;
+  return VKN_OK;
+}
+
+// a8: cls / mask FC stacks.  `obj_src` is the pending obj_feat; it is materialised into obj_out
+// (side output of the first launch).  mk_out [P,C] = fc_mask(...) ; cls_out [P,ncls].
+static int k_heads(Ctx &c, const VknHeadW &w, const RowSrc &obj_src, float *obj_out, float *cls_out,
+                   float *mk_out) {
+  const int C = c.s.C, P = c.P;
+  if (w.num_cls_fcs < 0 || w.num_cls_fcs > VKN_MAX_FCS || w.num_mask_fcs < 0 || w.num_mask_fcs > VKN_MAX_FCS)
+    VKN_FAIL(VKN_E_UNSUPPORTED, "num_cls_fcs / num_mask_fcs must be in [0, %d]", VKN_MAX_FCS);
+  RowSrc cs = obj_src, ms = obj_src;
+  bool need_side = obj_out != nullptr;
+  const int depth = w.num_cls_fcs > w.num_mask_fcs ? w.num_cls_fcs : w.num_mask_fcs;
+  for (int i = 0; i < depth; ++i) {
+    LinArgs two[2];
+    int n = 0;
+    if (i < w.num_cls_fcs) {
+      two[n] = lin(cs, w.cls_fc_w[i], C, nullptr, c.L.pre_c[i & 1], C, P, C, C, 0);
+      cs = src_ln(c.L.pre_c[i & 1], C, w.cls_ln_g[i], w.cls_ln_b[i], true);
+      ++n;
+    }
+    if (i < w.num_mask_fcs) {
+      two[n] = lin(ms, w.mask_fc_w[i], C, nullptr, c.L.pre_m[i & 1], C, P, C, C, 0);
+      ms = src_ln(c.L.pre_m[i & 1], C, w.mask_ln_g[i], w.mask_ln_b[i], true);
+      ++n;
+    }
+    if (need_side && i == 0) {   // both start from obj_src at depth 0
+      two[0].side = obj_out;
+      two[0].ldside = C;
+      need_side = false;
+    }
+    VKN_TRY(launch_linear(two, n, c.s.w_dtype, c.st));
+  }
+  LinArgs two[2];
+  two[0] = lin(ms, w.fc_mask_w, C, w.fc_mask_b, mk_out, C, P, C, C, 0);
+  two[1] = lin(cs, w.fc_cls_w, C, w.fc_cls_b, cls_out, c.s.num_classes, P, c.s.num_classes, C, 0);
+  if (need_side) {               // no FC layers at all: the final launch materialises obj_feat
+    two[0].side = obj_out;
+    two[0].ldside = C;
+  }
+  return launch_linear(two, 2, c.s.w_dtype, c.st);
+}
+
+// a9: new_mask = mk . (ft_w x + ft_b) = (mk . ft_w) x + mk . ft_b
+static int k_maskgemm(Ctx &c, const VknHeadW &w, const void *x, const float *mk, void *out) {
+  const int C = c.s.C, P = c.P;
+  const int lda = C + A_EXT_PAD;
+  LinArgs a = lin(src_copy(mk, C), w.ft_wt_ext, C, nullptr, c.L.a_ext, lda, P, C + 1, C, 0);
+  VKN_TRY(launch_linear(&a, 1, c.s.w_dtype, c.st));
+  if (c.use_tc) return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, out, c.st);
+  return launch_maskgemm_simt(c.s, x, c.L.a_ext, lda, out, c.st);
+}
+
+static int stage(Ctx &c, const VknHeadW &w, const void *x, const float *pf, const void *mask,
+                 const float *x_feat_in, float *cls, void *new_mask, float *obj, float *x_feat_out) {
+  const int C = c.s.C;
+  const float *xp = x_feat_in;
+  if (xp == nullptr) {
+    float *dst = x_feat_out ? x_feat_out : c.L.xp;
+    VKN_TRY(k_pool(c, w, x, mask, dst));
+    xp = dst;
+  } else if (x_feat_out && x_feat_out != x_feat_in) {
+    VKN_CUDA_OK(cudaMemcpyAsync(x_feat_out, x_feat_in, (size_t)c.P * C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  }
+  VKN_TRY(k_update(c, w.upd, xp, src_copy(pf, C), c.L.fc));
+  RowSrc o = src_ln(c.L.fc, C, w.upd.fc_norm_g, w.upd.fc_norm_b, true);       // kernel_updator.py:91-92
+  VKN_TRY(k_attn(c, w.attn, o, nullptr, nullptr, c.L.y));                     // kernel_update_head.py:206
+  RowSrc pend = src_ln(c.L.y, C, w.attn.norm_g, w.attn.norm_b, false);
+  if (c.s.with_ffn) VKN_TRY(k_ffn(c, w.ffn, pend, &pend));                    // :214-215
+  VKN_TRY(k_heads(c, w, pend, obj, cls, c.L.mk));                             // :217-227
+  if (new_mask) VKN_TRY(k_maskgemm(c, w, x, c.L.mk, new_mask));               // :247-260
+  return VKN_OK;
+}
+
+}  // namespace vkn
+
+using namespace vkn;
+
+extern "C" {
+
+int vkn_version(void) { return VKN_VERSION; }
+const char *vkn_last_error(void) { return g_err; }
+
+const char *vkn_kernel_names(void) {
+  return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_split3_kernel";
+}
+
+int vkn_workspace_bytes(const VknShape *shape, size_t *bytes) {
+  VKN_TRY(check_shape(shape));
+  if (!bytes) VKN_FAIL(VKN_E_INVALID, "null bytes pointer");
+  Layout L;
+  carve(*shape, nullptr, L);
+  *bytes = L.total;
+  return VKN_OK;
+}
+
+int vkn_mask_pool(const VknShape *s, const VknHeadW *w, const void *x, const void *mask_preds, float *x_feat,
+                  void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !x || !mask_preds || !x_feat) VKN_FAIL(VKN_E_INVALID, "vkn_mask_pool: null argument");
+  return k_pool(c, *w, x, mask_preds, x_feat);
+}
+
+int vkn_kernel_update(const VknShape *s, const VknUpdatorW *w, const float *x_feat, const float *proposal_feat,
+                      float *out, void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !x_feat || !proposal_feat || !out) VKN_FAIL(VKN_E_INVALID, "vkn_kernel_update: null argument");
+  VKN_TRY(k_update(c, *w, x_feat, src_copy(proposal_feat, s->C), c.L.fc));
+  return launch_rowop(src_ln(c.L.fc, s->C, w->fc_norm_g, w->fc_norm_b, true), out, s->C, c.P, s->C, c.st);
+}
+
+int vkn_mhsa_ln(const VknShape *s, const VknAttnW *w, const float *q_in, const float *kv_in, float *out,
+                void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !q_in || !out) VKN_FAIL(VKN_E_INVALID, "vkn_mhsa_ln: null argument");
+  RowSrc kv = src_copy(kv_in, s->C);
+  VKN_TRY(k_attn(c, *w, src_copy(q_in, s->C), q_in, (kv_in && kv_in != q_in) ? &kv : nullptr, c.L.y));
+  return launch_rowop(src_ln(c.L.y, s->C, w->norm_g, w->norm_b, false), out, s->C, c.P, s->C, c.st);
+}
+
+int vkn_ffn_ln(const VknShape *s, const VknFfnW *w, const float *in, float *out, void *workspace,
+               size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !in || !out) VKN_FAIL(VKN_E_INVALID, "vkn_ffn_ln: null argument");
+  RowSrc pend;
+  VKN_TRY(k_ffn(c, *w, src_copy(in, s->C), &pend));
+  return launch_rowop(pend, out, s->C, c.P, s->C, c.st);
+}
+
+int vkn_heads(const VknShape *s, const VknHeadW *w, const float *obj_feat, float *cls_score, float *mask_kernel,
+              void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !obj_feat || !cls_score || !mask_kernel) VKN_FAIL(VKN_E_INVALID, "vkn_heads: null argument");
+  return k_heads(c, *w, src_copy(obj_feat, s->C), nullptr, cls_score, mask_kernel);
+}
+
+int vkn_mask_gemm(const VknShape *s, const VknHeadW *w, const void *x, const float *mask_kernel,
+                  void *new_mask_preds, void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !x || !mask_kernel || !new_mask_preds) VKN_FAIL(VKN_E_INVALID, "vkn_mask_gemm: null argument");
+  return k_maskgemm(c, *w, x, mask_kernel, new_mask_preds);
+}
+
+int vkn_stage_forward(const VknShape *s, const VknHeadW *w, const void *x, const float *proposal_feat,
+                      const void *mask_preds, const float *x_feat_in, float *cls_score, void *new_mask_preds,
+                      float *obj_feat, float *x_feat_out, void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !x || !proposal_feat || !cls_score || !obj_feat || (!mask_preds && !x_feat_in))
+    VKN_FAIL(VKN_E_INVALID, "vkn_stage_forward: null argument");
+  return stage(c, *w, x, proposal_feat, mask_preds, x_feat_in, cls_score, new_mask_preds, obj_feat, x_feat_out);
+}
+
+int vkn_iter_forward(const VknShape *s, const VknHeadW *stages, int num_stages, const void *x,
+                     const float *proposal_feat, const void *mask_preds, float *cls_score, void *new_mask_preds,
+                     float *obj_feat, void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!stages || num_stages < 1 || !x || !proposal_feat || !mask_preds || !cls_score || !new_mask_preds || !obj_feat)
+    VKN_FAIL(VKN_E_INVALID, "vkn_iter_forward: null argument");
+  const float *pf = proposal_feat;
+  const void *mk = mask_preds;
+  for (int i = 0; i < num_stages; ++i) {
+    const bool last = i == num_stages - 1;
+    float *obj_o = last ? obj_feat : c.L.obj_pp[i & 1];
+    void *mask_o = last ? new_mask_preds : c.L.mask_pp[i & 1];
+    float *cls_o = last ? cls_score : c.L.cls_tmp;
+    VKN_TRY(stage(c, stages[i], x, pf, mk, nullptr, cls_o, mask_o, obj_o, nullptr));
+    pf = obj_o;
+    mk = mask_o;
+  }
+  return VKN_OK;
+}
+
+int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, const float *prev, const float *x_feat,
+                    float *out, void *workspace, size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!w || !cur || !prev || !out) VKN_FAIL(VKN_E_INVALID, "vkn_link_attend: null argument");
+  const int C = s->C;
+  RowSrc kv = src_copy(prev, C);
+  if (w->has_updator) {
+    if (!x_feat) VKN_FAIL(VKN_E_INVALID, "vkn_link_attend: the updator link needs x_feat");
+    VKN_TRY(k_update(c, w->upd, x_feat, src_copy(prev, C), c.L.link_fc));
+    kv = src_ln(c.L.link_fc, C, w->upd.fc_norm_g, w->upd.fc_norm_b, true);
+  }
+  VKN_TRY(k_attn(c, w->attn, src_copy(cur, C), cur, &kv, c.L.y));
+  RowSrc pend;
+  VKN_TRY(k_ffn(c, w->ffn, src_ln(c.L.y, C, w->attn.norm_g, w->attn.norm_b, false), &pend));
+  return launch_rowop(pend, out, C, c.P, C, c.st);
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Shared device/host helpers for libvknet (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "vknet.h"
+
+namespace vkn {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define VKN_FAIL(code, ...)          \
+  do {                               \
+    ::vkn::set_error(__VA_ARGS__);   \
+    return (code);                   \
+  } while (0)
+#define VKN_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) VKN_FAIL(VKN_E_CUDA, "%s -> %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define VKN_TRY(expr)           \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != VKN_OK) return rc__; \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- element access ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ void store_as(T *p, float v);
+template <>
+__device__ __forceinline__ void store_as<float>(float *p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_as<__nv_bfloat16>(__nv_bfloat16 *p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// 8 consecutive elements -> 8 floats (16-byte aligned for bf16, 32-byte for f32)
+__device__ __forceinline__ void load8(const float *p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4 *>(p);
+  const float4 b = *reinterpret_cast<const float4 *>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16 *p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4 *>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+// 4 consecutive elements
+__device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4 *>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16 *p, float (&v)[4]) {
+  const uint2 r = *reinterpret_cast<const uint2 *>(p);
+  v[0] = __uint_as_float(r.x << 16);
+  v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16);
+  v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(float *p, const float (&v)[4]) {
+  *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16 *p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t *>(&a);
+  r.y = *reinterpret_cast<uint32_t *>(&b);
+  *reinterpret_cast<uint2 *>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ---- the fused "rows" operators (smallops.cu) --------------------------------------------------
+enum Pro : int {
+  PRO_COPY = 0,     // v = S(a0)                      S(.) = sum of nsum slices (+ pbias[k] + pres[r][k])
+  PRO_LN = 1,       // v = LN0(S(a0))
+  PRO_LN_RELU = 2,  // v = relu(LN0(S(a0)))
+  PRO_MUL = 3,      // v = a0 * a1
+  PRO_GATE = 4      // v = sigmoid(LN0(a0)) * LN1(a1) + sigmoid(LN2(a2)) * LN3(a3)   (kernel_updator.py:74-88)
+};
+enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8 };
+
+struct RowSrc {
+  const float *a[4];
+  int lda[4];
+  const float *ln_g[4];
+  const float *ln_b[4];
+  int pro;
+  int nsum;                 // slices of a[0] to add (>= 1)
+  long long sum_stride;     // elements between slices
+  const float *pbias;       // optional [K] added before LN
+  const float *pres;        // optional [M,K] residual added before LN
+  int ldpres;
+};
+
+struct LinArgs {
+  RowSrc src;
+  const void *w;            // [N,K] row-major, weight dtype
+  int ldw;
+  const float *bias;        // [N] or null
+  const float *rowscale;    // [M] or null: bias is multiplied by rowscale[row] (EPI_ROWSCALE)
+  const float *res;         // [M,N] residual added in the epilogue (EPI_RES)
+  int ldres;
+  float *out;               // [M,N] (slice z of a split-K launch writes out + z * out_split_stride)
+  int ldo;
+  long long out_split_stride;
+  int ksplit;               // number of K slices (gridDim.z = nprob * ksplit)
+  float *side;              // optional: the prologue result [M,K], written by the n-block-0 CTAs
+  int ldside;
+  int M, N, K;
+  int epi;
+};
+
+// launches (all enqueue on `stream`, never synchronise)
+int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t stream);
+int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream);
+int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
+                     int ldo, int B, int N, int C, int heads, cudaStream_t stream);
+// SIMT fp32 engines for the two big contractions (gemm_simt.cu)
+int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
+                     int *nchunks, cudaStream_t stream);
+int pool_simt_chunks(const VknShape &s);
+int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
+                       float *xp0, float *cnt, cudaStream_t stream);
+int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, int lda, void *out,
+                         cudaStream_t stream);
+// tcgen05 / TMA engines (gemm_tc.cu)
+bool tc_supported(const VknShape &s);
+int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
+                   int *nchunks, cudaStream_t stream);
+int pool_tc_chunks(const VknShape &s);
+int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, void *a_split_ws,
+                       void *out, cudaStream_t stream);
+
+}  // namespace vkn

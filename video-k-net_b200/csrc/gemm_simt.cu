@@ -1,0 +1,253 @@
+// CUDA-core fp32 engines for the two big contractions of a stage.  They serve fp32 storage
+// (VKN_F32), shapes the tcgen05 engine does not take, and are the on-device cross-check of the
+// tensor-core engine.
+//
+//   pooling  (knet/det/kernel_update_head.py:190-195, feat_transform folded out):
+//       xp0[b,n,c] = sum_p 1[mask[b,n,p] > thr] * x[b,c,p]        cnt[b,n] = sum_p 1[...]
+//   mask conv (knet/det/kernel_update_head.py:247-260, feat_transform folded in):
+//       out[b,n,p] = sum_c a_ext[b*N+n, c] * x[b,c,p] + a_ext[b*N+n, C]
+#include "common.cuh"
+
+namespace vkn {
+
+constexpr int GT = 256;       // threads per CTA
+constexpr int TILE_N = 128;   // kernels per CTA tile
+constexpr int TILE_C = 64;    // channels per CTA tile (pooling)
+constexpr int TILE_P = 64;    // pixels per CTA tile (mask conv)
+constexpr int PK = 32;        // inner step
+constexpr int POOL_CHUNK = 256;  // pixels reduced by one pooling CTA
+
+// ---- pooling -----------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(GT) vkn_pool_simt_kernel(const XT *__restrict__ x, const XT *__restrict__ mask,
+                                                           float *__restrict__ partials,
+                                                           float *__restrict__ cnt_partials, int B, int N, int C,
+                                                           int HW, float thr) {
+  __shared__ __align__(16) float Ms[TILE_N][PK + 4];
+  __shared__ __align__(16) float Xs[TILE_C][PK + 4];
+  const int chunk = blockIdx.x, b = blockIdx.z;
+  const int cblocks = C / TILE_C;
+  const int cb = blockIdx.y % cblocks, nb = blockIdx.y / cblocks;
+  const int n0 = nb * TILE_N, c0 = cb * TILE_C;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int pbeg = chunk * POOL_CHUNK, pend = min(HW, pbeg + POOL_CHUNK);
+
+  float acc[8][4];
+  float cacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cacc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  const XT *mb = mask + (size_t)b * N * HW;
+  const XT *xb = x + (size_t)b * C * HW;
+  for (int p0 = pbeg; p0 < pend; p0 += PK) {
+    {
+      const int kk = tid & 31;
+      const int p = p0 + kk;
+#pragma unroll
+      for (int i = 0; i < TILE_N / 8; ++i) {
+        const int r = (tid >> 5) + 8 * i;
+        const int n = n0 + r;
+        float m = 0.f;
+        if (n < N && p < pend) m = (to_f32(mb[(size_t)n * HW + p]) > thr) ? 1.f : 0.f;
+        Ms[r][kk] = m;
+      }
+#pragma unroll
+      for (int i = 0; i < TILE_C / 8; ++i) {
+        const int r = (tid >> 5) + 8 * i;
+        float v = 0.f;
+        if (p < pend) v = to_f32(xb[(size_t)(c0 + r) * HW + p]);
+        Xs[r][kk] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < PK; kk += 4) {
+      float4 a4[8], b4[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a4[i] = *reinterpret_cast<const float4 *>(&Ms[ty + 16 * i][kk]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4 *>(&Xs[tx + 16 * j][kk]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cacc[i] += (a4[i].x + a4[i].y) + (a4[i].z + a4[i].w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a4[i].x, b4[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].y, b4[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].z, b4[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].w, b4[j].w, acc[i][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float *po = partials + ((size_t)chunk * B + b) * N * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + ty + 16 * i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) po[(size_t)n * C + c0 + tx + 16 * j] = acc[i][j];
+    if (cb == 0 && tx == 0) cnt_partials[((size_t)chunk * B + b) * N + n] = cacc[i];
+  }
+}
+
+int pool_simt_chunks(const VknShape &s) { return ceil_div(s.H * s.W, POOL_CHUNK); }
+
+int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
+                     int *nchunks, cudaStream_t stream) {
+  const int HW = s.H * s.W;
+  if (s.C % TILE_C != 0) VKN_FAIL(VKN_E_UNSUPPORTED, "pool: C %d must be a multiple of %d", s.C, TILE_C);
+  *nchunks = pool_simt_chunks(s);
+  dim3 grid(*nchunks, (s.C / TILE_C) * ceil_div(s.N, TILE_N), s.B);
+  if (s.x_dtype == VKN_BF16)
+    vkn_pool_simt_kernel<__nv_bfloat16><<<grid, GT, 0, stream>>>(
+        (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)mask, partials, cnt_partials, s.B, s.N, s.C, HW,
+        s.mask_thr_logit);
+  else
+    vkn_pool_simt_kernel<float><<<grid, GT, 0, stream>>>((const float *)x, (const float *)mask, partials,
+                                                         cnt_partials, s.B, s.N, s.C, HW, s.mask_thr_logit);
+  VKN_CUDA_OK(cudaGetLastError());
+  return VKN_OK;
+}
+
+// partials [nchunks][P*C] -> xp0 [P*C];  cnt_partials [nchunks][P] -> cnt [P]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__restrict__ partials,
+                                                              const float *__restrict__ cnt_partials, int nchunks,
+                                                              int PC, int P, float *__restrict__ xp0,
+                                                              float *__restrict__ cnt) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx < PC) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int ch = 0;
+    for (; ch + 4 <= nchunks; ch += 4) {
+      s0 += __ldg(partials + (size_t)ch * PC + idx);
+      s1 += __ldg(partials + (size_t)(ch + 1) * PC + idx);
+      s2 += __ldg(partials + (size_t)(ch + 2) * PC + idx);
+      s3 += __ldg(partials + (size_t)(ch + 3) * PC + idx);
+    }
+    for (; ch < nchunks; ++ch) s0 += __ldg(partials + (size_t)ch * PC + idx);
+    xp0[idx] = (s0 + s1) + (s2 + s3);
+  }
+  if (idx < P) {
+    float s = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) s += __ldg(cnt_partials + (size_t)ch * P + idx);
+    cnt[idx] = s;
+  }
+}
+
+int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
+                       float *xp0, float *cnt, cudaStream_t stream) {
+  const int P = s.B * s.N, PC = P * s.C;
+  vkn_pool_reduce_kernel<<<ceil_div(PC, 256), 256, 0, stream>>>(partials, cnt_partials, nchunks, PC, P, xp0, cnt);
+  VKN_CUDA_OK(cudaGetLastError());
+  return VKN_OK;
+}
+
+// ---- dynamic mask conv ---------------------------------------------------------------------------
+template <typename XT, bool VEC>
+__global__ void __launch_bounds__(GT) vkn_maskgemm_simt_kernel(const XT *__restrict__ x,
+                                                               const float *__restrict__ a_ext, int lda,
+                                                               XT *__restrict__ out, int N, int C, int HW) {
+  __shared__ __align__(16) float As[TILE_N][PK + 4];
+  __shared__ __align__(16) float Xs[PK][TILE_P + 4];
+  const int p0 = blockIdx.x * TILE_P, n0 = blockIdx.y * TILE_N, b = blockIdx.z;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const XT *xb = x + (size_t)b * C * HW;
+  const float *ab = a_ext + (size_t)b * N * lda;
+  for (int c0 = 0; c0 < C; c0 += PK) {
+    {  // A tile: 128 rows x 32 channels, 8 consecutive channels per thread
+      const int kk = (tid & 3) * 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = (tid >> 2) + 64 * i;
+        const int n = n0 + r;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (n < N) {
+          v0 = *reinterpret_cast<const float4 *>(ab + (size_t)n * lda + c0 + kk);
+          v1 = *reinterpret_cast<const float4 *>(ab + (size_t)n * lda + c0 + kk + 4);
+        }
+        *reinterpret_cast<float4 *>(&As[r][kk]) = v0;
+        *reinterpret_cast<float4 *>(&As[r][kk + 4]) = v1;
+      }
+      // x tile: 32 channels x 64 pixels, pixel-contiguous
+      const int px = tid & 63;
+#pragma unroll
+      for (int i = 0; i < PK / 4; ++i) {
+        const int kc = (tid >> 6) + 4 * i;
+        float v = 0.f;
+        if (p0 + px < HW) v = to_f32(xb[(size_t)(c0 + kc) * HW + p0 + px]);
+        Xs[kc][px] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < PK; kk += 4) {
+      float4 a4[8], b4[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a4[i] = *reinterpret_cast<const float4 *>(&As[ty + 16 * i][kk]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) b4[e] = *reinterpret_cast<const float4 *>(&Xs[kk + e][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float av[4] = {a4[i].x, a4[i].y, a4[i].z, a4[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[i][0] = fmaf(av[e], b4[e].x, acc[i][0]);
+          acc[i][1] = fmaf(av[e], b4[e].y, acc[i][1]);
+          acc[i][2] = fmaf(av[e], b4[e].z, acc[i][2]);
+          acc[i][3] = fmaf(av[e], b4[e].w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  XT *ob = out + (size_t)b * N * HW;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + ty + 16 * i;
+    if (n >= N) continue;
+    const float bias = __ldg(ab + (size_t)n * lda + C);
+    const int p = p0 + tx * 4;
+    float v[4] = {acc[i][0] + bias, acc[i][1] + bias, acc[i][2] + bias, acc[i][3] + bias};
+    if (VEC) {
+      if (p < HW) store4(ob + (size_t)n * HW + p, v);  // HW % 4 == 0: a 4-group never straddles the end
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (p + e < HW) store_as<XT>(ob + (size_t)n * HW + p + e, v[e]);
+    }
+  }
+}
+
+int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, int lda, void *out,
+                         cudaStream_t stream) {
+  const int HW = s.H * s.W;
+  if (s.C % PK != 0) VKN_FAIL(VKN_E_UNSUPPORTED, "mask gemm: C %d must be a multiple of %d", s.C, PK);
+  if (lda % 4 != 0) VKN_FAIL(VKN_E_INVALID, "mask gemm: lda %d must be a multiple of 4", lda);
+  dim3 grid(ceil_div(HW, TILE_P), ceil_div(s.N, TILE_N), s.B);
+  const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (s.x_dtype == VKN_BF16) {
+    auto xp = (const __nv_bfloat16 *)x;
+    auto op = (__nv_bfloat16 *)out;
+    if (vec) vkn_maskgemm_simt_kernel<__nv_bfloat16, true><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
+    else vkn_maskgemm_simt_kernel<__nv_bfloat16, false><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
+  } else {
+    auto xp = (const float *)x;
+    auto op = (float *)out;
+    if (vec) vkn_maskgemm_simt_kernel<float, true><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
+    else vkn_maskgemm_simt_kernel<float, false><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
+  }
+  VKN_CUDA_OK(cudaGetLastError());
+  return VKN_OK;
+}
+
+}  // namespace vkn

@@ -1,0 +1,91 @@
+"""Functional wrappers over the individual C-ABI operators (rows a3-a9 of the scope table).
+Weights come from a KernelUpdateHead-like module; tensors are torch CUDA tensors.  Used by the
+per-operator parity tests and by anyone who wants one piece of the stage.
+"""
+import torch
+
+from . import _lib
+
+_ws = _lib.Workspace()
+
+
+def _ctx(head, x_like, B, N, H, W, x_dtype=None):
+    dev = x_like.device
+    if not x_like.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    w, extra, wd = head.packed_weights(dev)
+    xd = _lib.dtype_code(x_like.dtype) if x_dtype is None else x_dtype
+    shape = head._shape(B, N, H, W, xd, wd)
+    ws, wsb = _ws.get(shape, dev)
+    return w, extra, shape, ws, wsb
+
+
+def mask_pool(head, x, mask_preds):
+    """x_feat [B,N,C] = sum_p 1[sigmoid(mask) > thr] * feat_transform(x)   (kernel_update_head.py:179-195)."""
+    B, Cc, H, W = x.shape
+    N = mask_preds.shape[1]
+    x = x.contiguous()
+    mask_preds = mask_preds.to(x.dtype).contiguous()
+    w, _, shape, ws, wsb = _ctx(head, x, B, N, H, W)
+    out = torch.empty(B, N, Cc, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().vkn_mask_pool(shape, w, _lib.ptr(x), _lib.ptr(mask_preds), _lib.ptr(out), ws, wsb,
+                                        _lib.stream_ptr()))
+    return out
+
+
+def kernel_update(head, x_feat, proposal_feat):
+    """KernelUpdator.forward on [B,N,C] rows (kernel_updator.py:56-94) -> [B,N,C]."""
+    B, N, Cc = x_feat.shape
+    xf = x_feat.float().contiguous()
+    pf = proposal_feat.reshape(B, N, Cc).float().contiguous()
+    w, _, shape, ws, wsb = _ctx(head, xf, B, N, 1, 1, _lib.VKN_F32)
+    out = torch.empty_like(xf)
+    _lib.check(_lib.lib().vkn_kernel_update(shape, w.upd, _lib.ptr(xf), _lib.ptr(pf), _lib.ptr(out), ws, wsb,
+                                            _lib.stream_ptr()))
+    return out
+
+
+def mhsa_ln(head, q_in, kv_in=None, attn_w=None):
+    """LN(q + MHA(q, kv, kv)) across the N kernels of each frame (kernel_update_head.py:204-208)."""
+    B, N, Cc = q_in.shape
+    q = q_in.float().contiguous()
+    kv = None if kv_in is None else kv_in.float().contiguous()
+    w, _, shape, ws, wsb = _ctx(head, q, B, N, 1, 1, _lib.VKN_F32)
+    out = torch.empty_like(q)
+    _lib.check(_lib.lib().vkn_mhsa_ln(shape, attn_w if attn_w is not None else w.attn, _lib.ptr(q), _lib.ptr(kv),
+                                      _lib.ptr(out), ws, wsb, _lib.stream_ptr()))
+    return out
+
+
+def ffn_ln(head, inp):
+    """LN(x + FFN(x)) (kernel_update_head.py:214-215)."""
+    B, N, Cc = inp.shape
+    a = inp.float().contiguous()
+    w, _, shape, ws, wsb = _ctx(head, a, B, N, 1, 1, _lib.VKN_F32)
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().vkn_ffn_ln(shape, w.ffn, _lib.ptr(a), _lib.ptr(out), ws, wsb, _lib.stream_ptr()))
+    return out
+
+
+def heads(head, obj_feat):
+    """cls_score [B,N,ncls], mask_kernel [B,N,C] (kernel_update_head.py:217-227)."""
+    B, N, Cc = obj_feat.shape
+    a = obj_feat.float().contiguous()
+    w, _, shape, ws, wsb = _ctx(head, a, B, N, 1, 1, _lib.VKN_F32)
+    cls = torch.empty(B, N, head.fc_cls.out_features, dtype=torch.float32, device=a.device)
+    mk = torch.empty_like(a)
+    _lib.check(_lib.lib().vkn_heads(shape, w, _lib.ptr(a), _lib.ptr(cls), _lib.ptr(mk), ws, wsb, _lib.stream_ptr()))
+    return cls, mk
+
+
+def mask_gemm(head, x, mask_kernel):
+    """new_mask [B,N,H,W] = mask_kernel . feat_transform(x)   (kernel_update_head.py:179-180, 247-260)."""
+    B, Cc, H, W = x.shape
+    N = mask_kernel.shape[1]
+    x = x.contiguous()
+    mk = mask_kernel.reshape(B, N, Cc).float().contiguous()
+    w, _, shape, ws, wsb = _ctx(head, x, B, N, H, W)
+    out = torch.empty(B, N, H, W, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().vkn_mask_gemm(shape, w, _lib.ptr(x), _lib.ptr(mk), _lib.ptr(out), ws, wsb,
+                                        _lib.stream_ptr()))
+    return out
