@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s/GPU of the S-stage KernelUpdateHead loop (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch of synthetic input: ONE frame per rank
+(cfg1: N=100 kernels, C=256, 200x88 feature map, S=3 stages, bf16 storage), i.e. a clip of
+`--gpus` frames sharded one frame per GPU.  With more than one GPU the step also performs the one
+exchange frame sharding needs (all-gather of the last-stage kernels over NCCL + the
+`previous_type='ffn'` link block, cfg3).
+
+  value     frames/s, whole job, inputs resident in HBM, CUDA-graph replay of the loop, CUDA-event timed,
+            max over ranks.  Inputs rotate over R distinct sets whose footprint exceeds L2.
+  e2e       same metric through the public API with HOST (pinned) inputs: H2D copies of x / kernels /
+            masks and the D2H read of the result tuple are inside the timed region.
+  roofline  dominant kernel of the step, timed live with CUDA events on its launch stream
+            (vkn_profile_begin/end), algorithmic bytes / time vs the measured HBM peak.
+  cpu_baseline  the CPU oracle port of the reference's PyTorch path (fp32, all host threads) on a bounded
+            sample of the same workload.
+--impl reference runs ONLY that CPU arm (rank 0) and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, 'video-k-net_b200')]
+
+CFG1 = dict(B=1, N=100, C=256, H=200, W=88, S=3, ncls=19, ffn=2048)
+METRIC = 'frames/sec/GPU (100 kernels, C=256, 200x88, S=3)'
+
+
+def head_cfg(link=False):
+    C = CFG1['C']
+    cfg = dict(num_classes=CFG1['ncls'], num_thing_classes=2, num_stuff_classes=17, num_ffn_fcs=2, num_heads=8,
+               num_cls_fcs=1, num_mask_fcs=1, feedforward_channels=CFG1['ffn'], in_channels=C, out_channels=C,
+               dropout=0.0, mask_thr=0.5, conv_kernel_size=1, mask_upsample_stride=2,
+               ffn_act_cfg=dict(type='ReLU', inplace=True), with_ffn=True,
+               feat_transform_cfg=dict(conv_cfg=dict(type='Conv2d'), act_cfg=None),
+               kernel_updator_cfg=dict(type='KernelUpdator', in_channels=C, feat_channels=C, out_channels=C,
+                                       input_feat_shape=3, act_cfg=dict(type='ReLU', inplace=True),
+                                       norm_cfg=dict(type='LN')),
+               loss_rank=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=0.1),
+               loss_mask=dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0),
+               loss_dice=dict(type='DiceLoss', loss_weight=4.0),
+               loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0))
+    if link:
+        cfg.update(previous='placeholder', previous_type='ffn')
+    return cfg
+
+
+def dummy_inputs(torch, seed):
+    """forward_dummy recipe (knet/det/kernel_iter_head.py:317-330)."""
+    g = torch.Generator().manual_seed(seed)
+    B, N, C, H, W = (CFG1[k] for k in 'BNCHW')
+    x = torch.randn(B, C, H, W, generator=g)
+    pf = torch.randn(B, N, C, generator=g)
+    mask = pf.bmm(x.view(B, C, -1)).view(B, N, H, W)
+    return x, pf, mask
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(',')])
+                if self.stop_flag:
+                    break
+        except Exception:   # noqa: BLE001 -- nvidia-smi missing: report empty clocks
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        reasons = []
+        for i, name in enumerate(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows):
+                reasons.append(name)
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=reasons, samples=len(sm))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path (the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, budget_s=120.0):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import knet_oracle as ko
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ko.default_cfg(num_classes=CFG1['ncls'], in_channels=CFG1['C'], feedforward_channels=CFG1['ffn'])
+    sds = [ko.random_state_dict(cfg, seed=s) for s in range(CFG1['S'])]
+    x, pf, mask = ko.dummy_inputs(CFG1['B'], CFG1['N'], CFG1['C'], CFG1['H'], CFG1['W'], seed=1)
+    times = []
+    with torch.no_grad():
+        for _ in range(max(1, min(warmup, 3))):
+            ko.iter_forward(sds, [cfg] * CFG1['S'], x, pf, mask)
+        t_all = time.perf_counter()
+        for _ in range(max(steps, 1)):
+            t0 = time.perf_counter()
+            ko.iter_forward(sds, [cfg] * CFG1['S'], x, pf, mask)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_all > budget_s:
+                break
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=1.0 / med, unit='frames/s', cores=cores, kind='port',
+                sample='%d frames of cfg1 (fp32, torch %s, %d threads), median %.2f ms/frame; the reference is pure '
+                       'Python and cannot travel to this box: the port restates it op for op and is pinned to it '
+                       'by tests/golden' % (len(times), torch.__version__, cores, med * 1e3)), med
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, med = cpu_arm(args.steps, args.warmup)
+    line = dict(impl='reference', metric=METRIC, value=cb['value'], unit='frames/s', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=med * 1e3, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='cfg1: B=1 frame, N=100 kernels, C=256, 200x88, S=3 (KITTI-STEP R-50 shape)',
+                            note='reference CPU PyTorch path (oracle port), one frame per step, all host threads'),
+                cpu_baseline=cb,
+                e2e=dict(value=cb['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vknet
+    from vknet import _lib
+    from vknet import dist as vdist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    S = CFG1['S']
+    B, N, C, H, W = (CFG1[k] for k in 'BNCHW')
+    HW = H * W
+
+    # random-init weights of the KITTI-STEP R-50 head (init_weights semantics), bf16 storage
+    torch.manual_seed(0)
+    heads = []
+    for s in range(S):
+        last_linked = world > 1 and s == S - 1
+        h = vknet.build_head(dict(type='VideoKernelUpdateHead' if last_linked else 'KernelUpdateHead',
+                                  **head_cfg(link=last_linked)))
+        h.init_weights()
+        heads.append(h.to(dev).bfloat16().eval())
+    loop = vknet.KernelIterLoop(heads)
+
+    # R rotating input sets; footprint of one set = x + mask_in + mask_out
+    set_bytes = (C * HW + 2 * N * HW) * 2
+    R = max(2, int(160e6 // set_bytes) + 1)
+    host_sets = [dummy_inputs(torch, seed=1 + rank * 1000 + r) for r in range(R)]
+    runners = []
+    for r in range(R):
+        x, pf, mask = host_sets[r]
+        lp = vknet.KernelIterLoop(heads)
+        lp._ws = loop._ws                       # one shared workspace
+        before = _lib.launch_count()
+        lp.capture(x.to(dev).bfloat16(), pf.to(dev), mask.to(dev).bfloat16())
+        runners.append(lp)
+    launches_per_step = None
+    before = _lib.launch_count()
+    loop(host_sets[0][0].to(dev).bfloat16(), host_sets[0][1].to(dev), host_sets[0][2].to(dev).bfloat16())
+    launches_per_step = _lib.launch_count() - before
+
+    link_head = heads[-1] if world > 1 else None
+
+    def exchange(obj_local):
+        """cfg3: all-gather of the last-stage kernels + the 'ffn' link block for this rank's frame."""
+        if world == 1:
+            return obj_local
+        w, links, wd = link_head.packed_weights(dev)
+        shape = link_head._shape(1, N, H, W, _lib.VKN_BF16, wd)
+        ws, wsb = link_head._ws.get(shape, dev)
+
+        def link_fn(cur, prev):
+            return link_head._link(shape, links['track'], cur.contiguous(), prev.contiguous(), None, ws, wsb)
+        return vdist.link_sharded_clip(link_fn, obj_local.reshape(1, N, C), world, rank, world)
+
+    def step(i):
+        cls, m, obj = runners[i % R].replay()
+        return exchange(obj)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+
+    # ---- e2e: host buffers in, result tuple out, copies inside the timed region ---------------------
+    pin = [tuple(t_.pin_memory() for t_ in (hs[0].bfloat16(), hs[1], hs[2].bfloat16())) for hs in host_sets[:4]]
+    out_host = (torch.empty(B, N, CFG1['ncls']).pin_memory(), torch.empty(B, N, H, W, dtype=torch.bfloat16).pin_memory(),
+                torch.empty(B, N, C).pin_memory())
+    h2d = sum(t_.numel() * t_.element_size() for t_ in pin[0])
+    d2h = sum(t_.numel() * t_.element_size() for t_ in out_host)
+
+    def e2e_step(i):
+        x, pf, mask = pin[i % len(pin)]
+        cls, m, obj = runners[0].replay(x, pf, mask)          # H2D into the graph's static buffers
+        obj = exchange(obj)
+        out_host[0].copy_(cls, non_blocking=True)
+        out_host[1].copy_(m, non_blocking=True)
+        out_host[2].copy_(obj.reshape(B, N, C), non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    sampler.stop()
+    e2e_ms = f0.elapsed_time(f1)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+
+    # ---- roofline of the dominant kernel: live per-kernel device times --------------------------------
+    acc = {}
+    reps = 20
+    xs, pfs, ms_ = (host_sets[0][0].to(dev).bfloat16(), host_sets[0][1].to(dev), host_sets[0][2].to(dev).bfloat16())
+    for _ in range(3):
+        loop(xs, pfs, ms_)
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        with _lib.profile() as p:
+            loop(xs, pfs, ms_)
+        for name, t_ms in p.records:
+            a = acc.setdefault(name, [0.0, 0])
+            a[0] += t_ms
+            a[1] += 1
+    per_kernel = {k: dict(total_ms_per_step=v[0] / reps, launches_per_step=v[1] // reps,
+                          avg_us=1e3 * v[0] / v[1]) for k, v in acc.items()}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]['total_ms_per_step'])
+    P = B * N
+    Fh, ncls = CFG1['ffn'], CFG1['ncls']
+    # algorithmic bytes per launch of each kernel family (DESIGN.md "kernels" table)
+    alg = {
+        'vkn_pool_tc_kernel': (C * HW + N * HW) * 2 + N * C * 4,
+        'vkn_pool_simt_kernel': (C * HW + N * HW) * 2 + N * C * 4,
+        'vkn_maskgemm_tc_kernel': (C * HW + N * HW) * 2 + 3 * N * C * 2,
+        'vkn_maskgemm_simt_kernel': (C * HW + N * HW) * 2 + N * C * 4,
+        'vkn_linear_kernel<32x64>': (Fh * C) * 2 + P * C * 4 + P * Fh * 4,          # FFN layer 1
+    }
+    peak, peak_src = measured_peaks()
+    roof = None
+    if dom in alg:
+        ach = alg[dom] / (per_kernel[dom]['avg_us'] * 1e-6) / 1e9
+        roof = dict(bound='hbm', kernel=dom, achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                    peak_source=peak_src, algorithmic_bytes_per_launch=alg[dom], avg_launch_us=per_kernel[dom]['avg_us'])
+    else:
+        roof = dict(bound='hbm', kernel=dom, achieved=None, peak=peak, unit='GB/s', frac=None, traffic=None,
+                    peak_source=peak_src, note='dominant kernel is launch/latency bound; see kernels table',
+                    avg_launch_us=per_kernel[dom]['avg_us'])
+    # whole-step figure: module-boundary algorithmic bytes per frame: 60.4 MB bf16
+    step_bytes = S * ((C * HW + 2 * N * HW) * 2 + (2041856 + 257 * ncls) * 2)
+    step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+    roof['step'] = dict(algorithmic_bytes_per_frame=step_bytes, achieved=step_gbs, frac=step_gbs / peak)
+
+    if rank == 0:
+        cb, _ = cpu_arm(steps=8, warmup=2, budget_s=20.0)
+        frames = args.steps * world
+        value = frames / (ms * 1e-3)
+        line = dict(metric=METRIC, value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+                    data='synthetic',
+                    config=dict(workload='cfg1 KITTI-STEP R-50 shape: 1 frame/GPU, N=100 kernels, C=256, 200x88, S=3, '
+                                         'bf16 storage of x/masks/weights, fp32 arithmetic' +
+                                         ('; + cfg3 link: all-gather of kernels and previous_type=ffn link block'
+                                          if world > 1 else ''),
+                                mode='CUDA-graph replay of vkn_iter_forward (S stages)',
+                                l2='inputs rotate over %d sets (%.0f MB > 126 MB L2); weights stay hot' % (
+                                    R, R * set_bytes / 1e6),
+                                engine='tcgen05+TMA' if _lib.lib() and heads[0].engine != _lib.ENGINE_SIMT else 'simt',
+                                parallelism='frame-shard x%d' % world),
+                    e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
+                    gpu_launches=int(launches_per_step * args.steps),
+                    clocks=sampler.summary(), roofline=roof, cpu_baseline=cb,
+                    kernels=per_kernel)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

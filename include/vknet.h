@@ -129,6 +129,17 @@ const char *vkn_last_error(void);
 /* Names of the device kernels this library launches, '\n' separated (for the bench's launch audit). */
 const char *vkn_kernel_names(void);
 
+/* Kernel launches issued by this library since it was loaded (graph replays are not counted: multiply
+ * the launches recorded during capture by the number of replays). */
+unsigned long long vkn_launch_count(void);
+
+/* Live per-kernel timing.  Between vkn_profile_begin() and vkn_profile_end() every launch is
+ * bracketed by CUDA events on the launching stream; _end synchronises on the last event and returns,
+ * in launch order, each kernel's name and device time in ms (time to the next launch on the stream).
+ * Not capturable in a CUDA graph; meant for bench.py's roofline section, not for production calls. */
+int vkn_profile_begin(void);
+int vkn_profile_end(const char **names, float *ms, int max_entries, int *count);
+
 /* Bytes of caller-provided scratch needed by the stage / link / iter entry points for `shape`. */
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes);
 

@@ -16,6 +16,28 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+// ---- launch accounting / profiling ------------------------------------------------------------------
+constexpr int PROF_MAX = 512;
+static unsigned long long g_launches = 0;
+static struct {
+  bool on = false;
+  int n = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[PROF_MAX + 1];
+  const char *names[PROF_MAX];
+  bool created = false;
+} g_prof;
+
+void launch_mark(const char *name, cudaStream_t stream) {
+  ++g_launches;
+  if (g_prof.on && g_prof.n < PROF_MAX) {
+    cudaEventRecord(g_prof.ev[g_prof.n], stream);
+    g_prof.names[g_prof.n] = name;
+    g_prof.st = stream;
+    ++g_prof.n;
+  }
+}
+
 constexpr int FFN_KSPLIT = 8;   // K-slices of the second FFN Linear (K = ffn_dim)
 constexpr int A_EXT_PAD = 8;    // a_ext row = C folded channels + bias column, padded to C + 8
 
@@ -343,6 +365,35 @@ const char *vkn_last_error(void) { return g_err; }
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
          "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_split3_kernel";
+}
+
+unsigned long long vkn_launch_count(void) { return g_launches; }
+
+int vkn_profile_begin(void) {
+  if (!g_prof.created) {
+    for (int i = 0; i <= PROF_MAX; ++i) VKN_CUDA_OK(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.created = true;
+  }
+  g_prof.n = 0;
+  g_prof.on = true;
+  return VKN_OK;
+}
+
+int vkn_profile_end(const char **names, float *ms, int max_entries, int *count) {
+  if (!g_prof.on) VKN_FAIL(VKN_E_INVALID, "vkn_profile_end without vkn_profile_begin");
+  g_prof.on = false;
+  if (!names || !ms || !count) VKN_FAIL(VKN_E_INVALID, "vkn_profile_end: null argument");
+  const int n = g_prof.n;
+  if (n > 0) {
+    VKN_CUDA_OK(cudaEventRecord(g_prof.ev[n], g_prof.st));
+    VKN_CUDA_OK(cudaEventSynchronize(g_prof.ev[n]));
+  }
+  *count = n < max_entries ? n : max_entries;
+  for (int i = 0; i < *count; ++i) {
+    names[i] = g_prof.names[i];
+    VKN_CUDA_OK(cudaEventElapsedTime(&ms[i], g_prof.ev[i], g_prof.ev[i + 1]));
+  }
+  return VKN_OK;
 }
 
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes) {

@@ -27,6 +27,13 @@ void set_error(const char *fmt, ...);
     if (rc__ != VKN_OK) return rc__; \
   } while (0)
 
+// ---- launch accounting / live per-kernel timing (vkn_profile_begin/end) ---------------------------
+// Every kernel launch goes through VKN_LAUNCH_MARK(name): it bumps the launch counter and, while a
+// profile is open, records a CUDA event on the launching stream so that vkn_profile_end can report the
+// device time of each launch (events bracket launches on the stream the kernels run on).
+void launch_mark(const char *name, cudaStream_t stream);
+#define VKN_LAUNCH_MARK(name, stream) ::vkn::launch_mark(name, stream)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

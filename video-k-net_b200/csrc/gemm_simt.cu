@@ -103,6 +103,7 @@ int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *
   if (s.C % TILE_C != 0) VKN_FAIL(VKN_E_UNSUPPORTED, "pool: C %d must be a multiple of %d", s.C, TILE_C);
   *nchunks = pool_simt_chunks(s);
   dim3 grid(*nchunks, (s.C / TILE_C) * ceil_div(s.N, TILE_N), s.B);
+  VKN_LAUNCH_MARK("vkn_pool_simt_kernel", stream);
   if (s.x_dtype == VKN_BF16)
     vkn_pool_simt_kernel<__nv_bfloat16><<<grid, GT, 0, stream>>>(
         (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)mask, partials, cnt_partials, s.B, s.N, s.C, HW,
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
 int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
                        float *xp0, float *cnt, cudaStream_t stream) {
   const int P = s.B * s.N, PC = P * s.C;
+  VKN_LAUNCH_MARK("vkn_pool_reduce_kernel", stream);
   vkn_pool_reduce_kernel<<<ceil_div(PC, 256), 256, 0, stream>>>(partials, cnt_partials, nchunks, PC, P, xp0, cnt);
   VKN_CUDA_OK(cudaGetLastError());
   return VKN_OK;
@@ -234,6 +236,7 @@ int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, i
   if (s.C % PK != 0) VKN_FAIL(VKN_E_UNSUPPORTED, "mask gemm: C %d must be a multiple of %d", s.C, PK);
   if (lda % 4 != 0) VKN_FAIL(VKN_E_INVALID, "mask gemm: lda %d must be a multiple of 4", lda);
   dim3 grid(ceil_div(HW, TILE_P), ceil_div(s.N, TILE_N), s.B);
+  VKN_LAUNCH_MARK("vkn_maskgemm_simt_kernel", stream);
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (s.x_dtype == VKN_BF16) {
     auto xp = (const __nv_bfloat16 *)x;

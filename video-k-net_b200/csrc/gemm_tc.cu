@@ -1,12 +1,546 @@
-// tcgen05 / TMA engines (placeholder until the tensor-core kernels land in this file).
+// tcgen05 / TMA engines for the two big contractions of a stage (bf16 storage, sm_100a only).
+//
+//   pooling   D[n, c] = sum_p  M[n, p] * x[c, p]          M = 1[mask > thr] in {0,1}  (exact in bf16)
+//             A = M tile   [128 kernels x 64 px]  K-major, written by the producer warps straight into
+//                          the 128B-swizzled UMMA layout (threshold fused: no sigmoid / compare / float temporaries)
+//             B = x tile   [C channels  x 64 px]  K-major, TMA (SWIZZLE_128B) from NCHW memory
+//             accumulators [128 x C] fp32 in TMEM; split over pixel ranges, partials reduced in fixed order.
+//
+//   mask conv D[p, n] = sum_c  x[c, p] * a[n, c]          a = mask_kernel . ft_w (fp32), split into three
+//             bf16 planes hi/mid/lo so that every product is exact and the fp32 TMEM accumulation
+//             carries fp32-level accuracy (the next stage thresholds these logits at 0).
+//             A = x tile   [128 px x 64 ch]  MN-major (pixels contiguous), TMA (SWIZZLE_128B) from NCHW
+//             B = a planes [Npad x 64 ch]    K-major, TMA (SWIZZLE_128B)
+//             accumulators [128 px x Npad] fp32 in TMEM; epilogue adds the folded bias, rounds to bf16 and
+//             stores pixel-contiguous (lane = pixel -> coalesced).
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane issues tcgen05.mma),
+// warps 2-5 operand producers / epilogue (TMEM -> registers -> global).  mbarrier pipelines between them.
+// Reference math: knet/det/kernel_update_head.py:190-195 and :247-260.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+
 namespace vkn {
-bool tc_supported(const VknShape &) { return false; }
-int pool_tc_chunks(const VknShape &) { return 0; }
-int launch_pool_tc(const VknShape &, const void *, const void *, float *, float *, int *, cudaStream_t) {
-  VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 pooling engine not built");
+
+constexpr int TC_THREADS = 192;
+constexpr int PX_BLK = 64;            // pixels per pipeline stage (pooling): 128 B of bf16 = one swizzle row
+constexpr int MASK_TILE_P = 128;      // pixels per CTA (mask conv) = UMMA M
+constexpr int CH_BLK = 64;            // channels per pipeline stage (mask conv)
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int launch_maskgemm_tc(const VknShape &, const void *, const float *, int, void *, void *, cudaStream_t) {
-  VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask-conv engine not built");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+}
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version bit (cute::UMMA::SmemDescriptor layout:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64)).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: D fp32, A/B bf16.
+static uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- host: tensor maps ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(EncodeTiledFn *fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VKN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) VKN_FAIL(VKN_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cached = (EncodeTiledFn)p;
+  }
+  *fn = cached;
+  return VKN_OK;
+}
+
+// bf16 tensor, rank 2 or 3, dims/box given innermost first; 128B swizzle (inner box = 64 elements).
+static int make_tmap_bf16(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint32_t *box) {
+  EncodeTiledFn enc;
+  VKN_TRY(get_encode(&enc));
+  cuuint64_t gdim[3];
+  cuuint64_t gstride[2];
+  cuuint32_t bx[3], estr[3];
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstride[i - 1] = stride;
+    stride *= dims[i];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstride, bx,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) VKN_FAIL(VKN_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VKN_OK;
+}
+
+static int npad_of(int N) { return ceil_div(N, 16) * 16; }
+
+bool tc_supported(const VknShape &s) {
+  const int HW = s.H * s.W;
+  if (s.x_dtype != VKN_BF16) return false;
+  if (HW % 8 != 0 || HW < PX_BLK) return false;          // TMA: 16-byte global strides; one full box at least
+  if (s.C % 64 != 0 || s.C > 256) return false;
+  if (npad_of(s.N) > 176) return false;                  // mask-conv B operand must fit the smem pipeline
+  return true;
+}
+
+// ---- pooling ------------------------------------------------------------------------------------
+struct PoolPlan {
+  int nblocks, bpc, nchunks, mtiles;
+};
+static PoolPlan pool_plan(const VknShape &s) {
+  PoolPlan p;
+  p.nblocks = ceil_div(s.H * s.W, PX_BLK);
+  p.mtiles = ceil_div(s.N, 128);
+  const int ctas_per_frame = p.nblocks * p.mtiles;
+  int target = 148 / (s.B > 148 ? 148 : s.B);            // CTAs available per frame for one wave
+  if (target < 1) target = 1;
+  p.bpc = ceil_div(ctas_per_frame, target);
+  if (p.bpc < 1) p.bpc = 1;
+  p.nchunks = ceil_div(p.nblocks, p.bpc);
+  return p;
+}
+int pool_tc_chunks(const VknShape &s) { return tc_supported(s) ? pool_plan(s).nchunks : 0; }
+
+constexpr int POOL_STAGES = 4;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16 *__restrict__ mask,
+                   float *__restrict__ partials, float *__restrict__ cnt_partials, int B, int N, int C, int HW,
+                   int nblocks, int bpc, float thr, uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t x_bytes = (uint32_t)C * 128u;          // C rows x 64 px x 2 B
+  const uint32_t m_bytes = 128u * 128u;
+  const uint32_t stage_bytes = x_bytes + m_bytes;
+  uint64_t *bars = (uint64_t *)(smem + POOL_STAGES * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // barrier slots: full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (STAGES + s), tmem_full = bar0 + 16 STAGES
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * POOL_STAGES + 1);
+  const uint32_t smem0 = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, mtile = blockIdx.y, b = blockIdx.z;
+  const int blk_beg = chunk * bpc;
+  const int nk = min(nblocks, blk_beg + bpc) - blk_beg;
+  const uint32_t ncols = (uint32_t)C;                    // 64 / 128 / 256: a power of two >= 32
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_x);
+      for (int s = 0; s < POOL_STAGES; ++s) {
+        mbar_init(bar0 + 8 * s, 1 + 4);                  // TMA expect_tx arrive + one arrive per producer warp
+        mbar_init(bar0 + 8 * (POOL_STAGES + s), 1);      // tcgen05.commit
+      }
+      mbar_init(bar0 + 16 * POOL_STAGES, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), ncols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % POOL_STAGES;
+        const uint32_t ph = (uint32_t)(i / POOL_STAGES) & 1u;
+        mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
+        mbar_expect_tx(bar0 + 8 * s, x_bytes);
+        tma_load_3d(smem0 + s * stage_bytes, &tmap_x, bar0 + 8 * s, (blk_beg + i) * PX_BLK, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % POOL_STAGES;
+        const uint32_t ph = (uint32_t)(i / POOL_STAGES) & 1u;
+        mbar_wait(bar0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t xs = smem0 + s * stage_bytes, ms = xs + x_bytes;
+#pragma unroll
+        for (int k = 0; k < PX_BLK / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(ms + k * 32, 0, 1024);
+          const uint64_t bd = umma_desc_sw128(xs + k * 32, 0, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar0 + 8 * (POOL_STAGES + s));        // frees the stage when these MMAs retire
+      }
+      umma_commit(bar0 + 16 * POOL_STAGES);               // accumulators complete
+    }
+  } else {
+    // ---- producers: threshold the mask logits into the swizzled A tile -------------------------
+    const int pt = threadIdx.x - 64;                      // 0..127
+    const int j = pt & 7;                                 // 16-byte chunk (8 pixels) within the 64-px row
+    const int rbase = pt >> 3;                            // rows rbase + 16 i
+    const __nv_bfloat16 *mb = mask + (size_t)b * N * HW;
+    float cnt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt[i] = 0.f;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % POOL_STAGES;
+      const uint32_t ph = (uint32_t)(it / POOL_STAGES) & 1u;
+      mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
+      uint8_t *mt = smem + s * stage_bytes + x_bytes;
+      const int p = (blk_beg + it) * PX_BLK + j * 8;
+      uint4 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = mtile * 128 + rbase + 16 * i;
+        raw[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (n < N && p < HW) raw[i] = __ldg(reinterpret_cast<const uint4 *>(mb + (size_t)n * HW + p));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rbase + 16 * i;
+        const int n = mtile * 128 + r;
+        const bool live = (n < N && p < HW);
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        uint32_t o[4];
+        float c = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+          const bool blo = live && (lo > thr), bhi = live && (hi > thr);
+          o[e] = (blo ? 0x3f80u : 0u) | (bhi ? 0x3f800000u : 0u);   // bf16 1.0 = 0x3f80
+          c += (blo ? 1.f : 0.f) + (bhi ? 1.f : 0.f);
+        }
+        cnt[i] += c;
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);   // Swizzle<3,4,3>
+        *reinterpret_cast<uint4 *>(mt + off) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * s);
+    }
+    // ---- epilogue: accumulators -> partial sums -----------------------------------------------
+    mbar_wait(bar0 + 16 * POOL_STAGES, 0);
+    tc_fence_after();
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const int n = mtile * 128 + q * 32 + lane;
+    float *po = partials + (((size_t)chunk * B + b) * N + n) * C;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (n < N) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4 *>(po + c0 + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                                 __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+      }
+    }
+    // pixel counts: the 8 chunk-threads of a row are adjacent lanes
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float c = cnt[i];
+      c += __shfl_xor_sync(0xffffffffu, c, 1);
+      c += __shfl_xor_sync(0xffffffffu, c, 2);
+      c += __shfl_xor_sync(0xffffffffu, c, 4);
+      const int nn = mtile * 128 + rbase + 16 * i;
+      if (j == 0 && nn < N) cnt_partials[((size_t)chunk * B + b) * N + nn] = c;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
+                   int *nchunks, cudaStream_t stream) {
+  if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 pooling: shape/dtype not supported");
+  const int HW = s.H * s.W;
+  const PoolPlan p = pool_plan(s);
+  *nchunks = p.nchunks;
+  CUtensorMap tmap;
+  const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)s.B};
+  const uint32_t box[3] = {(uint32_t)PX_BLK, (uint32_t)s.C, 1u};
+  VKN_TRY(make_tmap_bf16(&tmap, x, 3, dims, box));
+  const size_t smem = (size_t)POOL_STAGES * ((size_t)s.C * 128 + 128 * 128) + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  dim3 grid(p.nchunks, p.mtiles, s.B);
+  VKN_LAUNCH_MARK("vkn_pool_tc_kernel", stream);
+  vkn_pool_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, (const __nv_bfloat16 *)mask, partials, cnt_partials, s.B,
+                                                         s.N, s.C, HW, p.nblocks, p.bpc, s.mask_thr_logit,
+                                                         make_idesc_bf16(128, s.C, 0, 0));
+  VKN_CUDA_OK(cudaGetLastError());
+  return VKN_OK;
+}
+
+// ---- mask conv -------------------------------------------------------------------------------------
+// a_ext fp32 [P, lda] -> bf16 planes [3][B][Npad][C]  (hi = bf16(a), mid = bf16(a - hi), lo = bf16(a - hi - mid);
+// a == hi + mid + lo to 24 bits).  Padding rows n >= N are zero.
+__global__ void __launch_bounds__(256) vkn_split3_kernel(const float *__restrict__ a_ext, int lda,
+                                                         __nv_bfloat16 *__restrict__ planes, int B, int N, int Npad,
+                                                         int C) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int total = B * Npad * C;
+  if (idx >= total) return;
+  const int c = idx % C;
+  const int n = (idx / C) % Npad;
+  const int b = idx / (C * Npad);
+  float v = 0.f;
+  if (n < N) v = a_ext[((size_t)b * N + n) * lda + c];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  planes[idx] = hi;
+  planes[(size_t)total + idx] = mid;
+  planes[(size_t)2 * total + idx] = lo;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
+                       const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
+                       int Npad, int C, int HW, int stages, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t x_bytes = (uint32_t)CH_BLK * MASK_TILE_P * 2u;         // 64 ch x 128 px x 2 B = 16 KB
+  const uint32_t a_plane = (uint32_t)Npad * 128u;                       // Npad rows x 64 ch x 2 B
+  const uint32_t stage_bytes = x_bytes + 3u * a_plane;                  // (multiple of 1024: Npad % 16 == 0 -> a_plane % 2048 == 0)
+  uint64_t *bars = (uint64_t *)(smem + (size_t)stages * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (stages + s), tmem_full = bar0 + 16 stages
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * stages + 1);
+  float *bias_s = (float *)(tmem_slot + 2);                              // [Npad]
+  const uint32_t smem0 = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * MASK_TILE_P, b = blockIdx.z;
+  const int nk = C / CH_BLK;
+  const uint32_t ncols = Npad <= 128 ? 128u : 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_x);
+      prefetch_tmap(&tmap_a);
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(bar0 + 8 * s, 1);
+        mbar_init(bar0 + 8 * (stages + s), 1);
+      }
+      mbar_init(bar0 + 16 * stages, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), ncols);
+  }
+  for (int n = threadIdx.x; n < Npad; n += TC_THREADS)
+    bias_s[n] = (n < N) ? a_ext[((size_t)b * N + n) * lda + C] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(bar0 + 8 * (stages + s), ph ^ 1u);
+        mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+        const uint32_t xs = smem0 + s * stage_bytes;
+        // x tile: two 64-pixel column groups, each [64 ch rows x 128 B]
+        tma_load_3d(xs, &tmap_x, bar0 + 8 * s, p0, i * CH_BLK, b);
+        tma_load_3d(xs + x_bytes / 2, &tmap_x, bar0 + 8 * s, p0 + 64, i * CH_BLK, b);
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          tma_load_2d(xs + x_bytes + t * a_plane, &tmap_a, bar0 + 8 * s, i * CH_BLK, (t * B + b) * Npad);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(bar0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t xs = smem0 + s * stage_bytes;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+#pragma unroll
+          for (int k = 0; k < CH_BLK / 16; ++k) {
+            // A (x): MN-major; one UMMA_K step = 16 channel rows of 128 B = 2048 B
+            const uint64_t ad = umma_desc_sw128(xs + k * 2048, x_lbo, x_sbo);
+            // B (a plane t): K-major; UMMA_K step = 32 B inside the 128-B swizzle row
+            const uint64_t bd = umma_desc_sw128(xs + x_bytes + t * a_plane + k * 32, 0, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || t > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar0 + 8 * (stages + s));
+      }
+      umma_commit(bar0 + 16 * stages);
+    }
+  } else {
+    // ---- epilogue: TMEM lane = pixel, column = kernel ---------------------------------------------
+    mbar_wait(bar0 + 16 * stages, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int p = p0 + q * 32 + lane;
+    __nv_bfloat16 *ob = out + (size_t)b * N * HW + p;
+    for (int n0 = 0; n0 < Npad; n0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, r);
+      if (p < HW) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = n0 + e;
+          if (n < N) ob[(size_t)n * HW] = __float2bfloat16_rn(__uint_as_float(r[e]) + bias_s[n]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, void *a_split_ws, void *out,
+                       cudaStream_t stream) {
+  if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: shape/dtype not supported");
+  const int HW = s.H * s.W, Npad = npad_of(s.N);
+  const int total = s.B * Npad * s.C;
+  VKN_LAUNCH_MARK("vkn_split3_kernel", stream);
+  vkn_split3_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(a_ext, lda, (__nv_bfloat16 *)a_split_ws, s.B, s.N, Npad, s.C);
+  VKN_CUDA_OK(cudaGetLastError());
+  CUtensorMap tmx, tma;
+  {
+    const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)s.B};
+    const uint32_t box[3] = {64u, (uint32_t)CH_BLK, 1u};
+    VKN_TRY(make_tmap_bf16(&tmx, x, 3, dims, box));
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)s.C, (uint64_t)3 * s.B * Npad};
+    const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)Npad};
+    VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
+  }
+  const size_t stage_bytes = (size_t)CH_BLK * MASK_TILE_P * 2 + (size_t)3 * Npad * 128;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages > s.C / CH_BLK) stages = s.C / CH_BLK;
+  if (stages < 1) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: N %d too large for shared memory", s.N);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 1) * 8 + 16 + (size_t)Npad * 4 + 64;
+  static bool attr = false;
+  if (!attr) {
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  // x operand (A, MN-major, SWIZZLE_128B): 64-px groups are 8192 B apart (LBO), 8-channel-row groups 1024 B (SBO)
+  uint32_t x_lbo = (uint32_t)CH_BLK * 128u, x_sbo = 1024u;
+  if (const char *e = getenv("VKN_DEBUG_SWAP_LBO_SBO")) {
+    if (e[0] == '1') { uint32_t t = x_lbo; x_lbo = x_sbo; x_sbo = t; }
+  }
+  dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B);
+  VKN_LAUNCH_MARK("vkn_maskgemm_tc_kernel", stream);
+  vkn_maskgemm_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmx, tma, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad,
+                                                             s.C, HW, stages, make_idesc_bf16(128, Npad, 1, 0), x_lbo,
+                                                             x_sbo);
+  VKN_CUDA_OK(cudaGetLastError());
+  return VKN_OK;
+}
+
 }  // namespace vkn

@@ -267,6 +267,7 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
   // tile choice: wide outputs get the 32x64 tile, the C x C layers the 16x32 tile (more CTAs in flight)
   const bool big = maxN >= 1024;
   dim3 grid, block(NT);
+  VKN_LAUNCH_MARK(big ? "vkn_linear_kernel<32x64>" : "vkn_linear_kernel<16x32>", stream);
   if (big) {
     grid = dim3(ceil_div(maxN, 64), ceil_div(maxM, 32), nprob * ks);
     if (w_dtype == VKN_BF16) vkn_linear_kernel<__nv_bfloat16, 32, 64><<<grid, block, 0, stream>>>(b);
@@ -282,6 +283,7 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
 
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream) {
   VKN_TRY(check_src(src, K));
+  VKN_LAUNCH_MARK("vkn_rowop_kernel", stream);
   vkn_rowop_kernel<<<ceil_div(M, NT / 32), NT, 0, stream>>>(src, out, ldo, M, K);
   VKN_CUDA_OK(cudaGetLastError());
   return VKN_OK;
@@ -356,6 +358,7 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   }
   if (smem > 160 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: N %d too large for shared memory", N);
   dim3 grid(ceil_div(N, ATT_QB), heads, B);
+  VKN_LAUNCH_MARK("vkn_attention_kernel", stream);
   vkn_attention_kernel<<<grid, NT, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, N, hd,
                                                    1.0f / sqrtf((float)hd));
   VKN_CUDA_OK(cudaGetLastError());

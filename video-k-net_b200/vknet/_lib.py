@@ -62,7 +62,8 @@ class VknError(RuntimeError):
 _lib = None
 
 # every symbol include/vknet.h declares (tests check that the library exports all of them)
-SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_workspace_bytes', 'vkn_mask_pool',
+SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_launch_count', 'vkn_profile_begin',
+           'vkn_profile_end', 'vkn_workspace_bytes', 'vkn_mask_pool',
            'vkn_kernel_update', 'vkn_mhsa_ln', 'vkn_ffn_ln', 'vkn_heads', 'vkn_mask_gemm',
            'vkn_stage_forward', 'vkn_iter_forward', 'vkn_link_attend')
 
@@ -79,6 +80,10 @@ def lib():
     L.vkn_version.restype = C.c_int
     L.vkn_last_error.restype = C.c_char_p
     L.vkn_kernel_names.restype = C.c_char_p
+    L.vkn_launch_count.restype = C.c_ulonglong
+    L.vkn_profile_begin.restype = C.c_int
+    L.vkn_profile_end.restype = C.c_int
+    L.vkn_profile_end.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     S, sz = C.POINTER(VknShape), C.c_size_t
     L.vkn_workspace_bytes.argtypes = [S, C.POINTER(sz)]
     L.vkn_mask_pool.argtypes = [S, C.POINTER(VknHeadW), _vp, _vp, _vp, _vp, sz, _vp]
@@ -90,7 +95,7 @@ def lib():
     L.vkn_stage_forward.argtypes = [S, C.POINTER(VknHeadW), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, sz, _vp]
     L.vkn_iter_forward.argtypes = [S, C.POINTER(VknHeadW), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, sz, _vp]
     L.vkn_link_attend.argtypes = [S, C.POINTER(VknLinkW), _vp, _vp, _vp, _vp, _vp, sz, _vp]
-    for name in SYMBOLS[3:]:
+    for name in SYMBOLS[6:]:
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -145,3 +150,25 @@ class Workspace:
 
 def kernel_names():
     return lib().vkn_kernel_names().decode().split('\n')
+
+
+def launch_count():
+    return int(lib().vkn_launch_count())
+
+
+class profile:
+    """with profile() as p: ...calls...  ->  p.records = [(kernel_name, ms), ...] in launch order."""
+    MAX = 512
+
+    def __enter__(self):
+        check(lib().vkn_profile_begin())
+        self.records = []
+        return self
+
+    def __exit__(self, *exc):
+        names = (C.c_char_p * self.MAX)()
+        ms = (C.c_float * self.MAX)()
+        n = C.c_int(0)
+        check(lib().vkn_profile_end(names, ms, self.MAX, C.byref(n)))
+        self.records = [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+        return False
