@@ -187,6 +187,8 @@ def run_ours(args):
         h = vknet.build_head(dict(type='VideoKernelUpdateHead' if last_linked else 'KernelUpdateHead',
                                   **head_cfg(link=last_linked)))
         h.init_weights()
+        eng = os.environ.get('VKN_ENGINE', 'auto')
+        h.engine = dict(auto=_lib.ENGINE_AUTO, simt=_lib.ENGINE_SIMT, tc=_lib.ENGINE_TC)[eng]
         heads.append(h.to(dev).bfloat16().eval())
     loop = vknet.KernelIterLoop(heads)
 

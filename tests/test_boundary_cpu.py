@@ -126,3 +126,21 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dp, f)).read()
                 assert 'knet_oracle' not in src and 'ref_shim' not in src, f
+
+
+def test_alias_packages_overlay_the_rest_of_the_reference_package(tmp_path, built_lib):
+    """`knet.det.kernel_update_head` is ours, any other `knet.*` module still resolves to a `knet/`
+    directory later on sys.path (the reference tree): configs stay unchanged."""
+    import subprocess
+    import sys
+    fake = tmp_path / 'reftree' / 'knet' / 'det'
+    fake.mkdir(parents=True)
+    (tmp_path / 'reftree' / 'knet' / '__init__.py').write_text('')
+    (fake / '__init__.py').write_text('')
+    (fake / 'kernel_iter_head.py').write_text('MARK = "reference file"\n')
+    (fake / 'kernel_update_head.py').write_text('raise RuntimeError("the reference copy must be shadowed")\n')
+    code = ('import sys; sys.path[:0] = [%r, %r]; import knet.det.kernel_iter_head as a, knet.det.kernel_update_head as b; '
+            'print(a.MARK, b.KernelUpdateHead.__module__)' % (os.path.join(ROOT, 'video-k-net_b200'), str(tmp_path / 'reftree')))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == 'reference file vknet.kernel_update_head'

@@ -288,3 +288,52 @@ def test_error_behaviour(dev):
     bad = vknet.build_head(dict(type='KernelUpdateHead', **ko.default_cfg(in_channels=64, conv_kernel_size=3)))
     with pytest.raises(NotImplementedError):
         bad.to(dev)(x, torch.zeros(1, 6, 64, 3, 3, device=dev), mask)
+
+
+# ---- tcgen05/TMA engine vs the CUDA-core engine and the oracle (bf16 storage) ---------------------------
+@pytest.mark.parametrize('B,N,C,H,W', [(1, 100, 256, 200, 88), (2, 117, 256, 48, 156), (1, 166, 128, 16, 24),
+                                       (3, 10, 64, 8, 8), (4, 100, 256, 96, 160)])
+def test_tc_engine_matches_simt_engine_and_oracle(dev, B, N, C, H, W):
+    from vknet import _lib, ops
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=21))
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=12)
+    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
+    xb, mb = x.to(dev).bfloat16(), mask.to(dev).bfloat16()
+    out = {}
+    for name, eng in (('simt', _lib.ENGINE_SIMT), ('tc', _lib.ENGINE_TC)):
+        h.engine = eng
+        g = torch.Generator().manual_seed(2)
+        mk = torch.randn(B, N, C, generator=g)
+        out[name] = (ops.mask_pool(h, xb, mb), ops.mask_gemm(h, xb, mk.to(dev)), h(xb, pf.to(dev), mb))
+    xt, x_feat, _ = ko._pool(sd, cfg, x, pf, mask)
+    # pooling: every product is exact (0/1 x bf16); only the fp32 summation order differs
+    scale = x_feat.abs().max().item()
+    assert maxabs(out['tc'][0], x_feat) < 2e-5 * scale, 'tc pooling vs oracle'
+    assert maxabs(out['tc'][0], out['simt'][0]) < 2e-5 * scale, 'tc pooling vs simt'
+    # mask conv: 3-plane bf16 split of the fp32 kernels keeps fp32-level accuracy -> after the bf16 output
+    # rounding the two engines agree except for rare 1-ulp roundings
+    a, b = out['tc'][1].float(), out['simt'][1].float()
+    diff = (a - b).abs()
+    assert diff.max().item() <= 2 ** -7 * b.abs().max().item(), 'tc mask conv differs from simt by more than 1 bf16 ulp'
+    assert (diff > 0).float().mean().item() < 2e-3, 'tc mask conv: too many 1-ulp differences vs simt'
+    want = ko.kernel_update_head_forward(sd, cfg, x, pf, mask)
+    for name in ('simt', 'tc'):
+        cls, nm, obj = out[name][2]
+        assert maxabs(cls, want[0]) < TOL_BF16 and maxabs(obj, want[2]) < TOL_BF16, name
+        ref = ko.round_bf16(want[1])
+        mism = (nm.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item()
+        assert mism < 2e-3, '%s stage: argmax mismatch rate %g' % (name, mism)
+
+
+def test_profile_hooks_and_launch_count(dev):
+    from vknet import _lib
+    cfg = ko.default_cfg(num_classes=3, in_channels=64, feedforward_channels=64)
+    h = build_heads('KernelUpdateHead', cfg, [ko.random_state_dict(cfg)], dev)[0]
+    x, pf, mask = (t.to(dev) for t in ko.dummy_inputs(1, 6, 64, 8, 8))
+    n0 = _lib.launch_count()
+    with _lib.profile() as p:
+        h(x, pf, mask)
+    assert _lib.launch_count() - n0 == len(p.records) >= 10
+    assert all(name.startswith('vkn_') and ms >= 0 for name, ms in p.records)
