@@ -121,10 +121,7 @@ def _feat_transform(sd, x):
         return x
     w = sd['feat_transform.conv.weight'].to(x.dtype)
     assert w.shape[-1] == 1 and w.shape[-2] == 1, 'only the 1x1 feat_transform is on the shipped path'
-    B, C, H, W = x.shape
-    y = torch.einsum('oc,bcp->bop', w[:, :, 0, 0], x.reshape(B, C, H * W))
-    y = y + sd['feat_transform.conv.bias'].to(x.dtype)[None, :, None]
-    return y.reshape(B, -1, H, W)
+    return F.conv2d(x, w, sd['feat_transform.conv.bias'].to(x.dtype))   # the op nn.Conv2d dispatches to
 
 
 def _heads_and_conv(sd, cfg, obj_feat, x, B, N):

@@ -2,6 +2,7 @@
 // Everything here only enqueues kernels on the caller's stream: no allocation, no synchronisation.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,6 +28,15 @@ static struct {
   const char *names[PROF_MAX];
   bool created = false;
 } g_prof;
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("VKN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 void launch_mark(const char *name, cudaStream_t stream) {
   ++g_launches;
@@ -327,6 +337,14 @@ static int k_maskgemm(Ctx &c, const VknHeadW &w, const void *x, const float *mk,
   const int C = c.s.C, P = c.P;
   const int lda = C + A_EXT_PAD;
   LinArgs a = lin(src_copy(mk, C), w.ft_wt_ext, C, nullptr, c.L.a_ext, lda, P, C + 1, C, 0);
+  if (c.use_tc) {      // the tcgen05 engine consumes bf16 hi/mid/lo planes: emit them from this epilogue
+    a.epi |= EPI_SPLIT3;
+    a.split_planes = (__nv_bfloat16 *)c.L.a_split;
+    a.split_B = c.s.B;
+    a.split_N = c.s.N;
+    a.split_Npad = maskgemm_tc_npad(c.s);
+    a.split_C = C;
+  }
   VKN_TRY(launch_linear(&a, 1, c.s.w_dtype, c.st));
   if (c.use_tc) return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, out, c.st);
   return launch_maskgemm_simt(c.s, x, c.L.a_ext, lda, out, c.st);
@@ -364,7 +382,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_split3_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "vknet.h"
 
@@ -33,6 +34,32 @@ void set_error(const char *fmt, ...);
 // device time of each launch (events bracket launches on the stream the kernels run on).
 void launch_mark(const char *name, cudaStream_t stream);
 #define VKN_LAUNCH_MARK(name, stream) ::vkn::launch_mark(name, stream)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the stage chain is launched with programmaticStreamSerialization: its prologue
+// (barrier init, TMEM alloc, weight-tile prefetch -- data no kernel of the chain writes) overlaps the
+// previous kernel's tail; `pdl_wait()` must precede the first access to anything a previous kernel wrote
+// and every global store.  VKN_PDL=0 in the environment disables the attribute.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -110,7 +137,7 @@ enum Pro : int {
   PRO_MUL = 3,      // v = a0 * a1
   PRO_GATE = 4      // v = sigmoid(LN0(a0)) * LN1(a1) + sigmoid(LN2(a2)) * LN3(a3)   (kernel_updator.py:74-88)
 };
-enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8 };
+enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_SPLIT3 = 16 };
 
 struct RowSrc {
   const float *a[4];
@@ -141,6 +168,10 @@ struct LinArgs {
   int ldside;
   int M, N, K;
   int epi;
+  // EPI_SPLIT3: columns < split_C are also written as bf16 hi/mid/lo planes [3][B][Npad][split_C]
+  // (row p = b * split_N + n); the operand layout of the tcgen05 mask-conv engine.
+  __nv_bfloat16 *split_planes;
+  int split_B, split_N, split_Npad, split_C;
 };
 
 // launches (all enqueue on `stream`, never synchronise)
@@ -161,7 +192,8 @@ bool tc_supported(const VknShape &s);
 int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
                    int *nchunks, cudaStream_t stream);
 int pool_tc_chunks(const VknShape &s);
-int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, void *a_split_ws,
+int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws,
                        void *out, cudaStream_t stream);
+int maskgemm_tc_npad(const VknShape &s);
 
 }  // namespace vkn

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(GT) vkn_pool_simt_kernel(const XT *__restrict_
   const int n0 = nb * TILE_N, c0 = cb * TILE_C;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int pbeg = chunk * POOL_CHUNK, pend = min(HW, pbeg + POOL_CHUNK);
+  pdl_wait();
 
   float acc[8][4];
   float cacc[8];
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(GT) vkn_pool_simt_kernel(const XT *__restrict_
     }
     __syncthreads();
   }
+  pdl_trigger();
   float *po = partials + ((size_t)chunk * B + b) * N * C;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -105,38 +107,58 @@ int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *
   dim3 grid(*nchunks, (s.C / TILE_C) * ceil_div(s.N, TILE_N), s.B);
   VKN_LAUNCH_MARK("vkn_pool_simt_kernel", stream);
   if (s.x_dtype == VKN_BF16)
-    vkn_pool_simt_kernel<__nv_bfloat16><<<grid, GT, 0, stream>>>(
-        (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)mask, partials, cnt_partials, s.B, s.N, s.C, HW,
-        s.mask_thr_logit);
+    VKN_CUDA_OK(launch_chain(vkn_pool_simt_kernel<__nv_bfloat16>, grid, dim3(GT), 0, stream, (const __nv_bfloat16 *)x,
+                             (const __nv_bfloat16 *)mask, partials, cnt_partials, s.B, s.N, s.C, HW, s.mask_thr_logit));
   else
-    vkn_pool_simt_kernel<float><<<grid, GT, 0, stream>>>((const float *)x, (const float *)mask, partials,
-                                                         cnt_partials, s.B, s.N, s.C, HW, s.mask_thr_logit);
-  VKN_CUDA_OK(cudaGetLastError());
+    VKN_CUDA_OK(launch_chain(vkn_pool_simt_kernel<float>, grid, dim3(GT), 0, stream, (const float *)x,
+                             (const float *)mask, partials, cnt_partials, s.B, s.N, s.C, HW, s.mask_thr_logit));
   return VKN_OK;
 }
 
-// partials [nchunks][P*C] -> xp0 [P*C];  cnt_partials [nchunks][P] -> cnt [P]   (fixed order: deterministic)
+// partials [nchunks][P*C] -> xp0 [P*C];  cnt_partials [nchunks][P] -> cnt [P].
+// One CTA = 128 outputs (float4 per lane); its 8 warps each sum every 8th chunk with independent
+// 16-byte loads, then the 8 warp sums are combined in a FIXED order (deterministic, no atomics).
 __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__restrict__ partials,
                                                               const float *__restrict__ cnt_partials, int nchunks,
                                                               int PC, int P, float *__restrict__ xp0,
                                                               float *__restrict__ cnt) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float4 red[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 128 + lane * 4;
+  pdl_wait();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (idx < PC) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int ch = 0;
-    for (; ch + 4 <= nchunks; ch += 4) {
-      s0 += __ldg(partials + (size_t)ch * PC + idx);
-      s1 += __ldg(partials + (size_t)(ch + 1) * PC + idx);
-      s2 += __ldg(partials + (size_t)(ch + 2) * PC + idx);
-      s3 += __ldg(partials + (size_t)(ch + 3) * PC + idx);
+    float4 a0 = acc, a1 = acc;
+    int ch = warp;
+    for (; ch + 8 < nchunks; ch += 16) {
+      const float4 u = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)ch * PC + idx));
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)(ch + 8) * PC + idx));
+      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+      a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
     }
-    for (; ch < nchunks; ++ch) s0 += __ldg(partials + (size_t)ch * PC + idx);
-    xp0[idx] = (s0 + s1) + (s2 + s3);
+    if (ch < nchunks) {
+      const float4 u = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)ch * PC + idx));
+      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+    }
+    acc = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
   }
-  if (idx < P) {
-    float s = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) s += __ldg(cnt_partials + (size_t)ch * P + idx);
-    cnt[idx] = s;
+  red[warp][lane] = acc;
+  __syncthreads();
+  pdl_trigger();
+  if (warp == 0 && idx < PC) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 u = red[w][lane];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    *reinterpret_cast<float4 *>(xp0 + idx) = t;
+  }
+  const int ci = blockIdx.x * 256 + threadIdx.x;     // the first ceil(P/256) CTAs also reduce the pixel counts
+  if (ci < P) {
+    float s0 = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) s0 += __ldg(cnt_partials + (size_t)ch * P + ci);
+    cnt[ci] = s0;
   }
 }
 
@@ -144,8 +166,10 @@ int launch_pool_reduce(const VknShape &s, const float *partials, const float *cn
                        float *xp0, float *cnt, cudaStream_t stream) {
   const int P = s.B * s.N, PC = P * s.C;
   VKN_LAUNCH_MARK("vkn_pool_reduce_kernel", stream);
-  vkn_pool_reduce_kernel<<<ceil_div(PC, 256), 256, 0, stream>>>(partials, cnt_partials, nchunks, PC, P, xp0, cnt);
-  VKN_CUDA_OK(cudaGetLastError());
+  int grid = ceil_div(PC, 128);
+  if (grid < ceil_div(P, 256)) grid = ceil_div(P, 256);
+  VKN_CUDA_OK(launch_chain(vkn_pool_reduce_kernel, dim3(grid), dim3(256), 0, stream, partials, cnt_partials, nchunks, PC,
+                           P, xp0, cnt));
   return VKN_OK;
 }
 
@@ -165,6 +189,7 @@ __global__ void __launch_bounds__(GT) vkn_maskgemm_simt_kernel(const XT *__restr
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const XT *xb = x + (size_t)b * C * HW;
   const float *ab = a_ext + (size_t)b * N * lda;
+  pdl_wait();
   for (int c0 = 0; c0 < C; c0 += PK) {
     {  // A tile: 128 rows x 32 channels, 8 consecutive channels per thread
       const int kk = (tid & 3) * 8;
@@ -212,6 +237,7 @@ __global__ void __launch_bounds__(GT) vkn_maskgemm_simt_kernel(const XT *__restr
     }
     __syncthreads();
   }
+  pdl_trigger();
   XT *ob = out + (size_t)b * N * HW;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -241,13 +267,13 @@ int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, i
   if (s.x_dtype == VKN_BF16) {
     auto xp = (const __nv_bfloat16 *)x;
     auto op = (__nv_bfloat16 *)out;
-    if (vec) vkn_maskgemm_simt_kernel<__nv_bfloat16, true><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
-    else vkn_maskgemm_simt_kernel<__nv_bfloat16, false><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
+    if (vec) VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<__nv_bfloat16, true>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
+    else VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<__nv_bfloat16, false>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
   } else {
     auto xp = (const float *)x;
     auto op = (float *)out;
-    if (vec) vkn_maskgemm_simt_kernel<float, true><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
-    else vkn_maskgemm_simt_kernel<float, false><<<grid, GT, 0, stream>>>(xp, a_ext, lda, op, s.N, s.C, HW);
+    if (vec) VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<float, true>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
+    else VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<float, false>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
   }
   VKN_CUDA_OK(cudaGetLastError());
   return VKN_OK;

@@ -234,6 +234,7 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // setup above overlapped the previous kernel's tail; the mask logits come from it
 
   if (warp == 0) {
     if (lane == 0) {
@@ -311,6 +312,7 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
     // ---- epilogue: accumulators -> partial sums -----------------------------------------------
     mbar_wait(bar0 + 16 * POOL_STAGES, 0);
     tc_fence_after();
+    pdl_trigger();
     const int q = warp & 3;                                // TMEM lane quarter this warp may read
     const int n = mtile * 128 + q * 32 + lane;
     float *po = partials + (((size_t)chunk * B + b) * N + n) * C;
@@ -361,37 +363,16 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   }
   dim3 grid(p.nchunks, p.mtiles, s.B);
   VKN_LAUNCH_MARK("vkn_pool_tc_kernel", stream);
-  vkn_pool_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, (const __nv_bfloat16 *)mask, partials, cnt_partials, s.B,
-                                                         s.N, s.C, HW, p.nblocks, p.bpc, s.mask_thr_logit,
-                                                         make_idesc_bf16(128, s.C, 0, 0));
-  VKN_CUDA_OK(cudaGetLastError());
+  VKN_CUDA_OK(launch_chain(vkn_pool_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmap, (const __nv_bfloat16 *)mask,
+                           partials, cnt_partials, s.B, s.N, s.C, HW, p.nblocks, p.bpc, s.mask_thr_logit,
+                           make_idesc_bf16(128, s.C, 0, 0)));
   return VKN_OK;
 }
 
 // ---- mask conv -------------------------------------------------------------------------------------
-// a_ext fp32 [P, lda] -> bf16 planes [3][B][Npad][C]  (hi = bf16(a), mid = bf16(a - hi), lo = bf16(a - hi - mid);
-// a == hi + mid + lo to 24 bits).  Padding rows n >= N are zero.
-__global__ void __launch_bounds__(256) vkn_split3_kernel(const float *__restrict__ a_ext, int lda,
-                                                         __nv_bfloat16 *__restrict__ planes, int B, int N, int Npad,
-                                                         int C) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  const int total = B * Npad * C;
-  if (idx >= total) return;
-  const int c = idx % C;
-  const int n = (idx / C) % Npad;
-  const int b = idx / (C * Npad);
-  float v = 0.f;
-  if (n < N) v = a_ext[((size_t)b * N + n) * lda + c];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(hi);
-  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(mid);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
-  planes[idx] = hi;
-  planes[(size_t)total + idx] = mid;
-  planes[(size_t)2 * total + idx] = lo;
-}
-
+// The B operand (hi/mid/lo bf16 planes [3][B][Npad][C] of the folded kernels) is written by the fold
+// Linear's epilogue (smallops.cu, EPI_SPLIT3).  Padding rows n >= N are never written: they only feed
+// accumulator columns n >= N, which the epilogue discards.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
                        const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
@@ -426,6 +407,7 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), ncols);
   }
+  pdl_wait();     // a_ext / the planes come from the previous kernel
   for (int n = threadIdx.x; n < Npad; n += TC_THREADS)
     bias_s[n] = (n < N) ? a_ext[((size_t)b * N + n) * lda + C] : 0.f;
   tc_fence_before();
@@ -476,6 +458,7 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     // ---- epilogue: TMEM lane = pixel, column = kernel ---------------------------------------------
     mbar_wait(bar0 + 16 * stages, 0);
     tc_fence_after();
+    pdl_trigger();
     const int q = warp & 3;
     const int p = p0 + q * 32 + lane;
     __nv_bfloat16 *ob = out + (size_t)b * N * HW + p;
@@ -499,14 +482,12 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
-int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, void *a_split_ws, void *out,
+int maskgemm_tc_npad(const VknShape &s) { return npad_of(s.N); }
+
+int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws, void *out,
                        cudaStream_t stream) {
   if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: shape/dtype not supported");
   const int HW = s.H * s.W, Npad = npad_of(s.N);
-  const int total = s.B * Npad * s.C;
-  VKN_LAUNCH_MARK("vkn_split3_kernel", stream);
-  vkn_split3_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(a_ext, lda, (__nv_bfloat16 *)a_split_ws, s.B, s.N, Npad, s.C);
-  VKN_CUDA_OK(cudaGetLastError());
   CUtensorMap tmx, tma;
   {
     const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)s.B};
@@ -536,10 +517,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B);
   VKN_LAUNCH_MARK("vkn_maskgemm_tc_kernel", stream);
-  vkn_maskgemm_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmx, tma, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad,
-                                                             s.C, HW, stages, make_idesc_bf16(128, Npad, 1, 0), x_lbo,
-                                                             x_sbo);
-  VKN_CUDA_OK(cudaGetLastError());
+  VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmx, tma, a_ext, lda,
+                           (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, stages, make_idesc_bf16(128, Npad, 1, 0), x_lbo,
+                           x_sbo));
   return VKN_OK;
 }
 

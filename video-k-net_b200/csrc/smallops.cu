@@ -1,18 +1,28 @@
 // The N-kernel "rows" operators of the KernelUpdateHead stage: every Linear of KernelUpdator, MHSA,
 // FFN and the cls/mask heads runs through ONE fused kernel whose prologue applies the row-wise
 // transform feeding it (LayerNorm / ReLU / gate arithmetic, warp-shuffle reductions, staged through
-// shared memory) and whose epilogue adds bias / residual / ReLU.  Weights are streamed with 16-byte
-// vector loads; activations stay fp32.
+// shared memory) and whose epilogue adds bias / residual / ReLU (or emits the bf16 hi/mid/lo planes the
+// tcgen05 mask-conv engine consumes).
+//
+// Latency structure (these kernels are latency-, not bandwidth-bound): the whole [BN x K-chunk] weight
+// tile is fetched with 16-byte cp.async BEFORE the programmatic-dependency wait, so under PDL the weight
+// stream of kernel i+1 overlaps the tail of kernel i; the row panel (which depends on kernel i) is built
+// afterwards, then one barrier, then the full-K FMA loop out of shared memory.
 //
 // Reference math: knet/kernel_updator.py:56-94, knet/det/kernel_update_head.py:201-227.
 #include "common.cuh"
 
 namespace vkn {
 
-constexpr int KC = 256;   // K-chunk held in the shared-memory row panel
-constexpr int BK = 32;    // K-step of the weight tile
+constexpr int KC = 256;   // K-chunk held in shared memory (row panel and weight tile)
 constexpr int NT = 128;   // threads per CTA
 constexpr int KPL = KC / 32;  // panel elements per lane
+constexpr int AS_LD = KC + 4;   // panel row stride (floats): bank offset 4 per row -> conflict-free float4 reads
+
+template <typename WT>
+struct WTile {
+  static constexpr int LD = KC + (sizeof(WT) == 2 ? 8 : 4);   // elements; row stride = 528 B (bf16) / 1040 B (f32)
+};
 
 // ---- row-wise prologue ------------------------------------------------------------------------
 __device__ __forceinline__ void ln_inplace(float (&v)[KPL], int K, int lane, const float *g, const float *b) {
@@ -57,21 +67,19 @@ __device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, 
     return;
   }
   if (s.pro == PRO_GATE) {
-    float t[KPL], acc[KPL];
+    float t[KPL], u[KPL], w[KPL];
     fetch_plain(s.a[0], s.lda[0], row, 0, klen, lane, v);       // update gate pre-activation
-    ln_inplace(v, klen, lane, s.ln_g[0], s.ln_b[0]);
     fetch_plain(s.a[1], s.lda[1], row, 0, klen, lane, t);       // param_out
+    fetch_plain(s.a[2], s.lda[2], row, 0, klen, lane, u);       // input gate pre-activation
+    fetch_plain(s.a[3], s.lda[3], row, 0, klen, lane, w);       // input_out
+    ln_inplace(v, klen, lane, s.ln_g[0], s.ln_b[0]);
     ln_inplace(t, klen, lane, s.ln_g[1], s.ln_b[1]);
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) acc[i] = sigmoidf_(v[i]) * t[i];
-    fetch_plain(s.a[2], s.lda[2], row, 0, klen, lane, v);       // input gate pre-activation
-    ln_inplace(v, klen, lane, s.ln_g[2], s.ln_b[2]);
-    fetch_plain(s.a[3], s.lda[3], row, 0, klen, lane, t);       // input_out
-    ln_inplace(t, klen, lane, s.ln_g[3], s.ln_b[3]);
+    ln_inplace(u, klen, lane, s.ln_g[2], s.ln_b[2]);
+    ln_inplace(w, klen, lane, s.ln_g[3], s.ln_b[3]);
 #pragma unroll
     for (int i = 0; i < KPL; ++i) {
       const int k = lane + 32 * i;
-      v[i] = (k < klen) ? acc[i] + sigmoidf_(v[i]) * t[i] : 0.f;
+      v[i] = (k < klen) ? sigmoidf_(v[i]) * t[i] + sigmoidf_(u[i]) * w[i] : 0.f;
     }
     return;
   }
@@ -112,6 +120,8 @@ __device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, 
 // ---- standalone row operator (materialises a prologue result) ----------------------------------
 __global__ void __launch_bounds__(NT) vkn_rowop_kernel(const __grid_constant__ RowSrc src, float *out, int ldo,
                                                        int M, int K) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (NT / 32) + warp;
   if (row >= M) return;
@@ -132,24 +142,37 @@ struct LinBatch {
   LinArgs p[2];
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <typename WT, int BM, int BN>
 __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
   constexpr int TM = BM / (NT / 16);
   constexpr int TN = BN / 16;
+  constexpr int WLD = WTile<WT>::LD;
+  constexpr int EPV = 16 / sizeof(WT);           // elements per 16-byte cp.async
   static_assert(TM >= 1 && TN >= 1, "tile too small");
-  __shared__ __align__(16) float As[BM][KC + 4];
-  __shared__ __align__(16) float Ws[BN][BK + 4];
+  extern __shared__ __align__(16) uint8_t lin_smem[];
+  float(*As)[AS_LD] = reinterpret_cast<float(*)[AS_LD]>(lin_smem);
+  WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + sizeof(float) * BM * AS_LD);
 
   const int ks_total = batch.p[0].ksplit;
   const LinArgs &A = batch.p[blockIdx.z / ks_total];
   const int ks = blockIdx.z % ks_total;
   const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
-  if (row0 >= A.M || col0 >= A.N) return;
+  if (row0 >= A.M || col0 >= A.N) {
+    pdl_trigger();
+    return;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tx = tid & 15, ty = tid >> 4;
 
   int kper = (A.K + ks_total - 1) / ks_total;
-  kper = (kper + BK - 1) / BK * BK;
+  kper = (kper + 31) / 32 * 32;
   const int kbeg = ks * kper, kend = min(A.K, kbeg + kper);
 
   float acc[TM][TN];
@@ -159,9 +182,26 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   const WT *Wp = reinterpret_cast<const WT *>(A.w);
+  const uint32_t ws0 = (uint32_t)__cvta_generic_to_shared(&Ws[0][0]);
 
   for (int kc0 = kbeg; kc0 < kend; kc0 += KC) {
     const int kclen = min(KC, kend - kc0);
+    const int kpad = (kclen + 7) & ~7;
+    // ---- weight tile: BN rows x kclen columns, all 16-byte pieces in flight at once (zero-filled
+    //      beyond N / K).  Weights are never written inside the chain -> safe before the PDL wait.
+    {
+      const int pieces_per_row = kpad / EPV;
+      const int total = BN * pieces_per_row;
+      for (int idx = tid; idx < total; idx += NT) {
+        const int n = idx / pieces_per_row, pc = idx - n * pieces_per_row;
+        const int gk = kc0 + pc * EPV;
+        const bool live = (col0 + n < A.N) && (gk < kend);
+        const int valid = live ? min(EPV, kend - gk) : 0;
+        const WT *src = live ? Wp + (size_t)(col0 + n) * A.ldw + gk : Wp;
+        cp_async16(ws0 + (uint32_t)(n * WLD + pc * EPV) * (uint32_t)sizeof(WT), src, (uint32_t)(valid * sizeof(WT)));
+      }
+    }
+    if (kc0 == kbeg) pdl_wait();     // everything below reads what the previous kernel produced
     // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded)
     for (int r = warp; r < BM; r += NT / 32) {
       const int row = row0 + r;
@@ -182,45 +222,24 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
         }
       }
     }
+    cp_async_wait_all();
     __syncthreads();
-    for (int k0 = 0; k0 < kclen; k0 += BK) {
-      // ---- weight tile: BN rows x BK columns, 8 consecutive k per thread (16-byte bf16 loads)
+    if (kc0 + KC >= kend) pdl_trigger();   // last chunk staged: let the next kernel start its prefetch
+#pragma unroll 2
+    for (int kk = 0; kk < kpad; kk += 8) {
+      float a[TM][8], b[TN][8];
 #pragma unroll
-      for (int pass = 0; pass < BN / (NT / 4); ++pass) {
-        const int n = pass * (NT / 4) + (tid >> 2);
-        const int kk = (tid & 3) * 8;
-        const int gk = kc0 + k0 + kk;
-        float w[8];
-        if (col0 + n < A.N && gk + 8 <= kend) {
-          load8(Wp + (size_t)(col0 + n) * A.ldw + gk, w);
-        } else {
+      for (int i = 0; i < TM; ++i) load8(&As[ty + (NT / 16) * i][kk], a[i]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            w[e] = (col0 + n < A.N && gk + e < kend) ? to_f32(Wp[(size_t)(col0 + n) * A.ldw + gk + e]) : 0.f;
-        }
-        *reinterpret_cast<float4 *>(&Ws[n][kk]) = make_float4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<float4 *>(&Ws[n][kk + 4]) = make_float4(w[4], w[5], w[6], w[7]);
-      }
-      __syncthreads();
+      for (int j = 0; j < TN; ++j) load8(&Ws[tx + 16 * j][kk], b[j]);
 #pragma unroll
-      for (int kk = 0; kk < BK; kk += 4) {
-        float4 a4[TM], b4[TN];
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int i = 0; i < TM; ++i) a4[i] = *reinterpret_cast<const float4 *>(&As[ty + (NT / 16) * i][k0 + kk]);
+        for (int j = 0; j < TN; ++j)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) b4[j] = *reinterpret_cast<const float4 *>(&Ws[tx + 16 * j][kk]);
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) {
-            acc[i][j] = fmaf(a4[i].x, b4[j].x, acc[i][j]);
-            acc[i][j] = fmaf(a4[i].y, b4[j].y, acc[i][j]);
-            acc[i][j] = fmaf(a4[i].z, b4[j].z, acc[i][j]);
-            acc[i][j] = fmaf(a4[i].w, b4[j].w, acc[i][j]);
-          }
-      }
-      __syncthreads();
+          for (int e = 0; e < 8; ++e) acc[i][j] = fmaf(a[i][e], b[j][e], acc[i][j]);
     }
+    if (kc0 + KC < kend) __syncthreads();
   }
 
   float *outp = A.out + (size_t)ks * A.out_split_stride;
@@ -238,6 +257,19 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
       if (A.epi & EPI_RES) v += __ldg(A.res + (size_t)row * A.ldres + col);
       if (A.epi & EPI_RELU) v = fmaxf(v, 0.f);
       outp[(size_t)row * A.ldo + col] = v;
+      if ((A.epi & EPI_SPLIT3) && col < A.split_C) {
+        // v == hi + mid + lo to 24 bits; every bf16 x bf16 product in the mask conv is then exact
+        const int b = row / A.split_N, n = row - b * A.split_N;
+        const size_t plane = (size_t)A.split_B * A.split_Npad * A.split_C;
+        const size_t o = ((size_t)b * A.split_Npad + n) * A.split_C + col;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        A.split_planes[o] = hi;
+        A.split_planes[plane + o] = mid;
+        A.split_planes[2 * plane + o] = lo;
+      }
     }
   }
 }
@@ -245,6 +277,18 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
 static int check_src(const RowSrc &s, int K) {
   if (s.pro != PRO_COPY && K > KC) VKN_FAIL(VKN_E_UNSUPPORTED, "row transform %d needs K <= %d (got %d)", s.pro, KC, K);
   if (s.nsum < 1) VKN_FAIL(VKN_E_INVALID, "RowSrc.nsum must be >= 1");
+  return VKN_OK;
+}
+
+template <typename WT, int BM, int BN>
+static int launch_linear_t(const LinBatch &b, dim3 grid, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * BM * AS_LD + sizeof(WT) * BN * WTile<WT>::LD;
+  static bool attr = false;
+  if (!attr) {
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  VKN_CUDA_OK(launch_chain(vkn_linear_kernel<WT, BM, BN>, grid, dim3(NT), smem, stream, b));
   return VKN_OK;
 }
 
@@ -266,26 +310,21 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
   const int ks = b.p[0].ksplit;
   // tile choice: wide outputs get the 32x64 tile, the C x C layers the 16x32 tile (more CTAs in flight)
   const bool big = maxN >= 1024;
-  dim3 grid, block(NT);
   VKN_LAUNCH_MARK(big ? "vkn_linear_kernel<32x64>" : "vkn_linear_kernel<16x32>", stream);
   if (big) {
-    grid = dim3(ceil_div(maxN, 64), ceil_div(maxM, 32), nprob * ks);
-    if (w_dtype == VKN_BF16) vkn_linear_kernel<__nv_bfloat16, 32, 64><<<grid, block, 0, stream>>>(b);
-    else vkn_linear_kernel<float, 32, 64><<<grid, block, 0, stream>>>(b);
-  } else {
-    grid = dim3(ceil_div(maxN, 32), ceil_div(maxM, 16), nprob * ks);
-    if (w_dtype == VKN_BF16) vkn_linear_kernel<__nv_bfloat16, 16, 32><<<grid, block, 0, stream>>>(b);
-    else vkn_linear_kernel<float, 16, 32><<<grid, block, 0, stream>>>(b);
+    dim3 grid(ceil_div(maxN, 64), ceil_div(maxM, 32), nprob * ks);
+    if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 32, 64>(b, grid, stream);
+    return launch_linear_t<float, 32, 64>(b, grid, stream);
   }
-  VKN_CUDA_OK(cudaGetLastError());
-  return VKN_OK;
+  dim3 grid(ceil_div(maxN, 32), ceil_div(maxM, 16), nprob * ks);
+  if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 16, 32>(b, grid, stream);
+  return launch_linear_t<float, 16, 32>(b, grid, stream);
 }
 
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream) {
   VKN_TRY(check_src(src, K));
   VKN_LAUNCH_MARK("vkn_rowop_kernel", stream);
-  vkn_rowop_kernel<<<ceil_div(M, NT / 32), NT, 0, stream>>>(src, out, ldo, M, K);
-  VKN_CUDA_OK(cudaGetLastError());
+  VKN_CUDA_OK(launch_chain(vkn_rowop_kernel, dim3(ceil_div(M, NT / 32)), dim3(NT), 0, stream, src, out, ldo, M, K));
   return VKN_OK;
 }
 
@@ -293,7 +332,7 @@ int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStrea
 // One CTA = (query block, head, frame).  K and V of the head sit in shared memory ([N][hd+1], bank
 // conflict free); one warp per query: lane-parallel scores, shuffle softmax, lane-per-channel PV.
 // torch semantics (F.multi_head_attention_forward): q scaled by 1/sqrt(hd) BEFORE q.k^T.
-constexpr int ATT_QB = 16;
+constexpr int ATT_QB = 8;
 
 __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restrict__ q, int ldq,
                                                            const float *__restrict__ k, int ldk,
@@ -309,12 +348,26 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_QB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t rowb = (size_t)b * N;
-  for (int idx = tid; idx < N * hd; idx += NT) {
-    const int j = idx / hd, d = idx - j * hd;
-    Ks[j * hs + d] = __ldg(k + (rowb + j) * ldk + h * hd + d);
-    Vs[j * hs + d] = __ldg(v + (rowb + j) * ldv + h * hd + d);
+  pdl_wait();
+  if ((hd & 3) == 0 && (ldk & 3) == 0 && (ldv & 3) == 0) {
+    const int hd4 = hd >> 2;
+    for (int idx = tid; idx < N * hd4; idx += NT) {
+      const int j = idx / hd4, d = (idx - j * hd4) * 4;
+      const float4 kk = __ldg(reinterpret_cast<const float4 *>(k + (rowb + j) * ldk + h * hd + d));
+      const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + (rowb + j) * ldv + h * hd + d));
+      float *kd = Ks + j * hs + d, *vd = Vs + j * hs + d;
+      kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+      vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+    }
+  } else {
+    for (int idx = tid; idx < N * hd; idx += NT) {
+      const int j = idx / hd, d = idx - j * hd;
+      Ks[j * hs + d] = __ldg(k + (rowb + j) * ldk + h * hd + d);
+      Vs[j * hs + d] = __ldg(v + (rowb + j) * ldv + h * hd + d);
+    }
   }
   __syncthreads();
+  pdl_trigger();
   float *ps = Ps + (size_t)warp * N;
   float *qs = Qs + warp * 32;
   for (int qi = q0 + warp; qi < min(N, q0 + ATT_QB); qi += NT / 32) {
@@ -322,8 +375,14 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
     __syncwarp();
     float mx = -INFINITY;
     for (int j = lane; j < N; j += 32) {
-      float s = 0.f;
-      for (int d = 0; d < hd; ++d) s = fmaf(qs[d], Ks[j * hs + d], s);
+      float s0 = 0.f, s1 = 0.f;
+      int d = 0;
+      for (; d + 2 <= hd; d += 2) {
+        s0 = fmaf(qs[d], Ks[j * hs + d], s0);
+        s1 = fmaf(qs[d + 1], Ks[j * hs + d + 1], s1);
+      }
+      if (d < hd) s0 = fmaf(qs[d], Ks[j * hs + d], s0);
+      const float s = s0 + s1;
       ps[j] = s;
       mx = fmaxf(mx, s);
     }
@@ -337,9 +396,16 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
     sum = warp_sum(sum);
     __syncwarp();
     if (lane < hd) {
-      float o = 0.f;
-      for (int j = 0; j < N; ++j) o = fmaf(ps[j], Vs[j * hs + lane], o);
-      out[(rowb + qi) * ldo + h * hd + lane] = o / sum;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      int j = 0;
+      for (; j + 4 <= N; j += 4) {
+        o0 = fmaf(ps[j], Vs[j * hs + lane], o0);
+        o1 = fmaf(ps[j + 1], Vs[(j + 1) * hs + lane], o1);
+        o2 = fmaf(ps[j + 2], Vs[(j + 2) * hs + lane], o2);
+        o3 = fmaf(ps[j + 3], Vs[(j + 3) * hs + lane], o3);
+      }
+      for (; j < N; ++j) o0 = fmaf(ps[j], Vs[j * hs + lane], o0);
+      out[(rowb + qi) * ldo + h * hd + lane] = ((o0 + o1) + (o2 + o3)) / sum;
     }
     __syncwarp();
   }
@@ -359,9 +425,8 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   if (smem > 160 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: N %d too large for shared memory", N);
   dim3 grid(ceil_div(N, ATT_QB), heads, B);
   VKN_LAUNCH_MARK("vkn_attention_kernel", stream);
-  vkn_attention_kernel<<<grid, NT, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, N, hd,
-                                                   1.0f / sqrtf((float)hd));
-  VKN_CUDA_OK(cudaGetLastError());
+  VKN_CUDA_OK(launch_chain(vkn_attention_kernel, grid, dim3(NT), smem, stream, q, ldq, k, ldk, v, ldv, out, ldo, N, hd,
+                           1.0f / sqrtf((float)hd)));
   return VKN_OK;
 }
 
