@@ -205,51 +205,95 @@ def run_ours(args):
         heads.append(h.to(dev).bfloat16().eval())
     loop = vknet.KernelIterLoop(heads)
 
-    # R rotating input sets; footprint of one set = x + mask_in + mask_out
+    # R rotating input sets; footprint of one set = x + mask_in + mask_out.  NS independent frames are in
+    # flight at once (one CUDA stream each, own workspace): the loop of ONE frame is a chain of small
+    # latency-bound kernels that fills a fraction of the 148 SMs, so frames of different streams overlap.
     set_bytes = (C * HW + 2 * N * HW) * 2
+    NS = max(1, int(os.environ.get('VKN_STREAMS', '4')))
     R = max(2, int(160e6 // set_bytes) + 1)
     quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: fewer captures, no CPU arm
     if quick:
         R = 2
+    R = (R + NS - 1) // NS * NS
     host_sets = [dummy_inputs(torch, seed=1 + rank * 1000 + r) for r in range(R)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+    main = torch.cuda.current_stream(dev)
     runners = []
     for r in range(R):
         x, pf, mask = host_sets[r]
         lp = vknet.KernelIterLoop(heads)
-        lp._ws = loop._ws                       # one shared workspace
-        before = _lib.launch_count()
+        if r >= NS:
+            lp._ws = runners[r % NS]._ws        # runners of one stream share that stream's workspace
         lp.capture(x.to(dev).bfloat16(), pf.to(dev), mask.to(dev).bfloat16())
         runners.append(lp)
-    launches_per_step = None
     before = _lib.launch_count()
     loop(host_sets[0][0].to(dev).bfloat16(), host_sets[0][1].to(dev), host_sets[0][2].to(dev).bfloat16())
     launches_per_step = _lib.launch_count() - before
 
     link_head = heads[-1] if world > 1 else None
+    FPR = NS                                    # frames per rank between two exchanges (a clip = world * FPR frames)
 
-    def exchange(obj_local):
-        """cfg3: all-gather of the last-stage kernels + the 'ffn' link block for this rank's frame."""
-        if world == 1:
-            return obj_local
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for st in streams:
+            st.wait_event(ev)
+
+    def join():
+        for st in streams:
+            main.wait_stream(st)
+
+    def exchange(objs):
+        """cfg3: all-gather of this rank's last-stage kernels [FPR,N,C] + the 'ffn' link block (B = FPR)."""
+        obj_local = torch.cat([o.reshape(1, N, C) for o in objs], dim=0)
         w, links, wd = link_head.packed_weights(dev)
-        shape = link_head._shape(1, N, H, W, _lib.VKN_BF16, wd)
+        nf = obj_local.shape[0]
+        shape = link_head._shape(nf, N, H, W, _lib.VKN_BF16, wd)
         ws, wsb = link_head._ws.get(shape, dev)
 
         def link_fn(cur, prev):
             return link_head._link(shape, links['track'], cur.contiguous(), prev.contiguous(), None, ws, wsb)
-        return vdist.link_sharded_clip(link_fn, obj_local.reshape(1, N, C), world, rank, world)
+        return vdist.link_sharded_clip(link_fn, obj_local, world * nf, rank, world)
 
-    def step(i):
-        cls, m, obj = runners[i % R].replay()
-        return exchange(obj)
+    def run_frames(i0, n, hostio=None):
+        """frames i0 .. i0+n-1 of this rank, round-robin over the streams (fork/join on the main stream)."""
+        fork()
+        objs = []
+        for i in range(i0, i0 + n):
+            r = i % R
+            with torch.cuda.stream(streams[r % NS]):
+                if hostio is None:
+                    cls, m, obj = runners[r].replay()
+                else:
+                    pin, out_host = hostio
+                    xh, pfh, mh = pin[r % NS]
+                    cls, m, obj = runners[r % NS].replay(xh, pfh, mh)      # H2D into the graph's static buffers
+                    oh = out_host[r % NS]
+                    oh[0].copy_(cls, non_blocking=True)
+                    oh[1].copy_(m, non_blocking=True)
+                    if world == 1:
+                        oh[2].copy_(obj.reshape(B, N, C), non_blocking=True)
+                objs.append(obj)
+        join()
+        if world > 1:
+            track = exchange(objs)
+            if hostio is not None:
+                hostio[1][0][2][: track.shape[0]].copy_(track.reshape(-1, N, C)[: hostio[1][0][2].shape[0]], non_blocking=True)
+        return objs
+
+    def run(steps, hostio=None):
+        if world == 1:
+            run_frames(0, steps, hostio)
+        else:
+            for i0 in range(0, steps, FPR):
+                run_frames(i0, min(FPR, steps - i0), hostio)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    run(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -257,8 +301,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        step(i)
+    run(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -268,27 +311,17 @@ def run_ours(args):
     ms = t.item()
 
     # ---- e2e: host buffers in, result tuple out, copies inside the timed region ---------------------
-    pin = [tuple(t_.pin_memory() for t_ in (hs[0].bfloat16(), hs[1], hs[2].bfloat16())) for hs in host_sets[:4]]
-    out_host = (torch.empty(B, N, CFG1['ncls']).pin_memory(), torch.empty(B, N, H, W, dtype=torch.bfloat16).pin_memory(),
-                torch.empty(B, N, C).pin_memory())
+    pin = [tuple(t_.pin_memory() for t_ in (hs[0].bfloat16(), hs[1], hs[2].bfloat16())) for hs in host_sets[:NS]]
+    out_host = [(torch.empty(B, N, CFG1['ncls']).pin_memory(),
+                 torch.empty(B, N, H, W, dtype=torch.bfloat16).pin_memory(),
+                 torch.empty(max(B, FPR), N, C).pin_memory()) for _ in range(NS)]
     h2d = sum(t_.numel() * t_.element_size() for t_ in pin[0])
-    d2h = sum(t_.numel() * t_.element_size() for t_ in out_host)
-
-    def e2e_step(i):
-        x, pf, mask = pin[i % len(pin)]
-        cls, m, obj = runners[0].replay(x, pf, mask)          # H2D into the graph's static buffers
-        obj = exchange(obj)
-        out_host[0].copy_(cls, non_blocking=True)
-        out_host[1].copy_(m, non_blocking=True)
-        out_host[2].copy_(obj.reshape(B, N, C), non_blocking=True)
-
-    for i in range(3):
-        e2e_step(i)
+    d2h = (B * N * CFG1['ncls'] + B * N * C) * 4 + B * N * HW * 2
+    run(3, (pin, out_host))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    run(args.steps, (pin, out_host))
     f1.record()
     barrier()
     sampler.stop()
@@ -297,6 +330,16 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item()
+
+    # ---- single-frame latency (one stream, no overlap): the number the per-kernel table explains --------
+    torch.cuda.synchronize()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for i in range(args.steps):
+        runners[i % R].replay()
+    l1.record()
+    torch.cuda.synchronize()
+    latency_ms = l0.elapsed_time(l1) / args.steps
 
     # ---- roofline of the dominant kernel: live per-kernel device times --------------------------------
     acc = {}
@@ -349,9 +392,10 @@ def run_ours(args):
                     data='synthetic',
                     config=dict(workload='cfg1 KITTI-STEP R-50 shape: 1 frame/GPU, N=100 kernels, C=256, 200x88, S=3, '
                                          'bf16 storage of x/masks/weights, fp32 arithmetic' +
-                                         ('; + cfg3 link: all-gather of kernels and previous_type=ffn link block'
-                                          if world > 1 else ''),
-                                mode='CUDA-graph replay of vkn_iter_forward (S stages)',
+                                         ('; + cfg3 link: every %d frames/rank one all-gather of kernels and the previous_type=ffn '
+                                          'link block' % FPR if world > 1 else ''),
+                                mode='CUDA-graph replay of vkn_iter_forward (S stages); %d frames in flight on %d streams' % (NS, NS),
+                                single_stream_ms_per_frame=latency_ms,
                                 l2='inputs rotate over %d sets (%.0f MB > 126 MB L2); weights stay hot' % (
                                     R, R * set_bytes / 1e6),
                                 engine='tcgen05+TMA' if _lib.lib() and heads[0].engine != _lib.ENGINE_SIMT else 'simt',

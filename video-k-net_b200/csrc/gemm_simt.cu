@@ -128,19 +128,24 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
   pdl_wait();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (idx < PC) {
-    float4 a0 = acc, a1 = acc;
+    // chunks warp, warp+8, warp+16, ...: four independent 16-byte loads in flight per thread
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     int ch = warp;
-    for (; ch + 8 < nchunks; ch += 16) {
-      const float4 u = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)ch * PC + idx));
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)(ch + 8) * PC + idx));
-      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
-      a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+    for (; ch + 24 < nchunks; ch += 32) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)(ch + 8 * u) * PC + idx));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u].x += t[u].x; a[u].y += t[u].y; a[u].z += t[u].z; a[u].w += t[u].w; }
     }
-    if (ch < nchunks) {
-      const float4 u = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)ch * PC + idx));
-      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+    for (int u = 0; ch < nchunks; ch += 8, ++u) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)ch * PC + idx));
+      a[u & 3].x += t.x; a[u & 3].y += t.y; a[u & 3].z += t.z; a[u & 3].w += t.w;
     }
-    acc = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    acc = make_float4((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
+                      (a[0].z + a[1].z) + (a[2].z + a[3].z), (a[0].w + a[1].w) + (a[2].w + a[3].w));
   }
   red[warp][lane] = acc;
   __syncthreads();

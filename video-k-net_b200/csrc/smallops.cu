@@ -15,7 +15,7 @@
 namespace vkn {
 
 constexpr int KC = 256;   // K-chunk held in shared memory (row panel and weight tile)
-constexpr int NT = 128;   // threads per CTA
+constexpr int NT = 256;   // threads per CTA (8 warps: two per scheduler, the kernels are latency-bound)
 constexpr int KPL = KC / 32;  // panel elements per lane
 constexpr int AS_LD = KC + 4;   // panel row stride (floats): bank offset 4 per row -> conflict-free float4 reads
 
@@ -54,40 +54,52 @@ __device__ __forceinline__ void fetch_plain(const float *a, int lda, int row, in
   }
 }
 
-// One warp produces the transformed values of one row for columns k0 .. k0+klen (klen <= KC).
+// Row transform in two steps so that the global loads of ALL rows a warp owns are in flight before the
+// first LayerNorm reduction starts (the kernels are latency-bound: one exposed L2 round trip per row
+// was ~half of their run time).
+//   row_load  : raw values of up to 4 sources -> registers (sum of slices + bias + residual folded in)
+//   row_finish: LN / ReLU / gate arithmetic (warp-shuffle reductions)
 // LN-type modes require k0 == 0 and klen == K (host-checked).
-__device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, int klen, int lane,
-                                              float (&v)[KPL]) {
+struct RowRaw {
+  float v[4][KPL];
+};
+
+__device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int klen, int lane, RowRaw &r) {
   if (s.pro == PRO_MUL) {
-    float b[KPL];
-    fetch_plain(s.a[0], s.lda[0], row, k0, klen, lane, v);
-    fetch_plain(s.a[1], s.lda[1], row, k0, klen, lane, b);
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) v[i] *= b[i];
+    fetch_plain(s.a[0], s.lda[0], row, k0, klen, lane, r.v[0]);
+    fetch_plain(s.a[1], s.lda[1], row, k0, klen, lane, r.v[1]);
     return;
   }
   if (s.pro == PRO_GATE) {
-    float t[KPL], u[KPL], w[KPL];
-    fetch_plain(s.a[0], s.lda[0], row, 0, klen, lane, v);       // update gate pre-activation
-    fetch_plain(s.a[1], s.lda[1], row, 0, klen, lane, t);       // param_out
-    fetch_plain(s.a[2], s.lda[2], row, 0, klen, lane, u);       // input gate pre-activation
-    fetch_plain(s.a[3], s.lda[3], row, 0, klen, lane, w);       // input_out
-    ln_inplace(v, klen, lane, s.ln_g[0], s.ln_b[0]);
-    ln_inplace(t, klen, lane, s.ln_g[1], s.ln_b[1]);
-    ln_inplace(u, klen, lane, s.ln_g[2], s.ln_b[2]);
-    ln_inplace(w, klen, lane, s.ln_g[3], s.ln_b[3]);
+    fetch_plain(s.a[0], s.lda[0], row, 0, klen, lane, r.v[0]);   // update gate pre-activation
+    fetch_plain(s.a[1], s.lda[1], row, 0, klen, lane, r.v[1]);   // param_out
+    fetch_plain(s.a[2], s.lda[2], row, 0, klen, lane, r.v[2]);   // input gate pre-activation
+    fetch_plain(s.a[3], s.lda[3], row, 0, klen, lane, r.v[3]);   // input_out
+    return;
+  }
+  // PRO_COPY / PRO_LN / PRO_LN_RELU: fixed-order sum of slices (+ bias + residual)
+  float(&v)[KPL] = r.v[0];
+  const float *a0 = s.a[0] + (size_t)row * s.lda[0] + k0;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int k = lane + 32 * i;
+    v[i] = (k < klen) ? __ldg(a0 + k) : 0.f;
+  }
+  int sl = 1;
+  for (; sl + 4 <= s.nsum; sl += 4) {      // four independent slice loads per element in flight
+    const float *a = a0 + (size_t)sl * s.sum_stride;
 #pragma unroll
     for (int i = 0; i < KPL; ++i) {
       const int k = lane + 32 * i;
-      v[i] = (k < klen) ? sigmoidf_(v[i]) * t[i] + sigmoidf_(u[i]) * w[i] : 0.f;
+      if (k < klen) {
+        const float t0 = __ldg(a + k), t1 = __ldg(a + s.sum_stride + k);
+        const float t2 = __ldg(a + 2 * s.sum_stride + k), t3 = __ldg(a + 3 * s.sum_stride + k);
+        v[i] += (t0 + t1) + (t2 + t3);
+      }
     }
-    return;
   }
-  // PRO_COPY / PRO_LN / PRO_LN_RELU: sum of slices (+ bias + residual) first
-#pragma unroll
-  for (int i = 0; i < KPL; ++i) v[i] = 0.f;
-  for (int sl = 0; sl < s.nsum; ++sl) {
-    const float *a = s.a[0] + (size_t)sl * s.sum_stride + (size_t)row * s.lda[0] + k0;
+  for (; sl < s.nsum; ++sl) {
+    const float *a = a0 + (size_t)sl * s.sum_stride;
 #pragma unroll
     for (int i = 0; i < KPL; ++i) {
       const int k = lane + 32 * i;
@@ -108,6 +120,28 @@ __device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, 
       if (k < klen) v[i] += __ldg(s.pres + (size_t)row * s.ldpres + k0 + k);
     }
   }
+}
+
+__device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, RowRaw &r, float (&v)[KPL]) {
+  if (s.pro == PRO_MUL) {
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) v[i] = r.v[0][i] * r.v[1][i];
+    return;
+  }
+  if (s.pro == PRO_GATE) {
+    ln_inplace(r.v[0], klen, lane, s.ln_g[0], s.ln_b[0]);
+    ln_inplace(r.v[1], klen, lane, s.ln_g[1], s.ln_b[1]);
+    ln_inplace(r.v[2], klen, lane, s.ln_g[2], s.ln_b[2]);
+    ln_inplace(r.v[3], klen, lane, s.ln_g[3], s.ln_b[3]);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      v[i] = (k < klen) ? sigmoidf_(r.v[0][i]) * r.v[1][i] + sigmoidf_(r.v[2][i]) * r.v[3][i] : 0.f;
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) v[i] = r.v[0][i];
   if (s.pro == PRO_LN || s.pro == PRO_LN_RELU) {
     ln_inplace(v, klen, lane, s.ln_g[0], s.ln_b[0]);
     if (s.pro == PRO_LN_RELU) {
@@ -115,6 +149,13 @@ __device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, 
       for (int i = 0; i < KPL; ++i) v[i] = fmaxf(v[i], 0.f);
     }
   }
+}
+
+__device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, int klen, int lane,
+                                              float (&v)[KPL]) {
+  RowRaw r;
+  row_load(s, row, k0, klen, lane, r);
+  row_finish(s, klen, lane, r, v);
 }
 
 // ---- standalone row operator (materialises a prologue result) ----------------------------------
@@ -189,7 +230,18 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
     const int kpad = (kclen + 7) & ~7;
     // ---- weight tile: BN rows x kclen columns, all 16-byte pieces in flight at once (zero-filled
     //      beyond N / K).  Weights are never written inside the chain -> safe before the PDL wait.
-    {
+    if (kpad == KC) {                  // common case: constant trip counts, no integer division
+      constexpr int PPR = KC / EPV;    // pieces per row: 32 (bf16) / 64 (f32)
+      constexpr int RPP = NT / PPR;    // rows per pass
+      const int pc = tid % PPR, nb = tid / PPR;
+#pragma unroll
+      for (int n0 = 0; n0 < BN; n0 += RPP) {
+        const int n = n0 + nb;
+        const bool live = col0 + n < A.N;
+        const WT *src = live ? Wp + (size_t)(col0 + n) * A.ldw + kc0 + pc * EPV : Wp;
+        cp_async16(ws0 + (uint32_t)(n * WLD + pc * EPV) * (uint32_t)sizeof(WT), src, live ? 16u : 0u);
+      }
+    } else {
       const int pieces_per_row = kpad / EPV;
       const int total = BN * pieces_per_row;
       for (int idx = tid; idx < total; idx += NT) {
@@ -202,23 +254,38 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
       }
     }
     if (kc0 == kbeg) pdl_wait();     // everything below reads what the previous kernel produced
-    // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded)
-    for (int r = warp; r < BM; r += NT / 32) {
-      const int row = row0 + r;
-      float v[KPL];
-      if (row < A.M) {
-        row_transform(A.src, row, kc0, kclen, lane, v);
-      } else {
+    // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded).
+    //      Each warp owns RPW rows; the raw loads of all of them are issued before any reduction.
+    {
+      constexpr int NW = NT / 32, RPW = BM / NW, GRP = 2;     // two rows' loads in flight per warp
+      static_assert(BM % NW == 0 && RPW % GRP == 0, "rows per warp must be a multiple of the load group");
+#pragma unroll 1
+      for (int q0 = 0; q0 < RPW; q0 += GRP) {
+        RowRaw raw[GRP];
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) v[i] = 0.f;
-      }
+        for (int q = 0; q < GRP; ++q) {
+          const int row = row0 + warp + NW * (q0 + q);
+          if (row < A.M) row_load(A.src, row, kc0, kclen, lane, raw[q]);
+        }
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) As[r][lane + 32 * i] = v[i];
-      if (A.side != nullptr && blockIdx.x == 0 && row < A.M) {
+        for (int q = 0; q < GRP; ++q) {
+          const int r = warp + NW * (q0 + q), row = row0 + r;
+          float v[KPL];
+          if (row < A.M) {
+            row_finish(A.src, kclen, lane, raw[q], v);
+          } else {
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) {
-          const int k = lane + 32 * i;
-          if (k < kclen) A.side[(size_t)row * A.ldside + kc0 + k] = v[i];
+            for (int i = 0; i < KPL; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < KPL; ++i) As[r][lane + 32 * i] = v[i];
+          if (A.side != nullptr && blockIdx.x == 0 && row < A.M) {
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+              const int k = lane + 32 * i;
+              if (k < kclen) A.side[(size_t)row * A.ldside + kc0 + k] = v[i];
+            }
+          }
         }
       }
     }
@@ -343,8 +410,8 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
   const int hs = hd + 1;
   float *Ks = smem;                    // [N][hs]
   float *Vs = Ks + (size_t)N * hs;     // [N][hs]
-  float *Ps = Vs + (size_t)N * hs;     // [4 warps][N]
-  float *Qs = Ps + 4 * (size_t)N;      // [4 warps][32]
+  float *Ps = Vs + (size_t)N * hs;             // [NT/32 warps][N]
+  float *Qs = Ps + (NT / 32) * (size_t)N;      // [NT/32 warps][32]
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_QB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t rowb = (size_t)b * N;
@@ -416,7 +483,7 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   if (heads < 1 || C % heads != 0) VKN_FAIL(VKN_E_INVALID, "attention: C %d not divisible by heads %d", C, heads);
   const int hd = C / heads;
   if (hd > 32) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: head_dim %d > 32", hd);
-  const size_t smem = ((size_t)2 * N * (hd + 1) + 4 * (size_t)N + 4 * 32) * sizeof(float);
+  const size_t smem = ((size_t)2 * N * (hd + 1) + (NT / 32) * (size_t)N + (NT / 32) * 32) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
