@@ -205,47 +205,46 @@ def run_ours(args):
         heads.append(h.to(dev).bfloat16().eval())
     loop = vknet.KernelIterLoop(heads)
 
-    # R rotating input sets; footprint of one set = x + mask_in + mask_out.  NS independent frames are in
-    # flight at once (one CUDA stream each, own workspace): the loop of ONE frame is a chain of small
-    # latency-bound kernels that fills a fraction of the 148 SMs, so frames of different streams overlap.
-    set_bytes = (C * HW + 2 * N * HW) * 2
+    # Frames in flight: one CUDA graph = NS concurrent branches x BF frames each (vknet.FramesInFlight).
+    # The loop of ONE frame is a chain of small latency-bound kernels that fills a fraction of the 148
+    # SMs, so independent frames overlap.  Two such groups alternate; one group's inputs + outputs
+    # (NS*BF frames x 16.2 MB) exceed L2 (126 MB) for the default 4 x 4, so x and the masks stream from HBM.
     NS = max(1, int(os.environ.get('VKN_STREAMS', '4')))
-    R = max(2, int(160e6 // set_bytes) + 1)
-    quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: fewer captures, no CPU arm
+    BF = max(1, int(os.environ.get('VKN_BATCH', '4')))
+    quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: small group, no CPU arm
     if quick:
-        R = 2
-    R = (R + NS - 1) // NS * NS
-    host_sets = [dummy_inputs(torch, seed=1 + rank * 1000 + r) for r in range(R)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
-    main = torch.cuda.current_stream(dev)
-    runners = []
-    for r in range(R):
-        x, pf, mask = host_sets[r]
-        lp = vknet.KernelIterLoop(heads)
-        if r >= NS:
-            lp._ws = runners[r % NS]._ws        # runners of one stream share that stream's workspace
-        lp.capture(x.to(dev).bfloat16(), pf.to(dev), mask.to(dev).bfloat16())
-        runners.append(lp)
+        NS, BF = 1, 1
+    FPG = NS * BF                                           # frames per graph launch (per rank)
+    set_bytes = (C * HW + 2 * N * HW) * 2
+    G = max(2, int(160e6 // (set_bytes * FPG)) + 1)
+    seeds = iter(range(1 + rank * 100000, 10 ** 9))
+
+    def frame_batch():
+        xs, pfs, ms_ = zip(*[dummy_inputs(torch, next(seeds)) for _ in range(BF)])
+        return torch.cat(xs).bfloat16(), torch.cat(pfs), torch.cat(ms_).bfloat16()
+
+    groups, host_groups = [], []
+    for g_ in range(G):
+        batches = [frame_batch() for _ in range(NS)]
+        fif = vknet.FramesInFlight(heads, branches=NS, batch=BF)
+        fif.capture([tuple(t_.to(dev) for t_ in bt) for bt in batches])
+        groups.append(fif)
+        if g_ < 2:                                          # e2e groups: same frames, pinned host buffers in/out
+            pinned = [tuple(t_.pin_memory() for t_ in bt) for bt in batches]
+            hf = vknet.FramesInFlight(heads, branches=NS, batch=BF)
+            hf.loops = fif.loops                            # share workspaces
+            hf.capture(pinned, host_io=True)
+            host_groups.append(hf)
     before = _lib.launch_count()
-    loop(host_sets[0][0].to(dev).bfloat16(), host_sets[0][1].to(dev), host_sets[0][2].to(dev).bfloat16())
-    launches_per_step = _lib.launch_count() - before
+    x1, pf1, m1 = dummy_inputs(torch, 7)
+    loop(x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16())
+    launches_per_frame_call = _lib.launch_count() - before      # one vkn_iter_forward (any batch size)
 
     link_head = heads[-1] if world > 1 else None
-    FPR = NS                                    # frames per rank between two exchanges (a clip = world * FPR frames)
 
-    def fork():
-        ev = torch.cuda.Event()
-        ev.record(main)
-        for st in streams:
-            st.wait_event(ev)
-
-    def join():
-        for st in streams:
-            main.wait_stream(st)
-
-    def exchange(objs):
-        """cfg3: all-gather of this rank's last-stage kernels [FPR,N,C] + the 'ffn' link block (B = FPR)."""
-        obj_local = torch.cat([o.reshape(1, N, C) for o in objs], dim=0)
+    def exchange(outs):
+        """cfg3: all-gather of this rank's last-stage kernels [FPG,N,C] + the 'ffn' link block (B = FPG)."""
+        obj_local = torch.cat([o[2].reshape(-1, N, C) for o in outs], dim=0)
         w, links, wd = link_head.packed_weights(dev)
         nf = obj_local.shape[0]
         shape = link_head._shape(nf, N, H, W, _lib.VKN_BF16, wd)
@@ -255,45 +254,27 @@ def run_ours(args):
             return link_head._link(shape, links['track'], cur.contiguous(), prev.contiguous(), None, ws, wsb)
         return vdist.link_sharded_clip(link_fn, obj_local, world * nf, rank, world)
 
-    def run_frames(i0, n, hostio=None):
-        """frames i0 .. i0+n-1 of this rank, round-robin over the streams (fork/join on the main stream)."""
-        fork()
-        objs = []
-        for i in range(i0, i0 + n):
-            r = i % R
-            with torch.cuda.stream(streams[r % NS]):
-                if hostio is None:
-                    cls, m, obj = runners[r].replay()
-                else:
-                    pin, out_host = hostio
-                    xh, pfh, mh = pin[r % NS]
-                    cls, m, obj = runners[r % NS].replay(xh, pfh, mh)      # H2D into the graph's static buffers
-                    oh = out_host[r % NS]
-                    oh[0].copy_(cls, non_blocking=True)
-                    oh[1].copy_(m, non_blocking=True)
-                    if world == 1:
-                        oh[2].copy_(obj.reshape(B, N, C), non_blocking=True)
-                objs.append(obj)
-        join()
-        if world > 1:
-            track = exchange(objs)
-            if hostio is not None:
-                hostio[1][0][2][: track.shape[0]].copy_(track.reshape(-1, N, C)[: hostio[1][0][2].shape[0]], non_blocking=True)
-        return objs
+    track_host = torch.empty(FPG, N, C).pin_memory()
 
-    def run(steps, hostio=None):
-        if world == 1:
-            run_frames(0, steps, hostio)
-        else:
-            for i0 in range(0, steps, FPR):
-                run_frames(i0, min(FPR, steps - i0), hostio)
+    def run(frames, grp, host=False):
+        """process `frames` frames per rank (rounded up to whole graph launches); returns frames done."""
+        done, i = 0, 0
+        while done < frames:
+            outs = grp[i % len(grp)].replay()
+            if world > 1:
+                track = exchange(outs)
+                if host:
+                    track_host.copy_(track, non_blocking=True)
+            done += FPG
+            i += 1
+        return done
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    run(max(args.warmup, 3))
+    run(max(args.warmup, 3), groups)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -301,27 +282,23 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    run(args.steps)
+    frames_done = run(args.steps, groups)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+    ms = t.item() * args.steps / frames_done                # time of exactly `steps` frames per rank
 
     # ---- e2e: host buffers in, result tuple out, copies inside the timed region ---------------------
-    pin = [tuple(t_.pin_memory() for t_ in (hs[0].bfloat16(), hs[1], hs[2].bfloat16())) for hs in host_sets[:NS]]
-    out_host = [(torch.empty(B, N, CFG1['ncls']).pin_memory(),
-                 torch.empty(B, N, H, W, dtype=torch.bfloat16).pin_memory(),
-                 torch.empty(max(B, FPR), N, C).pin_memory()) for _ in range(NS)]
-    h2d = sum(t_.numel() * t_.element_size() for t_ in pin[0])
-    d2h = (B * N * CFG1['ncls'] + B * N * C) * 4 + B * N * HW * 2
-    run(3, (pin, out_host))
+    h2d = (C * HW + N * HW) * 2 + N * C * 4
+    d2h = (N * CFG1['ncls'] + N * C) * 4 + N * HW * 2
+    run(3, host_groups, host=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    run(args.steps, (pin, out_host))
+    frames_e2e = run(args.steps, host_groups, host=True)
     f1.record()
     barrier()
     sampler.stop()
@@ -329,22 +306,27 @@ def run_ours(args):
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = t.item()
+    e2e_ms = t.item() * args.steps / frames_e2e
 
-    # ---- single-frame latency (one stream, no overlap): the number the per-kernel table explains --------
+    # ---- single-frame latency (one stream, one frame per graph, no overlap) ----------------------------
+    single = vknet.KernelIterLoop(heads)
+    single.capture(x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16())
+    for _ in range(5):
+        single.replay()
     torch.cuda.synchronize()
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0.record()
-    for i in range(args.steps):
-        runners[i % R].replay()
+    for i in range(50):
+        single.replay()
     l1.record()
     torch.cuda.synchronize()
-    latency_ms = l0.elapsed_time(l1) / args.steps
+    latency_ms = l0.elapsed_time(l1) / 50
+    launches_per_step = launches_per_frame_call / BF
 
     # ---- roofline of the dominant kernel: live per-kernel device times --------------------------------
     acc = {}
     reps = 20
-    xs, pfs, ms_ = (host_sets[0][0].to(dev).bfloat16(), host_sets[0][1].to(dev), host_sets[0][2].to(dev).bfloat16())
+    xs, pfs, ms_ = x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16()
     for _ in range(3):
         loop(xs, pfs, ms_)
     torch.cuda.synchronize()
@@ -393,16 +375,17 @@ def run_ours(args):
                     config=dict(workload='cfg1 KITTI-STEP R-50 shape: 1 frame/GPU, N=100 kernels, C=256, 200x88, S=3, '
                                          'bf16 storage of x/masks/weights, fp32 arithmetic' +
                                          ('; + cfg3 link: every %d frames/rank one all-gather of kernels and the previous_type=ffn '
-                                          'link block' % FPR if world > 1 else ''),
-                                mode='CUDA-graph replay of vkn_iter_forward (S stages); %d frames in flight on %d streams' % (NS, NS),
+                                          'link block' % FPG if world > 1 else ''),
+                                mode='CUDA-graph replay of vkn_iter_forward (S stages); %d frames per graph launch = %d concurrent '
+                                     'branches x batch %d' % (FPG, NS, BF),
                                 single_stream_ms_per_frame=latency_ms,
-                                l2='inputs rotate over %d sets (%.0f MB > 126 MB L2); weights stay hot' % (
-                                    R, R * set_bytes / 1e6),
+                                l2='inputs rotate over %d groups of %d frames (%.0f MB > 126 MB L2); weights stay hot' % (
+                                    G, FPG, G * FPG * set_bytes / 1e6),
                                 engine='tcgen05+TMA' if _lib.lib() and heads[0].engine != _lib.ENGINE_SIMT else 'simt',
                                 parallelism='frame-shard x%d' % world),
                     e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
-                    gpu_launches=int(launches_per_step * args.steps),
+                    gpu_launches=int(round(launches_per_step * args.steps)),
                     clocks=sampler.summary(), roofline=roof, cpu_baseline=cb,
                     kernels=per_kernel)
         print(json.dumps(line))

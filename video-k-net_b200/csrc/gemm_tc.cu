@@ -194,12 +194,12 @@ static PoolPlan pool_plan(const VknShape &s) {
 }
 int pool_tc_chunks(const VknShape &s) { return tc_supported(s) ? pool_plan(s).nchunks : 0; }
 
-constexpr int POOL_STAGES = 4;
+constexpr int POOL_STAGES_MAX = 4;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16 *__restrict__ mask,
                    float *__restrict__ partials, float *__restrict__ cnt_partials, int B, int N, int C, int HW,
-                   int nblocks, int bpc, float thr, uint32_t idesc) {
+                   int nblocks, int bpc, float thr, uint32_t idesc, int POOL_STAGES) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t x_bytes = (uint32_t)C * 128u;          // C rows x 64 px x 2 B
@@ -314,17 +314,28 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
     tc_fence_after();
     pdl_trigger();
     const int q = warp & 3;                                // TMEM lane quarter this warp may read
-    const int n = mtile * 128 + q * 32 + lane;
-    float *po = partials + (((size_t)chunk * B + b) * N + n) * C;
+    // accumulator rows are TMEM lanes: thread = kernel row.  Staged through shared memory (the pipeline
+    // buffers are free once tmem_full fired) so that global stores are full 128-byte lines.
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)q * 32 * 36;      // [32 rows][36] per warp
+    const int nbase = mtile * 128 + q * 32;
     for (int c0 = 0; c0 < C; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (n < N) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<float4 *>(po + c0 + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
-                                                                 __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4 *>(stg + lane * 36 + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                                       __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), seg = lane & 7;
+        const int n = nbase + row;
+        if (n < N) {
+          const float4 v = *reinterpret_cast<const float4 *>(stg + row * 36 + seg * 4);
+          *reinterpret_cast<float4 *>(partials + (((size_t)chunk * B + b) * N + n) * C + c0 + seg * 4) = v;
+        }
       }
+      __syncwarp();
     }
     // pixel counts: the 8 chunk-threads of a row are adjacent lanes
 #pragma unroll
@@ -355,7 +366,11 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)s.B};
   const uint32_t box[3] = {(uint32_t)PX_BLK, (uint32_t)s.C, 1u};
   VKN_TRY(make_tmap_bf16(&tmap, x, 3, dims, box));
-  const size_t smem = (size_t)POOL_STAGES * ((size_t)s.C * 128 + 128 * 128) + 1024 + 256;
+  // pipeline depth = blocks per CTA (<= 4): a CTA that reduces 2 pixel blocks needs 2 stages, and the smaller
+  // footprint lets CTAs of other streams' kernels co-reside on the SM
+  const int pool_stages = p.bpc < POOL_STAGES_MAX ? p.bpc : POOL_STAGES_MAX;
+  size_t smem = (size_t)pool_stages * ((size_t)s.C * 128 + 128 * 128) + 1024 + 256;
+  if (smem < 4 * 32 * 36 * 4 + 2048) smem = 4 * 32 * 36 * 4 + 2048;      // epilogue staging
   static bool attr = false;
   if (!attr) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -365,7 +380,7 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   VKN_LAUNCH_MARK("vkn_pool_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_pool_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmap, (const __nv_bfloat16 *)mask,
                            partials, cnt_partials, s.B, s.N, s.C, HW, p.nblocks, p.bpc, s.mask_thr_logit,
-                           make_idesc_bf16(128, s.C, 0, 0)));
+                           make_idesc_bf16(128, s.C, 0, 0), pool_stages));
   return VKN_OK;
 }
 
@@ -408,7 +423,7 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     tmem_alloc(smem_u32(tmem_slot), ncols);
   }
   pdl_wait();     // a_ext / the planes come from the previous kernel
-  for (int n = threadIdx.x; n < Npad; n += TC_THREADS)
+  for (int n = threadIdx.x; n < ((Npad + 31) & ~31); n += TC_THREADS)
     bias_s[n] = (n < N) ? a_ext[((size_t)b * N + n) * lda + C] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -460,18 +475,28 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     tc_fence_after();
     pdl_trigger();
     const int q = warp & 3;
-    const int p = p0 + q * 32 + lane;
-    __nv_bfloat16 *ob = out + (size_t)b * N * HW + p;
+    // TMEM lane = pixel, column = kernel.  Each 32x32 chunk is transposed through shared memory (free
+    // after tmem_full) so that a lane stores 8 consecutive pixels of one kernel row: 16-byte stores.
+    __nv_bfloat16 *stg = reinterpret_cast<__nv_bfloat16 *>(smem) + (size_t)q * 32 * 40;   // [32 kernels][40] per warp
+    const int pw = p0 + q * 32;                               // first pixel of this warp
+    __nv_bfloat16 *ob = out + (size_t)b * N * HW;
     for (int n0 = 0; n0 < Npad; n0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, r);
-      if (p < HW) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int n = n0 + e;
-          if (n < N) ob[(size_t)n * HW] = __float2bfloat16_rn(__uint_as_float(r[e]) + bias_s[n]);
+      for (int e = 0; e < 32; ++e)
+        stg[e * 40 + lane] = __float2bfloat16_rn(__uint_as_float(r[e]) + bias_s[n0 + e]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int nl = it * 8 + (lane >> 2), seg = lane & 3;
+        const int n = n0 + nl, p = pw + seg * 8;
+        if (n < N && p < HW) {                                  // HW % 8 == 0: an 8-pixel segment never straddles the end
+          const uint4 v = *reinterpret_cast<const uint4 *>(stg + nl * 40 + seg * 8);
+          *reinterpret_cast<uint4 *>(ob + (size_t)n * HW + p) = v;
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -501,10 +526,10 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   }
   const size_t stage_bytes = (size_t)CH_BLK * MASK_TILE_P * 2 + (size_t)3 * Npad * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > 2) stages = 2;      // 2 stages hide the TMA latency of the 4-chunk K loop; smaller footprint -> co-residency
   if (stages > s.C / CH_BLK) stages = s.C / CH_BLK;
   if (stages < 1) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: N %d too large for shared memory", s.N);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 1) * 8 + 16 + (size_t)Npad * 4 + 64;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 1) * 8 + 16 + (size_t)(Npad + 32) * 4 + 64;
   static bool attr = false;
   if (!attr) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

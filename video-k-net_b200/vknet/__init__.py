@@ -11,7 +11,7 @@ from .registry import HEADS, TRANSFORMER_LAYER, build_head, build_transformer_la
 from .kernel_updator import KernelUpdator
 from .kernel_update_head import KernelUpdateHead
 from .video_kernel_update_head import VideoKernelUpdateHead
-from .iter_loop import KernelIterLoop
+from .iter_loop import FramesInFlight, KernelIterLoop
 
-__all__ = ['KernelUpdator', 'KernelUpdateHead', 'VideoKernelUpdateHead', 'KernelIterLoop', 'HEADS',
+__all__ = ['KernelUpdator', 'KernelUpdateHead', 'VideoKernelUpdateHead', 'KernelIterLoop', 'FramesInFlight', 'HEADS',
            'TRANSFORMER_LAYER', 'build_head', 'build_transformer_layer', 'VknError', 'kernel_names', '_lib']

@@ -89,3 +89,86 @@ class KernelIterLoop:
         self._graph.replay()
         B, N, Cc = st['obj'].shape
         return st['cls'], st['out_mask'], st['obj'].reshape(B, N, Cc, 1, 1)
+
+
+class FramesInFlight:
+    """Throughput form of the loop: ONE CUDA graph that runs `branches` independent frame batches
+    concurrently (fork/join inside the capture), each on its own stream with its own workspace.
+
+    The loop of one frame is a chain of small latency-bound kernels that occupies a fraction of the
+    148 SMs; frames are independent, so several are kept in flight.  With `host_io=True`
+    the graph also contains the host<->device copies: pinned host inputs -> static device buffers before
+    the loop and the result tuple -> pinned host buffers after it (one launch = the whole e2e step).
+    """
+
+    def __init__(self, heads, branches=4, batch=1):
+        self.heads = list(heads)
+        self.branches = branches
+        self.batch = batch
+        self.loops = [KernelIterLoop(self.heads) for _ in range(branches)]
+        self.static = []
+        self.host_in = []
+        self.host_out = []
+        self.graph = None
+
+    @torch.no_grad()
+    def capture(self, inputs, host_io=False):
+        """inputs: list (len == branches) of (x [b,C,H,W], proposal_feat [b,N,C], mask_preds [b,N,H,W])
+        device tensors (host_io=False) or pinned host tensors (host_io=True)."""
+        assert len(inputs) == self.branches
+        h0 = self.heads[0]
+        dev = next(h0.parameters()).device
+        streams = [torch.cuda.Stream(device=dev) for _ in range(self.branches)]
+        for (x, pf, mask), lp in zip(inputs, self.loops):
+            xd, pfd, md = x.to(dev, non_blocking=False), pf.to(dev), mask.to(dev)
+            xd, pfd, md, B, N, H, W, _ = h0._prepare(xd, pfd, md)
+            st = dict(x=xd.clone(), pf=pfd.clone(), mask=md.clone(),
+                      cls=torch.empty(B, N, h0.fc_cls.out_features, dtype=torch.float32, device=dev),
+                      out_mask=torch.empty(B, N, H, W, dtype=xd.dtype, device=dev),
+                      obj=torch.empty(B, N, h0.in_channels, dtype=torch.float32, device=dev))
+            self.static.append(st)
+            if host_io:
+                self.host_in.append((x, pf.reshape(st['pf'].shape), mask))
+                self.host_out.append(tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                                           for t in (st['cls'], st['out_mask'], st['obj'])))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up outside capture
+            for st, lp in zip(self.static, self.loops):
+                lp.forward(st['x'], st['pf'], st['mask'], out=(st['cls'], st['out_mask'], st['obj']))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            joins = []
+            for i, (st, lp, s) in enumerate(zip(self.static, self.loops, streams)):
+                s.wait_event(fork)
+                with torch.cuda.stream(s):
+                    if host_io:
+                        hx, hpf, hm = self.host_in[i]
+                        st['x'].copy_(hx, non_blocking=True)
+                        st['pf'].copy_(hpf, non_blocking=True)
+                        st['mask'].copy_(hm, non_blocking=True)
+                    lp.forward(st['x'], st['pf'], st['mask'], out=(st['cls'], st['out_mask'], st['obj']))
+                    if host_io:
+                        for dst, src in zip(self.host_out[i], (st['cls'], st['out_mask'], st['obj'])):
+                            dst.copy_(src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                    joins.append(ev)
+            for ev in joins:
+                cur.wait_event(ev)
+        self.graph = g
+        self._streams = streams
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        return [(st['cls'], st['out_mask'], st['obj']) for st in self.static]
+
+    @property
+    def frames_per_replay(self):
+        return self.branches * self.batch
