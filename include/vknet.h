@@ -55,7 +55,7 @@ enum {
 };
 
 typedef struct VknShape {
-  int32_t B;            /* frames in this call */
+  int32_t B;            /* kernel sets in this call (= frames unless frames_per_set > 1) */
   int32_t N;            /* kernels (proposals) per frame: 100 / 117 / 166 in the shipped configs */
   int32_t C;            /* channels (in_channels == feat_channels == out_channels); multiple of 64, <= 256 */
   int32_t H, W;         /* feature-map size; HW arbitrary */
@@ -66,6 +66,10 @@ typedef struct VknShape {
   int32_t w_dtype;      /* VKN_F32 | VKN_BF16: storage of weight matrices */
   int32_t with_ffn;     /* KernelUpdateHead(with_ffn=...) */
   int32_t engine;       /* VKN_ENGINE_* */
+  int32_t frames_per_set; /* F (0 or 1 = one frame per kernel set).  F > 1 is the clip head
+                           * KernelUpdateHeadVideo (knet_vis/tracker/kernel_update_head.py:209-374, gathered
+                           * mode): x / mask tensors hold B*F frames, ONE kernel set per clip pools the MEAN
+                           * over its F frames (:245-246) and convolves all of them (:329-339). */
   float mask_thr_logit; /* logit(hard_mask_thr): sigmoid(m) > thr  <=>  m > mask_thr_logit (0 for thr=0.5) */
 } VknShape;
 
@@ -109,7 +113,7 @@ typedef struct VknHeadW {
   VknFfnW ffn;             /* ffn.*, ffn_norm.* (ignored when with_ffn == 0) */
   int32_t num_cls_fcs, num_mask_fcs;
   const void *cls_fc_w[VKN_MAX_FCS];  const float *cls_ln_g[VKN_MAX_FCS], *cls_ln_b[VKN_MAX_FCS];
-  const void *fc_cls_w;  const float *fc_cls_b;     /* [num_classes,C] */
+  const void *fc_cls_w;  const float *fc_cls_b;     /* [num_classes,C]; NULL = head built with with_cls=False */
   const void *mask_fc_w[VKN_MAX_FCS]; const float *mask_ln_g[VKN_MAX_FCS], *mask_ln_b[VKN_MAX_FCS];
   const void *fc_mask_w; const float *fc_mask_b;    /* [C,C] */
 } VknHeadW;

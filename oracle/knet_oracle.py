@@ -245,6 +245,48 @@ def video_kernel_update_head_forward(sd, cfg, x, proposal_feat, mask_preds, prev
 
 
 # ----------------------------------------------------------------------------------------
+# KernelUpdateHeadVideo.forward  (knet_vis/tracker/kernel_update_head.py:209-374), query_merge_method='mean'
+# ----------------------------------------------------------------------------------------
+def kernel_update_head_video_forward(sd, cfg, x, proposal_feat, mask_preds):
+    """x [B,F,C,H,W], mask_preds [B,F,N,H,W].  proposal_feat 5-D [B,N,C,1,1] -> gathered mode
+    (with_cls=True): (cls [B,N,ncls], masks [B,F,N,H,W], obj [B,N,C,1,1]); 6-D [B,F,N,C,1,1] -> per-frame
+    mode (with_cls=False): (None, masks, obj [B,F,N,C,1,1])."""
+    B, Fr, C, H, W = x.shape
+    gathered = proposal_feat.dim() != 6                                            # :217-225
+    N = proposal_feat.shape[1] if gathered else proposal_feat.shape[2]
+    xt = _feat_transform(sd, x.reshape(B * Fr, C, H, W)).reshape(B, Fr, C, H, W)   # :227-228
+    m = hard_mask(mask_preds, cfg.get('hard_mask_thr', 0.5)).to(xt.dtype)          # :238-240
+    x_feat = torch.einsum('bfnhw,bfchw->bfnc', m, xt)                              # :246 / :266
+    if gathered:
+        x_feat = x_feat.mean(1)                                                    # :246
+        pf = proposal_feat.reshape(B, N, C, -1).permute(0, 1, 3, 2)                # :270
+        sets = B
+    else:
+        x_feat = x_feat.reshape(B * Fr, N, C)                                      # :275
+        pf = proposal_feat.reshape(B * Fr, N, C, -1).permute(0, 1, 3, 2)           # :274
+        sets = B * Fr
+    obj_feat = _update_attend_ffn(sd, cfg, x_feat, pf, sets, N)                    # :271-291
+    mask_feat = obj_feat
+    cls_score = None
+    if gathered:                                                                   # :295-301
+        cls_feat = obj_feat.sum(-2)
+        for i in range(cfg.get('num_cls_fcs', 1)):
+            cls_feat = torch.relu(layer_norm(linear(cls_feat, sd['cls_fcs.%d.weight' % (3 * i)]),
+                                             sd['cls_fcs.%d.weight' % (3 * i + 1)], sd['cls_fcs.%d.bias' % (3 * i + 1)]))
+        cls_score = linear(cls_feat, sd['fc_cls.weight'], sd['fc_cls.bias']).view(sets, N, -1)
+    for i in range(cfg.get('num_mask_fcs', 1)):                                    # :303-304
+        mask_feat = torch.relu(layer_norm(linear(mask_feat, sd['mask_fcs.%d.weight' % (3 * i)]),
+                                          sd['mask_fcs.%d.weight' % (3 * i + 1)], sd['mask_fcs.%d.bias' % (3 * i + 1)]))
+    mask_feat = linear(mask_feat, sd['fc_mask.weight'], sd['fc_mask.bias']).permute(0, 1, 3, 2).reshape(sets, N, C, 1, 1)
+    if gathered:                                                                   # :329-339
+        new_mask = torch.stack([F.conv2d(xt[i], mask_feat[i]) for i in range(B)], dim=0)
+        return cls_score, new_mask, obj_feat.permute(0, 1, 3, 2).reshape(B, N, C, 1, 1)
+    new_mask = torch.cat([F.conv2d(xt[i][j][None], mask_feat[i * Fr + j])          # :340-352
+                          for i in range(B) for j in range(Fr)], dim=0).reshape(B, Fr, N, H, W)
+    return None, new_mask, obj_feat.permute(0, 1, 3, 2).reshape(B, Fr, N, C, 1, 1)
+
+
+# ----------------------------------------------------------------------------------------
 # the S-stage loop  (knet/det/kernel_iter_head.py:118-137, 246-253; forward_dummy :317-330)
 # ----------------------------------------------------------------------------------------
 def iter_forward(sds, cfgs, x, proposal_feat, mask_preds, mask_round=None):

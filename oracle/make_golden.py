@@ -73,6 +73,44 @@ def case_video(name, B, N, C, H, W, Fh, ncls, seed, previous_type, previous_link
     print(name, 'ok')
 
 
+def case_clip(name, B, Fr, N, C, H, W, Fh, ncls, seed, with_cls):
+    """KernelUpdateHeadVideo (knet_vis tree: must run in a process where `knet` was not loaded)."""
+    ref = ref_shim.load('knet_vis')
+    cfg = ko.default_cfg(num_classes=ncls, in_channels=C, feedforward_channels=Fh)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Fr, C, H, W, generator=g)
+    if with_cls:
+        pf = torch.randn(B, N, C, 1, 1, generator=g)
+        mask = torch.einsum('bnc,bfchw->bfnhw', pf.view(B, N, C), x)
+    else:
+        pf = torch.randn(B, Fr, N, C, 1, 1, generator=g)
+        mask = torch.einsum('bfnc,bfchw->bfnhw', pf.view(B, Fr, N, C), x)
+    sd = ko.random_state_dict(cfg, seed=100 * seed)
+    if not with_cls:
+        sd = {k: v for k, v in sd.items() if not (k.startswith('cls_fcs') or k.startswith('fc_cls'))}
+    head = ref.KernelUpdateHeadVideo(with_cls=with_cls, num_proposals=N, **copy.deepcopy(cfg))
+    head.load_state_dict(sd, strict=True)
+    head.eval()
+    with torch.no_grad():
+        cls, nm, obj = head(x, pf, mask)
+    blob = dict(x=x.numpy(), proposal_feat=pf.numpy(), mask_preds=mask.numpy(),
+                meta=np.array([B, N, C, H, W, 1, Fh, ncls], dtype=np.int64), frames=np.array([Fr], dtype=np.int64))
+    blob.update(_pack('s0.w.', sd))
+    blob['s0.mask_preds'] = nm.numpy()
+    blob['s0.obj_feat'] = obj.numpy()
+    if cls is not None:
+        blob['s0.cls_score'] = cls.numpy()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **blob)
+    print(name, 'ok')
+
+
+def main_clip():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(4)
+    case_clip('clip_gathered_b2_f3_n10_c64_8x12', 2, 3, 10, 64, 8, 12, 128, 5, 8, True)
+    case_clip('clip_perframe_b1_f3_n10_c64_8x12', 1, 3, 10, 64, 8, 12, 128, 5, 9, False)
+
+
 def main():
     assert ref_shim.available(), '/root/reference is required to (re)generate the fixtures'
     os.makedirs(OUT, exist_ok=True)
@@ -89,4 +127,9 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'clip':      # knet_vis registers the same keys as knet: own process
+        main_clip()
+    else:
+        main()
+        import subprocess
+        subprocess.run([sys.executable, os.path.abspath(__file__), 'clip'], check=True)

@@ -175,7 +175,7 @@ def install():
     names = ['mmcv', 'mmcv.cnn', 'mmcv.cnn.bricks', 'mmcv.cnn.bricks.transformer', 'mmcv.runner',
              'mmdet', 'mmdet.core', 'mmdet.models', 'mmdet.models.builder',
              'mmdet.models.dense_heads', 'mmdet.models.dense_heads.atss_head',
-             'mmdet.models.losses', 'mmdet.utils', 'unitrack', 'unitrack.mask']
+             'mmdet.models.losses', 'mmdet.utils', 'unitrack', 'unitrack.mask', 'mmtrack', 'mmtrack.transform']
     mods = {n: _mod(n) for n in names}
     for n, m in mods.items():
         if '.' in n:
@@ -207,6 +207,7 @@ def install():
     mods['mmdet.utils'].get_root_logger = lambda *a, **k: __import__('logging').getLogger('ref')
     mods['unitrack.mask'].tensor_mask2box = lambda *a, **k: None
     mods['unitrack.mask'].mask2box = lambda *a, **k: None
+    mods['mmtrack.transform'].outs2results = lambda *a, **k: None
     _installed = True
 
 
@@ -245,6 +246,8 @@ def load(tree='knet'):
     else:
         out.kernel_updator = _load_file('_ref_knet_vis.kernel_updator', 'knet_vis/kernel_updator.py')
         out.det_head = _load_file('_ref_knet_vis.det.kernel_update_head', 'knet_vis/det/kernel_update_head.py')
+        out.tracker_head = _load_file('_ref_knet_vis.tracker.kernel_update_head', 'knet_vis/tracker/kernel_update_head.py')
         out.KernelUpdator = out.kernel_updator.KernelUpdator
         out.KernelUpdateHead = out.det_head.KernelUpdateHead
+        out.KernelUpdateHeadVideo = out.tracker_head.KernelUpdateHeadVideo
     return out

@@ -17,7 +17,7 @@ def golden_files(prefix):
 def load_golden(path):
     z = np.load(path)
     B, N, C, H, W, S, Fh, ncls = (int(v) for v in z['meta'])
-    t = {k: torch.from_numpy(z[k]) for k in z.files if k != 'meta'}
+    t = {k: torch.from_numpy(z[k]) for k in z.files if k not in ('meta', 'frames')}
     sds = []
     for s in range(S):
         pre = 's%d.w.' % s

@@ -61,7 +61,7 @@ def test_struct_sizes_match_header_layout(built_lib):
     import vknet
     L = vknet._lib
     p = ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(L.VknShape) == 13 * 4
+    assert ctypes.sizeof(L.VknShape) == 14 * 4
     assert ctypes.sizeof(L.VknUpdatorW) == 20 * p
     assert ctypes.sizeof(L.VknAttnW) == 6 * p and ctypes.sizeof(L.VknFfnW) == 6 * p
     assert ctypes.sizeof(L.VknHeadW) == (3 + 20 + 6 + 6 + 1 + 3 * 4 + 2 + 3 * 4 + 2) * p
@@ -92,12 +92,28 @@ def test_video_head_state_dict_contract(built_lib):
         head.load_state_dict(sd, strict=True)
 
 
+def test_clip_head_state_dict_contract(built_lib):
+    """KernelUpdateHeadVideo (knet_vis/tracker/kernel_update_head.py): with_cls=False drops the cls branch."""
+    import vknet
+    cfg = ko.default_cfg()
+    sd = ko.random_state_dict(cfg)
+    full = vknet.build_head(dict(type='KernelUpdateHeadVideo', with_cls=True, num_proposals=100, **cfg))
+    assert list(full.state_dict().keys()) == APPENDIX_C_KEYS
+    full.load_state_dict(sd, strict=True)
+    nocls = vknet.build_head(dict(type='KernelUpdateHeadVideo', with_cls=False, num_proposals=100, **cfg))
+    want = [k for k in APPENDIX_C_KEYS if not (k.startswith('cls_fcs') or k.startswith('fc_cls'))]
+    assert list(nocls.state_dict().keys()) == want
+    with pytest.raises(NotImplementedError):
+        vknet.build_head(dict(type='KernelUpdateHeadVideo', query_merge_method='attention', **cfg)).check_supported()
+
+
 def test_alias_packages_follow_the_reference_import_strings(built_lib):
     import importlib
     import vknet
     for mod, name in (('knet.kernel_updator', 'KernelUpdator'), ('knet.det.kernel_update_head', 'KernelUpdateHead'),
                       ('knet.video.kernel_update_head', 'VideoKernelUpdateHead'),
-                      ('knet_vis.kernel_updator', 'KernelUpdator'), ('knet_vis.det.kernel_update_head', 'KernelUpdateHead')):
+                      ('knet_vis.kernel_updator', 'KernelUpdator'), ('knet_vis.det.kernel_update_head', 'KernelUpdateHead'),
+                      ('knet_vis.tracker.kernel_update_head', 'KernelUpdateHeadVideo')):
         m = importlib.import_module(mod)
         assert getattr(m, name) is getattr(vknet, name)
     assert vknet.HEADS.get('KernelUpdateHead') is vknet.KernelUpdateHead

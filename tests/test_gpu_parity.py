@@ -93,6 +93,67 @@ def test_golden_video_links(dev, path):
     assert_masks(nm, t['noprev.mask_preds'], 'unlinked stage')
 
 
+# ---- clip head (knet_vis tracker): golden fixtures + larger clips on both engines --------------------------
+@pytest.mark.parametrize('path', golden_files('clip_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_golden_clip_head(dev, path):
+    import vknet
+    g = load_golden(path)
+    t = g['t']
+    with_cls = 's0.cls_score' in t
+    sd = g['sds'][0]
+    h = vknet.build_head(dict(type='KernelUpdateHeadVideo', with_cls=with_cls, num_proposals=g['N'], **g['cfg']))
+    h.load_state_dict(sd, strict=True)
+    h = h.to(dev).eval()
+    cls, nm, obj = h(t['x'].to(dev), t['proposal_feat'].to(dev), t['mask_preds'].to(dev))
+    assert nm.shape == t['s0.mask_preds'].shape and obj.shape == t['s0.obj_feat'].shape
+    assert maxabs(obj, t['s0.obj_feat']) < TOL_F32
+    if with_cls:
+        assert maxabs(cls, t['s0.cls_score']) < TOL_F32
+    else:
+        assert cls is None
+    B, Fr = nm.shape[:2]
+    assert_masks(nm.reshape(B * Fr, *nm.shape[2:]), t['s0.mask_preds'].reshape(B * Fr, *nm.shape[2:]), 'clip head')
+
+
+@pytest.mark.parametrize('B,Fr,N,C,H,W,with_cls,dt', [(1, 4, 100, 256, 96, 160, True, 'bf16'), (2, 3, 100, 128, 16, 24, True, 'f32'),
+                                                   (1, 4, 100, 256, 24, 40, False, 'bf16')])
+def test_clip_head_vs_oracle(dev, B, Fr, N, C, H, W, with_cls, dt):
+    """BASELINE cfg2-like clip (4 frames, 96x160) on the tcgen05 engine; fp32 storage on the SIMT engine."""
+    import vknet
+    cfg = ko.default_cfg(num_classes=40, in_channels=C, feedforward_channels=256)
+    sd = ko.random_state_dict(cfg, seed=33)
+    if dt == 'bf16':
+        sd = ko.round_state_dict_bf16(sd)
+    if not with_cls:
+        sd = {k: v for k, v in sd.items() if not (k.startswith('cls_fcs') or k.startswith('fc_cls'))}
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(B, Fr, C, H, W, generator=gen)
+    if with_cls:
+        pf = torch.randn(B, N, C, 1, 1, generator=gen)
+        mask = torch.einsum('bnc,bfchw->bfnhw', pf.view(B, N, C), x)
+    else:
+        pf = torch.randn(B, Fr, N, C, 1, 1, generator=gen)
+        mask = torch.einsum('bfnc,bfchw->bfnhw', pf.view(B, Fr, N, C), x)
+    if dt == 'bf16':
+        x, mask = ko.round_bf16(x), ko.round_bf16(mask)
+    want = ko.kernel_update_head_video_forward(sd, cfg, x, pf, mask)
+    h = vknet.build_head(dict(type='KernelUpdateHeadVideo', with_cls=with_cls, num_proposals=N, **cfg))
+    h.load_state_dict(sd, strict=True)
+    tdt = torch.bfloat16 if dt == 'bf16' else torch.float32
+    h = h.to(device=dev, dtype=tdt).eval()
+    cls, nm, obj = h(x.to(dev).to(tdt), pf.to(dev), mask.to(dev).to(tdt))
+    tol = TOL_BF16 if dt == 'bf16' else TOL_F32
+    assert maxabs(obj, want[2]) < tol
+    if with_cls:
+        assert maxabs(cls, want[0]) < tol
+    ref = want[1] if dt == 'f32' else ko.round_bf16(want[1])
+    if dt == 'f32':
+        assert_masks(nm.reshape(B * Fr, N, H, W), ref.reshape(B * Fr, N, H, W), 'clip')
+    else:
+        mism = (nm.float().cpu().argmax(2) != ref.argmax(2)).float().mean().item()
+        assert mism < 2e-3, 'clip bf16: argmax mismatch rate %g' % mism
+
+
 # ---- individual operators against the oracle ------------------------------------------------------
 @pytest.mark.parametrize('B,N,C,H,W,Fh', [(1, 10, 64, 8, 8, 64), (2, 37, 128, 7, 19, 96), (1, 100, 256, 24, 40, 2048)])
 def test_operators(dev, B, N, C, H, W, Fh):

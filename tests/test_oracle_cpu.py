@@ -36,11 +36,24 @@ def test_oracle_matches_reference_fixtures_video(path):
     assert maxabs(out[2], t['noprev.obj_feat']) < 2e-5
 
 
+@pytest.mark.parametrize('path', golden_files('clip_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_oracle_matches_reference_fixtures_clip_head(path):
+    g = load_golden(path)
+    t = g['t']
+    cls, nm, obj = ko.kernel_update_head_video_forward(g['sds'][0], g['cfg'], t['x'], t['proposal_feat'], t['mask_preds'])
+    assert maxabs(nm, t['s0.mask_preds']) < 2e-4 and maxabs(obj, t['s0.obj_feat']) < 2e-5
+    assert torch.equal(nm.argmax(2), t['s0.mask_preds'].argmax(2))
+    if 's0.cls_score' in t:
+        assert maxabs(cls, t['s0.cls_score']) < 2e-5
+    else:
+        assert cls is None
+
+
 def test_fixture_generator_is_committed_and_fixtures_exist():
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     assert os.path.exists(os.path.join(root, 'oracle', 'make_golden.py'))
-    assert len(golden_files('det_')) >= 3 and len(golden_files('video_')) >= 3
+    assert len(golden_files('det_')) >= 3 and len(golden_files('video_')) >= 3 and len(golden_files('clip_')) >= 2
 
 
 def _live_reference():

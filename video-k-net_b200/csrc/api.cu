@@ -65,6 +65,14 @@ struct Layout {
   size_t total;
 };
 
+// the same shape seen by the two big contractions: one entry of B per FRAME
+static VknShape frames_shape(const VknShape &s) {
+  VknShape f = s;
+  if (s.frames_per_set > 1) f.B = s.B * s.frames_per_set;
+  f.frames_per_set = 1;
+  return f;
+}
+
 static int pool_chunks_max(const VknShape &s) {
   int a = pool_simt_chunks(s);
   int b = pool_tc_chunks(s);
@@ -81,9 +89,10 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   };
   const size_t P = (size_t)s.B * s.N, C = s.C, F = s.ffn_dim, HW = (size_t)s.H * s.W;
   const size_t f = sizeof(float);
-  const int nch = pool_chunks_max(s);
-  L.pool_part = (float *)take((size_t)nch * P * C * f);
-  L.cnt_part = (float *)take((size_t)nch * P * f);
+  const size_t fps = s.frames_per_set > 1 ? s.frames_per_set : 1;   // frames per kernel set
+  const int nch = pool_chunks_max(frames_shape(s));
+  L.pool_part = (float *)take((size_t)nch * P * fps * C * f);
+  L.cnt_part = (float *)take((size_t)nch * P * fps * f);
   L.xp0 = (float *)take(P * C * f);
   L.cnt = (float *)take(P * f);
   L.xp = (float *)take(P * C * f);
@@ -110,7 +119,7 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   const size_t npad = (size_t)ceil_div(s.N, 128) * 128;
   L.a_split = take((size_t)3 * s.B * npad * C * 2);
   const size_t esz = s.x_dtype == VKN_BF16 ? 2 : 4;
-  for (int i = 0; i < 2; ++i) L.mask_pp[i] = take((size_t)s.B * s.N * HW * esz);
+  for (int i = 0; i < 2; ++i) L.mask_pp[i] = take((size_t)s.B * fps * s.N * HW * esz);
   for (int i = 0; i < 2; ++i) L.obj_pp[i] = (float *)take(P * C * f);
   L.cls_tmp = (float *)take(P * (size_t)s.num_classes * f);
   L.total = align_up(off, 256);
@@ -130,6 +139,7 @@ static int check_shape(const VknShape *s) {
     VKN_FAIL(VKN_E_INVALID, "bad dtype code");
   if (s->engine < VKN_ENGINE_AUTO || s->engine > VKN_ENGINE_TC) VKN_FAIL(VKN_E_INVALID, "bad engine code");
   if (s->N > 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "N = %d kernels per frame exceeds 1024", s->N);
+  if (s->frames_per_set < 0 || s->frames_per_set > 1024) VKN_FAIL(VKN_E_INVALID, "frames_per_set out of range");
   return VKN_OK;
 }
 
@@ -151,7 +161,7 @@ static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, 
     VKN_FAIL(VKN_E_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", ws_bytes, c.L.total);
   c.st = (cudaStream_t)stream;
   c.P = s->B * s->N;
-  const bool can = tc_supported(c.s);
+  const bool can = tc_supported(frames_shape(c.s));
   if (s->engine == VKN_ENGINE_TC && !can)
     VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 engine requested but the shape/dtype does not qualify");
   c.use_tc = (s->engine != VKN_ENGINE_SIMT) && can;
@@ -201,8 +211,9 @@ static const void *wrow(const Ctx &c, const void *w, size_t row, size_t ld) {
 // a3+a4: pooled feature with the feat_transform folded out -> xp [P,C]
 static int k_pool(Ctx &c, const VknHeadW &w, const void *x, const void *mask, float *xp) {
   int nch = 0;
-  if (c.use_tc) VKN_TRY(launch_pool_tc(c.s, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
-  else VKN_TRY(launch_pool_simt(c.s, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+  const VknShape fs = frames_shape(c.s);     // pooling runs per frame; the reduce folds chunks AND the F frames of a set
+  if (c.use_tc) VKN_TRY(launch_pool_tc(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+  else VKN_TRY(launch_pool_simt(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
   VKN_TRY(launch_pool_reduce(c.s, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st));
   // x_feat = xp0 . ft_w^T + cnt (x) ft_b      (sum_p M (W x + b) = W (sum_p M x) + (sum_p M) b)
   LinArgs a = lin(src_copy(c.L.xp0, c.s.C), w.ft_w, c.s.C, w.ft_b, xp, c.s.C, c.P, c.s.C, c.s.C, EPI_ROWSCALE);
@@ -301,11 +312,13 @@ static int k_heads(Ctx &c, const VknHeadW &w, const RowSrc &obj_src, float *obj_
     VKN_FAIL(VKN_E_UNSUPPORTED, "num_cls_fcs / num_mask_fcs must be in [0, %d]", VKN_MAX_FCS);
   RowSrc cs = obj_src, ms = obj_src;
   bool need_side = obj_out != nullptr;
-  const int depth = w.num_cls_fcs > w.num_mask_fcs ? w.num_cls_fcs : w.num_mask_fcs;
+  const bool with_cls = w.fc_cls_w != nullptr && cls_out != nullptr;   // KernelUpdateHeadVideo(with_cls=False)
+  const int ncls_fcs = with_cls ? w.num_cls_fcs : 0;
+  const int depth = ncls_fcs > w.num_mask_fcs ? ncls_fcs : w.num_mask_fcs;
   for (int i = 0; i < depth; ++i) {
     LinArgs two[2];
     int n = 0;
-    if (i < w.num_cls_fcs) {
+    if (i < ncls_fcs) {
       two[n] = lin(cs, w.cls_fc_w[i], C, nullptr, c.L.pre_c[i & 1], C, P, C, C, 0);
       cs = src_ln(c.L.pre_c[i & 1], C, w.cls_ln_g[i], w.cls_ln_b[i], true);
       ++n;
@@ -324,12 +337,12 @@ static int k_heads(Ctx &c, const VknHeadW &w, const RowSrc &obj_src, float *obj_
   }
   LinArgs two[2];
   two[0] = lin(ms, w.fc_mask_w, C, w.fc_mask_b, mk_out, C, P, C, C, 0);
-  two[1] = lin(cs, w.fc_cls_w, C, w.fc_cls_b, cls_out, c.s.num_classes, P, c.s.num_classes, C, 0);
+  if (with_cls) two[1] = lin(cs, w.fc_cls_w, C, w.fc_cls_b, cls_out, c.s.num_classes, P, c.s.num_classes, C, 0);
   if (need_side) {               // no FC layers at all: the final launch materialises obj_feat
     two[0].side = obj_out;
     two[0].ldside = C;
   }
-  return launch_linear(two, 2, c.s.w_dtype, c.st);
+  return launch_linear(two, with_cls ? 2 : 1, c.s.w_dtype, c.st);
 }
 
 // a9: new_mask = mk . (ft_w x + ft_b) = (mk . ft_w) x + mk . ft_b
@@ -481,7 +494,7 @@ int vkn_stage_forward(const VknShape *s, const VknHeadW *w, const void *x, const
                       float *obj_feat, float *x_feat_out, void *workspace, size_t workspace_bytes, void *stream) {
   Ctx c;
   VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
-  if (!w || !x || !proposal_feat || !cls_score || !obj_feat || (!mask_preds && !x_feat_in))
+  if (!w || !x || !proposal_feat || !obj_feat || (!mask_preds && !x_feat_in))
     VKN_FAIL(VKN_E_INVALID, "vkn_stage_forward: null argument");
   return stage(c, *w, x, proposal_feat, mask_preds, x_feat_in, cls_score, new_mask_preds, obj_feat, x_feat_out);
 }

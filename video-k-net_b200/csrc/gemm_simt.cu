@@ -115,33 +115,41 @@ int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *
   return VKN_OK;
 }
 
-// partials [nchunks][P*C] -> xp0 [P*C];  cnt_partials [nchunks][P] -> cnt [P].
-// One CTA = 128 outputs (float4 per lane); its 8 warps each sum every 8th chunk with independent
-// 16-byte loads, then the 8 warp sums are combined in a FIXED order (deterministic, no atomics).
+// partials [nchunks][B*F frames][N*C] -> xp0 [B][N*C];  cnt_partials [nchunks][B*F][N] -> cnt [B][N].
+// A kernel set b folds its nchunks * F slices (F = frames_per_set; the clip head averages the pooled
+// feature over its frames, knet_vis/tracker/kernel_update_head.py:245-246 -> scale = 1/F).
+// One CTA = 128 outputs (float4 per lane) of one set; its 8 warps each sum every 8th slice with four
+// independent 16-byte loads in flight, then the 8 warp sums are combined in a FIXED order
+// (deterministic, no atomics).
 __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__restrict__ partials,
                                                               const float *__restrict__ cnt_partials, int nchunks,
-                                                              int PC, int P, float *__restrict__ xp0,
-                                                              float *__restrict__ cnt) {
+                                                              int B, int F, int N, int NC, float scale,
+                                                              float *__restrict__ xp0, float *__restrict__ cnt) {
   __shared__ float4 red[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
   const int idx = blockIdx.x * 128 + lane * 4;
+  const int nsl = nchunks * F;
   pdl_wait();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (idx < PC) {
-    // chunks warp, warp+8, warp+16, ...: four independent 16-byte loads in flight per thread
+  auto slice = [&](int sl) -> size_t {       // slice (chunk, f) of set b
+    const int ch = sl / F, f = sl - ch * F;
+    return ((size_t)ch * B * F + (size_t)b * F + f);
+  };
+  if (idx < NC) {
     float4 a[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int ch = warp;
-    for (; ch + 24 < nchunks; ch += 32) {
+    int sl = warp;
+    for (; sl + 24 < nsl; sl += 32) {
       float4 t[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)(ch + 8 * u) * PC + idx));
+      for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const float4 *>(partials + slice(sl + 8 * u) * NC + idx));
 #pragma unroll
       for (int u = 0; u < 4; ++u) { a[u].x += t[u].x; a[u].y += t[u].y; a[u].z += t[u].z; a[u].w += t[u].w; }
     }
-    for (int u = 0; ch < nchunks; ch += 8, ++u) {
-      const float4 t = __ldg(reinterpret_cast<const float4 *>(partials + (size_t)ch * PC + idx));
+    for (int u = 0; sl < nsl; sl += 8, ++u) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(partials + slice(sl) * NC + idx));
       a[u & 3].x += t.x; a[u & 3].y += t.y; a[u & 3].z += t.z; a[u & 3].w += t.w;
     }
     acc = make_float4((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
@@ -150,31 +158,32 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
   red[warp][lane] = acc;
   __syncthreads();
   pdl_trigger();
-  if (warp == 0 && idx < PC) {
+  if (warp == 0 && idx < NC) {
     float4 t = red[0][lane];
 #pragma unroll
     for (int w = 1; w < 8; ++w) {
       const float4 u = red[w][lane];
       t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
-    *reinterpret_cast<float4 *>(xp0 + idx) = t;
+    *reinterpret_cast<float4 *>(xp0 + (size_t)b * NC + idx) = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
   }
-  const int ci = blockIdx.x * 256 + threadIdx.x;     // the first ceil(P/256) CTAs also reduce the pixel counts
-  if (ci < P) {
+  const int ci = blockIdx.x * 256 + threadIdx.x;     // the first ceil(N/256) CTAs of a set also reduce its pixel counts
+  if (ci < N) {
     float s0 = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) s0 += __ldg(cnt_partials + (size_t)ch * P + ci);
-    cnt[ci] = s0;
+    for (int sl = 0; sl < nsl; ++sl) s0 += __ldg(cnt_partials + slice(sl) * N + ci);
+    cnt[(size_t)b * N + ci] = s0 * scale;
   }
 }
 
 int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
                        float *xp0, float *cnt, cudaStream_t stream) {
-  const int P = s.B * s.N, PC = P * s.C;
+  const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
+  const int NC = s.N * s.C;
   VKN_LAUNCH_MARK("vkn_pool_reduce_kernel", stream);
-  int grid = ceil_div(PC, 128);
-  if (grid < ceil_div(P, 256)) grid = ceil_div(P, 256);
-  VKN_CUDA_OK(launch_chain(vkn_pool_reduce_kernel, dim3(grid), dim3(256), 0, stream, partials, cnt_partials, nchunks, PC,
-                           P, xp0, cnt));
+  int gx = ceil_div(NC, 128);
+  if (gx < ceil_div(s.N, 256)) gx = ceil_div(s.N, 256);
+  VKN_CUDA_OK(launch_chain(vkn_pool_reduce_kernel, dim3(gx, s.B), dim3(256), 0, stream, partials, cnt_partials, nchunks,
+                           s.B, F, s.N, NC, 1.0f / (float)F, xp0, cnt));
   return VKN_OK;
 }
 
@@ -182,7 +191,7 @@ int launch_pool_reduce(const VknShape &s, const float *partials, const float *cn
 template <typename XT, bool VEC>
 __global__ void __launch_bounds__(GT) vkn_maskgemm_simt_kernel(const XT *__restrict__ x,
                                                                const float *__restrict__ a_ext, int lda,
-                                                               XT *__restrict__ out, int N, int C, int HW) {
+                                                               XT *__restrict__ out, int N, int C, int HW, int F) {
   __shared__ __align__(16) float As[TILE_N][PK + 4];
   __shared__ __align__(16) float Xs[PK][TILE_P + 4];
   const int p0 = blockIdx.x * TILE_P, n0 = blockIdx.y * TILE_N, b = blockIdx.z;
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(GT) vkn_maskgemm_simt_kernel(const XT *__restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const XT *xb = x + (size_t)b * C * HW;
-  const float *ab = a_ext + (size_t)b * N * lda;
+  const float *ab = a_ext + (size_t)(b / F) * N * lda;      // frame b uses the kernels of set b / F
   pdl_wait();
   for (int c0 = 0; c0 < C; c0 += PK) {
     {  // A tile: 128 rows x 32 channels, 8 consecutive channels per thread
@@ -266,19 +275,20 @@ int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, i
   const int HW = s.H * s.W;
   if (s.C % PK != 0) VKN_FAIL(VKN_E_UNSUPPORTED, "mask gemm: C %d must be a multiple of %d", s.C, PK);
   if (lda % 4 != 0) VKN_FAIL(VKN_E_INVALID, "mask gemm: lda %d must be a multiple of 4", lda);
-  dim3 grid(ceil_div(HW, TILE_P), ceil_div(s.N, TILE_N), s.B);
+  const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
+  dim3 grid(ceil_div(HW, TILE_P), ceil_div(s.N, TILE_N), s.B * F);
   VKN_LAUNCH_MARK("vkn_maskgemm_simt_kernel", stream);
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (s.x_dtype == VKN_BF16) {
     auto xp = (const __nv_bfloat16 *)x;
     auto op = (__nv_bfloat16 *)out;
-    if (vec) VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<__nv_bfloat16, true>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
-    else VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<__nv_bfloat16, false>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
+    if (vec) VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<__nv_bfloat16, true>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW, F));
+    else VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<__nv_bfloat16, false>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW, F));
   } else {
     auto xp = (const float *)x;
     auto op = (float *)out;
-    if (vec) VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<float, true>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
-    else VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<float, false>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW));
+    if (vec) VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<float, true>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW, F));
+    else VKN_CUDA_OK(launch_chain(vkn_maskgemm_simt_kernel<float, false>, grid, dim3(GT), 0, stream, xp, a_ext, lda, op, s.N, s.C, HW, F));
   }
   VKN_CUDA_OK(cudaGetLastError());
   return VKN_OK;

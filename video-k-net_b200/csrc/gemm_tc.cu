@@ -391,7 +391,7 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
                        const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
-                       int Npad, int C, int HW, int stages, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo) {
+                       int Npad, int C, int HW, int stages, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t x_bytes = (uint32_t)CH_BLK * MASK_TILE_P * 2u;         // 64 ch x 128 px x 2 B = 16 KB
@@ -404,7 +404,8 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   float *bias_s = (float *)(tmem_slot + 2);                              // [Npad]
   const uint32_t smem0 = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p0 = blockIdx.x * MASK_TILE_P, b = blockIdx.z;
+  const int p0 = blockIdx.x * MASK_TILE_P, b = blockIdx.z;     // b = frame; its kernels are those of set kb
+  const int kb = b / F;
   const int nk = C / CH_BLK;
   const uint32_t ncols = Npad <= 128 ? 128u : 256u;
 
@@ -424,7 +425,7 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
   pdl_wait();     // a_ext / the planes come from the previous kernel
   for (int n = threadIdx.x; n < ((Npad + 31) & ~31); n += TC_THREADS)
-    bias_s[n] = (n < N) ? a_ext[((size_t)b * N + n) * lda + C] : 0.f;
+    bias_s[n] = (n < N) ? a_ext[((size_t)kb * N + n) * lda + C] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -443,7 +444,7 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         tma_load_3d(xs + x_bytes / 2, &tmap_x, bar0 + 8 * s, p0 + 64, i * CH_BLK, b);
 #pragma unroll
         for (int t = 0; t < 3; ++t)
-          tma_load_2d(xs + x_bytes + t * a_plane, &tmap_a, bar0 + 8 * s, i * CH_BLK, (t * B + b) * Npad);
+          tma_load_2d(xs + x_bytes + t * a_plane, &tmap_a, bar0 + 8 * s, i * CH_BLK, (t * B + kb) * Npad);
       }
     }
   } else if (warp == 1) {
@@ -513,9 +514,10 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
                        cudaStream_t stream) {
   if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: shape/dtype not supported");
   const int HW = s.H * s.W, Npad = npad_of(s.N);
+  const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
   CUtensorMap tmx, tma;
   {
-    const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)s.B};
+    const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)s.B * F};
     const uint32_t box[3] = {64u, (uint32_t)CH_BLK, 1u};
     VKN_TRY(make_tmap_bf16(&tmx, x, 3, dims, box));
   }
@@ -540,11 +542,11 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   if (const char *e = getenv("VKN_DEBUG_SWAP_LBO_SBO")) {
     if (e[0] == '1') { uint32_t t = x_lbo; x_lbo = x_sbo; x_sbo = t; }
   }
-  dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B);
+  dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);
   VKN_LAUNCH_MARK("vkn_maskgemm_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmx, tma, a_ext, lda,
                            (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, stages, make_idesc_bf16(128, Npad, 1, 0), x_lbo,
-                           x_sbo));
+                           x_sbo, F));
   return VKN_OK;
 }
 

@@ -11,7 +11,8 @@ from .registry import HEADS, TRANSFORMER_LAYER, build_head, build_transformer_la
 from .kernel_updator import KernelUpdator
 from .kernel_update_head import KernelUpdateHead
 from .video_kernel_update_head import VideoKernelUpdateHead
+from .tracker_kernel_update_head import KernelUpdateHeadVideo
 from .iter_loop import FramesInFlight, KernelIterLoop
 
-__all__ = ['KernelUpdator', 'KernelUpdateHead', 'VideoKernelUpdateHead', 'KernelIterLoop', 'FramesInFlight', 'HEADS',
+__all__ = ['KernelUpdator', 'KernelUpdateHead', 'VideoKernelUpdateHead', 'KernelUpdateHeadVideo', 'KernelIterLoop', 'FramesInFlight', 'HEADS',
            'TRANSFORMER_LAYER', 'build_head', 'build_transformer_layer', 'VknError', 'kernel_names', '_lib']

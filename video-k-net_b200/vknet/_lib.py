@@ -23,7 +23,7 @@ class VknShape(C.Structure):
     _fields_ = [('B', C.c_int32), ('N', C.c_int32), ('C', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('ffn_dim', C.c_int32), ('num_classes', C.c_int32), ('num_heads', C.c_int32),
                 ('x_dtype', C.c_int32), ('w_dtype', C.c_int32), ('with_ffn', C.c_int32),
-                ('engine', C.c_int32), ('mask_thr_logit', C.c_float)]
+                ('engine', C.c_int32), ('frames_per_set', C.c_int32), ('mask_thr_logit', C.c_float)]
 
 
 class VknUpdatorW(C.Structure):
@@ -123,9 +123,9 @@ def dtype_code(dt):
 
 
 def make_shape(B, N, Cc, H, W, ffn_dim, num_classes, num_heads, x_dtype, w_dtype, with_ffn=True,
-               engine=ENGINE_AUTO, mask_thr_logit=0.0):
+               engine=ENGINE_AUTO, mask_thr_logit=0.0, frames_per_set=1):
     return VknShape(B, N, Cc, H, W, ffn_dim, num_classes, num_heads, x_dtype, w_dtype, int(bool(with_ffn)),
-                    engine, float(mask_thr_logit))
+                    engine, int(frames_per_set), float(mask_thr_logit))
 
 
 def workspace_bytes(shape):

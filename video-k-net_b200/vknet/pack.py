@@ -97,7 +97,8 @@ def pack_head(pk, head):
     for i in range(nmask):
         w.mask_fc_w[i] = pk.mat(head.mask_fcs[3 * i].weight)
         w.mask_ln_g[i], w.mask_ln_b[i] = pk.vec(head.mask_fcs[3 * i + 1].weight), pk.vec(head.mask_fcs[3 * i + 1].bias)
-    w.fc_cls_w, w.fc_cls_b = pk.mat(head.fc_cls.weight), pk.vec(head.fc_cls.bias)
+    if head.fc_cls is not None:          # KernelUpdateHeadVideo(with_cls=False) has no cls branch
+        w.fc_cls_w, w.fc_cls_b = pk.mat(head.fc_cls.weight), pk.vec(head.fc_cls.bias)
     w.fc_mask_w, w.fc_mask_b = pk.mat(head.fc_mask.weight), pk.vec(head.fc_mask.bias)
     return w
 
