@@ -25,38 +25,54 @@ struct WTile {
 };
 
 // ---- row-wise prologue ------------------------------------------------------------------------
+// A warp owns a row; lane l holds the element PAIRS k = 64 p + 2 l, +1 (p = 0..3): 8-byte loads/stores,
+// and the pair is what one 32-bit bf16x2 word of the tensor-core operand planes holds.
+__device__ __forceinline__ int kidx(int lane, int i) { return ((i >> 1) << 6) + (lane << 1) + (i & 1); }
+
 __device__ __forceinline__ void ln_inplace(float (&v)[KPL], int K, int lane, const float *g, const float *b) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < KPL; ++i) s += v[i];  // out-of-range lanes hold 0
+  for (int i = 0; i < KPL; ++i) s += v[i];  // out-of-range slots hold 0
   const float mean = warp_sum(s) / (float)K;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < KPL; ++i) {
-    const int k = lane + 32 * i;
-    const float d = (k < K) ? v[i] - mean : 0.f;
+    const float d = (kidx(lane, i) < K) ? v[i] - mean : 0.f;
     q += d * d;
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + 1e-5f);
 #pragma unroll
-  for (int i = 0; i < KPL; ++i) {
-    const int k = lane + 32 * i;
-    if (k < K) v[i] = (v[i] - mean) * rstd * __ldg(g + k) + __ldg(b + k);
+  for (int p = 0; p < KPL / 2; ++p) {
+    const int k = kidx(lane, 2 * p);
+    if (k < K) {
+      const float2 gg = __ldg(reinterpret_cast<const float2 *>(g + k));
+      const float2 bb = __ldg(reinterpret_cast<const float2 *>(b + k));
+      v[2 * p] = (v[2 * p] - mean) * rstd * gg.x + bb.x;
+      v[2 * p + 1] = (v[2 * p + 1] - mean) * rstd * gg.y + bb.y;
+    }
   }
 }
 
-__device__ __forceinline__ void fetch_plain(const float *a, int lda, int row, int k0, int klen, int lane,
-                                            float (&v)[KPL]) {
+// v[2p], v[2p+1] (+)= a[k], a[k+1]   (k even, klen even: a pair never straddles the end)
+template <bool ACC>
+__device__ __forceinline__ void fetch_pairs(const float *a, int klen, int lane, float (&v)[KPL]) {
 #pragma unroll
-  for (int i = 0; i < KPL; ++i) {
-    const int k = lane + 32 * i;
-    v[i] = (k < klen) ? __ldg(a + (size_t)row * lda + k0 + k) : 0.f;
+  for (int p = 0; p < KPL / 2; ++p) {
+    const int k = kidx(lane, 2 * p);
+    float2 t = make_float2(0.f, 0.f);
+    if (k < klen) t = __ldg(reinterpret_cast<const float2 *>(a + k));
+    if (ACC) {
+      v[2 * p] += t.x;
+      v[2 * p + 1] += t.y;
+    } else {
+      v[2 * p] = t.x;
+      v[2 * p + 1] = t.y;
+    }
   }
 }
 
 // Row transform in two steps so that the global loads of ALL rows a warp owns are in flight before the
-// first LayerNorm reduction starts (the kernels are latency-bound: one exposed L2 round trip per row
-// was ~half of their run time).
+// first LayerNorm reduction starts (the kernels are latency-bound).
 //   row_load  : raw values of up to 4 sources -> registers (sum of slices + bias + residual folded in)
 //   row_finish: LN / ReLU / gate arithmetic (warp-shuffle reductions)
 // LN-type modes require k0 == 0 and klen == K (host-checked).
@@ -66,60 +82,32 @@ struct RowRaw {
 
 __device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int klen, int lane, RowRaw &r) {
   if (s.pro == PRO_MUL) {
-    fetch_plain(s.a[0], s.lda[0], row, k0, klen, lane, r.v[0]);
-    fetch_plain(s.a[1], s.lda[1], row, k0, klen, lane, r.v[1]);
+    fetch_pairs<false>(s.a[0] + (size_t)row * s.lda[0] + k0, klen, lane, r.v[0]);
+    fetch_pairs<false>(s.a[1] + (size_t)row * s.lda[1] + k0, klen, lane, r.v[1]);
     return;
   }
   if (s.pro == PRO_GATE) {
-    fetch_plain(s.a[0], s.lda[0], row, 0, klen, lane, r.v[0]);   // update gate pre-activation
-    fetch_plain(s.a[1], s.lda[1], row, 0, klen, lane, r.v[1]);   // param_out
-    fetch_plain(s.a[2], s.lda[2], row, 0, klen, lane, r.v[2]);   // input gate pre-activation
-    fetch_plain(s.a[3], s.lda[3], row, 0, klen, lane, r.v[3]);   // input_out
+    fetch_pairs<false>(s.a[0] + (size_t)row * s.lda[0], klen, lane, r.v[0]);   // update gate pre-activation
+    fetch_pairs<false>(s.a[1] + (size_t)row * s.lda[1], klen, lane, r.v[1]);   // param_out
+    fetch_pairs<false>(s.a[2] + (size_t)row * s.lda[2], klen, lane, r.v[2]);   // input gate pre-activation
+    fetch_pairs<false>(s.a[3] + (size_t)row * s.lda[3], klen, lane, r.v[3]);   // input_out
     return;
   }
   // PRO_COPY / PRO_LN / PRO_LN_RELU: fixed-order sum of slices (+ bias + residual)
   float(&v)[KPL] = r.v[0];
   const float *a0 = s.a[0] + (size_t)row * s.lda[0] + k0;
-#pragma unroll
-  for (int i = 0; i < KPL; ++i) {
-    const int k = lane + 32 * i;
-    v[i] = (k < klen) ? __ldg(a0 + k) : 0.f;
-  }
+  fetch_pairs<false>(a0, klen, lane, v);
   int sl = 1;
-  for (; sl + 4 <= s.nsum; sl += 4) {      // four independent slice loads per element in flight
-    const float *a = a0 + (size_t)sl * s.sum_stride;
+  for (; sl + 4 <= s.nsum; sl += 4) {      // four independent slices in flight, fixed association order
+    float t[4][KPL];
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < klen) {
-        const float t0 = __ldg(a + k), t1 = __ldg(a + s.sum_stride + k);
-        const float t2 = __ldg(a + 2 * s.sum_stride + k), t3 = __ldg(a + 3 * s.sum_stride + k);
-        v[i] += (t0 + t1) + (t2 + t3);
-      }
-    }
-  }
-  for (; sl < s.nsum; ++sl) {
-    const float *a = a0 + (size_t)sl * s.sum_stride;
+    for (int u = 0; u < 4; ++u) fetch_pairs<false>(a0 + (size_t)(sl + u) * s.sum_stride, klen, lane, t[u]);
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < klen) v[i] += __ldg(a + k);
-    }
+    for (int i = 0; i < KPL; ++i) v[i] += (t[0][i] + t[1][i]) + (t[2][i] + t[3][i]);
   }
-  if (s.pbias) {
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < klen) v[i] += __ldg(s.pbias + k0 + k);
-    }
-  }
-  if (s.pres) {
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < klen) v[i] += __ldg(s.pres + (size_t)row * s.ldpres + k0 + k);
-    }
-  }
+  for (; sl < s.nsum; ++sl) fetch_pairs<true>(a0 + (size_t)sl * s.sum_stride, klen, lane, v);
+  if (s.pbias) fetch_pairs<true>(s.pbias + k0, klen, lane, v);
+  if (s.pres) fetch_pairs<true>(s.pres + (size_t)row * s.ldpres + k0, klen, lane, v);
 }
 
 __device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, RowRaw &r, float (&v)[KPL]) {
@@ -134,10 +122,8 @@ __device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, 
     ln_inplace(r.v[2], klen, lane, s.ln_g[2], s.ln_b[2]);
     ln_inplace(r.v[3], klen, lane, s.ln_g[3], s.ln_b[3]);
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      v[i] = (k < klen) ? sigmoidf_(r.v[0][i]) * r.v[1][i] + sigmoidf_(r.v[2][i]) * r.v[3][i] : 0.f;
-    }
+    for (int i = 0; i < KPL; ++i)
+      v[i] = (kidx(lane, i) < klen) ? sigmoidf_(r.v[0][i]) * r.v[1][i] + sigmoidf_(r.v[2][i]) * r.v[3][i] : 0.f;
     return;
   }
 #pragma unroll
@@ -151,11 +137,12 @@ __device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, 
   }
 }
 
-__device__ __forceinline__ void row_transform(const RowSrc &s, int row, int k0, int klen, int lane,
-                                              float (&v)[KPL]) {
-  RowRaw r;
-  row_load(s, row, k0, klen, lane, r);
-  row_finish(s, klen, lane, r, v);
+__device__ __forceinline__ void store_pairs(float *dst, int klen, int lane, const float (&v)[KPL]) {
+#pragma unroll
+  for (int p = 0; p < KPL / 2; ++p) {
+    const int k = kidx(lane, 2 * p);
+    if (k < klen) *reinterpret_cast<float2 *>(dst + k) = make_float2(v[2 * p], v[2 * p + 1]);
+  }
 }
 
 // ---- standalone row operator (materialises a prologue result) ----------------------------------
@@ -168,13 +155,11 @@ __global__ void __launch_bounds__(NT) vkn_rowop_kernel(const __grid_constant__ R
   if (row >= M) return;
   for (int k0 = 0; k0 < K; k0 += KC) {
     const int klen = min(KC, K - k0);
+    RowRaw r;
     float v[KPL];
-    row_transform(src, row, k0, klen, lane, v);
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < klen) out[(size_t)row * ldo + k0 + k] = v[i];
-    }
+    row_load(src, row, k0, klen, lane, r);
+    row_finish(src, klen, lane, r, v);
+    store_pairs(out + (size_t)row * ldo + k0, klen, lane, v);
   }
 }
 
@@ -189,17 +174,60 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+// D(16x8, f32) += A(16x16, bf16 row) * B(16x8, bf16 col)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void lin_epilogue(const LinArgs &A, float *outp, int row, int col, float v) {
+  if (row >= A.M || col >= A.N) return;
+  if (A.epi & EPI_BIAS) v += ((A.epi & EPI_ROWSCALE) ? __ldg(A.rowscale + row) : 1.f) * __ldg(A.bias + col);
+  if (A.epi & EPI_RES) v += __ldg(A.res + (size_t)row * A.ldres + col);
+  if (A.epi & EPI_RELU) v = fmaxf(v, 0.f);
+  outp[(size_t)row * A.ldo + col] = v;
+  if ((A.epi & EPI_SPLIT3) && col < A.split_C) {
+    // v == hi + mid + lo to 24 bits; every bf16 x bf16 product in the mask conv is then exact
+    const int b = row / A.split_N, n = row - b * A.split_N;
+    const size_t plane = (size_t)A.split_B * A.split_Npad * A.split_C;
+    const size_t o = ((size_t)b * A.split_Npad + n) * A.split_C + col;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    A.split_planes[o] = hi;
+    A.split_planes[plane + o] = mid;
+    A.split_planes[2 * plane + o] = lo;
+  }
+}
+
+// Shared-memory layout.  fp32 weights: fp32 row panel As[BM][AS_LD] + Ws, FFMA main loop.
+// bf16 weights: the fp32 rows are split into three bf16 planes (v = hi + mid + lo to 24 bits) and the
+// main loop runs on tensor cores (mma.sync m16n8k16, fp32 accumulate): every product hi/mid/lo x w is
+// exact, so the result carries fp32-level accuracy while the FMA work leaves the CUDA cores.
+constexpr int PL_LD = KC + 8;   // plane row stride in bf16 (528 B: conflict-free 32-bit fragment loads)
+
+template <typename WT, int BM, int BN>
+struct LinSmem {
+  static constexpr bool TC = sizeof(WT) == 2;
+  static constexpr size_t panel_bytes = TC ? (size_t)3 * BM * PL_LD * 2 : (size_t)BM * AS_LD * 4;
+  static constexpr size_t w_bytes = (size_t)BN * WTile<WT>::LD * sizeof(WT);
+  static constexpr size_t red_bytes = TC ? (size_t)(NT / 32) * 32 * 4 * 4 : 0;
+  static constexpr size_t total = panel_bytes + w_bytes + red_bytes;
+};
 
 template <typename WT, int BM, int BN>
 __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
-  constexpr int TM = BM / (NT / 16);
-  constexpr int TN = BN / 16;
+  using SM = LinSmem<WT, BM, BN>;
   constexpr int WLD = WTile<WT>::LD;
   constexpr int EPV = 16 / sizeof(WT);           // elements per 16-byte cp.async
-  static_assert(TM >= 1 && TN >= 1, "tile too small");
   extern __shared__ __align__(16) uint8_t lin_smem[];
-  float(*As)[AS_LD] = reinterpret_cast<float(*)[AS_LD]>(lin_smem);
-  WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + sizeof(float) * BM * AS_LD);
+  float(*As)[AS_LD] = reinterpret_cast<float(*)[AS_LD]>(lin_smem);                 // fp32-weight path
+  __nv_bfloat16 *Pl = reinterpret_cast<__nv_bfloat16 *>(lin_smem);                 // bf16 path: [3][BM][PL_LD]
+  WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes);
+  float *red = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes);
 
   const int ks_total = batch.p[0].ksplit;
   const LinArgs &A = batch.p[blockIdx.z / ks_total];
@@ -210,24 +238,35 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
     return;
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tx = tid & 15, ty = tid >> 4;
 
   int kper = (A.K + ks_total - 1) / ks_total;
   kper = (kper + 31) / 32 * 32;
   const int kbeg = ks * kper, kend = min(A.K, kbeg + kper);
 
+  // FFMA path accumulators (fp32 weights)
+  constexpr int TM = BM / (NT / 16), TN = BN / 16;
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  // tensor-core path: 16x8 output tiles over the 8 warps (K split across warps when there are < 8 tiles)
+  constexpr int TILES_N = BN / 8, NTILES = (BM / 16) * TILES_N;
+  constexpr int KSW = NTILES >= 8 ? 1 : 8 / NTILES;      // warps sharing one tile along K
+  constexpr int TPW = NTILES >= 8 ? NTILES / 8 : 1;      // tiles per warp
+  float tacc[TPW][4];
+#pragma unroll
+  for (int t = 0; t < TPW; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tacc[t][e] = 0.f;
+  const int kh = KSW > 1 ? warp / NTILES : 0;
 
   const WT *Wp = reinterpret_cast<const WT *>(A.w);
   const uint32_t ws0 = (uint32_t)__cvta_generic_to_shared(&Ws[0][0]);
 
   for (int kc0 = kbeg; kc0 < kend; kc0 += KC) {
     const int kclen = min(KC, kend - kc0);
-    const int kpad = (kclen + 7) & ~7;
+    const int kpad = (kclen + 31) & ~31;
     // ---- weight tile: BN rows x kclen columns, all 16-byte pieces in flight at once (zero-filled
     //      beyond N / K).  Weights are never written inside the chain -> safe before the PDL wait.
     if (kpad == KC) {                  // common case: constant trip counts, no integer division
@@ -254,10 +293,10 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
       }
     }
     if (kc0 == kbeg) pdl_wait();     // everything below reads what the previous kernel produced
-    // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded).
-    //      Each warp owns RPW rows; the raw loads of all of them are issued before any reduction.
+    // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded to kpad).
+    //      Each warp owns RPW rows; the raw loads of GRP rows are issued before any reduction.
     {
-      constexpr int NW = NT / 32, RPW = BM / NW, GRP = 2;     // two rows' loads in flight per warp
+      constexpr int NW = NT / 32, RPW = BM / NW, GRP = 2;
       static_assert(BM % NW == 0 && RPW % GRP == 0, "rows per warp must be a multiple of the load group");
 #pragma unroll 1
       for (int q0 = 0; q0 < RPW; q0 += GRP) {
@@ -277,67 +316,123 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < KPL; ++i) v[i] = 0.f;
           }
+          if (SM::TC) {
 #pragma unroll
-          for (int i = 0; i < KPL; ++i) As[r][lane + 32 * i] = v[i];
-          if (A.side != nullptr && blockIdx.x == 0 && row < A.M) {
+            for (int p = 0; p < KPL / 2; ++p) {
+              const int k = kidx(lane, 2 * p);
+              uint32_t w3[3];
 #pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-              const int k = lane + 32 * i;
-              if (k < kclen) A.side[(size_t)row * A.ldside + kc0 + k] = v[i];
+              for (int t = 0; t < 3; ++t) w3[t] = 0u;
+              float x0 = v[2 * p], x1 = v[2 * p + 1];
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {          // hi, then the residuals
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                x0 -= __bfloat162float(h0);
+                x1 -= __bfloat162float(h1);
+                w3[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              }
+              if (k < kpad) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                  *reinterpret_cast<uint32_t *>(Pl + ((size_t)t * BM + r) * PL_LD + k) = w3[t];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < KPL / 2; ++p) {
+              const int k = kidx(lane, 2 * p);
+              *reinterpret_cast<float2 *>(&As[r][k]) = make_float2(v[2 * p], v[2 * p + 1]);
             }
           }
+          if (A.side != nullptr && blockIdx.x == 0 && row < A.M)
+            store_pairs(A.side + (size_t)row * A.ldside + kc0, kclen, lane, v);
         }
       }
     }
     cp_async_wait_all();
     __syncthreads();
     if (kc0 + KC >= kend) pdl_trigger();   // last chunk staged: let the next kernel start its prefetch
+    if (SM::TC) {
+      const int g = lane >> 2, t4 = lane & 3;
+      const int nsteps = kpad / 16;
+      const int s_beg = kh * nsteps / KSW, s_end = (kh + 1) * nsteps / KSW;
+#pragma unroll
+      for (int tt = 0; tt < TPW; ++tt) {
+        const int tile = KSW > 1 ? warp % NTILES : warp * TPW + tt;
+        const int tm = tile / TILES_N, tn = tile - tm * TILES_N;
+        const __nv_bfloat16 *wrow = reinterpret_cast<const __nv_bfloat16 *>(&Ws[tn * 8 + g][0]) + 2 * t4;
+        const __nv_bfloat16 *prow = Pl + (size_t)(tm * 16 + g) * PL_LD + 2 * t4;
 #pragma unroll 2
-    for (int kk = 0; kk < kpad; kk += 8) {
-      float a[TM][8], b[TN][8];
+        for (int st = s_beg; st < s_end; ++st) {
+          const int k0 = st * 16;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t *>(wrow + k0);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t *>(wrow + k0 + 8);
 #pragma unroll
-      for (int i = 0; i < TM; ++i) load8(&As[ty + (NT / 16) * i][kk], a[i]);
+          for (int t = 0; t < 3; ++t) {
+            const __nv_bfloat16 *pp = prow + (size_t)t * BM * PL_LD + k0;
+            uint32_t a[4];
+            a[0] = *reinterpret_cast<const uint32_t *>(pp);
+            a[1] = *reinterpret_cast<const uint32_t *>(pp + 8 * PL_LD);
+            a[2] = *reinterpret_cast<const uint32_t *>(pp + 8);
+            a[3] = *reinterpret_cast<const uint32_t *>(pp + 8 * PL_LD + 8);
+            mma_bf16_16816(tacc[tt], a, b0, b1);
+          }
+        }
+      }
+    } else {
+      const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll 2
+      for (int kk = 0; kk < kpad; kk += 8) {
+        float a[TM][8], b[TN][8];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) load8(&Ws[tx + 16 * j][kk], b[j]);
+        for (int i = 0; i < TM; ++i) load8(&As[ty + (NT / 16) * i][kk], a[i]);
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+        for (int j = 0; j < TN; ++j) load8(reinterpret_cast<const WT *>(&Ws[tx + 16 * j][kk]), b[j]);
 #pragma unroll
-        for (int j = 0; j < TN; ++j)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[i][j] = fmaf(a[i][e], b[j][e], acc[i][j]);
+          for (int j = 0; j < TN; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][j] = fmaf(a[i][e], b[j][e], acc[i][j]);
+      }
     }
     if (kc0 + KC < kend) __syncthreads();
   }
 
   float *outp = A.out + (size_t)ks * A.out_split_stride;
+  if (SM::TC) {
+    if (KSW > 1) {     // fold the K-halves: warps kh > 0 hand their fragments to the kh == 0 warp of the tile
+      if (kh > 0) {
 #pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int row = row0 + ty + (NT / 16) * i;
-    if (row >= A.M) continue;
-    const float rs = (A.epi & EPI_ROWSCALE) ? __ldg(A.rowscale + row) : 1.f;
+        for (int e = 0; e < 4; ++e) red[(warp * 32 + lane) * 4 + e] = tacc[0][e];
+      }
+      __syncthreads();
+      if (kh == 0) {
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int col = col0 + tx + 16 * j;
-      if (col >= A.N) continue;
-      float v = acc[i][j];
-      if (A.epi & EPI_BIAS) v += rs * __ldg(A.bias + col);
-      if (A.epi & EPI_RES) v += __ldg(A.res + (size_t)row * A.ldres + col);
-      if (A.epi & EPI_RELU) v = fmaxf(v, 0.f);
-      outp[(size_t)row * A.ldo + col] = v;
-      if ((A.epi & EPI_SPLIT3) && col < A.split_C) {
-        // v == hi + mid + lo to 24 bits; every bf16 x bf16 product in the mask conv is then exact
-        const int b = row / A.split_N, n = row - b * A.split_N;
-        const size_t plane = (size_t)A.split_B * A.split_Npad * A.split_C;
-        const size_t o = ((size_t)b * A.split_Npad + n) * A.split_C + col;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(hi);
-        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-        A.split_planes[o] = hi;
-        A.split_planes[plane + o] = mid;
-        A.split_planes[2 * plane + o] = lo;
+        for (int o = 1; o < KSW; ++o)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tacc[0][e] += red[((warp + o * NTILES) * 32 + lane) * 4 + e];
       }
     }
+    if (kh == 0) {
+      const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+      for (int tt = 0; tt < TPW; ++tt) {
+        const int tile = KSW > 1 ? warp % NTILES : warp * TPW + tt;
+        const int tm = tile / TILES_N, tn = tile - tm * TILES_N;
+        const int r = row0 + tm * 16 + g, c = col0 + tn * 8 + 2 * t4;
+        lin_epilogue(A, outp, r, c, tacc[tt][0]);
+        lin_epilogue(A, outp, r, c + 1, tacc[tt][1]);
+        lin_epilogue(A, outp, r + 8, c, tacc[tt][2]);
+        lin_epilogue(A, outp, r + 8, c + 1, tacc[tt][3]);
+      }
+    }
+  } else {
+    const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) lin_epilogue(A, outp, row0 + ty + (NT / 16) * i, col0 + tx + 16 * j, acc[i][j]);
   }
 }
 
@@ -349,7 +444,7 @@ static int check_src(const RowSrc &s, int K) {
 
 template <typename WT, int BM, int BN>
 static int launch_linear_t(const LinBatch &b, dim3 grid, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * BM * AS_LD + sizeof(WT) * BN * WTile<WT>::LD;
+  const size_t smem = LinSmem<WT, BM, BN>::total;
   static bool attr = false;
   if (!attr) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
