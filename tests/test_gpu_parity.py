@@ -398,3 +398,31 @@ def test_profile_hooks_and_launch_count(dev):
         h(x, pf, mask)
     assert _lib.launch_count() - n0 == len(p.records) >= 10
     assert all(name.startswith('vkn_') and ms >= 0 for name, ms in p.records)
+
+
+def test_frames_in_flight_graph_matches_single_frame_loop(dev):
+    """FramesInFlight (branches x batch in ONE graph, optional in-graph host I/O) == per-frame loop results."""
+    import vknet
+    cfg = ko.default_cfg(num_classes=19, in_channels=64, feedforward_channels=128)
+    sds = [ko.random_state_dict(cfg, seed=s) for s in range(2)]
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev)
+    loop = vknet.KernelIterLoop(heads)
+    branches, batch = 3, 2
+    ins = []
+    for b in range(branches):
+        parts = [ko.dummy_inputs(1, 20, 64, 16, 24, seed=10 * b + i) for i in range(batch)]
+        ins.append(tuple(torch.cat(p) for p in zip(*parts)))
+    want = [[t.clone() for t in loop(*(u.to(dev) for u in bt))] for bt in ins]
+    fif = vknet.FramesInFlight(heads, branches=branches, batch=batch).capture([tuple(u.to(dev) for u in bt) for bt in ins])
+    got = fif.replay()
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1]) and torch.equal(w[2].reshape(g[2].shape), g[2])
+    pinned = [tuple(u.pin_memory() for u in bt) for bt in ins]
+    hf = vknet.FramesInFlight(heads, branches=branches, batch=batch).capture(pinned, host_io=True)
+    for p in pinned:                      # new host contents are picked up by the next replay
+        p[0].mul_(1.0)
+    hf.replay()
+    torch.cuda.synchronize()
+    for w, ho in zip(want, hf.host_out):
+        assert torch.equal(w[0].cpu(), ho[0]) and torch.equal(w[1].cpu(), ho[1])

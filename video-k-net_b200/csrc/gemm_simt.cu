@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
   const int nsl = nchunks * F;
   pdl_wait();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto slice = [&](int sl) -> size_t {       // slice (chunk, f) of set b
+  auto slice = [&](int sl) -> size_t {       // slice (chunk, f) of set b -> frame-slice index in the partials
+    if (F == 1) return (size_t)sl * B + b;
     const int ch = sl / F, f = sl - ch * F;
     return ((size_t)ch * B * F + (size_t)b * F + f);
   };
@@ -167,11 +168,28 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
     }
     *reinterpret_cast<float4 *>(xp0 + (size_t)b * NC + idx) = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
   }
-  const int ci = blockIdx.x * 256 + threadIdx.x;     // the first ceil(N/256) CTAs of a set also reduce its pixel counts
-  if (ci < N) {
-    float s0 = 0.f;
-    for (int sl = 0; sl < nsl; ++sl) s0 += __ldg(cnt_partials + slice(sl) * N + ci);
-    cnt[(size_t)b * N + ci] = s0 * scale;
+  // pixel counts of the set: CTAs x < ceil(N/32) each own 32 kernels; warp w sums slices w, w+8, ...
+  // (lane = kernel), then the 8 warp sums are combined in fixed order.
+  __shared__ float cred[8][32];
+  const int n = blockIdx.x * 32 + lane;
+  if (blockIdx.x * 32 < N) {
+    float c0 = 0.f, c1 = 0.f;
+    if (n < N) {
+      int sl = warp;
+      for (; sl + 8 < nsl; sl += 16) {
+        c0 += __ldg(cnt_partials + slice(sl) * N + n);
+        c1 += __ldg(cnt_partials + slice(sl + 8) * N + n);
+      }
+      if (sl < nsl) c0 += __ldg(cnt_partials + slice(sl) * N + n);
+    }
+    cred[warp][lane] = c0 + c1;
+    __syncthreads();
+    if (warp == 0 && n < N) {
+      float t = cred[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += cred[w][lane];
+      cnt[(size_t)b * N + n] = t * scale;
+    }
   }
 }
 
@@ -181,7 +199,7 @@ int launch_pool_reduce(const VknShape &s, const float *partials, const float *cn
   const int NC = s.N * s.C;
   VKN_LAUNCH_MARK("vkn_pool_reduce_kernel", stream);
   int gx = ceil_div(NC, 128);
-  if (gx < ceil_div(s.N, 256)) gx = ceil_div(s.N, 256);
+  if (gx < ceil_div(s.N, 32)) gx = ceil_div(s.N, 32);
   VKN_CUDA_OK(launch_chain(vkn_pool_reduce_kernel, dim3(gx, s.B), dim3(256), 0, stream, partials, cnt_partials, nchunks,
                            s.B, F, s.N, NC, 1.0f / (float)F, xp0, cnt));
   return VKN_OK;

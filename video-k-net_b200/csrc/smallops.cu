@@ -45,8 +45,8 @@ __device__ __forceinline__ void ln_inplace(float (&v)[KPL], int K, int lane, con
   for (int p = 0; p < KPL / 2; ++p) {
     const int k = kidx(lane, 2 * p);
     if (k < K) {
-      const float2 gg = __ldg(reinterpret_cast<const float2 *>(g + k));
-      const float2 bb = __ldg(reinterpret_cast<const float2 *>(b + k));
+      const float2 gg = *reinterpret_cast<const float2 *>(g + k);     // global or shared (generic load)
+      const float2 bb = *reinterpret_cast<const float2 *>(b + k);
       v[2 * p] = (v[2 * p] - mean) * rstd * gg.x + bb.x;
       v[2 * p + 1] = (v[2 * p + 1] - mean) * rstd * gg.y + bb.y;
     }
@@ -110,17 +110,19 @@ __device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int k
   if (s.pres) fetch_pairs<true>(s.pres + (size_t)row * s.ldpres + k0, klen, lane, v);
 }
 
-__device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, RowRaw &r, float (&v)[KPL]) {
+// lnv: optional shared-memory copy of the LayerNorm vectors ([i] gamma at lnv + i*KC, beta at lnv + (4+i)*KC)
+__device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, RowRaw &r, float (&v)[KPL],
+                                           const float *lnv = nullptr) {
   if (s.pro == PRO_MUL) {
 #pragma unroll
     for (int i = 0; i < KPL; ++i) v[i] = r.v[0][i] * r.v[1][i];
     return;
   }
   if (s.pro == PRO_GATE) {
-    ln_inplace(r.v[0], klen, lane, s.ln_g[0], s.ln_b[0]);
-    ln_inplace(r.v[1], klen, lane, s.ln_g[1], s.ln_b[1]);
-    ln_inplace(r.v[2], klen, lane, s.ln_g[2], s.ln_b[2]);
-    ln_inplace(r.v[3], klen, lane, s.ln_g[3], s.ln_b[3]);
+    ln_inplace(r.v[0], klen, lane, lnv ? lnv + 0 * KC : s.ln_g[0], lnv ? lnv + 4 * KC : s.ln_b[0]);
+    ln_inplace(r.v[1], klen, lane, lnv ? lnv + 1 * KC : s.ln_g[1], lnv ? lnv + 5 * KC : s.ln_b[1]);
+    ln_inplace(r.v[2], klen, lane, lnv ? lnv + 2 * KC : s.ln_g[2], lnv ? lnv + 6 * KC : s.ln_b[2]);
+    ln_inplace(r.v[3], klen, lane, lnv ? lnv + 3 * KC : s.ln_g[3], lnv ? lnv + 7 * KC : s.ln_b[3]);
 #pragma unroll
     for (int i = 0; i < KPL; ++i)
       v[i] = (kidx(lane, i) < klen) ? sigmoidf_(r.v[0][i]) * r.v[1][i] + sigmoidf_(r.v[2][i]) * r.v[3][i] : 0.f;
@@ -129,7 +131,7 @@ __device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, 
 #pragma unroll
   for (int i = 0; i < KPL; ++i) v[i] = r.v[0][i];
   if (s.pro == PRO_LN || s.pro == PRO_LN_RELU) {
-    ln_inplace(v, klen, lane, s.ln_g[0], s.ln_b[0]);
+    ln_inplace(v, klen, lane, lnv ? lnv : s.ln_g[0], lnv ? lnv + 4 * KC : s.ln_b[0]);
     if (s.pro == PRO_LN_RELU) {
 #pragma unroll
       for (int i = 0; i < KPL; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -182,9 +184,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void lin_epilogue(const LinArgs &A, float *outp, int row, int col, float v) {
+__device__ __forceinline__ void lin_epilogue(const LinArgs &A, float *outp, const float *bias_s, int col0, int row, int col,
+                                             float v) {
   if (row >= A.M || col >= A.N) return;
-  if (A.epi & EPI_BIAS) v += ((A.epi & EPI_ROWSCALE) ? __ldg(A.rowscale + row) : 1.f) * __ldg(A.bias + col);
+  if (A.epi & EPI_BIAS) v += ((A.epi & EPI_ROWSCALE) ? __ldg(A.rowscale + row) : 1.f) * bias_s[col - col0];
   if (A.epi & EPI_RES) v += __ldg(A.res + (size_t)row * A.ldres + col);
   if (A.epi & EPI_RELU) v = fmaxf(v, 0.f);
   outp[(size_t)row * A.ldo + col] = v;
@@ -215,7 +218,8 @@ struct LinSmem {
   static constexpr size_t panel_bytes = TC ? (size_t)3 * BM * PL_LD * 2 : (size_t)BM * AS_LD * 4;
   static constexpr size_t w_bytes = (size_t)BN * WTile<WT>::LD * sizeof(WT);
   static constexpr size_t red_bytes = TC ? (size_t)(NT / 32) * 32 * 4 * 4 : 0;
-  static constexpr size_t total = panel_bytes + w_bytes + red_bytes;
+  static constexpr size_t vec_bytes = (size_t)(9 * KC + BN) * 4;   // LN gamma/beta x4, pre-LN bias, epilogue bias
+  static constexpr size_t total = panel_bytes + w_bytes + red_bytes + vec_bytes;
 };
 
 template <typename WT, int BM, int BN>
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
   __nv_bfloat16 *Pl = reinterpret_cast<__nv_bfloat16 *>(lin_smem);                 // bf16 path: [3][BM][PL_LD]
   WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes);
   float *red = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes);
+  float *vecs = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes + SM::red_bytes);   // [9][KC] + [BN]
 
   const int ks_total = batch.p[0].ksplit;
   const LinArgs &A = batch.p[blockIdx.z / ks_total];
@@ -264,6 +269,30 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
   const WT *Wp = reinterpret_cast<const WT *>(A.w);
   const uint32_t ws0 = (uint32_t)__cvta_generic_to_shared(&Ws[0][0]);
 
+  // ---- parameter vectors (LayerNorm affine, biases) are weights too: stage them in shared memory before the
+  //      PDL wait so that no dependent global round trip is left inside the LN / epilogue code.
+  const RowSrc &S = A.src;
+  {
+    const uint32_t v0 = (uint32_t)__cvta_generic_to_shared(vecs);
+    const int nln = (S.pro == PRO_GATE) ? 4 : ((S.pro == PRO_LN || S.pro == PRO_LN_RELU) ? 1 : 0);
+    const int kq = min(A.K, KC) / 4;                       // 16-byte pieces per vector (LN modes have K <= KC)
+    for (int idx = tid; idx < nln * 2 * kq; idx += NT) {
+      const int vsel = idx / kq, pc = idx - vsel * kq;     // vsel: 0..nln-1 gamma, nln..2nln-1 beta
+      const float *src = (vsel < nln ? S.ln_g[vsel] : S.ln_b[vsel - nln]) + pc * 4;
+      const int slot = vsel < nln ? vsel : 4 + (vsel - nln);
+      cp_async16(v0 + (uint32_t)(slot * KC + pc * 4) * 4u, src, 16u);
+    }
+    if (A.epi & EPI_BIAS) {
+      for (int pc = tid; pc < BN / 4; pc += NT) {
+        const int c = col0 + pc * 4;
+        const int valid = c < A.N ? min(4, A.N - c) : 0;
+        cp_async16(v0 + (uint32_t)(9 * KC + pc * 4) * 4u, valid ? A.bias + c : A.bias, (uint32_t)valid * 4u);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");      // group "vectors" (older than the weight tile group)
+  }
+  const float *bias_s = vecs + 9 * KC;
+
   for (int kc0 = kbeg; kc0 < kend; kc0 += KC) {
     const int kclen = min(KC, kend - kc0);
     const int kpad = (kclen + 31) & ~31;
@@ -292,7 +321,12 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
         cp_async16(ws0 + (uint32_t)(n * WLD + pc * EPV) * (uint32_t)sizeof(WT), src, (uint32_t)(valid * sizeof(WT)));
       }
     }
-    if (kc0 == kbeg) pdl_wait();     // everything below reads what the previous kernel produced
+    asm volatile("cp.async.commit_group;" ::: "memory");      // group "weight tile"
+    if (kc0 == kbeg) {
+      pdl_wait();                    // everything below reads what the previous kernel produced
+      asm volatile("cp.async.wait_group 1;" ::: "memory");     // the vector group has landed (tile may be in flight)
+      __syncthreads();
+    }
     // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded to kpad).
     //      Each warp owns RPW rows; the raw loads of GRP rows are issued before any reduction.
     {
@@ -304,14 +338,14 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
 #pragma unroll
         for (int q = 0; q < GRP; ++q) {
           const int row = row0 + warp + NW * (q0 + q);
-          if (row < A.M) row_load(A.src, row, kc0, kclen, lane, raw[q]);
+          if (row < A.M) row_load(S, row, kc0, kclen, lane, raw[q]);
         }
 #pragma unroll
         for (int q = 0; q < GRP; ++q) {
           const int r = warp + NW * (q0 + q), row = row0 + r;
           float v[KPL];
           if (row < A.M) {
-            row_finish(A.src, kclen, lane, raw[q], v);
+            row_finish(S, kclen, lane, raw[q], v, vecs);
           } else {
 #pragma unroll
             for (int i = 0; i < KPL; ++i) v[i] = 0.f;
@@ -421,10 +455,10 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
         const int tile = KSW > 1 ? warp % NTILES : warp * TPW + tt;
         const int tm = tile / TILES_N, tn = tile - tm * TILES_N;
         const int r = row0 + tm * 16 + g, c = col0 + tn * 8 + 2 * t4;
-        lin_epilogue(A, outp, r, c, tacc[tt][0]);
-        lin_epilogue(A, outp, r, c + 1, tacc[tt][1]);
-        lin_epilogue(A, outp, r + 8, c, tacc[tt][2]);
-        lin_epilogue(A, outp, r + 8, c + 1, tacc[tt][3]);
+        lin_epilogue(A, outp, bias_s, col0, r, c, tacc[tt][0]);
+        lin_epilogue(A, outp, bias_s, col0, r, c + 1, tacc[tt][1]);
+        lin_epilogue(A, outp, bias_s, col0, r + 8, c, tacc[tt][2]);
+        lin_epilogue(A, outp, bias_s, col0, r + 8, c + 1, tacc[tt][3]);
       }
     }
   } else {
@@ -432,7 +466,7 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) lin_epilogue(A, outp, row0 + ty + (NT / 16) * i, col0 + tx + 16 * j, acc[i][j]);
+      for (int j = 0; j < TN; ++j) lin_epilogue(A, outp, bias_s, col0, row0 + ty + (NT / 16) * i, col0 + tx + 16 * j, acc[i][j]);
   }
 }
 
