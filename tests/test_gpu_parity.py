@@ -426,3 +426,25 @@ def test_frames_in_flight_graph_matches_single_frame_loop(dev):
     torch.cuda.synchronize()
     for w, ho in zip(want, hf.host_out):
         assert torch.equal(w[0].cpu(), ho[0]) and torch.equal(w[1].cpu(), ho[1])
+
+
+def test_persistent_mask_conv_equals_tiled_mask_conv(dev, monkeypatch):
+    """The persistent (resident-planes) tcgen05 mask conv issues the same MMAs per tile as the one-tile-per-CTA
+    kernel, so their outputs must be bit-identical; both are exercised on a ragged last tile."""
+    from vknet import _lib, ops
+    B, N, C, H, W = 3, 100, 256, 40, 52          # HW = 2080 = 16 tiles + a 32-pixel tail
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=4))
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    h.engine = _lib.ENGINE_TC
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=3)
+    xb = x.to(dev).bfloat16()
+    mk = torch.randn(B, N, C, generator=torch.Generator().manual_seed(1)).to(dev)
+    monkeypatch.setenv('VKN_MASK_PERSIST', '0')
+    a = ops.mask_gemm(h, xb, mk).clone()
+    monkeypatch.setenv('VKN_MASK_PERSIST', '1')
+    b = ops.mask_gemm(h, xb, mk).clone()
+    assert torch.equal(a, b)
+    xt = ko._feat_transform(sd, ko.round_bf16(x))
+    want = torch.einsum('bnc,bchw->bnhw', mk.cpu(), xt)
+    assert (b.float().cpu() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()

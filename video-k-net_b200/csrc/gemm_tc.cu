@@ -273,19 +273,26 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
     float cnt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cnt[i] = 0.f;
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % POOL_STAGES;
-      const uint32_t ph = (uint32_t)(it / POOL_STAGES) & 1u;
-      mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
-      uint8_t *mt = smem + s * stage_bytes + x_bytes;
+    // software pipeline: the mask logits of block it+1 are requested before block it is thresholded, so
+    // the global-load latency of every block but the first is hidden behind the previous one
+    uint4 raw[8], nxt[8] = {};
+    auto load_block = [&](int it, uint4 (&dst)[8]) {
       const int p = (blk_beg + it) * PX_BLK + j * 8;
-      uint4 raw[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int n = mtile * 128 + rbase + 16 * i;
-        raw[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (n < N && p < HW) raw[i] = __ldg(reinterpret_cast<const uint4 *>(mb + (size_t)n * HW + p));
+        dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (n < N && p < HW) dst[i] = __ldg(reinterpret_cast<const uint4 *>(mb + (size_t)n * HW + p));
       }
+    };
+    load_block(0, raw);
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % POOL_STAGES;
+      const uint32_t ph = (uint32_t)(it / POOL_STAGES) & 1u;
+      if (it + 1 < nk) load_block(it + 1, nxt);
+      mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
+      uint8_t *mt = smem + s * stage_bytes + x_bytes;
+      const int p = (blk_beg + it) * PX_BLK + j * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rbase + 16 * i;
@@ -308,6 +315,8 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
       fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8 * s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) raw[i] = nxt[i];
     }
     // ---- epilogue: accumulators -> partial sums -----------------------------------------------
     mbar_wait(bar0 + 16 * POOL_STAGES, 0);
@@ -508,6 +517,153 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   }
 }
 
+// ---- mask conv, persistent form for frame batches ------------------------------------------------------
+// When a launch holds several pixel tiles per SM (frame batches / clips), re-streaming the kernel planes for
+// every tile (172 KB at N=100) costs ~3x the x traffic.  Here a CTA owns ONE frame's planes -- all three
+// bf16 planes x all K chunks stay resident in shared memory -- and walks that frame's pixel tiles:
+// only x streams (2-stage TMA ring), accumulators are double-buffered in TMEM so the tensor core works on
+// tile i+1 while the epilogue warps drain tile i.  Requires Npad <= 112 (planes + ring must fit 227 KB).
+constexpr int MP_XS = 2;      // x ring depth
+constexpr int MP_ACC = 2;     // TMEM accumulator buffers (128 columns each)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
+                               const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
+                               int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nk = C / CH_BLK;
+  const uint32_t x_bytes = (uint32_t)CH_BLK * MASK_TILE_P * 2u;         // 16 KB
+  const uint32_t a_plane = (uint32_t)Npad * 128u;                       // one plane, one 64-channel chunk
+  const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
+  uint8_t *xring = smem + planes_bytes;                                 // (planes_bytes is a multiple of 1024)
+  uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 4 warps x 2560 B
+  uint64_t *bars = (uint64_t *)(stg_base + 4 * 32 * 40 * 2);
+  const uint32_t bar0 = smem_u32(bars);
+  // barriers: 0 planes_full | 1..2 x_full | 3..4 x_empty | 5..6 acc_full | 7..8 acc_empty
+  uint32_t *tmem_slot = (uint32_t *)(bars + 9);
+  float *bias_s = (float *)(tmem_slot + 2);
+  const uint32_t smem0 = smem_u32(smem), xring0 = smem_u32(xring);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, kb = b / F;
+  const int ntiles = (HW + MASK_TILE_P - 1) / MASK_TILE_P;
+  const int cpf = gridDim.x;                                            // CTAs per frame
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_x);
+      prefetch_tmap(&tmap_a);
+      mbar_init(bar0, 1);
+      for (int s = 0; s < MP_XS; ++s) {
+        mbar_init(bar0 + 8 * (1 + s), 1);
+        mbar_init(bar0 + 8 * (3 + s), 1);
+      }
+      for (int a = 0; a < MP_ACC; ++a) {
+        mbar_init(bar0 + 8 * (5 + a), 1);
+        mbar_init(bar0 + 8 * (7 + a), 4);                               // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 128u * MP_ACC);
+  }
+  pdl_wait();     // a_ext / the planes come from the previous kernel
+  for (int n = threadIdx.x; n < ((Npad + 31) & ~31); n += TC_THREADS)
+    bias_s[n] = (n < N) ? a_ext[((size_t)kb * N + n) * lda + C] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar0, planes_bytes);
+      for (int c = 0; c < nk; ++c)
+        for (int t = 0; t < 3; ++t)
+          tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += cpf) {
+        const int p0 = tile * MASK_TILE_P;
+        for (int c = 0; c < nk; ++c, ++it) {
+          const int s = it % MP_XS;
+          const uint32_t ph = (uint32_t)(it / MP_XS) & 1u;
+          mbar_wait(bar0 + 8 * (3 + s), ph ^ 1u);
+          mbar_expect_tx(bar0 + 8 * (1 + s), x_bytes);
+          tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (1 + s), p0, c * CH_BLK, b);
+          tma_load_3d(xring0 + s * x_bytes + x_bytes / 2, &tmap_x, bar0 + 8 * (1 + s), p0 + 64, c * CH_BLK, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar0, 0);
+      int it = 0, li = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
+        const int buf = li % MP_ACC;
+        mbar_wait(bar0 + 8 * (7 + buf), ((uint32_t)(li / MP_ACC) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t dt = tmem_base + (uint32_t)buf * 128u;
+        for (int c = 0; c < nk; ++c, ++it) {
+          const int s = it % MP_XS;
+          mbar_wait(bar0 + 8 * (1 + s), (uint32_t)(it / MP_XS) & 1u);
+          tc_fence_after();
+          const uint32_t xs = xring0 + s * x_bytes;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#pragma unroll
+            for (int k = 0; k < CH_BLK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(xs + k * 2048, x_lbo, x_sbo);
+              const uint64_t bd = umma_desc_sw128(smem0 + (uint32_t)(c * 3 + t) * a_plane + k * 32, 0, 1024);
+              umma_bf16(dt, ad, bd, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar0 + 8 * (3 + s));
+        }
+        umma_commit(bar0 + 8 * (5 + buf));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    __nv_bfloat16 *stg = reinterpret_cast<__nv_bfloat16 *>(stg_base) + (size_t)q * 32 * 40;
+    __nv_bfloat16 *ob = out + (size_t)b * N * HW;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
+      const int buf = li % MP_ACC;
+      mbar_wait(bar0 + 8 * (5 + buf), (uint32_t)(li / MP_ACC) & 1u);
+      tc_fence_after();
+      if (tile + cpf >= ntiles) pdl_trigger();
+      const int pw = tile * MASK_TILE_P + q * 32;
+      for (int n0 = 0; n0 < Npad; n0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + n0), r);
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          stg[e * 40 + lane] = __float2bfloat16_rn(__uint_as_float(r[e]) + bias_s[n0 + e]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int nl = it * 8 + (lane >> 2), seg = lane & 3;
+          const int n = n0 + nl, p = pw + seg * 8;
+          if (n < N && p < HW) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(stg + nl * 40 + seg * 8);
+            *reinterpret_cast<uint4 *>(ob + (size_t)n * HW + p) = v;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();                 // this warp's TMEM reads of `buf` are done
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (7 + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128u * MP_ACC);
+  }
+}
+
 int maskgemm_tc_npad(const VknShape &s) { return npad_of(s.N); }
 
 int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws, void *out,
@@ -541,6 +697,27 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   uint32_t x_lbo = (uint32_t)CH_BLK * 128u, x_sbo = 1024u;
   if (const char *e = getenv("VKN_DEBUG_SWAP_LBO_SBO")) {
     if (e[0] == '1') { uint32_t t = x_lbo; x_lbo = x_sbo; x_sbo = t; }
+  }
+  const int ntiles = ceil_div(HW, MASK_TILE_P), frames = s.B * F;
+  bool persist = Npad <= 112 && ntiles * frames >= 2 * 148;      // several tiles per SM: keep the planes resident
+  if (const char *e = getenv("VKN_MASK_PERSIST")) persist = (e[0] == '1') && Npad <= 112;
+  if (persist) {
+    int cpf = 148 / frames;
+    if (cpf < 1) cpf = 1;
+    if (cpf > ntiles) cpf = ntiles;
+    const size_t psmem = (size_t)(s.C / CH_BLK) * 3 * Npad * 128 + MP_XS * (size_t)CH_BLK * MASK_TILE_P * 2 + 4 * 32 * 40 * 2 +
+                         9 * 8 + 16 + (size_t)(Npad + 32) * 4 + 1024 + 64;
+    static bool pattr = false;
+    if (!pattr) {
+      VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      pattr = true;
+    }
+    if (psmem > 227 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "persistent mask conv: shared memory %zu exceeds 227 KB", psmem);
+    VKN_LAUNCH_MARK("vkn_maskgemm_tc_persist_kernel", stream);
+    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(cpf, 1, frames), dim3(TC_THREADS), psmem, stream, tmx, tma,
+                             a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
+                             x_lbo, x_sbo, F));
+    return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);
   VKN_LAUNCH_MARK("vkn_maskgemm_tc_kernel", stream);

@@ -259,11 +259,16 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
   constexpr int TILES_N = BN / 8, NTILES = (BM / 16) * TILES_N;
   constexpr int KSW = NTILES >= 8 ? 1 : 8 / NTILES;      // warps sharing one tile along K
   constexpr int TPW = NTILES >= 8 ? NTILES / 8 : 1;      // tiles per warp
-  float tacc[TPW][4];
+  float tacc[TPW][4];          // final accumulators
+  float pacc[TPW][3][4];       // one independent MMA chain per bf16 plane (hi / mid / lo)
 #pragma unroll
   for (int t = 0; t < TPW; ++t)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) tacc[t][e] = 0.f;
+    for (int e = 0; e < 4; ++e) {
+      tacc[t][e] = 0.f;
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) pacc[t][pl][e] = 0.f;
+    }
   const int kh = KSW > 1 ? warp / NTILES : 0;
 
   const WT *Wp = reinterpret_cast<const WT *>(A.w);
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
             a[1] = *reinterpret_cast<const uint32_t *>(pp + 8 * PL_LD);
             a[2] = *reinterpret_cast<const uint32_t *>(pp + 8);
             a[3] = *reinterpret_cast<const uint32_t *>(pp + 8 * PL_LD + 8);
-            mma_bf16_16816(tacc[tt], a, b0, b1);
+            mma_bf16_16816(pacc[tt][t], a, b0, b1);
           }
         }
       }
@@ -435,6 +440,10 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
 
   float *outp = A.out + (size_t)ks * A.out_split_stride;
   if (SM::TC) {
+#pragma unroll
+    for (int t = 0; t < TPW; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tacc[t][e] = (pacc[t][2][e] + pacc[t][1][e]) + pacc[t][0][e];   // small terms first
     if (KSW > 1) {     // fold the K-halves: warps kh > 0 hand their fragments to the kh == 0 warp of the tile
       if (kh > 0) {
 #pragma unroll
@@ -506,11 +515,11 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
   const int ks = b.p[0].ksplit;
   // tile choice: wide outputs get the 32x64 tile, the C x C layers the 16x32 tile (more CTAs in flight)
   const bool big = maxN >= 1024;
-  VKN_LAUNCH_MARK(big ? "vkn_linear_kernel<32x64>" : "vkn_linear_kernel<16x32>", stream);
-  if (big) {
-    dim3 grid(ceil_div(maxN, 64), ceil_div(maxM, 32), nprob * ks);
-    if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 32, 64>(b, grid, stream);
-    return launch_linear_t<float, 32, 64>(b, grid, stream);
+  VKN_LAUNCH_MARK(big ? "vkn_linear_kernel<16x64>" : "vkn_linear_kernel<16x32>", stream);
+  if (big) {       // 16 x 64: eight 16x8 tensor-core tiles = one per warp over the full K; 224 CTAs for FFN layer 1
+    dim3 grid(ceil_div(maxN, 64), ceil_div(maxM, 16), nprob * ks);
+    if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 16, 64>(b, grid, stream);
+    return launch_linear_t<float, 16, 64>(b, grid, stream);
   }
   dim3 grid(ceil_div(maxN, 32), ceil_div(maxM, 16), nprob * ks);
   if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 16, 32>(b, grid, stream);
