@@ -76,22 +76,27 @@ __device__ __forceinline__ void fetch_pairs(const float *a, int klen, int lane, 
 //   row_load  : raw values of up to 4 sources -> registers (sum of slices + bias + residual folded in)
 //   row_finish: LN / ReLU / gate arithmetic (warp-shuffle reductions)
 // LN-type modes require k0 == 0 and klen == K (host-checked).
-struct RowRaw {
-  float v[4][KPL];
+template <int NSRC>
+struct RowRawT {
+  float v[NSRC][KPL];
 };
+using RowRaw = RowRawT<4>;
 
-__device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int klen, int lane, RowRaw &r) {
+template <int NSRC>
+__device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int klen, int lane, RowRawT<NSRC> &r) {
   if (s.pro == PRO_MUL) {
     fetch_pairs<false>(s.a[0] + (size_t)row * s.lda[0] + k0, klen, lane, r.v[0]);
     fetch_pairs<false>(s.a[1] + (size_t)row * s.lda[1] + k0, klen, lane, r.v[1]);
     return;
   }
-  if (s.pro == PRO_GATE) {
-    fetch_pairs<false>(s.a[0] + (size_t)row * s.lda[0], klen, lane, r.v[0]);   // update gate pre-activation
-    fetch_pairs<false>(s.a[1] + (size_t)row * s.lda[1], klen, lane, r.v[1]);   // param_out
-    fetch_pairs<false>(s.a[2] + (size_t)row * s.lda[2], klen, lane, r.v[2]);   // input gate pre-activation
-    fetch_pairs<false>(s.a[3] + (size_t)row * s.lda[3], klen, lane, r.v[3]);   // input_out
-    return;
+  if constexpr (NSRC == 4) {
+    if (s.pro == PRO_GATE) {
+      fetch_pairs<false>(s.a[0] + (size_t)row * s.lda[0], klen, lane, r.v[0]);   // update gate pre-activation
+      fetch_pairs<false>(s.a[1] + (size_t)row * s.lda[1], klen, lane, r.v[1]);   // param_out
+      fetch_pairs<false>(s.a[2] + (size_t)row * s.lda[2], klen, lane, r.v[2]);   // input gate pre-activation
+      fetch_pairs<false>(s.a[3] + (size_t)row * s.lda[3], klen, lane, r.v[3]);   // input_out
+      return;
+    }
   }
   // PRO_COPY / PRO_LN / PRO_LN_RELU: fixed-order sum of slices (+ bias + residual)
   float(&v)[KPL] = r.v[0];
@@ -111,13 +116,15 @@ __device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int k
 }
 
 // lnv: optional shared-memory copy of the LayerNorm vectors ([i] gamma at lnv + i*KC, beta at lnv + (4+i)*KC)
-__device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, RowRaw &r, float (&v)[KPL],
+template <int NSRC>
+__device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, RowRawT<NSRC> &r, float (&v)[KPL],
                                            const float *lnv = nullptr) {
   if (s.pro == PRO_MUL) {
 #pragma unroll
     for (int i = 0; i < KPL; ++i) v[i] = r.v[0][i] * r.v[1][i];
     return;
   }
+  if constexpr (NSRC == 4) {
   if (s.pro == PRO_GATE) {
     ln_inplace(r.v[0], klen, lane, lnv ? lnv + 0 * KC : s.ln_g[0], lnv ? lnv + 4 * KC : s.ln_b[0]);
     ln_inplace(r.v[1], klen, lane, lnv ? lnv + 1 * KC : s.ln_g[1], lnv ? lnv + 5 * KC : s.ln_b[1]);
@@ -127,6 +134,7 @@ __device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, 
     for (int i = 0; i < KPL; ++i)
       v[i] = (kidx(lane, i) < klen) ? sigmoidf_(r.v[0][i]) * r.v[1][i] + sigmoidf_(r.v[2][i]) * r.v[3][i] : 0.f;
     return;
+  }
   }
 #pragma unroll
   for (int i = 0; i < KPL; ++i) v[i] = r.v[0][i];
@@ -222,8 +230,8 @@ struct LinSmem {
   static constexpr size_t total = panel_bytes + w_bytes + red_bytes + vec_bytes;
 };
 
-template <typename WT, int BM, int BN>
-__global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
+template <typename WT, int BM, int BN, int NSRC>
+__global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
   using SM = LinSmem<WT, BM, BN>;
   constexpr int WLD = WTile<WT>::LD;
   constexpr int EPV = 16 / sizeof(WT);           // elements per 16-byte cp.async
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(NT) vkn_linear_kernel(const __grid_constant__ 
       static_assert(BM % NW == 0 && RPW % GRP == 0, "rows per warp must be a multiple of the load group");
 #pragma unroll 1
       for (int q0 = 0; q0 < RPW; q0 += GRP) {
-        RowRaw raw[GRP];
+        RowRawT<NSRC> raw[GRP];
 #pragma unroll
         for (int q = 0; q < GRP; ++q) {
           const int row = row0 + warp + NW * (q0 + q);
@@ -485,16 +493,24 @@ static int check_src(const RowSrc &s, int K) {
   return VKN_OK;
 }
 
-template <typename WT, int BM, int BN>
-static int launch_linear_t(const LinBatch &b, dim3 grid, cudaStream_t stream) {
+template <typename WT, int BM, int BN, int NSRC>
+static int launch_linear_n(const LinBatch &b, dim3 grid, cudaStream_t stream) {
   const size_t smem = LinSmem<WT, BM, BN>::total;
   static bool attr = false;
   if (!attr) {
-    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN, NSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  VKN_CUDA_OK(launch_chain(vkn_linear_kernel<WT, BM, BN>, grid, dim3(NT), smem, stream, b));
+  VKN_CUDA_OK(launch_chain(vkn_linear_kernel<WT, BM, BN, NSRC>, grid, dim3(NT), smem, stream, b));
   return VKN_OK;
+}
+
+// NSRC = 4 only for the KernelUpdator gate prologue (four LayerNorm'd sources); every other prologue needs at
+// most two row sources, which keeps the register footprint at 3 CTAs per SM.
+template <typename WT, int BM, int BN>
+static int launch_linear_t(const LinBatch &b, dim3 grid, cudaStream_t stream) {
+  const bool gate = b.p[0].src.pro == PRO_GATE || b.p[1].src.pro == PRO_GATE;
+  return gate ? launch_linear_n<WT, BM, BN, 4>(b, grid, stream) : launch_linear_n<WT, BM, BN, 2>(b, grid, stream);
 }
 
 int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t stream) {
