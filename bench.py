@@ -328,7 +328,9 @@ def run_ours(args):
     # ---- roofline of the dominant kernel: live per-kernel device times --------------------------------
     acc = {}
     reps = 20
-    xs, pfs, ms_ = x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16()
+    # profiled at the batch size of the throughput mode (BF frames per call): the operating point `value` is quoted on
+    xb_, pfb_, mb_ = frame_batch()
+    xs, pfs, ms_ = xb_.to(dev), pfb_.to(dev), mb_.to(dev)
     for _ in range(3):
         loop(xs, pfs, ms_)
     torch.cuda.synchronize()
@@ -341,27 +343,53 @@ def run_ours(args):
             a[1] += 1
     per_kernel = {k: dict(total_ms_per_step=v[0] / reps, launches_per_step=v[1] // reps,
                           avg_us=1e3 * v[0] / v[1]) for k, v in acc.items()}
-    dom = max(per_kernel, key=lambda k: per_kernel[k]['total_ms_per_step'])
-    P = B * N
+    P = BF * N
     Fh, ncls = CFG1['ffn'], CFG1['ncls']
-    # algorithmic bytes per launch of each kernel family (DESIGN.md "kernels" table)
-    alg = {
-        'vkn_pool_tc_kernel': (C * HW + N * HW) * 2 + N * C * 4,
-        'vkn_pool_simt_kernel': (C * HW + N * HW) * 2 + N * C * 4,
-        'vkn_maskgemm_tc_kernel': (C * HW + N * HW) * 2 + 3 * N * C * 2,
-        'vkn_maskgemm_simt_kernel': (C * HW + N * HW) * 2 + N * C * 4,
-        'vkn_linear_kernel<32x64>': (Fh * C) * 2 + P * C * 4 + P * Fh * 4,          # FFN layer 1
+    Npad = (N + 15) // 16 * 16
+    # Algorithmic bytes per STEP (S stages) of each kernel family -- what the math has to move, not what a
+    # particular tiling moves.  Row operators: every weight once (bf16) + fp32 rows in/out.
+    w_stage = (2041856 + 257 * ncls) * 2
+    rows_stage = 4 * (P * C * (2 + 6 + 6 + 5 + 5 + 3 + 2 + 8 + 9 + 3 + 2) + P * Fh * 2 + P * ncls) + BF * 3 * Npad * C * 2
+    fam_bytes = {
+        'pool': S * BF * ((C * HW + N * HW) * 2 + N * C * 4),
+        'maskgemm': S * BF * ((C * HW + N * HW) * 2 + 3 * Npad * C * 2),
+        'linear': S * (w_stage + rows_stage),
+        'attention': S * (P * 3 * C * 4 + P * C * 4),
+        'pool_reduce': S * (P * C * 4),
     }
+
+    def family(name):
+        for key in ('pool_reduce', 'pool', 'maskgemm', 'linear', 'attention'):
+            if key in name:
+                return key
+        return name
+    fam = {}
+    for k, v in per_kernel.items():
+        f_ = fam.setdefault(family(k), dict(total_ms_per_step=0.0, launches_per_step=0))
+        f_['total_ms_per_step'] += v['total_ms_per_step']
+        f_['launches_per_step'] += v['launches_per_step']
     peak, peak_src = measured_peaks()
-    roof = None
-    if dom in alg:
-        ach = alg[dom] / (per_kernel[dom]['avg_us'] * 1e-6) / 1e9
-        roof = dict(bound='hbm', kernel=dom, achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
-                    peak_source=peak_src, algorithmic_bytes_per_launch=alg[dom], avg_launch_us=per_kernel[dom]['avg_us'])
-    else:
-        roof = dict(bound='hbm', kernel=dom, achieved=None, peak=peak, unit='GB/s', frac=None, traffic=None,
-                    peak_source=peak_src, note='dominant kernel is launch/latency bound; see kernels table',
-                    avg_launch_us=per_kernel[dom]['avg_us'])
+    traffic = {}
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')       # dram bytes per launch from ncu --set full
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    for k, f_ in fam.items():
+        if k in fam_bytes:
+            f_['algorithmic_bytes_per_launch'] = fam_bytes[k] / max(1, f_['launches_per_step'])
+            f_['achieved_gbs'] = fam_bytes[k] / (f_['total_ms_per_step'] * 1e-3) / 1e9
+            f_['frac'] = f_['achieved_gbs'] / peak
+            f_['ncu_dram_bytes_per_launch'] = traffic.get(k)
+    dom = max(fam, key=lambda k: fam[k]['total_ms_per_step'])
+    d_ = fam[dom]
+    roof = dict(bound='hbm', kernel={'linear': 'vkn_linear_kernel (row operators, %d launches/step)' % d_['launches_per_step'],
+                                     'pool': 'vkn_pool_tc_kernel', 'maskgemm': 'vkn_maskgemm_tc_kernel'}.get(dom, dom),
+                achieved=d_.get('achieved_gbs'), peak=peak, unit='GB/s', frac=d_.get('frac'), traffic=traffic.get(dom),
+                peak_source=peak_src, algorithmic_bytes_per_launch=d_.get('algorithmic_bytes_per_launch'),
+                avg_launch_us=1e3 * d_['total_ms_per_step'] / max(1, d_['launches_per_step']),
+                profiled_batch=BF,
+                note='times are CUDA-event brackets on the launch stream (vkn_profile_begin/end), one call of %d frame(s), eager launches; ' % BF +
+                     'the family with the largest share of the step is reported, all families under "families"',
+                families=fam)
     # whole-step figure: module-boundary algorithmic bytes per frame: 60.4 MB bf16
     step_bytes = S * ((C * HW + 2 * N * HW) * 2 + (2041856 + 257 * ncls) * 2)
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
