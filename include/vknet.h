@@ -144,6 +144,12 @@ unsigned long long vkn_launch_count(void);
 int vkn_profile_begin(void);
 int vkn_profile_end(const char **names, float *ms, int max_entries, int *count);
 
+/* Debug only: when `buf` (device memory, n_u64 zero-initialised 64-bit words) is set, every following row-operator
+ * launch writes per-CTA phase timestamps (%globaltimer, ns) into its own block of the buffer: block i = launch i,
+ * 8 words per CTA (entry, prefetch issued, dependency resolved, panel built, tile visible, main loop done,
+ * stores issued).  Returns the block stride in words.  Pass NULL to switch it off.  tools/linear_timeline.py */
+int vkn_debug_timestamps(unsigned long long *buf, size_t n_u64);
+
 /* Bytes of caller-provided scratch needed by the stage / link / iter entry points for `shape`. */
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes);
 

@@ -29,6 +29,15 @@ static struct {
   bool created = false;
 } g_prof;
 
+// ---- debug: per-CTA phase timestamps of the row-operator launches (tools/linear_timeline.py) ---------------
+constexpr size_t DBG_STRIDE = 4096 * 8;       // u64 per launch: up to 4096 CTAs x 8 slots
+static unsigned long long *g_ts = nullptr;
+static size_t g_ts_cap = 0, g_ts_launch = 0;
+unsigned long long *debug_ts_slot() {
+  if (!g_ts || (g_ts_launch + 1) * DBG_STRIDE > g_ts_cap) return nullptr;
+  return g_ts + (g_ts_launch++) * DBG_STRIDE;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -48,7 +57,7 @@ void launch_mark(const char *name, cudaStream_t stream) {
   }
 }
 
-constexpr int FFN_KSPLIT = 8;   // K-slices of the second FFN Linear (K = ffn_dim)
+constexpr int FFN_KSPLIT = 8;   // max K-slices of the second FFN Linear (K = ffn_dim); fewer when there are many rows
 constexpr int A_EXT_PAD = 8;    // a_ext row = C folded channels + bias column, padded to C + 8
 
 // ---- workspace ----------------------------------------------------------------------------------
@@ -290,11 +299,16 @@ static int k_ffn(Ctx &c, const VknFfnW &w, const RowSrc &in_src, RowSrc *pending
   a.ldside = C;
   VKN_TRY(launch_linear(&a, 1, c.s.w_dtype, c.st));
   LinArgs b = lin(src_copy(c.L.h, F), w.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
-  b.ksplit = FFN_KSPLIT;
+  // enough K-slices to fill ~3 CTAs on every SM (16 x 32 output tiles), at most FFN_KSPLIT, at least 256 of K each
+  int ksp = 444 / (ceil_div(C, 32) * ceil_div(P, 16));
+  ksp = ksp >= 8 ? 8 : (ksp >= 4 ? 4 : (ksp >= 2 ? 2 : 1));
+  while (ksp > 1 && F / ksp < 256) ksp /= 2;
+  if (ksp > FFN_KSPLIT) ksp = FFN_KSPLIT;
+  b.ksplit = ksp;
   b.out_split_stride = (long long)P * C;
   VKN_TRY(launch_linear(&b, 1, c.s.w_dtype, c.st));
   RowSrc r = src_ln(c.L.zpart, C, w.norm_g, w.norm_b, false);
-  r.nsum = FFN_KSPLIT;
+  r.nsum = ksp;
   r.sum_stride = (long long)P * C;
   r.pbias = w.b2;
   r.pres = c.L.o2;
@@ -399,6 +413,13 @@ const char *vkn_kernel_names(void) {
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
+
+int vkn_debug_timestamps(unsigned long long *buf, size_t n_u64) {
+  g_ts = buf;
+  g_ts_cap = buf ? n_u64 : 0;
+  g_ts_launch = 0;
+  return (int)(DBG_STRIDE);
+}
 
 int vkn_profile_begin(void) {
   if (!g_prof.created) {

@@ -172,10 +172,12 @@ struct LinArgs {
   // (row p = b * split_N + n); the operand layout of the tcgen05 mask-conv engine.
   __nv_bfloat16 *split_planes;
   int split_B, split_N, split_Npad, split_C;
+  unsigned long long *dbg;   // optional: per-CTA phase timestamps (vkn_debug_timestamps), null in production
 };
 
 // launches (all enqueue on `stream`, never synchronise)
 int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t stream);
+unsigned long long *debug_ts_slot();   // api.cu: next launch's timestamp block or null
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream);
 int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
                      int ldo, int B, int N, int C, int heads, cudaStream_t stream);

@@ -185,7 +185,9 @@ static PoolPlan pool_plan(const VknShape &s) {
   p.nblocks = ceil_div(s.H * s.W, PX_BLK);
   p.mtiles = ceil_div(s.N, 128);
   const int ctas_per_frame = p.nblocks * p.mtiles;
-  int target = 148 / (s.B > 148 ? 148 : s.B);            // CTAs available per frame for one wave
+  int sms = 148;
+  if (const char *e = getenv("VKN_POOL_CTAS")) sms = atoi(e) > 0 ? atoi(e) : 148;   // tuning knob: CTAs per launch
+  int target = sms / (s.B > sms ? sms : s.B);            // CTAs available per frame for one wave
   if (target < 1) target = 1;
   p.bpc = ceil_div(ctas_per_frame, target);
   if (p.bpc < 1) p.bpc = 1;

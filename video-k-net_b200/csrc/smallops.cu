@@ -178,6 +178,17 @@ struct LinBatch {
   LinArgs p[2];
 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VKN_TS(slot)                                                                                   \
+  do {                                                                                                 \
+    if (A.dbg != nullptr && tid == 0)                                                                  \
+      A.dbg[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
+  } while (0)
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -224,7 +235,8 @@ template <typename WT, int BM, int BN>
 struct LinSmem {
   static constexpr bool TC = sizeof(WT) == 2;
   static constexpr size_t panel_bytes = TC ? (size_t)3 * BM * PL_LD * 2 : (size_t)BM * AS_LD * 4;
-  static constexpr size_t w_bytes = (size_t)BN * WTile<WT>::LD * sizeof(WT);
+  static constexpr size_t w_one = (size_t)BN * WTile<WT>::LD * sizeof(WT);
+  static constexpr size_t w_bytes = 2 * w_one;                         // double-buffered across K chunks
   static constexpr size_t red_bytes = TC ? (size_t)(NT / 32) * 32 * 4 * 4 : 0;
   static constexpr size_t vec_bytes = (size_t)(9 * KC + BN) * 4;   // LN gamma/beta x4, pre-LN bias, epilogue bias
   static constexpr size_t total = panel_bytes + w_bytes + red_bytes + vec_bytes;
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
   extern __shared__ __align__(16) uint8_t lin_smem[];
   float(*As)[AS_LD] = reinterpret_cast<float(*)[AS_LD]>(lin_smem);                 // fp32-weight path
   __nv_bfloat16 *Pl = reinterpret_cast<__nv_bfloat16 *>(lin_smem);                 // bf16 path: [3][BM][PL_LD]
-  WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes);
+  WT(*Ws0)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes);
   float *red = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes);
   float *vecs = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes + SM::red_bytes);   // [9][KC] + [BN]
 
@@ -251,6 +263,7 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
     return;
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  VKN_TS(0);                        // entry
 
   int kper = (A.K + ks_total - 1) / ks_total;
   kper = (kper + 31) / 32 * 32;
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
   const int kh = KSW > 1 ? warp / NTILES : 0;
 
   const WT *Wp = reinterpret_cast<const WT *>(A.w);
-  const uint32_t ws0 = (uint32_t)__cvta_generic_to_shared(&Ws[0][0]);
+  const uint32_t ws_base = (uint32_t)__cvta_generic_to_shared(&Ws0[0][0]);
 
   // ---- parameter vectors (LayerNorm affine, biases) are weights too: stage them in shared memory before the
   //      PDL wait so that no dependent global round trip is left inside the LN / epilogue code.
@@ -306,11 +319,12 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
   }
   const float *bias_s = vecs + 9 * KC;
 
-  for (int kc0 = kbeg; kc0 < kend; kc0 += KC) {
+  // weight tile of one K chunk: BN rows x kclen columns, all 16-byte pieces in flight at once (zero-filled
+  // beyond N / K).  Weights are never written inside the chain -> safe before the PDL wait.
+  auto issue_w = [&](int kc0, int buf) {
     const int kclen = min(KC, kend - kc0);
     const int kpad = (kclen + 31) & ~31;
-    // ---- weight tile: BN rows x kclen columns, all 16-byte pieces in flight at once (zero-filled
-    //      beyond N / K).  Weights are never written inside the chain -> safe before the PDL wait.
+    const uint32_t ws0 = ws_base + (uint32_t)(buf * SM::w_one);
     if (kpad == KC) {                  // common case: constant trip counts, no integer division
       constexpr int PPR = KC / EPV;    // pieces per row: 32 (bf16) / 64 (f32)
       constexpr int RPP = NT / PPR;    // rows per pass
@@ -334,10 +348,24 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
         cp_async16(ws0 + (uint32_t)(n * WLD + pc * EPV) * (uint32_t)sizeof(WT), src, (uint32_t)(valid * sizeof(WT)));
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");      // group "weight tile"
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_w(kbeg, 0);
+
+  int cbuf = 0;
+  for (int kc0 = kbeg; kc0 < kend; kc0 += KC, cbuf ^= 1) {
+    const int kclen = min(KC, kend - kc0);
+    const int kpad = (kclen + 31) & ~31;
+    WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes + (size_t)cbuf * SM::w_one);
+    const bool more = kc0 + KC < kend;
+    if (more) issue_w(kc0 + KC, cbuf ^ 1);          // next chunk's weights stream while this chunk is built / multiplied
     if (kc0 == kbeg) {
+      VKN_TS(1);                     // prefetches issued
       pdl_wait();                    // everything below reads what the previous kernel produced
-      asm volatile("cp.async.wait_group 1;" ::: "memory");     // the vector group has landed (tile may be in flight)
+      VKN_TS(2);                     // dependency resolved
+      // groups in flight: vectors, W(0) [, W(1)]: the vector group must have landed before the LN code runs
+      if (more) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
     }
     // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded to kpad).
@@ -396,9 +424,12 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
         }
       }
     }
-    cp_async_wait_all();
+    VKN_TS(3);                       // panel built
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");    // this chunk's tile landed; the next may be in flight
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (kc0 + KC >= kend) pdl_trigger();   // last chunk staged: let the next kernel start its prefetch
+    VKN_TS(4);                       // tile + panel visible
+    if (!more) pdl_trigger();   // last chunk staged: let the next kernel start its prefetch
     if (SM::TC) {
       const int g = lane >> 2, t4 = lane & 3;
       const int nsteps = kpad / 16;
@@ -443,9 +474,10 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
             for (int e = 0; e < 8; ++e) acc[i][j] = fmaf(a[i][e], b[j][e], acc[i][j]);
       }
     }
-    if (kc0 + KC < kend) __syncthreads();
+    if (more) __syncthreads();
   }
 
+  VKN_TS(5);                         // main loop done
   float *outp = A.out + (size_t)ks * A.out_split_stride;
   if (SM::TC) {
 #pragma unroll
@@ -485,6 +517,7 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
 #pragma unroll
       for (int j = 0; j < TN; ++j) lin_epilogue(A, outp, bias_s, col0, row0 + ty + (NT / 16) * i, col0 + tx + 16 * j, acc[i][j]);
   }
+  VKN_TS(6);                         // stores issued
 }
 
 static int check_src(const RowSrc &s, int K) {
@@ -528,6 +561,11 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
     maxN = max(maxN, b.p[i].N);
   }
   if (nprob == 1) b.p[1] = b.p[0];
+  {
+    unsigned long long *ts = debug_ts_slot();
+    b.p[0].dbg = ts;
+    b.p[1].dbg = ts;
+  }
   const int ks = b.p[0].ksplit;
   // tile choice: wide outputs get the 32x64 tile, the C x C layers the 16x32 tile (more CTAs in flight)
   const bool big = maxN >= 1024;
