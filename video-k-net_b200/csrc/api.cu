@@ -115,7 +115,7 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   L.att = (float *)take(P * C * f);
   L.y = (float *)take(P * C * f);
   L.o2 = (float *)take(P * C * f);
-  L.h = (float *)take(P * F * f);
+  L.h = (float *)take(P * F * 6);          // fp32 hidden [P,F] or its three bf16 planes [3][P,F]
   L.zpart = (float *)take((size_t)FFN_KSPLIT * P * C * f);
   for (int i = 0; i < 2; ++i) {
     L.pre_c[i] = (float *)take(P * C * f);
@@ -294,11 +294,27 @@ static int k_attn(Ctx &c, const VknAttnW &w, const RowSrc &qsrc, const float *id
 // Returns the pending source: LN_ffn(o2 + b2 + sum_k zpart_k).
 static int k_ffn(Ctx &c, const VknFfnW &w, const RowSrc &in_src, RowSrc *pending) {
   const int C = c.s.C, P = c.P, F = c.s.ffn_dim;
+  // bf16 weights: the hidden activation is only ever the A operand of the second Linear's tensor-core loop, so the
+  // first Linear emits it directly as bf16 hi/mid/lo planes (no fp32 copy, no re-split in the consumer's prologue)
+  const bool planes = c.s.w_dtype == VKN_BF16;
   LinArgs a = lin(in_src, w.w1, C, w.b1, c.L.h, F, P, F, C, EPI_RELU);
   a.side = c.L.o2;
   a.ldside = C;
+  if (planes) {
+    a.epi |= EPI_SPLIT3 | EPI_NOOUT;
+    a.split_planes = (__nv_bfloat16 *)c.L.h;
+    a.split_B = 1;
+    a.split_N = P;
+    a.split_Npad = P;
+    a.split_C = F;
+  }
   VKN_TRY(launch_linear(&a, 1, c.s.w_dtype, c.st));
-  LinArgs b = lin(src_copy(c.L.h, F), w.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
+  RowSrc hsrc = src_copy(c.L.h, F);
+  if (planes) {
+    hsrc.pro = PRO_PLANES;
+    hsrc.sum_stride = (long long)P * F;       // plane stride (elements)
+  }
+  LinArgs b = lin(hsrc, w.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
   // enough K-slices to fill ~3 CTAs on every SM (16 x 32 output tiles), at most FFN_KSPLIT, at least 256 of K each
   int ksp = 444 / (ceil_div(C, 32) * ceil_div(P, 16));
   ksp = ksp >= 8 ? 8 : (ksp >= 4 ? 4 : (ksp >= 2 ? 2 : 1));

@@ -127,7 +127,8 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// ex2.approx-based exponential (max rel. error ~2 ulp) + IEEE divide: error well below fp32 round-off of the gate sum
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
 
 // ---- the fused "rows" operators (smallops.cu) --------------------------------------------------
 enum Pro : int {
@@ -135,9 +136,11 @@ enum Pro : int {
   PRO_LN = 1,       // v = LN0(S(a0))
   PRO_LN_RELU = 2,  // v = relu(LN0(S(a0)))
   PRO_MUL = 3,      // v = a0 * a1
-  PRO_GATE = 4      // v = sigmoid(LN0(a0)) * LN1(a1) + sigmoid(LN2(a2)) * LN3(a3)   (kernel_updator.py:74-88)
+  PRO_GATE = 4,     // v = sigmoid(LN0(a0)) * LN1(a1) + sigmoid(LN2(a2)) * LN3(a3)   (kernel_updator.py:74-88)
+  PRO_PLANES = 5    // a0 points at bf16 hi/mid/lo planes [3][M][lda] written by a producer's EPI_SPLIT3 epilogue
+                    // (plane stride = sum_stride elements): copied with cp.async, no register pass (tensor-core path only)
 };
-enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_SPLIT3 = 16 };
+enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_SPLIT3 = 16, EPI_NOOUT = 32 };
 
 struct RowSrc {
   const float *a[4];

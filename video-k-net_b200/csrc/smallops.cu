@@ -53,6 +53,51 @@ __device__ __forceinline__ void ln_inplace(float (&v)[KPL], int K, int lane, con
   }
 }
 
+// Four LayerNorms of the same row at once (the KernelUpdator gate prologue): the four pairs of warp
+// reductions are interleaved so their shuffle latencies overlap instead of adding up.
+__device__ __forceinline__ void ln4_inplace(float (&v)[4][KPL], int K, int lane, const float *const (&g)[4],
+                                            const float *const (&b)[4]) {
+  float s[4], q[4], mean[4], rstd[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    s[t] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) s[t] += v[t][i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    mean[t] = s[t] / (float)K;
+    q[t] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const float d = (kidx(lane, i) < K) ? v[t][i] - mean[t] : 0.f;
+      q[t] += d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) q[t] += __shfl_xor_sync(0xffffffffu, q[t], o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) rstd[t] = 1.0f / sqrtf(q[t] / (float)K + 1e-5f);
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int p = 0; p < KPL / 2; ++p) {
+      const int k = kidx(lane, 2 * p);
+      if (k < K) {
+        const float2 gg = *reinterpret_cast<const float2 *>(g[t] + k);
+        const float2 bb = *reinterpret_cast<const float2 *>(b[t] + k);
+        v[t][2 * p] = (v[t][2 * p] - mean[t]) * rstd[t] * gg.x + bb.x;
+        v[t][2 * p + 1] = (v[t][2 * p + 1] - mean[t]) * rstd[t] * gg.y + bb.y;
+      }
+    }
+}
+
 // v[2p], v[2p+1] (+)= a[k], a[k+1]   (k even, klen even: a pair never straddles the end)
 template <bool ACC>
 __device__ __forceinline__ void fetch_pairs(const float *a, int klen, int lane, float (&v)[KPL]) {
@@ -126,10 +171,11 @@ __device__ __forceinline__ void row_finish(const RowSrc &s, int klen, int lane, 
   }
   if constexpr (NSRC == 4) {
   if (s.pro == PRO_GATE) {
-    ln_inplace(r.v[0], klen, lane, lnv ? lnv + 0 * KC : s.ln_g[0], lnv ? lnv + 4 * KC : s.ln_b[0]);
-    ln_inplace(r.v[1], klen, lane, lnv ? lnv + 1 * KC : s.ln_g[1], lnv ? lnv + 5 * KC : s.ln_b[1]);
-    ln_inplace(r.v[2], klen, lane, lnv ? lnv + 2 * KC : s.ln_g[2], lnv ? lnv + 6 * KC : s.ln_b[2]);
-    ln_inplace(r.v[3], klen, lane, lnv ? lnv + 3 * KC : s.ln_g[3], lnv ? lnv + 7 * KC : s.ln_b[3]);
+    const float *const g4[4] = {lnv ? lnv : s.ln_g[0], lnv ? lnv + KC : s.ln_g[1], lnv ? lnv + 2 * KC : s.ln_g[2],
+                                lnv ? lnv + 3 * KC : s.ln_g[3]};
+    const float *const b4[4] = {lnv ? lnv + 4 * KC : s.ln_b[0], lnv ? lnv + 5 * KC : s.ln_b[1],
+                                lnv ? lnv + 6 * KC : s.ln_b[2], lnv ? lnv + 7 * KC : s.ln_b[3]};
+    ln4_inplace(r.v, klen, lane, g4, b4);
 #pragma unroll
     for (int i = 0; i < KPL; ++i)
       v[i] = (kidx(lane, i) < klen) ? sigmoidf_(r.v[0][i]) * r.v[1][i] + sigmoidf_(r.v[2][i]) * r.v[3][i] : 0.f;
@@ -209,7 +255,7 @@ __device__ __forceinline__ void lin_epilogue(const LinArgs &A, float *outp, cons
   if (A.epi & EPI_BIAS) v += ((A.epi & EPI_ROWSCALE) ? __ldg(A.rowscale + row) : 1.f) * bias_s[col - col0];
   if (A.epi & EPI_RES) v += __ldg(A.res + (size_t)row * A.ldres + col);
   if (A.epi & EPI_RELU) v = fmaxf(v, 0.f);
-  outp[(size_t)row * A.ldo + col] = v;
+  if (!(A.epi & EPI_NOOUT)) outp[(size_t)row * A.ldo + col] = v;
   if ((A.epi & EPI_SPLIT3) && col < A.split_C) {
     // v == hi + mid + lo to 24 bits; every bf16 x bf16 product in the mask conv is then exact
     const int b = row / A.split_N, n = row - b * A.split_N;
@@ -243,7 +289,8 @@ struct LinSmem {
 };
 
 template <typename WT, int BM, int BN, int NSRC>
-__global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
+__global__ void __launch_bounds__(NT, (BM > 16 || BN > 32) ? (BM >= 64 ? 1 : 2) : (NSRC == 4 ? 2 : 3))
+    vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
   using SM = LinSmem<WT, BM, BN>;
   constexpr int WLD = WTile<WT>::LD;
   constexpr int EPV = 16 / sizeof(WT);           // elements per 16-byte cp.async
@@ -358,11 +405,29 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
     const int kpad = (kclen + 31) & ~31;
     WT(*Ws)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes + (size_t)cbuf * SM::w_one);
     const bool more = kc0 + KC < kend;
-    if (more) issue_w(kc0 + KC, cbuf ^ 1);          // next chunk's weights stream while this chunk is built / multiplied
+    const bool planes_in = SM::TC && A.src.pro == PRO_PLANES;
     if (kc0 == kbeg) {
       VKN_TS(1);                     // prefetches issued
       pdl_wait();                    // everything below reads what the previous kernel produced
       VKN_TS(2);                     // dependency resolved
+    }
+    if (planes_in) {
+      // the producer already wrote the three bf16 planes of these rows: plain 16-byte copies, zero-filled tails
+      const __nv_bfloat16 *src_pl = reinterpret_cast<const __nv_bfloat16 *>(A.src.a[0]);
+      const uint32_t pl0 = (uint32_t)__cvta_generic_to_shared(Pl);
+      const int ppr = kpad / 8;                                  // 16-byte pieces per row
+      for (int idx = tid; idx < 3 * BM * ppr; idx += NT) {
+        const int pc = idx % ppr, r = (idx / ppr) % BM, t = idx / (ppr * BM);
+        const int row = row0 + r, gk = kc0 + pc * 8;
+        const bool live = row < A.M && gk < kend;
+        const int valid = live ? min(8, kend - gk) : 0;
+        const __nv_bfloat16 *src = live ? src_pl + (size_t)t * A.src.sum_stride + (size_t)row * A.src.lda[0] + gk : src_pl;
+        cp_async16(pl0 + (uint32_t)(((size_t)t * BM + r) * PL_LD + pc * 8) * 2u, src, (uint32_t)valid * 2u);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (more) issue_w(kc0 + KC, cbuf ^ 1);          // next chunk's weights stream while this chunk is built / multiplied
+    if (kc0 == kbeg && !planes_in) {
       // groups in flight: vectors, W(0) [, W(1)]: the vector group must have landed before the LN code runs
       if (more) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -370,7 +435,7 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
     }
     // ---- panel: transformed rows row0..row0+BM, columns kc0..kc0+kclen (zero padded to kpad).
     //      Each warp owns RPW rows; the raw loads of GRP rows are issued before any reduction.
-    {
+    if (!planes_in) {
       constexpr int NW = NT / 32, RPW = BM / NW, GRP = 2;
       static_assert(BM % NW == 0 && RPW % GRP == 0, "rows per warp must be a multiple of the load group");
 #pragma unroll 1
@@ -521,7 +586,8 @@ __global__ void __launch_bounds__(NT, NSRC == 4 ? 2 : 3) vkn_linear_kernel(const
 }
 
 static int check_src(const RowSrc &s, int K) {
-  if (s.pro != PRO_COPY && K > KC) VKN_FAIL(VKN_E_UNSUPPORTED, "row transform %d needs K <= %d (got %d)", s.pro, KC, K);
+  if (s.pro != PRO_COPY && s.pro != PRO_PLANES && K > KC)
+    VKN_FAIL(VKN_E_UNSUPPORTED, "row transform %d needs K <= %d (got %d)", s.pro, KC, K);
   if (s.nsum < 1) VKN_FAIL(VKN_E_INVALID, "RowSrc.nsum must be >= 1");
   return VKN_OK;
 }
@@ -555,6 +621,8 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
     if (b.p[i].ksplit < 1) b.p[i].ksplit = 1;
     if (b.p[i].ksplit != b.p[0].ksplit) VKN_FAIL(VKN_E_INVALID, "launch_linear: batched problems must share ksplit");
     VKN_TRY(check_src(b.p[i].src, b.p[i].K));
+    if (b.p[i].src.pro == PRO_PLANES && w_dtype != VKN_BF16)
+      VKN_FAIL(VKN_E_INVALID, "launch_linear: plane inputs need the tensor-core (bf16 weight) path");
     if (b.p[i].ldw % 8 != 0 || (reinterpret_cast<uintptr_t>(b.p[i].w) & 15))
       VKN_FAIL(VKN_E_INVALID, "launch_linear: weight rows must be 16-byte aligned (ldw %d)", b.p[i].ldw);
     maxM = max(maxM, b.p[i].M);
@@ -567,21 +635,32 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
     b.p[1].dbg = ts;
   }
   const int ks = b.p[0].ksplit;
-  // tile choice: wide outputs get the 32x64 tile, the C x C layers the 16x32 tile (more CTAs in flight)
-  const bool big = maxN >= 1024;
-  VKN_LAUNCH_MARK(big ? "vkn_linear_kernel<16x64>" : "vkn_linear_kernel<16x32>", stream);
-  if (big) {       // 16 x 64: eight 16x8 tensor-core tiles = one per warp over the full K; 224 CTAs for FFN layer 1
-    dim3 grid(ceil_div(maxN, 64), ceil_div(maxM, 16), nprob * ks);
-    if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 16, 64>(b, grid, stream);
-    return launch_linear_t<float, 16, 64>(b, grid, stream);
+  // Tile choice.  These kernels are latency-bound, so the grid is kept to about one resident wave: 16-row tiles
+  // for a single frame (56-224 CTAs), 32 / 64 rows per CTA once frame batches bring hundreds of rows (the weight
+  // tile and the fixed per-CTA latency are then shared by more rows); 64-column tiles for the wide FFN layer.
+  const int bm = maxM <= 128 ? 16 : (maxM <= 448 ? 32 : 64);
+  const bool wide = maxN >= 1024;
+  static const char *names[2][3] = {{"vkn_linear_kernel<16x32>", "vkn_linear_kernel<32x32>", "vkn_linear_kernel<64x32>"},
+                                    {"vkn_linear_kernel<16x64>", "vkn_linear_kernel<32x64>", "vkn_linear_kernel<64x64>"}};
+  VKN_LAUNCH_MARK(names[wide][bm == 16 ? 0 : (bm == 32 ? 1 : 2)], stream);
+  dim3 grid(ceil_div(maxN, wide ? 64 : 32), ceil_div(maxM, bm), nprob * ks);
+#define VKN_LIN_DISPATCH(BM_, BN_)                                                                \
+  return w_dtype == VKN_BF16 ? launch_linear_t<__nv_bfloat16, BM_, BN_>(b, grid, stream)            \
+                             : launch_linear_t<float, BM_, BN_>(b, grid, stream)
+  if (wide) {
+    if (bm == 16) VKN_LIN_DISPATCH(16, 64);
+    if (bm == 32) VKN_LIN_DISPATCH(32, 64);
+    VKN_LIN_DISPATCH(64, 64);
   }
-  dim3 grid(ceil_div(maxN, 32), ceil_div(maxM, 16), nprob * ks);
-  if (w_dtype == VKN_BF16) return launch_linear_t<__nv_bfloat16, 16, 32>(b, grid, stream);
-  return launch_linear_t<float, 16, 32>(b, grid, stream);
+  if (bm == 16) VKN_LIN_DISPATCH(16, 32);
+  if (bm == 32) VKN_LIN_DISPATCH(32, 32);
+  VKN_LIN_DISPATCH(64, 32);
+#undef VKN_LIN_DISPATCH
 }
 
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream) {
   VKN_TRY(check_src(src, K));
+  if (src.pro == PRO_PLANES) VKN_FAIL(VKN_E_INVALID, "launch_rowop: plane inputs are only consumed by launch_linear");
   VKN_LAUNCH_MARK("vkn_rowop_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_rowop_kernel, dim3(ceil_div(M, NT / 32)), dim3(NT), 0, stream, src, out, ldo, M, K));
   return VKN_OK;
