@@ -66,7 +66,8 @@ struct Layout {
   float *pool_part, *cnt_part, *xp0, *cnt, *xp;
   // rows
   float *dyn, *inp, *igp, *ugp, *fc, *o, *qkv, *att, *y, *o2, *h, *zpart, *pre_c[2], *pre_m[2], *mk, *a_ext;
-  float *link_fc, *link_cur;
+  float *link_fc, *link_cur, *obj_tmp;
+  void *row_planes;  // bf16 hi/mid/lo planes [3][P][C] of a materialised row transform (gate output, pre-head rows)
   void *a_split;     // tcgen05 engine: bf16 hi/mid/lo planes of a_ext
   // iter loop
   void *mask_pp[2];
@@ -125,6 +126,8 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   L.a_ext = (float *)take(P * (C + A_EXT_PAD) * f);
   L.link_fc = (float *)take(P * C * f);
   L.link_cur = (float *)take(P * C * f);
+  L.obj_tmp = (float *)take(P * C * f);
+  L.row_planes = take((size_t)3 * P * C * 2);
   const size_t npad = (size_t)ceil_div(s.N, 128) * 128;
   L.a_split = take((size_t)3 * s.B * npad * C * 2);
   const size_t esz = s.x_dtype == VKN_BF16 ? 2 : 4;
@@ -254,6 +257,16 @@ static int k_update(Ctx &c, const VknUpdatorW &w, const float *xp, const RowSrc 
   gt.a[1] = c.L.dyn + C;   gt.lda[1] = 2 * C;  gt.ln_g[1] = w.norm_out_g;   gt.ln_b[1] = w.norm_out_b;
   gt.a[2] = c.L.igp;       gt.lda[2] = C;      gt.ln_g[2] = w.inorm_in_g;   gt.ln_b[2] = w.inorm_in_b;
   gt.a[3] = c.L.inp + C;   gt.lda[3] = 2 * C;  gt.ln_g[3] = w.inorm_out_g;  gt.ln_b[3] = w.inorm_out_b;
+  if (c.s.w_dtype == VKN_BF16) {
+    // the gate (4 LayerNorms + 2 sigmoids per element) is evaluated once per row and handed to fc_layer as the
+    // bf16 planes its tensor-core loop consumes; fused into the Linear it would be redone by all 8 column-block CTAs
+    VKN_TRY(launch_rowprep(gt, nullptr, 0, c.L.row_planes, C, (long long)P * C, P, C, c.st));
+    RowSrc pl = src_copy((const float *)c.L.row_planes, C);
+    pl.pro = PRO_PLANES;
+    pl.sum_stride = (long long)P * C;
+    LinArgs f = lin(pl, w.fc_w, C, w.fc_b, fc_out, C, P, C, C, 0);                        // :90
+    return launch_linear(&f, 1, c.s.w_dtype, c.st);
+  }
   LinArgs f = lin(gt, w.fc_w, C, w.fc_b, fc_out, C, P, C, C, 0);                          // :90
   return launch_linear(&f, 1, c.s.w_dtype, c.st);
 }
@@ -342,6 +355,17 @@ static int k_heads(Ctx &c, const VknHeadW &w, const RowSrc &obj_src, float *obj_
     VKN_FAIL(VKN_E_UNSUPPORTED, "num_cls_fcs / num_mask_fcs must be in [0, %d]", VKN_MAX_FCS);
   RowSrc cs = obj_src, ms = obj_src;
   bool need_side = obj_out != nullptr;
+  if (c.s.w_dtype == VKN_BF16 && obj_src.pro != PRO_COPY && obj_src.pro != PRO_PLANES) {
+    // obj_feat = LN(residual + bias + sum of FFN K-slices): done once per row -> fp32 obj_feat + bf16 planes that both
+    // head branches consume, instead of inside every column-block CTA of the first head Linear
+    VKN_TRY(launch_rowprep(obj_src, obj_out ? obj_out : c.L.obj_tmp, C, c.L.row_planes, C, (long long)P * C, P, C, c.st));
+    RowSrc pl = src_copy((const float *)c.L.row_planes, C);
+    pl.pro = PRO_PLANES;
+    pl.sum_stride = (long long)P * C;
+    cs = pl;
+    ms = pl;
+    need_side = false;
+  }
   const bool with_cls = w.fc_cls_w != nullptr && cls_out != nullptr;   // KernelUpdateHeadVideo(with_cls=False)
   const int ncls_fcs = with_cls ? w.num_cls_fcs : 0;
   const int depth = ncls_fcs > w.num_mask_fcs ? ncls_fcs : w.num_mask_fcs;

@@ -182,6 +182,9 @@ struct LinArgs {
 int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t stream);
 unsigned long long *debug_ts_slot();   // api.cu: next launch's timestamp block or null
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream);
+// row transform once per row -> fp32 rows (optional) and / or bf16 hi/mid/lo planes [3][M][ldp] (optional)
+int launch_rowprep(const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int M, int K,
+                   cudaStream_t stream);
 int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
                      int ldo, int B, int N, int C, int heads, cudaStream_t stream);
 // SIMT fp32 engines for the two big contractions (gemm_simt.cu)

@@ -10,6 +10,8 @@
 // afterwards, then one barrier, then the full-K FMA loop out of shared memory.
 //
 // Reference math: knet/kernel_updator.py:56-94, knet/det/kernel_update_head.py:201-227.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vkn {
@@ -201,22 +203,44 @@ __device__ __forceinline__ void store_pairs(float *dst, int klen, int lane, cons
   }
 }
 
-// ---- standalone row operator (materialises a prologue result) ----------------------------------
-__global__ void __launch_bounds__(NT) vkn_rowop_kernel(const __grid_constant__ RowSrc src, float *out, int ldo,
-                                                       int M, int K) {
+// ---- row operator: one warp per row -----------------------------------------------------------------
+// Materialises a prologue ONCE per row (the fused Linear recomputes it in each of its column-block CTAs, which
+// is fine for a LayerNorm but not for the KernelUpdator gate: 4 LayerNorms + 2 sigmoids per element).  Output:
+// fp32 rows and / or the three bf16 planes a tensor-core Linear consumes with PRO_PLANES.
+constexpr int ROW_NT = 128;
+__global__ void __launch_bounds__(ROW_NT) vkn_rowop_kernel(const __grid_constant__ RowSrc src, float *out, int ldo,
+                                                          __nv_bfloat16 *planes, int ldp, long long plane_stride,
+                                                          int M, int K) {
   pdl_wait();
-  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (NT / 32) + warp;
-  if (row >= M) return;
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    const int klen = min(KC, K - k0);
-    RowRaw r;
-    float v[KPL];
-    row_load(src, row, k0, klen, lane, r);
-    row_finish(src, klen, lane, r, v);
-    store_pairs(out + (size_t)row * ldo + k0, klen, lane, v);
+  const int row = blockIdx.x * (ROW_NT / 32) + warp;
+  if (row < M) {
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      const int klen = min(KC, K - k0);
+      RowRaw r;
+      float v[KPL];
+      row_load(src, row, k0, klen, lane, r);
+      row_finish(src, klen, lane, r, v);
+      if (out != nullptr) store_pairs(out + (size_t)row * ldo + k0, klen, lane, v);
+      if (planes != nullptr) {
+#pragma unroll
+        for (int p = 0; p < KPL / 2; ++p) {
+          const int k = kidx(lane, 2 * p);
+          float x0 = v[2 * p], x1 = v[2 * p + 1];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {          // hi, then the residuals: v == hi + mid + lo to 24 bits
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+            x0 -= __bfloat162float(h0);
+            x1 -= __bfloat162float(h1);
+            if (k < klen)
+              *reinterpret_cast<uint32_t *>(planes + (size_t)t * plane_stride + (size_t)row * ldp + k0 + k) =
+                  (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          }
+        }
+      }
+    }
   }
+  pdl_trigger();
 }
 
 // ---- fused rows x Linear ----------------------------------------------------------------------
@@ -638,7 +662,8 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
   // Tile choice.  These kernels are latency-bound, so the grid is kept to about one resident wave: 16-row tiles
   // for a single frame (56-224 CTAs), 32 / 64 rows per CTA once frame batches bring hundreds of rows (the weight
   // tile and the fixed per-CTA latency are then shared by more rows); 64-column tiles for the wide FFN layer.
-  const int bm = maxM <= 128 ? 16 : (maxM <= 448 ? 32 : 64);
+  int bm = 16;    // measured on B200: 32/64-row tiles lose to more waves of 16-row CTAs (serial row groups per warp)
+  if (const char *e = getenv("VKN_LINEAR_BM")) bm = atoi(e) == 32 ? 32 : (atoi(e) == 64 ? 64 : 16);
   const bool wide = maxN >= 1024;
   static const char *names[2][3] = {{"vkn_linear_kernel<16x32>", "vkn_linear_kernel<32x32>", "vkn_linear_kernel<64x32>"},
                                     {"vkn_linear_kernel<16x64>", "vkn_linear_kernel<32x64>", "vkn_linear_kernel<64x64>"}};
@@ -661,8 +686,16 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream) {
   VKN_TRY(check_src(src, K));
   if (src.pro == PRO_PLANES) VKN_FAIL(VKN_E_INVALID, "launch_rowop: plane inputs are only consumed by launch_linear");
+  return launch_rowprep(src, out, ldo, nullptr, 0, 0, M, K, stream);
+}
+
+int launch_rowprep(const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int M, int K,
+                   cudaStream_t stream) {
+  VKN_TRY(check_src(src, K));
+  if (src.pro == PRO_PLANES) VKN_FAIL(VKN_E_INVALID, "launch_rowprep: plane inputs are only consumed by launch_linear");
   VKN_LAUNCH_MARK("vkn_rowop_kernel", stream);
-  VKN_CUDA_OK(launch_chain(vkn_rowop_kernel, dim3(ceil_div(M, NT / 32)), dim3(NT), 0, stream, src, out, ldo, M, K));
+  VKN_CUDA_OK(launch_chain(vkn_rowop_kernel, dim3(ceil_div(M, ROW_NT / 32)), dim3(ROW_NT), 0, stream, src, out, ldo,
+                           (__nv_bfloat16 *)planes, ldp, plane_stride, M, K));
   return VKN_OK;
 }
 
