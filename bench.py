@@ -211,8 +211,8 @@ def run_ours(args):
     # The loop of ONE frame is a chain of small latency-bound kernels that fills a fraction of the 148
     # SMs, so independent frames overlap.  Two such groups alternate; one group's inputs + outputs
     # (NS*BF frames x 16.2 MB) exceed L2 (126 MB) for the default 4 x 4, so x and the masks stream from HBM.
-    NS = max(1, int(os.environ.get('VKN_STREAMS', '4')))
-    BF = max(1, int(os.environ.get('VKN_BATCH', '4')))
+    NS = max(1, int(os.environ.get('VKN_STREAMS', '2')))
+    BF = max(1, int(os.environ.get('VKN_BATCH', '8')))
     quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: small group, no CPU arm
     if quick:
         NS, BF = 1, 1
