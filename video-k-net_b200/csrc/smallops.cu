@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(ROW_NT) vkn_rowop_kernel(const __grid_constant
 // ---- fused rows x Linear ----------------------------------------------------------------------
 struct LinBatch {
   LinArgs p[2];
+  int nwbuf;      // weight-tile buffers carved from shared memory: 1 (K fits one chunk) or 2
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -306,14 +307,15 @@ struct LinSmem {
   static constexpr bool TC = sizeof(WT) == 2;
   static constexpr size_t panel_bytes = TC ? (size_t)3 * BM * PL_LD * 2 : (size_t)BM * AS_LD * 4;
   static constexpr size_t w_one = (size_t)BN * WTile<WT>::LD * sizeof(WT);
-  static constexpr size_t w_bytes = 2 * w_one;                         // double-buffered across K chunks
+  static constexpr size_t w_bytes = 2 * w_one;                         // double-buffered across K chunks (multi-chunk launches)
   static constexpr size_t red_bytes = TC ? (size_t)(NT / 32) * 32 * 4 * 4 : 0;
   static constexpr size_t vec_bytes = (size_t)(9 * KC + BN) * 4;   // LN gamma/beta x4, pre-LN bias, epilogue bias
   static constexpr size_t total = panel_bytes + w_bytes + red_bytes + vec_bytes;
+  static constexpr size_t total_single = panel_bytes + w_one + red_bytes + vec_bytes;   // launches whose K fits one chunk
 };
 
 template <typename WT, int BM, int BN, int NSRC>
-__global__ void __launch_bounds__(NT, (BM > 16 || BN > 32) ? (BM >= 64 ? 1 : 2) : (NSRC == 4 ? 2 : 3))
+__global__ void __launch_bounds__(NT, BN > 32 ? 2 : (NSRC == 4 ? 2 : 3))
     vkn_linear_kernel(const __grid_constant__ LinBatch batch) {
   using SM = LinSmem<WT, BM, BN>;
   constexpr int WLD = WTile<WT>::LD;
@@ -322,8 +324,9 @@ __global__ void __launch_bounds__(NT, (BM > 16 || BN > 32) ? (BM >= 64 ? 1 : 2) 
   float(*As)[AS_LD] = reinterpret_cast<float(*)[AS_LD]>(lin_smem);                 // fp32-weight path
   __nv_bfloat16 *Pl = reinterpret_cast<__nv_bfloat16 *>(lin_smem);                 // bf16 path: [3][BM][PL_LD]
   WT(*Ws0)[WLD] = reinterpret_cast<WT(*)[WLD]>(lin_smem + SM::panel_bytes);
-  float *red = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes);
-  float *vecs = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + SM::w_bytes + SM::red_bytes);   // [9][KC] + [BN]
+  const size_t wtot = (size_t)batch.nwbuf * SM::w_one;
+  float *red = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + wtot);
+  float *vecs = reinterpret_cast<float *>(lin_smem + SM::panel_bytes + wtot + SM::red_bytes);   // [9][KC] + [BN]
 
   const int ks_total = batch.p[0].ksplit;
   const LinArgs &A = batch.p[blockIdx.z / ks_total];
@@ -618,10 +621,11 @@ static int check_src(const RowSrc &s, int K) {
 
 template <typename WT, int BM, int BN, int NSRC>
 static int launch_linear_n(const LinBatch &b, dim3 grid, cudaStream_t stream) {
-  const size_t smem = LinSmem<WT, BM, BN>::total;
+  const size_t smem = b.nwbuf == 2 ? LinSmem<WT, BM, BN>::total : LinSmem<WT, BM, BN>::total_single;
   static bool attr = false;
   if (!attr) {
-    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN, NSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN, NSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)LinSmem<WT, BM, BN>::total));
     attr = true;
   }
   VKN_CUDA_OK(launch_chain(vkn_linear_kernel<WT, BM, BN, NSRC>, grid, dim3(NT), smem, stream, b));
@@ -654,32 +658,39 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
   }
   if (nprob == 1) b.p[1] = b.p[0];
   {
+    int kmax = 0;
+    for (int i = 0; i < nprob; ++i) {
+      int kper = ceil_div(b.p[i].K, b.p[i].ksplit);
+      kper = (kper + 31) / 32 * 32;
+      kmax = max(kmax, kper);
+    }
+    b.nwbuf = kmax > KC ? 2 : 1;
+  }
+  {
     unsigned long long *ts = debug_ts_slot();
     b.p[0].dbg = ts;
     b.p[1].dbg = ts;
   }
   const int ks = b.p[0].ksplit;
-  // Tile choice.  These kernels are latency-bound, so the grid is kept to about one resident wave: 16-row tiles
-  // for a single frame (56-224 CTAs), 32 / 64 rows per CTA once frame batches bring hundreds of rows (the weight
-  // tile and the fixed per-CTA latency are then shared by more rows); 64-column tiles for the wide FFN layer.
-  int bm = 16;    // measured on B200: 32/64-row tiles lose to more waves of 16-row CTAs (serial row groups per warp)
-  if (const char *e = getenv("VKN_LINEAR_BM")) bm = atoi(e) == 32 ? 32 : (atoi(e) == 64 ? 64 : 16);
-  const bool wide = maxN >= 1024;
-  static const char *names[2][3] = {{"vkn_linear_kernel<16x32>", "vkn_linear_kernel<32x32>", "vkn_linear_kernel<64x32>"},
-                                    {"vkn_linear_kernel<16x64>", "vkn_linear_kernel<32x64>", "vkn_linear_kernel<64x64>"}};
-  VKN_LAUNCH_MARK(names[wide][bm == 16 ? 0 : (bm == 32 ? 1 : 2)], stream);
-  dim3 grid(ceil_div(maxN, wide ? 64 : 32), ceil_div(maxM, bm), nprob * ks);
-#define VKN_LIN_DISPATCH(BM_, BN_)                                                                \
-  return w_dtype == VKN_BF16 ? launch_linear_t<__nv_bfloat16, BM_, BN_>(b, grid, stream)            \
-                             : launch_linear_t<float, BM_, BN_>(b, grid, stream)
-  if (wide) {
-    if (bm == 16) VKN_LIN_DISPATCH(16, 64);
-    if (bm == 32) VKN_LIN_DISPATCH(32, 64);
-    VKN_LIN_DISPATCH(64, 64);
+  // Tile choice.  These kernels are latency-bound, so the grid is kept near one resident wave.  Always 16-row
+  // tiles (32/64-row tiles measured slower: more serial row groups per warp).  Columns: 32 for a single frame
+  // (56-224 CTAs), 64 for the wide FFN layer, and 128 once frame batches bring hundreds of rows -- the row prologue
+  // is then recomputed by 2 instead of 8 column-block CTAs and the CTA count drops 4x.
+  int bn = maxN >= 1024 ? 64 : 32;
+  if (maxM > 128 && maxN >= 128) bn = 128;
+  if (const char *e = getenv("VKN_LINEAR_BN")) {
+    const int v = atoi(e);
+    if (v == 32 || v == 64 || v == 128) bn = v;
   }
-  if (bm == 16) VKN_LIN_DISPATCH(16, 32);
-  if (bm == 32) VKN_LIN_DISPATCH(32, 32);
-  VKN_LIN_DISPATCH(64, 32);
+  static const char *names[3] = {"vkn_linear_kernel<16x32>", "vkn_linear_kernel<16x64>", "vkn_linear_kernel<16x128>"};
+  VKN_LAUNCH_MARK(names[bn == 32 ? 0 : (bn == 64 ? 1 : 2)], stream);
+  dim3 grid(ceil_div(maxN, bn), ceil_div(maxM, 16), nprob * ks);
+#define VKN_LIN_DISPATCH(BN_)                                                                   \
+  return w_dtype == VKN_BF16 ? launch_linear_t<__nv_bfloat16, 16, BN_>(b, grid, stream)          \
+                             : launch_linear_t<float, 16, BN_>(b, grid, stream)
+  if (bn == 32) VKN_LIN_DISPATCH(32);
+  if (bn == 64) VKN_LIN_DISPATCH(64);
+  VKN_LIN_DISPATCH(128);
 #undef VKN_LIN_DISPATCH
 }
 
