@@ -213,6 +213,18 @@ int vkn_iter_forward(const VknShape *s, const VknHeadW *stages, int num_stages, 
 int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, const float *prev,
                     const float *x_feat, float *out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- next row: the tail of ConvKernelHead._decode_init_proposals ----------------------
+ * knet/det/kernel_head.py:212, 234-254 with the shipped settings proposal_feats_with_obj=True, use_binary=True:
+ *   mask_preds[b,n,p]     = init_w[n,:] . loc_feats[b,:,p] + init_b[n]              (init_kernels, a 1x1 conv)
+ *   obj[b,n,:]            = sum_p 1[sigmoid(mask_preds[b,n,p]) > 0.5] * x_feats[b,:,p]
+ *   proposal_feats[b,n,:] = init_w[n,:] + obj[b,n,:]
+ * The same two tcgen05 kernels as the stages, with ONE static kernel set shared by all B frames.
+ * shape: B frames, N = num_proposals, C, H, W, x_dtype (loc_feats / x_feats / mask_preds storage); the row-operator
+ * fields (ffn_dim, num_classes, num_heads) are ignored but must be valid.  init_w [N,C] fp32, init_b [N] fp32 or NULL. */
+int vkn_init_proposals(const VknShape *s, const float *init_w, const float *init_b, const void *loc_feats,
+                       const void *x_feats, void *mask_preds, float *proposal_feats, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

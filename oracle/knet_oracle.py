@@ -287,6 +287,22 @@ def kernel_update_head_video_forward(sd, cfg, x, proposal_feat, mask_preds):
 
 
 # ----------------------------------------------------------------------------------------
+# next row: tail of ConvKernelHead._decode_init_proposals  (knet/det/kernel_head.py:196-265)
+# ----------------------------------------------------------------------------------------
+def init_proposals(init_w, init_b, loc_feats, x_feats, use_binary=True):
+    """init_w [N,C,1,1], init_b [N] | None, loc_feats / x_feats [B,C,H,W].
+    -> (proposal_feats [B,N,C,1,1], mask_preds [B,N,H,W]) for proposal_feats_with_obj=True."""
+    mask_preds = F.conv2d(loc_feats, init_w.to(loc_feats.dtype), None if init_b is None else init_b.to(loc_feats.dtype))  # :212
+    sigmoid_masks = mask_preds.sigmoid()                                           # :241
+    nonzero = sigmoid_masks > 0.5                                                  # :242
+    m = nonzero.to(x_feats.dtype) if use_binary else nonzero.to(x_feats.dtype) * sigmoid_masks   # :243-246
+    obj_feats = torch.einsum('bnhw,bchw->bnc', m, x_feats)                         # :247
+    B, N = mask_preds.shape[:2]
+    proposal_feats = init_w[None].expand(B, *init_w.shape) + obj_feats.view(B, N, -1, 1, 1)     # :236-238, 252-254
+    return proposal_feats, mask_preds
+
+
+# ----------------------------------------------------------------------------------------
 # the S-stage loop  (knet/det/kernel_iter_head.py:118-137, 246-253; forward_dummy :317-330)
 # ----------------------------------------------------------------------------------------
 def iter_forward(sds, cfgs, x, proposal_feat, mask_preds, mask_round=None):

@@ -73,6 +73,30 @@ def case_video(name, B, N, C, H, W, Fh, ncls, seed, previous_type, previous_link
     print(name, 'ok')
 
 
+def case_init(name, B, N, C, H, W, seed):
+    """ConvKernelHead._decode_init_proposals through the real reference class (neck stubbed to a passthrough,
+    no loc/seg convs): pins the init-kernel conv, the thresholded pooling and the proposal assembly."""
+    ref = ref_shim.load('knet')
+    g = torch.Generator().manual_seed(seed)
+    head = ref.ConvKernelHead(num_proposals=N, in_channels=C, out_channels=C, num_loc_convs=0, num_seg_convs=0,
+                              localization_fpn=dict(type='Passthrough'), semantic_fpn=True, num_classes=7,
+                              use_binary=True, proposal_feats_with_obj=True, feat_downsample_stride=1,
+                              num_thing_classes=3, num_stuff_classes=4, cat_stuff_mask=False)
+    with torch.no_grad():
+        head.init_kernels.weight.copy_(torch.randn(N, C, 1, 1, generator=g) * 0.3)
+    head.eval()
+    loc = torch.randn(B, C, H, W, generator=g)
+    sem = torch.randn(B, C, H, W, generator=g)
+    with torch.no_grad():
+        prop, x_feats, mask_preds, cls_scores, seg_preds = head._decode_init_proposals((loc, sem), [dict()] * B)
+    assert torch.equal(x_feats, sem + loc)
+    blob = dict(loc_feats=loc.numpy(), x_feats=x_feats.numpy(), init_w=head.init_kernels.weight.detach().numpy(),
+                proposal_feats=prop.numpy(), mask_preds=mask_preds.numpy(),
+                meta=np.array([B, N, C, H, W, 0, 0, 0], dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **blob)
+    print(name, 'ok')
+
+
 def case_clip(name, B, Fr, N, C, H, W, Fh, ncls, seed, with_cls):
     """KernelUpdateHeadVideo (knet_vis tree: must run in a process where `knet` was not loaded)."""
     ref = ref_shim.load('knet_vis')
@@ -124,6 +148,7 @@ def main():
     case_video('video_link_ffn_b2_n12_c64_9x11', 2, 12, 64, 9, 11, 128, 5, 4, 'ffn', None)
     case_video('video_link_update_b2_n12_c64_9x11', 2, 12, 64, 9, 11, 128, 5, 5, 'update', 'update_dynamic_cov')
     case_video('video_link_cov_ffn_b1_n12_c64_9x11', 1, 12, 64, 9, 11, 128, 5, 6, 'ffn', 'update_dynamic_cov')
+    case_init('init_b2_n20_c64_12x16', 2, 20, 64, 12, 16, 10)
 
 
 if __name__ == '__main__':

@@ -186,6 +186,8 @@ def install():
     cnn.bias_init_with_prob = bias_init_with_prob
     cnn.build_activation_layer = build_activation_layer
     cnn.build_norm_layer = build_norm_layer
+    cnn.normal_init = lambda module, mean=0, std=1, bias=0: (nn.init.normal_(module.weight, mean, std),
+                                                            module.bias is not None and nn.init.constant_(module.bias, bias))
     tr = mods['mmcv.cnn.bricks.transformer']
     tr.TRANSFORMER_LAYER = Registry('transformer_layer')
     tr.FFN = FFN
@@ -198,10 +200,18 @@ def install():
         lambda *a: func(*a, **kw), *args))))
     core.bbox2result = lambda *a, **k: None
     core.mask_matrix_nms = lambda *a, **k: None
+    core.build_assigner = lambda *a, **k: None
+    core.build_sampler = lambda *a, **k: None
+    core.reduce_mean = lambda t: t
     bld = mods['mmdet.models.builder']
     bld.HEADS = Registry('head')
     bld.build_loss = lambda cfg: _FakeLoss(**{k: v for k, v in cfg.items() if k == 'use_sigmoid'})
     bld.build_head = lambda cfg: bld.HEADS.build(cfg)
+
+    class _PassthroughNeck(nn.Module):      # stands in for SemanticFPNWrapper: hands the given feature maps through
+        def forward(self, feats):
+            return list(feats)
+    bld.build_neck = lambda cfg: _PassthroughNeck()
     mods['mmdet.models.dense_heads.atss_head'].reduce_mean = lambda t: t
     mods['mmdet.models.losses'].accuracy = lambda *a, **k: None
     mods['mmdet.utils'].get_root_logger = lambda *a, **k: __import__('logging').getLogger('ref')
@@ -243,6 +253,8 @@ def load(tree='knet'):
         out.KernelUpdator = out.kernel_updator.KernelUpdator
         out.KernelUpdateHead = out.det_head.KernelUpdateHead
         out.VideoKernelUpdateHead = out.video_head.VideoKernelUpdateHead
+        out.kernel_head = _load_file('_ref_knet.det.kernel_head', 'knet/det/kernel_head.py')
+        out.ConvKernelHead = out.kernel_head.ConvKernelHead
     else:
         out.kernel_updator = _load_file('_ref_knet_vis.kernel_updator', 'knet_vis/kernel_updator.py')
         out.det_head = _load_file('_ref_knet_vis.det.kernel_update_head', 'knet_vis/det/kernel_update_head.py')

@@ -448,3 +448,34 @@ def test_persistent_mask_conv_equals_tiled_mask_conv(dev, monkeypatch):
     xt = ko._feat_transform(sd, ko.round_bf16(x))
     want = torch.einsum('bnc,bchw->bnhw', mk.cpu(), xt)
     assert (b.float().cpu() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+
+
+# ---- next row: ConvKernelHead tail = the same two contractions with static kernels ------------
+def test_init_proposals_golden_and_full_size(dev):
+    import numpy as np
+    from vknet import _lib, ops
+    z = np.load(golden_files('init_')[0])
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    N, C = t['init_w'].shape[:2]
+    conv = torch.nn.Conv2d(C, N, 1, bias=False)
+    conv.weight.data.copy_(t['init_w'])
+    prop, mask = ops.init_proposals(conv.to(dev), t['loc_feats'].to(dev), t['x_feats'].to(dev))
+    assert maxabs(prop, t['proposal_feats']) < 1e-4 * t['proposal_feats'].abs().max().item()
+    assert_masks(mask, t['mask_preds'], 'init masks', rel=1e-5)
+    # BASELINE shapes, bf16 storage, both engines
+    B, N, C, H, W = 2, 100, 256, 200, 88
+    g = torch.Generator().manual_seed(0)
+    w = ko.round_bf16(torch.randn(N, C, 1, 1, generator=g) * 0.2)
+    loc, sem = ko.round_bf16(torch.randn(B, C, H, W, generator=g)), ko.round_bf16(torch.randn(B, C, H, W, generator=g))
+    xf = ko.round_bf16(loc + sem)
+    want_p, want_m = ko.init_proposals(w, None, loc, xf)
+    conv = torch.nn.Conv2d(C, N, 1, bias=False)
+    conv.weight.data.copy_(w)
+    for eng in (_lib.ENGINE_SIMT, _lib.ENGINE_TC):
+        p, m = ops.init_proposals(conv.to(dev), loc.to(dev).bfloat16(), xf.to(dev).bfloat16(), engine=eng)
+        ref_m = ko.round_bf16(want_m)
+        assert (m.float().cpu() - ref_m).abs().max().item() <= 2 ** -7 * ref_m.abs().max().item()
+        flips = ((m.float().cpu() > 0) != (want_m > 0)).sum().item()
+        assert flips <= 4, 'threshold disagreements vs the fp32 oracle: %d' % flips
+        if flips == 0:
+            assert maxabs(p, want_p) < 1e-4 * want_p.abs().max().item()

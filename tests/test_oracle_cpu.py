@@ -106,3 +106,13 @@ def test_threshold_sliver_is_documented_behaviour():
     ours = m > 0.0
     assert torch.equal(ref[[0, 1, 2, 5, 6]], ours[[0, 1, 2, 5, 6]])
     assert not ref[3] and ours[3]      # the sliver
+
+
+def test_oracle_matches_reference_fixture_init_proposals():
+    """tail of ConvKernelHead._decode_init_proposals, fixture produced by the real class."""
+    import numpy as np
+    z = np.load(golden_files('init_')[0])
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    prop, mask = ko.init_proposals(t['init_w'], None, t['loc_feats'], t['x_feats'])
+    assert maxabs(prop, t['proposal_feats']) < 2e-5 * t['proposal_feats'].abs().max().item()
+    assert maxabs(mask, t['mask_preds']) < 2e-5 * t['mask_preds'].abs().max().item()

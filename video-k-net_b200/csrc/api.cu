@@ -449,7 +449,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -579,6 +579,39 @@ int vkn_iter_forward(const VknShape *s, const VknHeadW *stages, int num_stages, 
     mk = mask_o;
   }
   return VKN_OK;
+}
+
+int vkn_init_proposals(const VknShape *s, const float *init_w, const float *init_b, const void *loc_feats,
+                       const void *x_feats, void *mask_preds, float *proposal_feats, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  Ctx c;
+  VKN_TRY(make_ctx(s, workspace, workspace_bytes, stream, c));
+  if (!init_w || !loc_feats || !x_feats || !mask_preds || !proposal_feats)
+    VKN_FAIL(VKN_E_INVALID, "vkn_init_proposals: null argument");
+  if (s->frames_per_set > 1) VKN_FAIL(VKN_E_INVALID, "vkn_init_proposals: frames_per_set must be 1 (B counts frames)");
+  const int C = s->C, N = s->N, lda = C + A_EXT_PAD;
+  // (1) the static kernels as the mask-conv operand: a_ext rows [init_w | init_b], plus the bf16 planes for tcgen05
+  VknShape one = c.s;          // ONE kernel set shared by all B frames
+  one.B = 1;
+  one.frames_per_set = s->B;
+  VKN_TRY(launch_pack_kernels(init_w, init_b, N, C, c.L.a_ext, lda, c.use_tc ? c.L.a_split : nullptr,
+                              maskgemm_tc_npad(one), c.st));
+  // (2) mask_preds = init_kernels(loc_feats)
+  if (c.use_tc) VKN_TRY(launch_maskgemm_tc(one, loc_feats, c.L.a_ext, lda, c.L.a_split, mask_preds, c.st));
+  else VKN_TRY(launch_maskgemm_simt(one, loc_feats, c.L.a_ext, lda, mask_preds, c.st));
+  // (3) obj = hard-mask pooling of x_feats (threshold 0.5 <=> logit 0), per frame
+  VknShape fs = c.s;
+  fs.mask_thr_logit = 0.f;
+  int nch = 0;
+  if (c.use_tc) VKN_TRY(launch_pool_tc(fs, x_feats, mask_preds, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+  else VKN_TRY(launch_pool_simt(fs, x_feats, mask_preds, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+  VKN_TRY(launch_pool_reduce(fs, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st));
+  // (4) proposal_feats = init_w (broadcast over frames) + obj
+  RowSrc r = src_copy(c.L.xp0, C);
+  r.pres = init_w;
+  r.ldpres = C;
+  r.pres_mod = N;
+  return launch_rowop(r, proposal_feats, C, c.P, C, c.st);
 }
 
 int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, const float *prev, const float *x_feat,

@@ -153,6 +153,7 @@ struct RowSrc {
   const float *pbias;       // optional [K] added before LN
   const float *pres;        // optional [M,K] residual added before LN
   int ldpres;
+  int pres_mod;             // > 0: the residual row is (row % pres_mod) -- one [pres_mod,K] block broadcast over frames
 };
 
 struct LinArgs {
@@ -180,6 +181,9 @@ struct LinArgs {
 
 // launches (all enqueue on `stream`, never synchronise)
 int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t stream);
+// static kernels [N,C] (+ bias [N]) -> a_ext rows [w | b | pad] and, when planes != null, bf16 hi/mid/lo planes [3][1][Npad][C]
+int launch_pack_kernels(const float *w, const float *b, int N, int C, float *a_ext, int lda, void *planes, int Npad,
+                        cudaStream_t stream);
 unsigned long long *debug_ts_slot();   // api.cu: next launch's timestamp block or null
 int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStream_t stream);
 // row transform once per row -> fp32 rows (optional) and / or bf16 hi/mid/lo planes [3][M][ldp] (optional)

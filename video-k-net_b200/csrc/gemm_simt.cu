@@ -205,6 +205,38 @@ int launch_pool_reduce(const VknShape &s, const float *partials, const float *cn
   return VKN_OK;
 }
 
+// ---- static kernels -> mask-conv operand (vkn_init_proposals) ----------------------------------------------------
+__global__ void __launch_bounds__(256) vkn_pack_kernels_kernel(const float *__restrict__ w, const float *__restrict__ b,
+                                                               int N, int C, float *__restrict__ a_ext, int lda,
+                                                               __nv_bfloat16 *__restrict__ planes, int Npad) {
+  pdl_wait();
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx < N * C) {
+    const int n = idx / C, c = idx - n * C;
+    const float v = w[idx];
+    a_ext[(size_t)n * lda + c] = v;
+    if (c == 0) a_ext[(size_t)n * lda + C] = b ? b[n] : 0.f;
+    if (planes != nullptr) {
+      const size_t plane = (size_t)Npad * C, o = (size_t)n * C + c;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      planes[o] = hi;
+      planes[plane + o] = mid;
+      planes[2 * plane + o] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    }
+  }
+  pdl_trigger();
+}
+
+int launch_pack_kernels(const float *w, const float *b, int N, int C, float *a_ext, int lda, void *planes, int Npad,
+                        cudaStream_t stream) {
+  VKN_LAUNCH_MARK("vkn_pack_kernels_kernel", stream);
+  VKN_CUDA_OK(launch_chain(vkn_pack_kernels_kernel, dim3(ceil_div(N * C, 256)), dim3(256), 0, stream, w, b, N, C, a_ext, lda,
+                           (__nv_bfloat16 *)planes, Npad));
+  return VKN_OK;
+}
+
 // ---- dynamic mask conv ---------------------------------------------------------------------------
 template <typename XT, bool VEC>
 __global__ void __launch_bounds__(GT) vkn_maskgemm_simt_kernel(const XT *__restrict__ x,

@@ -159,7 +159,7 @@ __device__ __forceinline__ void row_load(const RowSrc &s, int row, int k0, int k
   }
   for (; sl < s.nsum; ++sl) fetch_pairs<true>(a0 + (size_t)sl * s.sum_stride, klen, lane, v);
   if (s.pbias) fetch_pairs<true>(s.pbias + k0, klen, lane, v);
-  if (s.pres) fetch_pairs<true>(s.pres + (size_t)row * s.ldpres + k0, klen, lane, v);
+  if (s.pres) fetch_pairs<true>(s.pres + (size_t)(s.pres_mod > 0 ? row % s.pres_mod : row) * s.ldpres + k0, klen, lane, v);
 }
 
 // lnv: optional shared-memory copy of the LayerNorm vectors ([i] gamma at lnv + i*KC, beta at lnv + (4+i)*KC)
@@ -622,10 +622,11 @@ static int check_src(const RowSrc &s, int K) {
 template <typename WT, int BM, int BN, int NSRC>
 static int launch_linear_n(const LinBatch &b, dim3 grid, cudaStream_t stream) {
   const size_t smem = b.nwbuf == 2 ? LinSmem<WT, BM, BN>::total : LinSmem<WT, BM, BN>::total_single;
+  if (smem > 227 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "linear tile %dx%d needs %zu bytes of shared memory", BM, BN, smem);
   static bool attr = false;
   if (!attr) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN, NSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)LinSmem<WT, BM, BN>::total));
+                                     (int)(LinSmem<WT, BM, BN>::total < 227 * 1024 ? LinSmem<WT, BM, BN>::total : 227 * 1024)));
     attr = true;
   }
   VKN_CUDA_OK(launch_chain(vkn_linear_kernel<WT, BM, BN, NSRC>, grid, dim3(NT), smem, stream, b));
@@ -677,10 +678,10 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
   // (56-224 CTAs), 64 for the wide FFN layer, and 128 once frame batches bring hundreds of rows -- the row prologue
   // is then recomputed by 2 instead of 8 column-block CTAs and the CTA count drops 4x.
   int bn = maxN >= 1024 ? 64 : 32;
-  if (maxM > 128 && maxN >= 128) bn = 128;
+  if (maxM > 128 && maxN >= 128) bn = w_dtype == VKN_BF16 ? 128 : 64;   // fp32 weight tiles of 128 columns do not fit double-buffered
   if (const char *e = getenv("VKN_LINEAR_BN")) {
     const int v = atoi(e);
-    if (v == 32 || v == 64 || v == 128) bn = v;
+    if (v == 32 || v == 64 || (v == 128 && w_dtype == VKN_BF16)) bn = v;
   }
   static const char *names[3] = {"vkn_linear_kernel<16x32>", "vkn_linear_kernel<16x64>", "vkn_linear_kernel<16x128>"};
   VKN_LAUNCH_MARK(names[bn == 32 ? 0 : (bn == 64 ? 1 : 2)], stream);

@@ -89,3 +89,31 @@ def mask_gemm(head, x, mask_kernel):
     _lib.check(_lib.lib().vkn_mask_gemm(shape, w, _lib.ptr(x), _lib.ptr(mk), _lib.ptr(out), ws, wsb,
                                         _lib.stream_ptr()))
     return out
+
+
+def init_proposals(init_kernels, loc_feats, x_feats, engine=_lib.ENGINE_AUTO):
+    """Tail of ConvKernelHead._decode_init_proposals (knet/det/kernel_head.py:212, 234-254) with the
+    shipped settings proposal_feats_with_obj=True, use_binary=True:
+        mask_preds = init_kernels(loc_feats);  obj = einsum(1[sigmoid(mask_preds) > 0.5], x_feats);
+        proposal_feats = init_kernels.weight + obj
+    init_kernels: the nn.Conv2d(C, N, 1) of the head.  Returns (proposal_feats [B,N,C,1,1] fp32, mask_preds [B,N,H,W])."""
+    w = init_kernels.weight
+    if w.shape[-1] != 1 or w.shape[-2] != 1:
+        raise NotImplementedError('conv_kernel_size != 1 is not on the shipped path')
+    if not x_feats.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    B, Cc, H, W = x_feats.shape
+    N = w.shape[0]
+    x_feats = x_feats.contiguous()
+    loc_feats = loc_feats.to(x_feats.dtype).contiguous()
+    xd = _lib.dtype_code(x_feats.dtype)
+    wf = w.detach().reshape(N, Cc).to(device=x_feats.device, dtype=torch.float32).contiguous()
+    bf = None if init_kernels.bias is None else init_kernels.bias.detach().to(device=x_feats.device, dtype=torch.float32).contiguous()
+    shape = _lib.make_shape(B, N, Cc, H, W, 32, 1, 8 if Cc % 8 == 0 and Cc // 8 <= 32 else Cc // 32, xd, _lib.VKN_F32,
+                            True, engine, 0.0)
+    ws, wsb = _ws.get(shape, x_feats.device)
+    mask = torch.empty(B, N, H, W, dtype=x_feats.dtype, device=x_feats.device)
+    prop = torch.empty(B, N, Cc, dtype=torch.float32, device=x_feats.device)
+    _lib.check(_lib.lib().vkn_init_proposals(shape, _lib.ptr(wf), _lib.ptr(bf), _lib.ptr(loc_feats), _lib.ptr(x_feats),
+                                             _lib.ptr(mask), _lib.ptr(prop), ws, wsb, _lib.stream_ptr()))
+    return prop.reshape(B, N, Cc, 1, 1), mask
