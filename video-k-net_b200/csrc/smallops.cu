@@ -673,12 +673,11 @@ int launch_linear(const LinArgs *probs, int nprob, int w_dtype, cudaStream_t str
     b.p[1].dbg = ts;
   }
   const int ks = b.p[0].ksplit;
-  // Tile choice.  These kernels are latency-bound, so the grid is kept near one resident wave.  Always 16-row
-  // tiles (32/64-row tiles measured slower: more serial row groups per warp).  Columns: 32 for a single frame
-  // (56-224 CTAs), 64 for the wide FFN layer, and 128 once frame batches bring hundreds of rows -- the row prologue
-  // is then recomputed by 2 instead of 8 column-block CTAs and the CTA count drops 4x.
-  int bn = maxN >= 1024 ? 64 : 32;
-  if (maxM > 128 && maxN >= 128) bn = w_dtype == VKN_BF16 ? 128 : 64;   // fp32 weight tiles of 128 columns do not fit double-buffered
+  // Tile choice (measured on B200, tools/kernel_times.py + VKN_LINEAR_BN sweep): always 16-row tiles (32/64-row
+  // tiles lose to more waves of 16-row CTAs: serial row groups per warp); 64 columns is the best or within 2 % of
+  // the best column width from 100 to 800 rows (32 columns recompute the row prologue in 8 CTAs instead of 4;
+  // 128 columns leave too few CTAs for a single frame).
+  int bn = maxN >= 64 ? 64 : 32;
   if (const char *e = getenv("VKN_LINEAR_BN")) {
     const int v = atoi(e);
     if (v == 32 || v == 64 || (v == 128 && w_dtype == VKN_BF16)) bn = v;
