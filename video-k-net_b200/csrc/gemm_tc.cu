@@ -196,21 +196,22 @@ static PoolPlan pool_plan(const VknShape &s) {
 }
 int pool_tc_chunks(const VknShape &s) { return tc_supported(s) ? pool_plan(s).nchunks : 0; }
 
-constexpr int POOL_STAGES_MAX = 4;
+constexpr int POOL_STAGES_MAX = 3;     // (x 32 KB + raw logits 16 KB + A tile 16 KB) x 3 = 192 KB at C = 256
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16 *__restrict__ mask,
+vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_m,
                    float *__restrict__ partials, float *__restrict__ cnt_partials, int B, int N, int C, int HW,
                    int nblocks, int bpc, float thr, uint32_t idesc, int POOL_STAGES) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t x_bytes = (uint32_t)C * 128u;          // C rows x 64 px x 2 B
-  const uint32_t m_bytes = 128u * 128u;
-  const uint32_t stage_bytes = x_bytes + m_bytes;
+  const uint32_t m_bytes = 128u * 128u;                 // 128 kernels x 64 px x 2 B: raw logits, and the {0,1} A tile
+  const uint32_t stage_bytes = x_bytes + 2u * m_bytes;  // x | raw mask logits (TMA) | thresholded A tile
   uint64_t *bars = (uint64_t *)(smem + POOL_STAGES * stage_bytes);
   const uint32_t bar0 = smem_u32(bars);
-  // barrier slots: full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (STAGES + s), tmem_full = bar0 + 16 STAGES
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * POOL_STAGES + 1);
+  // barrier slots: full[s] = bar0 + 8 s (TMA: x + raw logits), empty[s] = bar0 + 8 (STAGES + s) (MMA retired),
+  // tmem_full = bar0 + 16 STAGES, afull[s] = bar0 + 8 (2 STAGES + 1 + s) (A tile written by the 4 producer warps)
+  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * POOL_STAGES + 1);
   const uint32_t smem0 = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,9 +223,11 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&tmap_x);
+      prefetch_tmap(&tmap_m);
       for (int s = 0; s < POOL_STAGES; ++s) {
-        mbar_init(bar0 + 8 * s, 1 + 4);                  // TMA expect_tx arrive + one arrive per producer warp
+        mbar_init(bar0 + 8 * s, 1);                      // TMA expect_tx arrive (x tile + raw mask tile)
         mbar_init(bar0 + 8 * (POOL_STAGES + s), 1);      // tcgen05.commit
+        mbar_init(bar0 + 8 * (2 * POOL_STAGES + 1 + s), 4);   // one arrive per producer warp
       }
       mbar_init(bar0 + 16 * POOL_STAGES, 1);
       fence_barrier_init();
@@ -244,8 +247,9 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
         const int s = i % POOL_STAGES;
         const uint32_t ph = (uint32_t)(i / POOL_STAGES) & 1u;
         mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
-        mbar_expect_tx(bar0 + 8 * s, x_bytes);
+        mbar_expect_tx(bar0 + 8 * s, x_bytes + m_bytes);
         tma_load_3d(smem0 + s * stage_bytes, &tmap_x, bar0 + 8 * s, (blk_beg + i) * PX_BLK, 0, b);
+        tma_load_3d(smem0 + s * stage_bytes + x_bytes, &tmap_m, bar0 + 8 * s, (blk_beg + i) * PX_BLK, mtile * 128, b);
       }
     }
   } else if (warp == 1) {
@@ -253,9 +257,10 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
       for (int i = 0; i < nk; ++i) {
         const int s = i % POOL_STAGES;
         const uint32_t ph = (uint32_t)(i / POOL_STAGES) & 1u;
-        mbar_wait(bar0 + 8 * s, ph);
+        mbar_wait(bar0 + 8 * s, ph);                              // x tile landed
+        mbar_wait(bar0 + 8 * (2 * POOL_STAGES + 1 + s), ph);      // A tile written
         tc_fence_after();
-        const uint32_t xs = smem0 + s * stage_bytes, ms = xs + x_bytes;
+        const uint32_t xs = smem0 + s * stage_bytes, ms = xs + x_bytes + m_bytes;
 #pragma unroll
         for (int k = 0; k < PX_BLK / 16; ++k) {
           const uint64_t ad = umma_desc_sw128(ms + k * 32, 0, 1024);
@@ -271,36 +276,26 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
     const int pt = threadIdx.x - 64;                      // 0..127
     const int j = pt & 7;                                 // 16-byte chunk (8 pixels) within the 64-px row
     const int rbase = pt >> 3;                            // rows rbase + 16 i
-    const __nv_bfloat16 *mb = mask + (size_t)b * N * HW;
     float cnt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cnt[i] = 0.f;
-    // software pipeline: the mask logits of block it+1 are requested before block it is thresholded, so
-    // the global-load latency of every block but the first is hidden behind the previous one
-    uint4 raw[8], nxt[8] = {};
-    auto load_block = [&](int it, uint4 (&dst)[8]) {
-      const int p = (blk_beg + it) * PX_BLK + j * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int n = mtile * 128 + rbase + 16 * i;
-        dst[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (n < N && p < HW) dst[i] = __ldg(reinterpret_cast<const uint4 *>(mb + (size_t)n * HW + p));
-      }
-    };
-    load_block(0, raw);
+    // The raw logits arrive by TMA in the same 128B-swizzled [row][64 px] layout the A tile uses, so a thread
+    // reads and writes the SAME offset: no global-load latency on this path, the ring prefetches POOL_STAGES deep.
     for (int it = 0; it < nk; ++it) {
       const int s = it % POOL_STAGES;
       const uint32_t ph = (uint32_t)(it / POOL_STAGES) & 1u;
-      if (it + 1 < nk) load_block(it + 1, nxt);
-      mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
-      uint8_t *mt = smem + s * stage_bytes + x_bytes;
+      mbar_wait(bar0 + 8 * s, ph);
+      const uint8_t *rawt = smem + s * stage_bytes + x_bytes;
+      uint8_t *mt = smem + s * stage_bytes + x_bytes + m_bytes;
       const int p = (blk_beg + it) * PX_BLK + j * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rbase + 16 * i;
         const int n = mtile * 128 + r;
         const bool live = (n < N && p < HW);
-        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);   // Swizzle<3,4,3>
+        const uint4 rw = *reinterpret_cast<const uint4 *>(rawt + off);
+        const uint32_t w[4] = {rw.x, rw.y, rw.z, rw.w};
         uint32_t o[4];
         float c = 0.f;
 #pragma unroll
@@ -311,14 +306,11 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat
           c += (blo ? 1.f : 0.f) + (bhi ? 1.f : 0.f);
         }
         cnt[i] += c;
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);   // Swizzle<3,4,3>
         *reinterpret_cast<uint4 *>(mt + off) = make_uint4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * s);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) raw[i] = nxt[i];
+      if (lane == 0) mbar_arrive(bar0 + 8 * (2 * POOL_STAGES + 1 + s));
     }
     // ---- epilogue: accumulators -> partial sums -----------------------------------------------
     mbar_wait(bar0 + 16 * POOL_STAGES, 0);
@@ -380,7 +372,13 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   // pipeline depth = blocks per CTA (<= 4): a CTA that reduces 2 pixel blocks needs 2 stages, and the smaller
   // footprint lets CTAs of other streams' kernels co-reside on the SM
   const int pool_stages = p.bpc < POOL_STAGES_MAX ? p.bpc : POOL_STAGES_MAX;
-  size_t smem = (size_t)pool_stages * ((size_t)s.C * 128 + 128 * 128) + 1024 + 256;
+  size_t smem = (size_t)pool_stages * ((size_t)s.C * 128 + 2 * 128 * 128) + 1024 + 256;
+  CUtensorMap tmap_m;
+  {
+    const uint64_t mdims[3] = {(uint64_t)HW, (uint64_t)s.N, (uint64_t)s.B};
+    const uint32_t mbox[3] = {(uint32_t)PX_BLK, 128u, 1u};
+    VKN_TRY(make_tmap_bf16(&tmap_m, mask, 3, mdims, mbox));
+  }
   if (smem < 4 * 32 * 36 * 4 + 2048) smem = 4 * 32 * 36 * 4 + 2048;      // epilogue staging
   static bool attr = false;
   if (!attr) {
@@ -389,7 +387,7 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   }
   dim3 grid(p.nchunks, p.mtiles, s.B);
   VKN_LAUNCH_MARK("vkn_pool_tc_kernel", stream);
-  VKN_CUDA_OK(launch_chain(vkn_pool_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmap, (const __nv_bfloat16 *)mask,
+  VKN_CUDA_OK(launch_chain(vkn_pool_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmap, tmap_m,
                            partials, cnt_partials, s.B, s.N, s.C, HW, p.nblocks, p.bpc, s.mask_thr_logit,
                            make_idesc_bf16(128, s.C, 0, 0), pool_stages));
   return VKN_OK;
