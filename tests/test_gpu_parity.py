@@ -479,3 +479,64 @@ def test_init_proposals_golden_and_full_size(dev):
         assert flips <= 4, 'threshold disagreements vs the fp32 oracle: %d' % flips
         if flips == 0:
             assert maxabs(p, want_p) < 1e-4 * want_p.abs().max().item()
+
+
+# ---- tcgen05 row engine (planes handed between row GEMMs) vs the warp-MMA chain and the oracle -------------------
+@pytest.mark.parametrize('B,N,C,H,W,Fh,S', [(1, 20, 64, 16, 24, 512, 2), (2, 100, 256, 40, 24, 512, 2),
+                                             (5, 100, 256, 24, 40, 2048, 1), (3, 117, 128, 16, 24, 192, 2)])
+def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H, W, Fh, S):
+    import vknet
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=Fh)
+    sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=90 + s)) for s in range(S)]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=16)
+    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
+    want = ko.iter_forward(sds, [cfg] * S, x, pf, mask, mask_round=ko.round_bf16)
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
+    xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
+    outs = {}
+    for mode, rows_min in (('warp', '0'), ('tc', '1')):
+        monkeypatch.setenv('VKN_ROWS_TC_MIN', rows_min)
+        obj, m = pfd, mb
+        res = []
+        for h in heads:
+            cls, m, obj = h(xb, obj, m)
+            res.append((cls.clone(), m.clone(), obj.clone()))
+        outs[mode] = res
+        loop = vknet.KernelIterLoop(heads)          # one-call loop: obj planes ping-pong between stages
+        cls_l, m_l, obj_l = loop(xb, pfd, mb)
+        assert torch.equal(m_l, res[-1][1]) and torch.equal(obj_l, res[-1][2]) and torch.equal(cls_l, res[-1][0]), mode
+    for s in range(S):
+        cls, m, obj = outs['tc'][s]
+        assert maxabs(cls, want[s][0]) < TOL_BF16 and maxabs(obj, want[s][2]) < TOL_BF16, 'row engine stage %d' % s
+        ref = want[s][1]
+        assert (m.float().cpu() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+        assert (m.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item() < 2e-3
+    # both engines multiply exact bf16 products with fp32 accumulation: first-stage kernels agree to fp32 round-off
+    assert maxabs(outs['tc'][0][2], outs['warp'][0][2].cpu()) < 2e-4
+    assert maxabs(outs['tc'][0][0], outs['warp'][0][0].cpu()) < 2e-4
+
+
+def test_row_engine_tc_variants(dev, monkeypatch):
+    """with_ffn=False, no feat_transform, deeper FC stacks, non-default threshold, video head (x_feat handed in)."""
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    C = 64
+    cfg = ko.default_cfg(num_classes=5, in_channels=C, feedforward_channels=64, with_ffn=False,
+                         feat_transform_cfg=None, num_mask_fcs=3, num_cls_fcs=2, hard_mask_thr=0.7)
+    sd = ko.random_state_dict(cfg, seed=1)
+    g = torch.Generator().manual_seed(8)
+    for i in (1, 2):
+        sd['mask_fcs.%d.weight' % (3 * i)] = ko._xavier(g, C, C)
+        ko._ln_params(g, sd, 'mask_fcs.%d.' % (3 * i + 1), C)
+    sd['cls_fcs.3.weight'] = ko._xavier(g, C, C)
+    ko._ln_params(g, sd, 'cls_fcs.4.', C)
+    for k in [k for k in sd if k.startswith('ffn')]:
+        del sd[k]
+    sd = ko.round_state_dict_bf16(sd)
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    x, pf, mask = ko.dummy_inputs(2, 14, C, 8, 16, seed=2)
+    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
+    want = ko.kernel_update_head_forward(sd, cfg, x, pf, mask)
+    cls, nm, obj = h(x.to(dev).bfloat16(), pf.to(dev), mask.to(dev).bfloat16())
+    assert maxabs(cls, want[0]) < TOL_BF16 and maxabs(obj, want[2]) < TOL_BF16
+    ref = ko.round_bf16(want[1])
+    assert (nm.float().cpu() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()

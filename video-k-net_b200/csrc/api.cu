@@ -69,6 +69,8 @@ struct Layout {
   float *link_fc, *link_cur, *obj_tmp;
   void *row_planes;  // bf16 hi/mid/lo planes [3][P][C] of a materialised row transform (gate output, pre-head rows)
   void *a_split;     // tcgen05 engine: bf16 hi/mid/lo planes of a_ext
+  void *pl[4];       // tcgen05 row engine: bf16 hi/mid/lo planes [3][P][C] handed from one row operator to the next
+  void *obj_pl[2];   // planes of a stage's obj_feat (= the next stage's proposal_feat), ping-pong across stages
   // iter loop
   void *mask_pp[2];
   float *obj_pp[2], *cls_tmp;
@@ -128,6 +130,8 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   L.link_cur = (float *)take(P * C * f);
   L.obj_tmp = (float *)take(P * C * f);
   L.row_planes = take((size_t)3 * P * C * 2);
+  for (int i = 0; i < 4; ++i) L.pl[i] = take((size_t)3 * P * C * 2);
+  for (int i = 0; i < 2; ++i) L.obj_pl[i] = take((size_t)3 * P * C * 2);
   const size_t npad = (size_t)ceil_div(s.N, 128) * 128;
   L.a_split = take((size_t)3 * s.B * npad * C * 2);
   const size_t esz = s.x_dtype == VKN_BF16 ? 2 : 4;
@@ -161,6 +165,7 @@ struct Ctx {
   cudaStream_t st;
   int P;
   bool use_tc;
+  bool rows_tc;     // row operators on the tcgen05 row engine (planes handed between launches)
 };
 
 static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, Ctx &c) {
@@ -177,6 +182,11 @@ static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, 
   if (s->engine == VKN_ENGINE_TC && !can)
     VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 engine requested but the shape/dtype does not qualify");
   c.use_tc = (s->engine != VKN_ENGINE_SIMT) && can;
+  // Row engine: below a few hundred rows the fused-prologue warp-MMA chain (fewer launches) wins; above, the
+  // tcgen05 row GEMM (measured crossover: profiles/, VKN_ROWS_TC_MIN overrides; 0 disables).
+  int rows_min = 400;
+  if (const char *e = getenv("VKN_ROWS_TC_MIN")) rows_min = atoi(e);
+  c.rows_tc = c.use_tc && s->w_dtype == VKN_BF16 && rows_min > 0 && c.P >= rows_min;
   return VKN_OK;
 }
 
@@ -417,8 +427,156 @@ static int k_maskgemm(Ctx &c, const VknHeadW &w, const void *x, const float *mk,
   return launch_maskgemm_simt(c.s, x, c.L.a_ext, lda, out, c.st);
 }
 
+
+// ---- the same stage on the tcgen05 row engine (many rows in flight) --------------------------------
+// Every row transform is evaluated ONCE per row (row operator / GEMM epilogue) and handed to the next GEMM as bf16
+// hi/mid/lo planes, so the GEMMs are plain  planes x W^T  on tensor cores with TMA-fed operands.
+static RowSrc src_planes(const void *pl, int ld, long long plane_stride) {
+  RowSrc r = src_copy((const float *)pl, ld);
+  r.pro = PRO_PLANES;
+  r.sum_stride = plane_stride;
+  return r;
+}
+static void out_planes(LinArgs &a, void *pl, int rows, int ld) {
+  a.epi |= EPI_SPLIT3;
+  a.split_planes = (__nv_bfloat16 *)pl;
+  a.split_B = 1;
+  a.split_N = rows;
+  a.split_Npad = rows;
+  a.split_C = ld;
+}
+
+static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *pf, const void *pf_planes, const void *mask,
+                        const float *x_feat_in, float *cls, void *new_mask, float *obj, float *x_feat_out,
+                        void *obj_planes_out) {
+  const int C = c.s.C, P = c.P, F = c.s.ffn_dim;
+  const long long PS = (long long)P * C;
+  void *PLA = c.L.pl[0], *PLB = c.L.pl[1], *PLC = c.L.pl[2], *PLD = c.L.pl[3];
+  if (obj_planes_out == nullptr) obj_planes_out = c.L.obj_pl[0];
+  // a3+a4 (+a2 folded): pooled feature -> x_feat fp32 + planes (PLB)
+  if (x_feat_in == nullptr) {
+    float *xf = x_feat_out ? x_feat_out : c.L.xp;
+    int nch = 0;
+    const VknShape fs = frames_shape(c.s);
+    VKN_TRY(launch_pool_tc(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+    VKN_TRY(launch_pool_reduce(c.s, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st, PLA));
+    LinArgs a = lin(src_planes(PLA, C, PS), w.ft_w, C, w.ft_b, xf, C, P, C, C, EPI_ROWSCALE);
+    a.rowscale = c.L.cnt;
+    out_planes(a, PLB, P, C);
+    VKN_TRY(launch_linear_tc(&a, 1, c.st));
+  } else {
+    float *copy_to = (x_feat_out && x_feat_out != x_feat_in) ? x_feat_out : nullptr;
+    VKN_TRY(launch_rowprep(src_copy(x_feat_in, C), copy_to, C, PLB, C, PS, P, C, c.st));
+  }
+  if (pf_planes == nullptr) {
+    VKN_TRY(launch_rowprep(src_copy(pf, C), nullptr, 0, PLC, C, PS, P, C, c.st));
+    pf_planes = PLC;
+  }
+  // a5 KernelUpdator (kernel_updator.py:56-94)
+  const VknUpdatorW &u = w.upd;
+  LinArgs two[2];
+  two[0] = lin(src_planes(PLB, C, PS), u.dyn_w, C, u.dyn_b, c.L.dyn, 2 * C, P, 2 * C, C, 0);          // :59
+  two[1] = lin(src_planes(pf_planes, C, PS), u.inp_w, C, u.inp_b, c.L.inp, 2 * C, P, 2 * C, C, 0);    // :65-66
+  VKN_TRY(launch_linear_tc(two, 2, c.st));
+  RowSrc g;
+  memset(&g, 0, sizeof(g));
+  g.pro = PRO_MUL;                                                                                     // :70
+  g.nsum = 1;
+  g.a[0] = c.L.inp;  g.lda[0] = 2 * C;
+  g.a[1] = c.L.dyn;  g.lda[1] = 2 * C;
+  VKN_TRY(launch_rowprep(g, nullptr, 0, PLA, C, PS, P, C, c.st));
+  two[0] = lin(src_planes(PLA, C, PS), u.ig_w, C, u.ig_b, c.L.igp, C, P, C, C, 0);                    // :74
+  two[1] = lin(src_planes(PLA, C, PS), u.ug_w, C, u.ug_b, c.L.ugp, C, P, C, C, 0);                    // :75
+  VKN_TRY(launch_linear_tc(two, 2, c.st));
+  RowSrc gt;
+  memset(&gt, 0, sizeof(gt));
+  gt.pro = PRO_GATE;                                                                                   // :76-88
+  gt.nsum = 1;
+  gt.a[0] = c.L.ugp;       gt.lda[0] = C;      gt.ln_g[0] = u.norm_in_g;    gt.ln_b[0] = u.norm_in_b;
+  gt.a[1] = c.L.dyn + C;   gt.lda[1] = 2 * C;  gt.ln_g[1] = u.norm_out_g;   gt.ln_b[1] = u.norm_out_b;
+  gt.a[2] = c.L.igp;       gt.lda[2] = C;      gt.ln_g[2] = u.inorm_in_g;   gt.ln_b[2] = u.inorm_in_b;
+  gt.a[3] = c.L.inp + C;   gt.lda[3] = 2 * C;  gt.ln_g[3] = u.inorm_out_g;  gt.ln_b[3] = u.inorm_out_b;
+  VKN_TRY(launch_rowprep(gt, nullptr, 0, PLB, C, PS, P, C, c.st));
+  LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.fc, C, P, C, C, 0);                  // :90
+  VKN_TRY(launch_linear_tc(&f, 1, c.st));
+  VKN_TRY(launch_rowprep(src_ln(c.L.fc, C, u.fc_norm_g, u.fc_norm_b, true), c.L.o, C, PLA, C, PS, P, C, c.st));   // :91-92
+  // a6 MHSA + LN (kernel_update_head.py:204-208)
+  LinArgs qkv = lin(src_planes(PLA, C, PS), w.attn.in_w, C, w.attn.in_b, c.L.qkv, 3 * C, P, 3 * C, C, 0);
+  VKN_TRY(launch_linear_tc(&qkv, 1, c.st));
+  VKN_TRY(launch_attention(c.L.qkv, 3 * C, c.L.qkv + C, 3 * C, c.L.qkv + 2 * C, 3 * C, nullptr, C, c.s.B, c.s.N, C,
+                           c.s.num_heads, c.st, PLB, PS));
+  LinArgs op = lin(src_planes(PLB, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.y, C, P, C, C, EPI_RES);
+  op.res = c.L.o;
+  op.ldres = C;
+  VKN_TRY(launch_linear_tc(&op, 1, c.st));
+  float *obj_dst = obj ? obj : c.L.obj_tmp;
+  RowSrc an = src_ln(c.L.y, C, w.attn.norm_g, w.attn.norm_b, false);
+  if (c.s.with_ffn) {
+    // a7 FFN + LN (:214-215)
+    VKN_TRY(launch_rowprep(an, c.L.o2, C, PLA, C, PS, P, C, c.st));
+    LinArgs f1 = lin(src_planes(PLA, C, PS), w.ffn.w1, C, w.ffn.b1, nullptr, F, P, F, C, EPI_RELU | EPI_NOOUT);
+    out_planes(f1, c.L.h, P, F);
+    VKN_TRY(launch_linear_tc(&f1, 1, c.st));
+    LinArgs f2 = lin(src_planes(c.L.h, F, (long long)P * F), w.ffn.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
+    const int nk = ceil_div(F, 64);
+    int ksp = 148 / (ceil_div(P, 128) * ceil_div(C, 128));
+    ksp = ksp >= 8 ? 8 : (ksp >= 4 ? 4 : (ksp >= 2 ? 2 : 1));
+    while (ksp > 1 && (nk % ksp != 0 || nk / ksp < 4)) ksp /= 2;
+    f2.ksplit = ksp;
+    f2.out_split_stride = PS;
+    VKN_TRY(launch_linear_tc(&f2, 1, c.st));
+    RowSrc r = src_ln(c.L.zpart, C, w.ffn.norm_g, w.ffn.norm_b, false);
+    r.nsum = ksp;
+    r.sum_stride = PS;
+    r.pbias = w.ffn.b2;
+    r.pres = c.L.o2;
+    r.ldpres = C;
+    VKN_TRY(launch_rowprep(r, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
+  } else {
+    VKN_TRY(launch_rowprep(an, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
+  }
+  // a8 heads (:217-227)
+  if (w.num_cls_fcs < 0 || w.num_cls_fcs > VKN_MAX_FCS || w.num_mask_fcs < 0 || w.num_mask_fcs > VKN_MAX_FCS)
+    VKN_FAIL(VKN_E_UNSUPPORTED, "num_cls_fcs / num_mask_fcs must be in [0, %d]", VKN_MAX_FCS);
+  const bool with_cls = w.fc_cls_w != nullptr && cls != nullptr;
+  const int ncls_fcs = with_cls ? w.num_cls_fcs : 0;
+  const int depth = ncls_fcs > w.num_mask_fcs ? ncls_fcs : w.num_mask_fcs;
+  const void *cs = obj_planes_out, *ms = obj_planes_out;
+  for (int i = 0; i < depth; ++i) {
+    int n = 0;
+    if (i < ncls_fcs) two[n++] = lin(src_planes(cs, C, PS), w.cls_fc_w[i], C, nullptr, c.L.pre_c[0], C, P, C, C, 0);
+    if (i < w.num_mask_fcs) two[n++] = lin(src_planes(ms, C, PS), w.mask_fc_w[i], C, nullptr, c.L.pre_m[0], C, P, C, C, 0);
+    VKN_TRY(launch_linear_tc(two, n, c.st));
+    if (i < ncls_fcs) {
+      VKN_TRY(launch_rowprep(src_ln(c.L.pre_c[0], C, w.cls_ln_g[i], w.cls_ln_b[i], true), nullptr, 0, PLA, C, PS, P, C, c.st));
+      cs = PLA;
+    }
+    if (i < w.num_mask_fcs) {
+      VKN_TRY(launch_rowprep(src_ln(c.L.pre_m[0], C, w.mask_ln_g[i], w.mask_ln_b[i], true), nullptr, 0, PLB, C, PS, P, C, c.st));
+      ms = PLB;
+    }
+  }
+  two[0] = lin(src_planes(ms, C, PS), w.fc_mask_w, C, w.fc_mask_b, c.L.mk, C, P, C, C, 0);
+  out_planes(two[0], PLD, P, C);
+  if (with_cls) two[1] = lin(src_planes(cs, C, PS), w.fc_cls_w, C, w.fc_cls_b, cls, c.s.num_classes, P, c.s.num_classes, C, 0);
+  VKN_TRY(launch_linear_tc(two, with_cls ? 2 : 1, c.st));
+  if (new_mask == nullptr) return VKN_OK;
+  // a9 (+a2 folded): a = mk . ft_w (planes for the mask conv), bias column mk . ft_b
+  const int lda = C + A_EXT_PAD;
+  LinArgs a = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, c.L.a_ext, lda, P, C + 1, C, EPI_SPLIT3);
+  a.split_planes = (__nv_bfloat16 *)c.L.a_split;
+  a.split_B = c.s.B;
+  a.split_N = c.s.N;
+  a.split_Npad = maskgemm_tc_npad(c.s);
+  a.split_C = C;
+  VKN_TRY(launch_linear_tc(&a, 1, c.st));
+  return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st);
+}
+
 static int stage(Ctx &c, const VknHeadW &w, const void *x, const float *pf, const void *mask,
-                 const float *x_feat_in, float *cls, void *new_mask, float *obj, float *x_feat_out) {
+                 const float *x_feat_in, float *cls, void *new_mask, float *obj, float *x_feat_out,
+                 const void *pf_planes = nullptr, void *obj_planes_out = nullptr) {
+  if (c.rows_tc) return stage_planes(c, w, x, pf, pf_planes, mask, x_feat_in, cls, new_mask, obj, x_feat_out, obj_planes_out);
   const int C = c.s.C;
   const float *xp = x_feat_in;
   if (xp == nullptr) {
@@ -449,7 +607,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -574,7 +732,8 @@ int vkn_iter_forward(const VknShape *s, const VknHeadW *stages, int num_stages, 
     float *obj_o = last ? obj_feat : c.L.obj_pp[i & 1];
     void *mask_o = last ? new_mask_preds : c.L.mask_pp[i & 1];
     float *cls_o = last ? cls_score : c.L.cls_tmp;
-    VKN_TRY(stage(c, stages[i], x, pf, mk, nullptr, cls_o, mask_o, obj_o, nullptr));
+    VKN_TRY(stage(c, stages[i], x, pf, mk, nullptr, cls_o, mask_o, obj_o, nullptr,
+                  i > 0 ? c.L.obj_pl[(i - 1) & 1] : nullptr, c.L.obj_pl[i & 1]));
     pf = obj_o;
     mk = mask_o;
   }

@@ -190,13 +190,17 @@ int launch_rowop(const RowSrc &src, float *out, int ldo, int M, int K, cudaStrea
 int launch_rowprep(const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int M, int K,
                    cudaStream_t stream);
 int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
-                     int ldo, int B, int N, int C, int heads, cudaStream_t stream);
+                     int ldo, int B, int N, int C, int heads, cudaStream_t stream, void *planes = nullptr,
+                     long long plane_stride = 0);
+// tcgen05 row GEMM (rowgemm_tc.cu): same contract as launch_linear for PRO_PLANES inputs and bf16 weights
+bool linear_tc_supported(const LinArgs &a);
+int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream);
 // SIMT fp32 engines for the two big contractions (gemm_simt.cu)
 int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
                      int *nchunks, cudaStream_t stream);
 int pool_simt_chunks(const VknShape &s);
 int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
-                       float *xp0, float *cnt, cudaStream_t stream);
+                       float *xp0, float *cnt, cudaStream_t stream, void *planes = nullptr);
 int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, int lda, void *out,
                          cudaStream_t stream);
 // tcgen05 / TMA engines (gemm_tc.cu)

@@ -124,7 +124,8 @@ int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *
 __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__restrict__ partials,
                                                               const float *__restrict__ cnt_partials, int nchunks,
                                                               int B, int F, int N, int NC, float scale,
-                                                              float *__restrict__ xp0, float *__restrict__ cnt) {
+                                                              float *__restrict__ xp0, float *__restrict__ cnt,
+                                                              __nv_bfloat16 *__restrict__ planes) {
   __shared__ float4 red[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -166,7 +167,25 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
       const float4 u = red[w][lane];
       t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
-    *reinterpret_cast<float4 *>(xp0 + (size_t)b * NC + idx) = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
+    const float v4[4] = {t.x * scale, t.y * scale, t.z * scale, t.w * scale};
+    *reinterpret_cast<float4 *>(xp0 + (size_t)b * NC + idx) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+    if (planes != nullptr) {       // A operand of the tcgen05 row GEMM that follows: bf16 hi/mid/lo planes [3][B*N][C]
+      uint16_t h[3][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float xr = v4[e];
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const __nv_bfloat16 hb = __float2bfloat16_rn(xr);
+          xr -= __bfloat162float(hb);
+          h[pl][e] = __bfloat16_as_ushort(hb);
+        }
+      }
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+        *reinterpret_cast<uint2 *>(planes + (size_t)pl * B * NC + (size_t)b * NC + idx) =
+            make_uint2((uint32_t)h[pl][0] | ((uint32_t)h[pl][1] << 16), (uint32_t)h[pl][2] | ((uint32_t)h[pl][3] << 16));
+    }
   }
   // pixel counts of the set: CTAs x < ceil(N/32) each own 32 kernels; warp w sums slices w, w+8, ...
   // (lane = kernel), then the 8 warp sums are combined in fixed order.
@@ -194,14 +213,14 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
 }
 
 int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
-                       float *xp0, float *cnt, cudaStream_t stream) {
+                       float *xp0, float *cnt, cudaStream_t stream, void *planes) {
   const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
   const int NC = s.N * s.C;
   VKN_LAUNCH_MARK("vkn_pool_reduce_kernel", stream);
   int gx = ceil_div(NC, 128);
   if (gx < ceil_div(s.N, 32)) gx = ceil_div(s.N, 32);
   VKN_CUDA_OK(launch_chain(vkn_pool_reduce_kernel, dim3(gx, s.B), dim3(256), 0, stream, partials, cnt_partials, nchunks,
-                           s.B, F, s.N, NC, 1.0f / (float)F, xp0, cnt));
+                           s.B, F, s.N, NC, 1.0f / (float)F, xp0, cnt, (__nv_bfloat16 *)planes));
   return VKN_OK;
 }
 

@@ -1,0 +1,312 @@
+// tcgen05 engine for the row operators of a stage when many rows are in flight (P = frames x kernels >= a few
+// hundred): every nn.Linear of KernelUpdator / MultiheadAttention / FFN / the FC heads
+// (knet/kernel_updator.py:56-94, knet/det/kernel_update_head.py:204-227) is   Y = epi(X . W^T)   with
+//
+//   A = X as three bf16 planes hi/mid/lo [3][M][K] (X = hi + mid + lo to 24 bits, written once per row by the
+//       producing kernel), K-major, TMA (SWIZZLE_128B), one 3-D box {64 k, 128 rows, 3 planes} per pipeline stage
+//   B = W [N][K] bf16 as stored by the module, K-major, TMA (SWIZZLE_128B), box {64 k, BN}
+//   D = [128 rows x BN] fp32 in TMEM; the three planes accumulate into the same tile (every bf16 x bf16 product is
+//       exact, so the result carries fp32-level accuracy: DESIGN.md section 4)
+//
+// Epilogue: thread = row (TMEM lane); bias (x rowscale), residual, ReLU; fp32 rows and / or bf16 planes for the next
+// GEMM, transposed through shared memory so that global stores are full lines.  Split-K over blockIdx.z; two
+// problems per launch.  Weight tiles and bias are prefetched BEFORE griddepcontrol.wait (PDL).
+#include "tc.cuh"
+
+namespace vkn {
+
+struct RgProb {
+  CUtensorMap tmA;
+  CUtensorMap tmW;
+  const float *bias, *rowscale, *res;
+  float *out;
+  __nv_bfloat16 *planes;
+  long long out_split_stride, plane_elems;
+  int ldres, ldo, M, N, K, epi, split_N, split_Npad, split_C;
+};
+struct RgBatch {
+  RgProb p[2];
+  int ksplit, stages, BN;
+  uint32_t idesc;
+};
+
+constexpr uint32_t RG_A_PLANE = 128u * 128u;        // 128 rows x 64 k x 2 B
+constexpr uint32_t RG_A_BYTES = 3u * RG_A_PLANE;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __grid_constant__ RgBatch batch) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int BN = batch.BN, STG = batch.stages, ks_total = batch.ksplit;
+  const RgProb &P = batch.p[blockIdx.z / ks_total];
+  const int ks = blockIdx.z % ks_total;
+  const int row0 = blockIdx.y * 128, col0 = blockIdx.x * BN;
+  if (row0 >= P.M || col0 >= P.N) {
+    pdl_trigger();
+    return;
+  }
+  const uint32_t w_bytes = (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = RG_A_BYTES + w_bytes;
+  uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // full[s] = bar0 + 8 s (TMA: A planes + W tile), empty[s] = bar0 + 8 (STG + s) (MMAs retired), tmem_full = bar0 + 16 STG
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 1);
+  float *bias_s = (float *)(tmem_slot + 2);
+  const uint32_t smem0 = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk_total = (P.K + 63) / 64;
+  const int kper = nk_total / ks_total;               // host guarantees divisibility
+  const int kb = ks * kper, nk = kper;
+  const uint32_t ncols = BN < 32 ? 32u : (uint32_t)BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&P.tmA);
+      prefetch_tmap(&P.tmW);
+      for (int s = 0; s < STG; ++s) {
+        mbar_init(bar0 + 8 * s, 1);
+        mbar_init(bar0 + 8 * (STG + s), 1);
+      }
+      mbar_init(bar0 + 16 * STG, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), ncols);
+  }
+  for (int i = threadIdx.x; i < BN; i += TC_THREADS)       // bias is a weight: staged before the PDL wait
+    bias_s[i] = ((P.epi & EPI_BIAS) && col0 + i < P.N) ? __ldg(P.bias + col0 + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int npre = nk < STG ? nk : STG;
+      for (int i = 0; i < npre; ++i) {                      // weight tiles: nobody in the chain writes them
+        mbar_expect_tx(bar0 + 8 * i, stage_bytes);
+        tma_load_2d(smem0 + i * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * i, (kb + i) * 64, col0);
+      }
+      pdl_wait();                                           // the A planes come from the previous kernel
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STG;
+        const uint32_t ph = (uint32_t)(i / STG) & 1u;
+        if (i >= npre) {
+          mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u);
+          mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+          tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, (kb + i) * 64, col0);
+        }
+        tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, (kb + i) * 64, row0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STG;
+        const uint32_t ph = (uint32_t)(i / STG) & 1u;
+        mbar_wait(bar0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t as = smem0 + s * stage_bytes, wsm = as + RG_A_BYTES;
+#pragma unroll
+        for (int pl = 2; pl >= 0; --pl) {                   // lo, mid, hi: small terms first
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_sw128(as + (uint32_t)pl * RG_A_PLANE + k * 32, 0, 1024);
+            const uint64_t bd = umma_desc_sw128(wsm + k * 32, 0, 1024);
+            umma_bf16(tmem_base, ad, bd, batch.idesc, (i > 0 || pl < 2 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar0 + 8 * (STG + s));
+      }
+      umma_commit(bar0 + 16 * STG);
+    }
+  } else {
+    pdl_wait();                                             // residual / rowscale reads, and every global store
+    mbar_wait(bar0 + 16 * STG, 0);
+    tc_fence_after();
+    pdl_trigger();
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)q * 32 * 36;   // pipeline buffers are free now
+    const int epi = P.epi;
+    float *outp = P.out + (size_t)ks * P.out_split_stride;
+    const bool out_vec = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
+    const bool res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
+    const bool pl_vec = (P.split_C % 4 == 0);
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (col0 + c0 >= P.N) break;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4 *>(stg + lane * 36 + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                                       __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+      __syncwarp();
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3), seg = lane & 7;
+        const int row = row0 + q * 32 + rr, col = col0 + c0 + seg * 4;
+        if (row < P.M && col < P.N) {
+          const float4 a4 = *reinterpret_cast<const float4 *>(stg + rr * 36 + seg * 4);
+          float v[4] = {a4.x, a4.y, a4.z, a4.w};
+          const int nv = min(4, P.N - col);
+          if (epi & EPI_BIAS) {
+            const float rs = (epi & EPI_ROWSCALE) ? __ldg(P.rowscale + row) : 1.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += rs * bias_s[c0 + seg * 4 + e];
+          }
+          if (epi & EPI_RES) {
+            const float *rp = P.res + (size_t)row * P.ldres + col;
+            if (res_vec && nv == 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4 *>(rp));
+              v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+            } else {
+              for (int e = 0; e < nv; ++e) v[e] += __ldg(rp + e);
+            }
+          }
+          if (epi & EPI_RELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (!(epi & EPI_NOOUT)) {
+            float *op = outp + (size_t)row * P.ldo + col;
+            if (out_vec && nv == 4) *reinterpret_cast<float4 *>(op) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int e = 0; e < nv; ++e) op[e] = v[e];
+          }
+          if ((epi & EPI_SPLIT3) && col < P.split_C) {
+            const int b = row / P.split_N, n = row - b * P.split_N;
+            const size_t o = ((size_t)b * P.split_Npad + n) * P.split_C + col;
+            const int np = min(4, P.split_C - col);
+            uint16_t h[3][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float xr = v[e];
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {                 // v == hi + mid + lo to 24 bits
+                const __nv_bfloat16 hb = __float2bfloat16_rn(xr);
+                xr -= __bfloat162float(hb);
+                h[t][e] = __bfloat16_as_ushort(hb);
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              __nv_bfloat16 *pp = P.planes + (size_t)t * P.plane_elems + o;
+              if (pl_vec && np == 4) {
+                *reinterpret_cast<uint2 *>(pp) = make_uint2((uint32_t)h[t][0] | ((uint32_t)h[t][1] << 16),
+                                                            (uint32_t)h[t][2] | ((uint32_t)h[t][3] << 16));
+              } else {
+                for (int e = 0; e < np; ++e) pp[e] = __ushort_as_bfloat16(h[t][e]);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+static int rg_env(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && atoi(e) > 0) ? atoi(e) : dflt;
+}
+
+bool linear_tc_supported(const LinArgs &a) {
+  if (a.src.pro != PRO_PLANES) return false;
+  if (a.K % 8 != 0 || a.ldw % 8 != 0 || a.src.lda[0] % 8 != 0 || a.src.sum_stride % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(a.w) & 15) || (reinterpret_cast<uintptr_t>(a.src.a[0]) & 15)) return false;
+  return true;
+}
+
+// Same contract as launch_linear (smallops.cu) for PRO_PLANES inputs and bf16 weights.
+int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
+  if (nprob < 1 || nprob > 2) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: nprob %d", nprob);
+  RgBatch b;
+  memset(&b, 0, sizeof(b));
+  int maxM = 0, maxN = 0, nkmax = 0;
+  const int ks = probs[0].ksplit < 1 ? 1 : probs[0].ksplit;
+  for (int i = 0; i < nprob; ++i) {
+    const LinArgs &a = probs[i];
+    if (!linear_tc_supported(a))
+      VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: needs bf16 plane inputs with 16-byte aligned rows (K %d, ldw %d, lda %d)", a.K,
+               a.ldw, a.src.lda[0]);
+    if ((a.ksplit < 1 ? 1 : a.ksplit) != ks) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: batched problems must share ksplit");
+    const int nk = ceil_div(a.K, 64);
+    if (nk % ks != 0) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: K = %d does not split into %d slices of 64-blocks", a.K, ks);
+    if (a.side != nullptr) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: side outputs are not supported");
+    maxM = max(maxM, a.M);
+    maxN = max(maxN, a.N);
+    nkmax = max(nkmax, nk / ks);
+  }
+  // column tile: the widest of {128, 64, 32} that still gives ~one CTA per SM pair (latency-bound launches want
+  // the work spread; wide tiles only pay when the A planes would otherwise be re-read by many column CTAs)
+  const int mt = ceil_div(maxM, 128);
+  int BN = 32;
+  for (int cand = 128; cand >= 32; cand >>= 1) {
+    if (cand > 32 && cand / 2 >= maxN) continue;                    // tile wider than the problem
+    if ((long long)mt * ceil_div(maxN, cand) * nprob * ks >= 74 || cand == 32) {
+      BN = cand;
+      break;
+    }
+  }
+  BN = rg_env("VKN_RG_BN", BN);
+  if (BN != 32 && BN != 64 && BN != 128 && BN != 256) VKN_FAIL(VKN_E_INVALID, "VKN_RG_BN must be 32, 64, 128 or 256");
+  const size_t stage_bytes = (size_t)RG_A_BYTES + (size_t)BN * 128;
+  int stages = rg_env("VKN_RG_STAGES", 4);
+  if (stages > nkmax) stages = nkmax;
+  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 1024 + (2 * st + 1) * 8 + 16 + (size_t)BN * 4 + 64; };
+  while (stages > 1 && smem_of(stages) > 227 * 1024) --stages;
+  size_t smem = smem_of(stages);
+  if (smem < 4 * 32 * 36 * 4 + 2048) smem = 4 * 32 * 36 * 4 + 2048;
+  b.ksplit = ks;
+  b.stages = stages;
+  b.BN = BN;
+  b.idesc = make_idesc_bf16(128, BN, 0, 0);
+  for (int i = 0; i < nprob; ++i) {
+    const LinArgs &a = probs[i];
+    RgProb &p = b.p[i];
+    const uint64_t adims[3] = {(uint64_t)a.K, (uint64_t)a.M, 3};
+    const uint64_t astr[2] = {(uint64_t)a.src.lda[0] * 2, (uint64_t)a.src.sum_stride * 2};
+    const uint32_t abox[3] = {64u, 128u, 3u};
+    VKN_TRY(make_tmap_bf16_strided(&p.tmA, a.src.a[0], 3, adims, astr, abox));
+    const uint64_t wdims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    const uint64_t wstr[1] = {(uint64_t)a.ldw * 2};
+    const uint32_t wbox[2] = {64u, (uint32_t)BN};
+    VKN_TRY(make_tmap_bf16_strided(&p.tmW, a.w, 2, wdims, wstr, wbox));
+    p.bias = a.bias;
+    p.rowscale = a.rowscale;
+    p.res = a.res;
+    p.out = a.out;
+    p.planes = a.split_planes;
+    p.out_split_stride = a.out_split_stride;
+    p.plane_elems = (long long)a.split_B * a.split_Npad * a.split_C;
+    p.ldres = a.ldres;
+    p.ldo = a.ldo;
+    p.M = a.M;
+    p.N = a.N;
+    p.K = a.K;
+    p.epi = a.epi;
+    p.split_N = a.split_N > 0 ? a.split_N : 1;
+    p.split_Npad = a.split_Npad;
+    p.split_C = a.split_C;
+    if ((a.epi & EPI_BIAS) && ks > 1) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: bias with split-K belongs to the consumer");
+    if ((a.epi & EPI_SPLIT3) && !a.split_planes) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_SPLIT3 without a plane buffer");
+    if (!(a.epi & EPI_NOOUT) && !a.out) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: null output");
+  }
+  if (nprob == 1) b.p[1] = b.p[0];
+  static bool attr = false;
+  if (!attr) {
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  dim3 grid(ceil_div(maxN, BN), mt, nprob * ks);
+  VKN_LAUNCH_MARK("vkn_rowgemm_tc_kernel", stream);
+  VKN_CUDA_OK(launch_chain(vkn_rowgemm_tc_kernel, grid, dim3(TC_THREADS), smem, stream, b));
+  return VKN_OK;
+}
+
+}  // namespace vkn

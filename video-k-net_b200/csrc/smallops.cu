@@ -720,7 +720,8 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
                                                            const float *__restrict__ k, int ldk,
                                                            const float *__restrict__ v, int ldv,
                                                            float *__restrict__ out, int ldo, int N, int hd,
-                                                           float scale) {
+                                                           float scale, __nv_bfloat16 *__restrict__ planes,
+                                                           long long plane_stride) {
   extern __shared__ float smem[];
   const int hs = hd + 1;
   float *Ks = smem;                    // [N][hs]
@@ -787,14 +788,24 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
         o3 = fmaf(ps[j + 3], Vs[(j + 3) * hs + lane], o3);
       }
       for (; j < N; ++j) o0 = fmaf(ps[j], Vs[j * hs + lane], o0);
-      out[(rowb + qi) * ldo + h * hd + lane] = ((o0 + o1) + (o2 + o3)) / sum;
+      const float ov = ((o0 + o1) + (o2 + o3)) / sum;
+      if (out != nullptr) out[(rowb + qi) * ldo + h * hd + lane] = ov;
+      if (planes != nullptr) {     // A operand of the out-projection on the tcgen05 row engine
+        float xr = ov;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const __nv_bfloat16 hb = __float2bfloat16_rn(xr);
+          xr -= __bfloat162float(hb);
+          planes[(size_t)pl * plane_stride + (rowb + qi) * ldo + h * hd + lane] = hb;
+        }
+      }
     }
     __syncwarp();
   }
 }
 
 int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
-                     int ldo, int B, int N, int C, int heads, cudaStream_t stream) {
+                     int ldo, int B, int N, int C, int heads, cudaStream_t stream, void *planes, long long plane_stride) {
   if (heads < 1 || C % heads != 0) VKN_FAIL(VKN_E_INVALID, "attention: C %d not divisible by heads %d", C, heads);
   const int hd = C / heads;
   if (hd > 32) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: head_dim %d > 32", hd);
@@ -808,7 +819,7 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   dim3 grid(ceil_div(N, ATT_QB), heads, B);
   VKN_LAUNCH_MARK("vkn_attention_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_attention_kernel, grid, dim3(NT), smem, stream, q, ldq, k, ldk, v, ldv, out, ldo, N, hd,
-                           1.0f / sqrtf((float)hd)));
+                           1.0f / sqrtf((float)hd), (__nv_bfloat16 *)planes, plane_stride));
   return VKN_OK;
 }
 
