@@ -214,7 +214,7 @@ def run_ours(args):
     NS = max(1, int(os.environ.get('VKN_STREAMS', '2')))
     BF = max(1, int(os.environ.get('VKN_BATCH', '8')))
     quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: small group, no CPU arm
-    if quick:
+    if quick and 'VKN_STREAMS' not in os.environ and 'VKN_BATCH' not in os.environ:
         NS, BF = 1, 1
     FPG = NS * BF                                           # frames per graph launch (per rank)
     set_bytes = (C * HW + 2 * N * HW) * 2

@@ -9,7 +9,7 @@
 //       exact, so the result carries fp32-level accuracy: DESIGN.md section 4)
 //
 // Epilogue: thread = row (TMEM lane); bias (x rowscale), residual, ReLU; fp32 rows and / or bf16 planes for the next
-// GEMM, transposed through shared memory so that global stores are full lines.  Split-K over blockIdx.z; two
+// GEMM, 32 columns per thread in registers, 16-byte stores.  Split-K over blockIdx.z; two
 // problems per launch.  Weight tiles and bias are prefetched BEFORE griddepcontrol.wait (PDL).
 #include "tc.cuh"
 
@@ -28,12 +28,26 @@ struct RgBatch {
   RgProb p[2];
   int ksplit, stages, BN;
   uint32_t idesc;
+  unsigned long long *dbg;     // optional per-CTA phase timestamps (vkn_debug_timestamps), null in production
 };
+
+__device__ __forceinline__ unsigned long long rg_time() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define RG_TS(slot)                                                                                                 \
+  do {                                                                                                              \
+    if (batch.dbg != nullptr)                                                                                       \
+      batch.dbg[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = rg_time(); \
+  } while (0)
 
 constexpr uint32_t RG_A_PLANE = 128u * 128u;        // 128 rows x 64 k x 2 B
 constexpr uint32_t RG_A_BYTES = 3u * RG_A_PLANE;
 
-__global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __grid_constant__ RgBatch batch) {
+constexpr int RG_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+
+__global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __grid_constant__ RgBatch batch) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int BN = batch.BN, STG = batch.stages, ks_total = batch.ksplit;
@@ -53,6 +67,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
   float *bias_s = (float *)(tmem_slot + 2);
   const uint32_t smem0 = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) RG_TS(0);
   const int nk_total = (P.K + 63) / 64;
   const int kper = nk_total / ks_total;               // host guarantees divisibility
   const int kb = ks * kper, nk = kper;
@@ -72,12 +87,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), ncols);
   }
-  for (int i = threadIdx.x; i < BN; i += TC_THREADS)       // bias is a weight: staged before the PDL wait
+  for (int i = threadIdx.x; i < BN; i += RG_THREADS)       // bias is a weight: staged before the PDL wait
     bias_s[i] = ((P.epi & EPI_BIAS) && col0 + i < P.N) ? __ldg(P.bias + col0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) RG_TS(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -87,6 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
         tma_load_2d(smem0 + i * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * i, (kb + i) * 64, col0);
       }
       pdl_wait();                                           // the A planes come from the previous kernel
+      RG_TS(2);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STG;
         const uint32_t ph = (uint32_t)(i / STG) & 1u;
@@ -105,6 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
         const uint32_t ph = (uint32_t)(i / STG) & 1u;
         mbar_wait(bar0 + 8 * s, ph);
         tc_fence_after();
+        if (i == 0) RG_TS(3);
         const uint32_t as = smem0 + s * stage_bytes, wsm = as + RG_A_BYTES;
 #pragma unroll
         for (int pl = 2; pl >= 0; --pl) {                   // lo, mid, hi: small terms first
@@ -118,89 +136,105 @@ __global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
         umma_commit(bar0 + 8 * (STG + s));
       }
       umma_commit(bar0 + 16 * STG);
+      RG_TS(4);
     }
   } else {
+    // ---- epilogue: 8 warps, thread = row (TMEM lane); the two warps of a lane quarter take alternate 32-column
+    //      blocks.  A thread owns 32 consecutive columns of its row in registers: bias / residual / ReLU / the plane
+    //      split run as 32 independent chains and leave as 16-byte stores (no shared-memory round trip).
     pdl_wait();                                             // residual / rowscale reads, and every global store
     mbar_wait(bar0 + 16 * STG, 0);
     tc_fence_after();
     pdl_trigger();
+    if (threadIdx.x == 64) RG_TS(5);
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
-    float *stg = reinterpret_cast<float *>(smem) + (size_t)q * 32 * 36;   // pipeline buffers are free now
+    const int half = (warp - 2) >> 2;                       // 0: even column blocks, 1: odd
     const int epi = P.epi;
+    const int row = row0 + q * 32 + lane;
+    const bool live = row < P.M;
     float *outp = P.out + (size_t)ks * P.out_split_stride;
     const bool out_vec = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
     const bool res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
-    const bool pl_vec = (P.split_C % 4 == 0);
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (col0 + c0 >= P.N) break;
+    const bool pl_vec = (P.split_C % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 15) == 0);
+    const float rs = (live && (epi & EPI_ROWSCALE)) ? __ldg(P.rowscale + row) : 1.f;
+    size_t prow = (size_t)row;                              // row of the plane buffer this thread writes
+    if ((epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
+      const int b = row / P.split_N;
+      prow = (size_t)b * P.split_Npad + (row - b * P.split_N);
+    }
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (!live) continue;
+      const int nc = min(32, P.N - col);
+      float v[32];
 #pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<float4 *>(stg + lane * 36 + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
-                                                                       __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-      __syncwarp();
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + (lane >> 3), seg = lane & 7;
-        const int row = row0 + q * 32 + rr, col = col0 + c0 + seg * 4;
-        if (row < P.M && col < P.N) {
-          const float4 a4 = *reinterpret_cast<const float4 *>(stg + rr * 36 + seg * 4);
-          float v[4] = {a4.x, a4.y, a4.z, a4.w};
-          const int nv = min(4, P.N - col);
-          if (epi & EPI_BIAS) {
-            const float rs = (epi & EPI_ROWSCALE) ? __ldg(P.rowscale + row) : 1.f;
+      for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+      if (epi & EPI_BIAS) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] += rs * bias_s[c0 + seg * 4 + e];
+        for (int e = 0; e < 32; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c0 + e);
+          v[e] = fmaf(rs, b4.x, v[e]); v[e + 1] = fmaf(rs, b4.y, v[e + 1]);
+          v[e + 2] = fmaf(rs, b4.z, v[e + 2]); v[e + 3] = fmaf(rs, b4.w, v[e + 3]);
+        }
+      }
+      if (epi & EPI_RES) {
+        const float *rp = P.res + (size_t)row * P.ldres + col;
+        if (res_vec && nc == 32) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(rp + e));
+            v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
           }
-          if (epi & EPI_RES) {
-            const float *rp = P.res + (size_t)row * P.ldres + col;
-            if (res_vec && nv == 4) {
-              const float4 t = __ldg(reinterpret_cast<const float4 *>(rp));
-              v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-            } else {
-              for (int e = 0; e < nv; ++e) v[e] += __ldg(rp + e);
-            }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nc) v[e] += __ldg(rp + e);
+        }
+      }
+      if (epi & EPI_RELU) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+      if (!(epi & EPI_NOOUT)) {
+        float *op = outp + (size_t)row * P.ldo + col;
+        if (out_vec && nc == 32) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4 *>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nc) op[e] = v[e];
+        }
+      }
+      if ((epi & EPI_SPLIT3) && col < P.split_C) {
+        const int np = min(32, P.split_C - col);
+        __nv_bfloat16 *pp = P.planes + prow * P.split_C + col;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {                       // v == hi + mid + lo to 24 bits
+          uint32_t w[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
+            v[e] -= __bfloat162float(h0);
+            v[e + 1] -= __bfloat162float(h1);
+            w[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           }
-          if (epi & EPI_RELU) {
+          __nv_bfloat16 *pt = pp + (size_t)t * P.plane_elems;
+          if (pl_vec && np == 32) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (!(epi & EPI_NOOUT)) {
-            float *op = outp + (size_t)row * P.ldo + col;
-            if (out_vec && nv == 4) *reinterpret_cast<float4 *>(op) = make_float4(v[0], v[1], v[2], v[3]);
-            else for (int e = 0; e < nv; ++e) op[e] = v[e];
-          }
-          if ((epi & EPI_SPLIT3) && col < P.split_C) {
-            const int b = row / P.split_N, n = row - b * P.split_N;
-            const size_t o = ((size_t)b * P.split_Npad + n) * P.split_C + col;
-            const int np = min(4, P.split_C - col);
-            uint16_t h[3][4];
+            for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4 *>(pt + 2 * e) = make_uint4(w[e], w[e + 1], w[e + 2], w[e + 3]);
+          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float xr = v[e];
-#pragma unroll
-              for (int t = 0; t < 3; ++t) {                 // v == hi + mid + lo to 24 bits
-                const __nv_bfloat16 hb = __float2bfloat16_rn(xr);
-                xr -= __bfloat162float(hb);
-                h[t][e] = __bfloat16_as_ushort(hb);
-              }
-            }
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              __nv_bfloat16 *pp = P.planes + (size_t)t * P.plane_elems + o;
-              if (pl_vec && np == 4) {
-                *reinterpret_cast<uint2 *>(pp) = make_uint2((uint32_t)h[t][0] | ((uint32_t)h[t][1] << 16),
-                                                            (uint32_t)h[t][2] | ((uint32_t)h[t][3] << 16));
-              } else {
-                for (int e = 0; e < np; ++e) pp[e] = __ushort_as_bfloat16(h[t][e]);
-              }
-            }
+            for (int e = 0; e < 32; ++e)
+              if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
           }
         }
       }
-      __syncwarp();
     }
+    if (threadIdx.x == 64) RG_TS(6);
   }
   tc_fence_before();
   __syncthreads();
@@ -208,6 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
     tc_fence_after();
     tmem_dealloc(tmem_base, ncols);
   }
+  if (threadIdx.x == 0) RG_TS(7);
 }
 
 static int rg_env(const char *name, int dflt) {
@@ -256,16 +291,16 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
   BN = rg_env("VKN_RG_BN", BN);
   if (BN != 32 && BN != 64 && BN != 128 && BN != 256) VKN_FAIL(VKN_E_INVALID, "VKN_RG_BN must be 32, 64, 128 or 256");
   const size_t stage_bytes = (size_t)RG_A_BYTES + (size_t)BN * 128;
-  int stages = rg_env("VKN_RG_STAGES", 4);
+  int stages = rg_env("VKN_RG_STAGES", 2);   // 2 x 56 KB: CTAs of concurrent branches co-reside (measured best)
   if (stages > nkmax) stages = nkmax;
   auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 1024 + (2 * st + 1) * 8 + 16 + (size_t)BN * 4 + 64; };
   while (stages > 1 && smem_of(stages) > 227 * 1024) --stages;
   size_t smem = smem_of(stages);
-  if (smem < 4 * 32 * 36 * 4 + 2048) smem = 4 * 32 * 36 * 4 + 2048;
   b.ksplit = ks;
   b.stages = stages;
   b.BN = BN;
   b.idesc = make_idesc_bf16(128, BN, 0, 0);
+  b.dbg = debug_ts_slot();
   for (int i = 0; i < nprob; ++i) {
     const LinArgs &a = probs[i];
     RgProb &p = b.p[i];
@@ -305,7 +340,7 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
   }
   dim3 grid(ceil_div(maxN, BN), mt, nprob * ks);
   VKN_LAUNCH_MARK("vkn_rowgemm_tc_kernel", stream);
-  VKN_CUDA_OK(launch_chain(vkn_rowgemm_tc_kernel, grid, dim3(TC_THREADS), smem, stream, b));
+  VKN_CUDA_OK(launch_chain(vkn_rowgemm_tc_kernel, grid, dim3(RG_THREADS), smem, stream, b));
   return VKN_OK;
 }
 

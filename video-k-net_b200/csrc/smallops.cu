@@ -721,14 +721,14 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
                                                            const float *__restrict__ v, int ldv,
                                                            float *__restrict__ out, int ldo, int N, int hd,
                                                            float scale, __nv_bfloat16 *__restrict__ planes,
-                                                           long long plane_stride) {
+                                                           long long plane_stride, int qb) {
   extern __shared__ float smem[];
   const int hs = hd + 1;
   float *Ks = smem;                    // [N][hs]
   float *Vs = Ks + (size_t)N * hs;     // [N][hs]
   float *Ps = Vs + (size_t)N * hs;             // [NT/32 warps][N]
   float *Qs = Ps + (NT / 32) * (size_t)N;      // [NT/32 warps][32]
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_QB;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * qb;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t rowb = (size_t)b * N;
   pdl_wait();
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
   pdl_trigger();
   float *ps = Ps + (size_t)warp * N;
   float *qs = Qs + warp * 32;
-  for (int qi = q0 + warp; qi < min(N, q0 + ATT_QB); qi += NT / 32) {
+  for (int qi = q0 + warp; qi < min(N, q0 + qb); qi += NT / 32) {
     if (lane < hd) qs[lane] = __ldg(q + (rowb + qi) * ldq + h * hd + lane) * scale;
     __syncwarp();
     float mx = -INFINITY;
@@ -816,10 +816,15 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
     attr_set = true;
   }
   if (smem > 160 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: N %d too large for shared memory", N);
-  dim3 grid(ceil_div(N, ATT_QB), heads, B);
+  // queries per CTA: one per warp for a single frame (latency), more when many (head, frame) pairs are in flight --
+  // every CTA stages the K and V of its head, so fewer, longer CTAs stop re-reading them (one wave of <= ~296 CTAs)
+  int qb = ATT_QB;
+  (void)B;   // (measured: longer CTAs lose -- the kernel is bound by its per-query instruction stream, not by K/V staging)
+  if (const char *e = getenv("VKN_ATT_QB")) qb = atoi(e) >= ATT_QB ? atoi(e) / ATT_QB * ATT_QB : qb;
+  dim3 grid(ceil_div(N, qb), heads, B);
   VKN_LAUNCH_MARK("vkn_attention_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_attention_kernel, grid, dim3(NT), smem, stream, q, ldq, k, ldk, v, ldv, out, ldo, N, hd,
-                           1.0f / sqrtf((float)hd), (__nv_bfloat16 *)planes, plane_stride));
+                           1.0f / sqrtf((float)hd), (__nv_bfloat16 *)planes, plane_stride, qb));
   return VKN_OK;
 }
 
