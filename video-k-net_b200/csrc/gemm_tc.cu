@@ -377,9 +377,12 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 // When a launch holds several pixel tiles per SM (frame batches / clips), re-streaming the kernel planes for
 // every tile (172 KB at N=100) costs ~3x the x traffic.  Here a CTA owns ONE frame's planes -- all three
 // bf16 planes x all K chunks stay resident in shared memory -- and walks that frame's pixel tiles:
-// only x streams (2-stage TMA ring), accumulators are double-buffered in TMEM so the tensor core works on
+// only x streams (3-stage TMA ring), accumulators are double-buffered in TMEM so the tensor core works on
 // tile i+1 while the epilogue warps drain tile i.  Requires Npad <= 112 (planes + ring must fit 227 KB).
-constexpr int MP_XS = 2;      // x ring depth
+// A resident plane chunk holds round_up(N, 8) rows (whole 8-row swizzle atoms), not Npad: the MMA (N = Npad) then
+// reads up to 8 rows past it -- whatever follows in shared memory -- which only feeds accumulator columns >= N that
+// the epilogue never stores.  The 12 KB this saves at N = 100 is what makes the third ring stage fit.
+constexpr int MP_XS = 3;      // x ring depth (48 KB of x in flight per SM)
 constexpr int MP_ACC = 2;     // TMEM accumulator buffers (128 columns each)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -390,14 +393,15 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
   const uint32_t x_bytes = (uint32_t)CH_BLK * MASK_TILE_P * 2u;         // 16 KB
-  const uint32_t a_plane = (uint32_t)Npad * 128u;                       // one plane, one 64-channel chunk
+  const uint32_t a_plane = (uint32_t)((N + 7) & ~7) * 128u;             // one plane, one 64-channel chunk (8-row atoms)
   const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
   uint8_t *xring = smem + planes_bytes;                                 // (planes_bytes is a multiple of 1024)
   uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 4 warps x 2560 B
   uint64_t *bars = (uint64_t *)(stg_base + 4 * 32 * 40 * 2);
   const uint32_t bar0 = smem_u32(bars);
-  // barriers: 0 planes_full | 1..2 x_full | 3..4 x_empty | 5..6 acc_full | 7..8 acc_empty
-  uint32_t *tmem_slot = (uint32_t *)(bars + 9);
+  // barriers: 0 planes_full | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a
+  constexpr int X_FULL = 1, X_EMPTY = 1 + MP_XS, ACC_FULL = 1 + 2 * MP_XS, ACC_EMPTY = 1 + 2 * MP_XS + MP_ACC;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 1 + 2 * MP_XS + 2 * MP_ACC);
   float *bias_s = (float *)(tmem_slot + 2);
   const uint32_t smem0 = smem_u32(smem), xring0 = smem_u32(xring);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,12 +415,12 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       prefetch_tmap(&tmap_a);
       mbar_init(bar0, 1);
       for (int s = 0; s < MP_XS; ++s) {
-        mbar_init(bar0 + 8 * (1 + s), 1);
-        mbar_init(bar0 + 8 * (3 + s), 1);
+        mbar_init(bar0 + 8 * (X_FULL + s), 1);
+        mbar_init(bar0 + 8 * (X_EMPTY + s), 1);
       }
       for (int a = 0; a < MP_ACC; ++a) {
-        mbar_init(bar0 + 8 * (5 + a), 1);
-        mbar_init(bar0 + 8 * (7 + a), 4);                               // one arrive per epilogue warp
+        mbar_init(bar0 + 8 * (ACC_FULL + a), 1);
+        mbar_init(bar0 + 8 * (ACC_EMPTY + a), 4);                               // one arrive per epilogue warp
       }
       fence_barrier_init();
     }
@@ -443,10 +447,10 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         for (int c = 0; c < nk; ++c, ++it) {
           const int s = it % MP_XS;
           const uint32_t ph = (uint32_t)(it / MP_XS) & 1u;
-          mbar_wait(bar0 + 8 * (3 + s), ph ^ 1u);
-          mbar_expect_tx(bar0 + 8 * (1 + s), x_bytes);
-          tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (1 + s), p0, c * CH_BLK, b);
-          tma_load_3d(xring0 + s * x_bytes + x_bytes / 2, &tmap_x, bar0 + 8 * (1 + s), p0 + 64, c * CH_BLK, b);
+          mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u);
+          mbar_expect_tx(bar0 + 8 * (X_FULL + s), x_bytes);
+          tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (X_FULL + s), p0, c * CH_BLK, b);
+          tma_load_3d(xring0 + s * x_bytes + x_bytes / 2, &tmap_x, bar0 + 8 * (X_FULL + s), p0 + 64, c * CH_BLK, b);
         }
       }
     }
@@ -456,12 +460,12 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       int it = 0, li = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
         const int buf = li % MP_ACC;
-        mbar_wait(bar0 + 8 * (7 + buf), ((uint32_t)(li / MP_ACC) & 1u) ^ 1u);
+        mbar_wait(bar0 + 8 * (ACC_EMPTY + buf), ((uint32_t)(li / MP_ACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t dt = tmem_base + (uint32_t)buf * 128u;
         for (int c = 0; c < nk; ++c, ++it) {
           const int s = it % MP_XS;
-          mbar_wait(bar0 + 8 * (1 + s), (uint32_t)(it / MP_XS) & 1u);
+          mbar_wait(bar0 + 8 * (X_FULL + s), (uint32_t)(it / MP_XS) & 1u);
           tc_fence_after();
           const uint32_t xs = xring0 + s * x_bytes;
 #pragma unroll
@@ -473,9 +477,9 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
               umma_bf16(dt, ad, bd, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(bar0 + 8 * (3 + s));
+          umma_commit(bar0 + 8 * (X_EMPTY + s));
         }
-        umma_commit(bar0 + 8 * (5 + buf));
+        umma_commit(bar0 + 8 * (ACC_FULL + buf));
       }
     }
   } else {
@@ -485,7 +489,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     int li = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
       const int buf = li % MP_ACC;
-      mbar_wait(bar0 + 8 * (5 + buf), (uint32_t)(li / MP_ACC) & 1u);
+      mbar_wait(bar0 + 8 * (ACC_FULL + buf), (uint32_t)(li / MP_ACC) & 1u);
       tc_fence_after();
       if (tile + cpf >= ntiles) pdl_trigger();
       const int pw = tile * MASK_TILE_P + q * 32;
@@ -509,7 +513,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       }
       tc_fence_before();                 // this warp's TMEM reads of `buf` are done
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (7 + buf));
+      if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
     }
   }
   tc_fence_before();
@@ -561,8 +565,14 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     int cpf = 148 / frames;
     if (cpf < 1) cpf = 1;
     if (cpf > ntiles) cpf = ntiles;
-    const size_t psmem = (size_t)(s.C / CH_BLK) * 3 * Npad * 128 + MP_XS * (size_t)CH_BLK * MASK_TILE_P * 2 + 4 * 32 * 40 * 2 +
-                         9 * 8 + 16 + (size_t)(Npad + 32) * 4 + 1024 + 64;
+    const int rows8 = (s.N + 7) & ~7;
+    {     // resident planes: whole 8-row atoms only (see the kernel comment)
+      const uint64_t dims[2] = {(uint64_t)s.C, (uint64_t)3 * s.B * Npad};
+      const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)rows8};
+      VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
+    }
+    const size_t psmem = (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + MP_XS * (size_t)CH_BLK * MASK_TILE_P * 2 + 4 * 32 * 40 * 2 +
+                         (1 + 2 * MP_XS + 2 * MP_ACC) * 8 + 16 + (size_t)(Npad + 32) * 4 + 1024 + 64;
     static bool pattr = false;
     if (!pattr) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -84,11 +84,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
       mbar_init(bar0 + 16 * STG, 1);
       fence_barrier_init();
     }
-    __syncwarp();
+  } else if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), ncols);
   }
-  for (int i = threadIdx.x; i < BN; i += RG_THREADS)       // bias is a weight: staged before the PDL wait
-    bias_s[i] = ((P.epi & EPI_BIAS) && col0 + i < P.N) ? __ldg(P.bias + col0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -142,6 +140,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
     // ---- epilogue: 8 warps, thread = row (TMEM lane); the two warps of a lane quarter take alternate 32-column
     //      blocks.  A thread owns 32 consecutive columns of its row in registers: bias / residual / ReLU / the plane
     //      split run as 32 independent chains and leave as 16-byte stores (no shared-memory round trip).
+    // bias is a weight: staged by the epilogue warps (off the CTA's critical path), before the PDL wait
+    for (int i = threadIdx.x - 64; i < BN; i += RG_THREADS - 64)
+      bias_s[i] = ((P.epi & EPI_BIAS) && col0 + i < P.N) ? __ldg(P.bias + col0 + i) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(RG_THREADS - 64) : "memory");
     pdl_wait();                                             // residual / rowscale reads, and every global store
     mbar_wait(bar0 + 16 * STG, 0);
     tc_fence_after();
