@@ -540,3 +540,23 @@ def test_row_engine_tc_variants(dev, monkeypatch):
     assert maxabs(cls, want[0]) < TOL_BF16 and maxabs(obj, want[2]) < TOL_BF16
     ref = ko.round_bf16(want[1])
     assert (nm.float().cpu() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('B,N,C', [(1, 10, 64), (2, 37, 128), (3, 117, 64), (16, 100, 256), (2, 166, 128)])
+def test_attention_four_queries_per_warp_kernel(dev, monkeypatch, B, N, C):
+    """The batched attention kernel (4 queries per warp, picked when many (head, frame) pairs are in flight) against
+    the oracle and against the one-query-per-warp kernel, on ragged N (partial last query group / key sweep)."""
+    from vknet import ops
+    cfg = ko.default_cfg(num_classes=11, in_channels=C, feedforward_channels=64)
+    sd = ko.random_state_dict(cfg, seed=5)
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev)[0]
+    rows = torch.randn(B, N, C, generator=torch.Generator().manual_seed(4))
+    seq = rows.permute(1, 0, 2)
+    want = ko.layer_norm(ko.mha_block(seq, seq, seq, seq, sd, 'attention.', 8), sd['attention_norm.weight'],
+                         sd['attention_norm.bias']).permute(1, 0, 2)
+    monkeypatch.setenv('VKN_ATT4', '1')
+    got4 = ops.mhsa_ln(h, rows.to(dev)).clone()
+    monkeypatch.setenv('VKN_ATT4', '0')
+    got1 = ops.mhsa_ln(h, rows.to(dev)).clone()
+    assert maxabs(got4, want) < 1e-4 and maxabs(got1, want) < 1e-4
+    assert maxabs(got4, got1.cpu()) < 2e-5

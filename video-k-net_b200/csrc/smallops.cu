@@ -804,6 +804,145 @@ __global__ void __launch_bounds__(NT) vkn_attention_kernel(const float *__restri
   }
 }
 
+// Batched form (many (head, frame) pairs in flight): a warp carries FOUR queries through each pass, so every K / V
+// element fetched from shared memory feeds four FMAs and the four queries' q / p values arrive as one broadcast
+// 16-byte load ([d][4] and [key][4] layouts).  The single-query kernel above is bound by its shared-memory loads
+// (~330 per query); this one needs ~90.  Same arithmetic per (query, key, channel), same softmax order.
+constexpr int ATT4_QB = 32;    // queries per CTA: 8 warps x 4
+
+__global__ void __launch_bounds__(NT) vkn_attention4_kernel(const float *__restrict__ q, int ldq,
+                                                            const float *__restrict__ k, int ldk,
+                                                            const float *__restrict__ v, int ldv,
+                                                            float *__restrict__ out, int ldo, int N, int hd,
+                                                            float scale, __nv_bfloat16 *__restrict__ planes,
+                                                            long long plane_stride) {
+  extern __shared__ float smem[];
+  const int hs = hd + 1;
+  float *Ks = smem;                                  // [N][hs]
+  float *Vs = Ks + (size_t)N * hs;                   // [N][hs]
+  float *Ps = Vs + (size_t)N * hs;                   // [8 warps][N][4]
+  Ps = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(Ps) + 15) & ~(uintptr_t)15);
+  float *Qs = Ps + (NT / 32) * (size_t)N * 4;        // [8 warps][32][4]
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT4_QB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t rowb = (size_t)b * N;
+  pdl_wait();
+  if ((hd & 3) == 0 && (ldk & 3) == 0 && (ldv & 3) == 0) {
+    const int hd4 = hd >> 2;
+    for (int idx = tid; idx < N * hd4; idx += NT) {
+      const int j = idx / hd4, d = (idx - j * hd4) * 4;
+      const float4 kk = __ldg(reinterpret_cast<const float4 *>(k + (rowb + j) * ldk + h * hd + d));
+      const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + (rowb + j) * ldv + h * hd + d));
+      float *kd = Ks + j * hs + d, *vd = Vs + j * hs + d;
+      kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+      vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+    }
+  } else {
+    for (int idx = tid; idx < N * hd; idx += NT) {
+      const int j = idx / hd, d = idx - j * hd;
+      Ks[j * hs + d] = __ldg(k + (rowb + j) * ldk + h * hd + d);
+      Vs[j * hs + d] = __ldg(v + (rowb + j) * ldv + h * hd + d);
+    }
+  }
+  __syncthreads();
+  pdl_trigger();
+  float4 *ps4 = reinterpret_cast<float4 *>(Ps) + (size_t)warp * N;
+  float4 *qs4 = reinterpret_cast<float4 *>(Qs) + warp * 32;
+  const int qbase = q0 + warp * 4;
+  if (qbase >= N) return;
+  const int nq = min(4, N - qbase);
+  if (lane < hd) {
+    float qv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qv[i] = i < nq ? __ldg(q + (rowb + qbase + i) * ldq + h * hd + lane) * scale : 0.f;
+    qs4[lane] = make_float4(qv[0], qv[1], qv[2], qv[3]);
+  }
+  __syncwarp();
+  // pass 1: raw scores of 4 queries x (4 keys per lane per sweep); running max per query
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int j0 = 0; j0 < N; j0 += 128) {
+    float sc[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[t][i] = 0.f;
+    int jr[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) jr[t] = min(j0 + lane + 32 * t, N - 1) * hs;
+    for (int d = 0; d < hd; ++d) {
+      const float4 q4 = qs4[d];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float kv = Ks[jr[t] + d];
+        sc[t][0] = fmaf(q4.x, kv, sc[t][0]);
+        sc[t][1] = fmaf(q4.y, kv, sc[t][1]);
+        sc[t][2] = fmaf(q4.z, kv, sc[t][2]);
+        sc[t][3] = fmaf(q4.w, kv, sc[t][3]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = j0 + lane + 32 * t;
+      if (j < N) {
+        ps4[j] = make_float4(sc[t][0], sc[t][1], sc[t][2], sc[t][3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx[i] = fmaxf(mx[i], sc[t][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mx[i] = warp_max(mx[i]);
+  // pass 2: exponentials (each lane revisits the keys it wrote) and their sums
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = lane; j < N; j += 32) {
+    float4 e = ps4[j];
+    e.x = expf(e.x - mx[0]); e.y = expf(e.y - mx[1]); e.z = expf(e.z - mx[2]); e.w = expf(e.w - mx[3]);
+    ps4[j] = e;
+    sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sum[i] = warp_sum(sum[i]);
+  __syncwarp();
+  // pass 3: lane = channel; every V element feeds the four queries
+  if (lane < hd) {
+    float o[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = 0.f;
+    int j = 0;
+    for (; j + 2 <= N; j += 2) {
+      const float4 p0 = ps4[j], p1 = ps4[j + 1];
+      const float v0 = Vs[j * hs + lane], v1 = Vs[(j + 1) * hs + lane];
+      o[0][0] = fmaf(p0.x, v0, o[0][0]); o[1][0] = fmaf(p0.y, v0, o[1][0]);
+      o[2][0] = fmaf(p0.z, v0, o[2][0]); o[3][0] = fmaf(p0.w, v0, o[3][0]);
+      o[0][1] = fmaf(p1.x, v1, o[0][1]); o[1][1] = fmaf(p1.y, v1, o[1][1]);
+      o[2][1] = fmaf(p1.z, v1, o[2][1]); o[3][1] = fmaf(p1.w, v1, o[3][1]);
+    }
+    if (j < N) {
+      const float4 p0 = ps4[j];
+      const float v0 = Vs[j * hs + lane];
+      o[0][0] = fmaf(p0.x, v0, o[0][0]); o[1][0] = fmaf(p0.y, v0, o[1][0]);
+      o[2][0] = fmaf(p0.z, v0, o[2][0]); o[3][0] = fmaf(p0.w, v0, o[3][0]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < nq) {
+        const float ov = (o[i][0] + o[i][1]) / sum[i];
+        const size_t off = (rowb + qbase + i) * ldo + h * hd + lane;
+        if (out != nullptr) out[off] = ov;
+        if (planes != nullptr) {
+          float xr = ov;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(xr);
+            xr -= __bfloat162float(hb);
+            planes[(size_t)pl * plane_stride + off] = hb;
+          }
+        }
+      }
+    }
+  }
+}
+
 int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
                      int ldo, int B, int N, int C, int heads, cudaStream_t stream, void *planes, long long plane_stride) {
   if (heads < 1 || C % heads != 0) VKN_FAIL(VKN_E_INVALID, "attention: C %d not divisible by heads %d", C, heads);
@@ -821,6 +960,21 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   int qb = ATT_QB;
   (void)B;   // (measured: longer CTAs lose -- the kernel is bound by its per-query instruction stream, not by K/V staging)
   if (const char *e = getenv("VKN_ATT_QB")) qb = atoi(e) >= ATT_QB ? atoi(e) / ATT_QB * ATT_QB : qb;
+  bool four = (long long)ceil_div(N, ATT4_QB) * heads * B >= 120;     // enough CTAs for every SM: the batched form
+  if (const char *e = getenv("VKN_ATT4")) four = e[0] == '1';
+  if (four) {
+    const size_t smem4 = ((size_t)2 * N * (hd + 1) + 4 + (NT / 32) * (size_t)N * 4 + (NT / 32) * 32 * 4) * sizeof(float);
+    static bool attr4 = false;
+    if (!attr4) {
+      VKN_CUDA_OK(cudaFuncSetAttribute(vkn_attention4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr4 = true;
+    }
+    if (smem4 > 200 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: N %d too large for shared memory", N);
+    VKN_LAUNCH_MARK("vkn_attention4_kernel", stream);
+    VKN_CUDA_OK(launch_chain(vkn_attention4_kernel, dim3(ceil_div(N, ATT4_QB), heads, B), dim3(NT), smem4, stream, q, ldq, k,
+                             ldk, v, ldv, out, ldo, N, hd, 1.0f / sqrtf((float)hd), (__nv_bfloat16 *)planes, plane_stride));
+    return VKN_OK;
+  }
   dim3 grid(ceil_div(N, qb), heads, B);
   VKN_LAUNCH_MARK("vkn_attention_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_attention_kernel, grid, dim3(NT), smem, stream, q, ldq, k, ldk, v, ldv, out, ldo, N, hd,
