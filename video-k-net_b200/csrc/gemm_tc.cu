@@ -70,7 +70,7 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint32_t *tmem_slot = (uint32_t *)(bars + 3 * POOL_STAGES + 1);
   const uint32_t smem0 = smem_u32(smem);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int chunk = blockIdx.x, mtile = blockIdx.y, b = blockIdx.z;
   const int blk_beg = chunk * bpc;
   const int nk = min(nblocks, blk_beg + bpc) - blk_beg;
@@ -109,23 +109,28 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % POOL_STAGES;
-        const uint32_t ph = (uint32_t)(i / POOL_STAGES) & 1u;
-        mbar_wait(bar0 + 8 * s, ph);                              // x tile landed
-        mbar_wait(bar0 + 8 * (2 * POOL_STAGES + 1 + s), ph);      // A tile written
-        tc_fence_after();
-        const uint32_t xs = smem0 + s * stage_bytes, ms = xs + x_bytes + m_bytes;
+    // warp-uniform issue loop, one elected lane issues (see elect_one() in tc.cuh)
+    const uint64_t bdesc0 = umma_desc_sw128(smem0, 0, 1024);
+    const uint64_t adesc0 = bdesc0 + (uint64_t)((x_bytes + m_bytes) >> 4);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nk; ++i) {
+      mbar_wait(bar0 + 8 * s, ph);                              // x tile landed
+      mbar_wait(bar0 + 8 * (2 * POOL_STAGES + 1 + s), ph);      // A tile written
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
 #pragma unroll
-        for (int k = 0; k < PX_BLK / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(ms + k * 32, 0, 1024);
-          const uint64_t bd = umma_desc_sw128(xs + k * 32, 0, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < PX_BLK / 16; ++k)
+          umma_bf16(tmem_base, adesc0 + so + (uint64_t)(k * 2), bdesc0 + so + (uint64_t)(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar0 + 8 * (POOL_STAGES + s));        // frees the stage when these MMAs retire
+        if (i == nk - 1) umma_commit(bar0 + 16 * POOL_STAGES);   // accumulators complete
       }
-      umma_commit(bar0 + 16 * POOL_STAGES);               // accumulators complete
+      __syncwarp();
+      if (++s == POOL_STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   } else {
     // ---- producers: threshold the mask logits into the swizzled A tile -------------------------
@@ -268,7 +273,7 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint32_t *tmem_slot = (uint32_t *)(bars + 2 * stages + 1);
   float *bias_s = (float *)(tmem_slot + 2);                              // [Npad]
   const uint32_t smem0 = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int p0 = blockIdx.x * MASK_TILE_P, b = blockIdx.z;     // b = frame; its kernels are those of set kb
   const int kb = b / F;
   const int nk = C / CH_BLK;
@@ -313,27 +318,34 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (uint32_t)(i / stages) & 1u;
-        mbar_wait(bar0 + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t xs = smem0 + s * stage_bytes;
+    // warp-uniform issue loop, one elected lane issues (see elect_one() in tc.cuh)
+    // A (x): MN-major; one UMMA_K step = 16 channel rows of 128 B = 2048 B
+    // B (a plane t): K-major; UMMA_K step = 32 B inside the 128-B swizzle row
+    const uint64_t adesc0 = umma_desc_sw128(smem0, x_lbo, x_sbo);
+    const uint64_t bdesc0 = umma_desc_sw128(smem0 + x_bytes, 0, 1024);
+    const uint32_t a_plane16 = a_plane >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nk; ++i) {
+      mbar_wait(bar0 + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
 #pragma unroll
-          for (int k = 0; k < CH_BLK / 16; ++k) {
-            // A (x): MN-major; one UMMA_K step = 16 channel rows of 128 B = 2048 B
-            const uint64_t ad = umma_desc_sw128(xs + k * 2048, x_lbo, x_sbo);
-            // B (a plane t): K-major; UMMA_K step = 32 B inside the 128-B swizzle row
-            const uint64_t bd = umma_desc_sw128(xs + x_bytes + t * a_plane + k * 32, 0, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || t > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < CH_BLK / 16; ++k)
+            umma_bf16(tmem_base, adesc0 + so + (uint64_t)(k * (2048 >> 4)), bdesc0 + so + (uint64_t)((uint32_t)t * a_plane16 + k * 2),
+                      idesc, (i > 0 || t > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(bar0 + 8 * (stages + s));
+        if (i == nk - 1) umma_commit(bar0 + 16 * stages);
       }
-      umma_commit(bar0 + 16 * stages);
+      __syncwarp();
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   } else {
     // ---- epilogue: TMEM lane = pixel, column = kernel ---------------------------------------------
@@ -382,13 +394,27 @@ vkn_maskgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 // A resident plane chunk holds round_up(N, 8) rows (whole 8-row swizzle atoms), not Npad: the MMA (N = Npad) then
 // reads up to 8 rows past it -- whatever follows in shared memory -- which only feeds accumulator columns >= N that
 // the epilogue never stores.  The 12 KB this saves at N = 100 is what makes the third ring stage fit.
-constexpr int MP_XS = 3;      // x ring depth (48 KB of x in flight per SM)
+constexpr int MP_XS_MAX = 4;  // x ring depth (16 KB stages): as many as fit next to the planes and the 16 KB store staging
+// Debug accounting (vkn_debug_timestamps): cycles each warp role spends blocked on a barrier, per CTA.
+//   slot 0 CTA cycles | 1 TMA: ring slot free | 2 MMA: x landed | 3 MMA: accumulator free | 4 epilogue: accumulator
+//   ready | 5 epilogue: staging box free + barriers | 6 tiles | 7 marker
+#define MP_WAIT(acc, stmt)                 \
+  do {                                     \
+    if (dbg != nullptr) {                  \
+      const long long t0__ = clock64();    \
+      stmt;                                \
+      acc += clock64() - t0__;             \
+    } else {                               \
+      stmt;                                \
+    }                                      \
+  } while (0)
 constexpr int MP_ACC = 2;     // TMEM accumulator buffers (128 columns each)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
-                               const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
-                               int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F) {
+                               const __grid_constant__ CUtensorMap tmap_o, const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
+                               int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int MP_XS,
+                               unsigned long long *dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
@@ -396,23 +422,28 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   const uint32_t a_plane = (uint32_t)((N + 7) & ~7) * 128u;             // one plane, one 64-channel chunk (8-row atoms)
   const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
   uint8_t *xring = smem + planes_bytes;                                 // (planes_bytes is a multiple of 1024)
-  uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 4 warps x 2560 B
-  uint64_t *bars = (uint64_t *)(stg_base + 4 * 32 * 40 * 2);
+  uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 2 x [32 kernels][128 px] bf16
+  uint64_t *bars = (uint64_t *)(stg_base + 2 * 32 * MASK_TILE_P * 2);
   const uint32_t bar0 = smem_u32(bars);
   // barriers: 0 planes_full | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a
-  constexpr int X_FULL = 1, X_EMPTY = 1 + MP_XS, ACC_FULL = 1 + 2 * MP_XS, ACC_EMPTY = 1 + 2 * MP_XS + MP_ACC;
+  const int X_FULL = 1, X_EMPTY = 1 + MP_XS, ACC_FULL = 1 + 2 * MP_XS, ACC_EMPTY = 1 + 2 * MP_XS + MP_ACC;
   uint32_t *tmem_slot = (uint32_t *)(bars + 1 + 2 * MP_XS + 2 * MP_ACC);
   float *bias_s = (float *)(tmem_slot + 2);
   const uint32_t smem0 = smem_u32(smem), xring0 = smem_u32(xring);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int b = blockIdx.z, kb = b / F;
   const int ntiles = (HW + MASK_TILE_P - 1) / MASK_TILE_P;
   const int cpf = gridDim.x;                                            // CTAs per frame
+  const long long t_start = dbg ? clock64() : 0;
+  long long w0 = 0, w1 = 0;
+  long long w2 = 0, w3 = 0, w4 = 0;
+  if (dbg) dbg += ((size_t)blockIdx.z * gridDim.x + blockIdx.x) * 16;     // <= 148 CTAs x 16 slots
 
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&tmap_x);
       prefetch_tmap(&tmap_a);
+      prefetch_tmap(&tmap_o);
       mbar_init(bar0, 1);
       for (int s = 0; s < MP_XS; ++s) {
         mbar_init(bar0 + 8 * (X_FULL + s), 1);
@@ -447,73 +478,108 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         for (int c = 0; c < nk; ++c, ++it) {
           const int s = it % MP_XS;
           const uint32_t ph = (uint32_t)(it / MP_XS) & 1u;
-          mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u);
+          MP_WAIT(w0, mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u));
           mbar_expect_tx(bar0 + 8 * (X_FULL + s), x_bytes);
           tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (X_FULL + s), p0, c * CH_BLK, b);
           tma_load_3d(xring0 + s * x_bytes + x_bytes / 2, &tmap_x, bar0 + 8 * (X_FULL + s), p0 + 64, c * CH_BLK, b);
         }
       }
+      if (dbg) dbg[1] = (unsigned long long)w0;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(bar0, 0);
-      int it = 0, li = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
-        const int buf = li % MP_ACC;
-        mbar_wait(bar0 + 8 * (ACC_EMPTY + buf), ((uint32_t)(li / MP_ACC) & 1u) ^ 1u);
+    // Warp-uniform issue loop (all lanes wait, one elected lane issues): descriptors are 64-bit bases plus small
+    // immediates kept in uniform registers -- a single thread walking divergent code needed ~15 dependent
+    // instructions per tcgen05.mma (48 MMAs per tile).
+    mbar_wait(bar0, 0);
+    const uint64_t adesc0 = umma_desc_sw128(xring0, x_lbo, x_sbo);
+    const uint64_t bdesc0 = umma_desc_sw128(smem0, 0, 1024);
+    const uint32_t a_plane16 = a_plane >> 4;
+    int s = 0;
+    uint32_t xph = 0, li = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
+      const uint32_t buf = li & 1u;
+      MP_WAIT(w1, mbar_wait(bar0 + 8 * (ACC_EMPTY + buf), ((li >> 1) & 1u) ^ 1u));
+      tc_fence_after();
+      const uint32_t dt = tmem_base + buf * 128u;
+      for (int c = 0; c < nk; ++c) {
+        MP_WAIT(w0, mbar_wait(bar0 + 8 * (X_FULL + s), xph));
         tc_fence_after();
-        const uint32_t dt = tmem_base + (uint32_t)buf * 128u;
-        for (int c = 0; c < nk; ++c, ++it) {
-          const int s = it % MP_XS;
-          mbar_wait(bar0 + 8 * (X_FULL + s), (uint32_t)(it / MP_XS) & 1u);
-          tc_fence_after();
-          const uint32_t xs = xring0 + s * x_bytes;
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * (x_bytes >> 4));
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(c * 3) * a_plane16);
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
 #pragma unroll
-            for (int k = 0; k < CH_BLK / 16; ++k) {
-              const uint64_t ad = umma_desc_sw128(xs + k * 2048, x_lbo, x_sbo);
-              const uint64_t bd = umma_desc_sw128(smem0 + (uint32_t)(c * 3 + t) * a_plane + k * 32, 0, 1024);
-              umma_bf16(dt, ad, bd, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < CH_BLK / 16; ++k)
+              umma_bf16(dt, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)((uint32_t)t * a_plane16 + k * 2), idesc,
+                        (c > 0 || t > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(bar0 + 8 * (X_EMPTY + s));
+          if (c == nk - 1) umma_commit(bar0 + 8 * (ACC_FULL + buf));
         }
-        umma_commit(bar0 + 8 * (ACC_FULL + buf));
+        __syncwarp();
+        if (++s == MP_XS) {
+          s = 0;
+          xph ^= 1u;
+        }
       }
     }
+    if (dbg && lane == 0) {
+      dbg[2] = (unsigned long long)w0;
+      dbg[3] = (unsigned long long)w1;
+      dbg[6] = li;
+      dbg[7] = 0x6d61736b67656d6dull;
+    }
   } else {
+    // ---- epilogue: TMEM lane = pixel, column = kernel.  32 kernels x 128 pixels at a time are rounded to bf16 into a
+    //      dense [32][128 px] staging box (lane = pixel: a warp writes 64 contiguous bytes, one conflict-free wavefront)
+    //      and leave as ONE TMA store of full 256-byte rows; the box is double-buffered against the store reading it.
+    //      (The earlier per-warp transpose cost 47 % of the shared-memory data pipe the tensor core reads through.)
     const int q = warp & 3;
-    __nv_bfloat16 *stg = reinterpret_cast<__nv_bfloat16 *>(stg_base) + (size_t)q * 32 * 40;
-    __nv_bfloat16 *ob = out + (size_t)b * N * HW;
+    const bool leader = threadIdx.x == 64;
+    const uint32_t stg0 = smem_u32(stg_base), bias0 = smem_u32(bias_s);
+    uint32_t jj = 0;
     int li = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
       const int buf = li % MP_ACC;
-      mbar_wait(bar0 + 8 * (ACC_FULL + buf), (uint32_t)(li / MP_ACC) & 1u);
+      MP_WAIT(w0, mbar_wait(bar0 + 8 * (ACC_FULL + buf), (uint32_t)(li / MP_ACC) & 1u));
       tc_fence_after();
       if (tile + cpf >= ntiles) pdl_trigger();
-      const int pw = tile * MASK_TILE_P + q * 32;
-      for (int n0 = 0; n0 < Npad; n0 += 32) {
+      for (int n0 = 0; n0 < Npad; n0 += 32, ++jj) {
+        float4 bq[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bq[e] = lds_f4(bias0 + (uint32_t)(n0 + 4 * e) * 4u);
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + n0), r);
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          stg[e * 40 + lane] = __float2bfloat16_rn(__uint_as_float(r[e]) + bias_s[n0 + e]);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int nl = it * 8 + (lane >> 2), seg = lane & 3;
-          const int n = n0 + nl, p = pw + seg * 8;
-          if (n < N && p < HW) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(stg + nl * 40 + seg * 8);
-            *reinterpret_cast<uint4 *>(ob + (size_t)n * HW + p) = v;
-          }
+        MP_WAIT(w2, tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + n0), r));
+        if (n0 + 32 >= Npad) {             // accumulators of this tile are in registers: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
         }
-        __syncwarp();
+        MP_WAIT(w1, if (leader) bulk_wait_group_read<1>();   // the store issued two chunks ago has read its box
+                named_bar_sync(1, 128));
+        const uint32_t sb = stg0 + (jj & 1u) * (uint32_t)(32 * MASK_TILE_P * 2) + (uint32_t)(q * 32 + lane) * 2u;
+        MP_WAIT(w3, _Pragma("unroll") for (int e = 0; e < 8; ++e) {
+          sts_u16(sb + (4 * e + 0) * (MASK_TILE_P * 2), bf16_bits(__uint_as_float(r[4 * e + 0]) + bq[e].x));
+          sts_u16(sb + (4 * e + 1) * (MASK_TILE_P * 2), bf16_bits(__uint_as_float(r[4 * e + 1]) + bq[e].y));
+          sts_u16(sb + (4 * e + 2) * (MASK_TILE_P * 2), bf16_bits(__uint_as_float(r[4 * e + 2]) + bq[e].z));
+          sts_u16(sb + (4 * e + 3) * (MASK_TILE_P * 2), bf16_bits(__uint_as_float(r[4 * e + 3]) + bq[e].w));
+        });
+        MP_WAIT(w4, fence_proxy_async(); named_bar_sync(1, 128));
+        if (leader) {
+          tma_store_3d(&tmap_o, stg0 + (jj & 1u) * (uint32_t)(32 * MASK_TILE_P * 2), tile * MASK_TILE_P, n0, b);
+          bulk_commit_group();
+        }
       }
-      tc_fence_before();                 // this warp's TMEM reads of `buf` are done
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
+    }
+    if (leader) bulk_wait_all();
+    if (dbg && leader) {
+      dbg[4] = (unsigned long long)w0;
+      dbg[5] = (unsigned long long)w1;
+      dbg[8] = (unsigned long long)w2;
+      dbg[9] = (unsigned long long)w3;
+      dbg[10] = (unsigned long long)w4;
+      dbg[0] = (unsigned long long)(clock64() - t_start);
     }
   }
   tc_fence_before();
@@ -571,8 +637,14 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)rows8};
       VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
     }
-    const size_t psmem = (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + MP_XS * (size_t)CH_BLK * MASK_TILE_P * 2 + 4 * 32 * 40 * 2 +
-                         (1 + 2 * MP_XS + 2 * MP_ACC) * 8 + 16 + (size_t)(Npad + 32) * 4 + 1024 + 64;
+    auto psmem_of = [&](int xs) {
+      return (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + xs * (size_t)CH_BLK * MASK_TILE_P * 2 + 2 * 32 * MASK_TILE_P * 2 +
+             (1 + 2 * xs + 2 * MP_ACC) * 8 + 16 +
+             (size_t)(Npad + 32) * 4 + 1024 + 64;
+    };
+    int xs_depth = MP_XS_MAX;
+    while (xs_depth > 2 && psmem_of(xs_depth) > 227 * 1024) --xs_depth;
+    const size_t psmem = psmem_of(xs_depth);
     static bool pattr = false;
     if (!pattr) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -580,9 +652,15 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     }
     if (psmem > 227 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "persistent mask conv: shared memory %zu exceeds 227 KB", psmem);
     VKN_LAUNCH_MARK("vkn_maskgemm_tc_persist_kernel", stream);
+    CUtensorMap tmo;
+    {
+      const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.N, (uint64_t)frames};
+      const uint32_t box[3] = {(uint32_t)MASK_TILE_P, 32u, 1u};
+      VKN_TRY(make_tmap_bf16_plain(&tmo, out, dims, box));
+    }
     VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(cpf, 1, frames), dim3(TC_THREADS), psmem, stream, tmx, tma,
-                             a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
-                             x_lbo, x_sbo, F));
+                             tmo, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
+                             x_lbo, x_sbo, F, xs_depth, debug_ts_slot()));
     return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);

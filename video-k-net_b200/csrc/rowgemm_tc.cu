@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
   uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 1);
   float *bias_s = (float *)(tmem_slot + 2);
   const uint32_t smem0 = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) RG_TS(0);
   const int nk_total = (P.K + 63) / 64;
   const int kper = nk_total / ks_total;               // host guarantees divisibility
@@ -114,27 +114,36 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STG;
-        const uint32_t ph = (uint32_t)(i / STG) & 1u;
-        mbar_wait(bar0 + 8 * s, ph);
-        tc_fence_after();
+    // warp-uniform issue loop, one elected lane issues (see elect_one() in tc.cuh)
+    const uint64_t adesc0 = umma_desc_sw128(smem0, 0, 1024);
+    const uint64_t bdesc0 = adesc0 + (uint64_t)(RG_A_BYTES >> 4);
+    const uint32_t idesc = batch.idesc;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nk; ++i) {
+      mbar_wait(bar0 + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
         if (i == 0) RG_TS(3);
-        const uint32_t as = smem0 + s * stage_bytes, wsm = as + RG_A_BYTES;
+        const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
 #pragma unroll
         for (int pl = 2; pl >= 0; --pl) {                   // lo, mid, hi: small terms first
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_sw128(as + (uint32_t)pl * RG_A_PLANE + k * 32, 0, 1024);
-            const uint64_t bd = umma_desc_sw128(wsm + k * 32, 0, 1024);
-            umma_bf16(tmem_base, ad, bd, batch.idesc, (i > 0 || pl < 2 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, adesc0 + so + (uint64_t)(pl * (int)(RG_A_PLANE >> 4) + k * 2), bdesc0 + so + (uint64_t)(k * 2), idesc,
+                      (i > 0 || pl < 2 || k > 0) ? 1u : 0u);
         }
         umma_commit(bar0 + 8 * (STG + s));
+        if (i == nk - 1) {
+          umma_commit(bar0 + 16 * STG);
+          RG_TS(4);
+        }
       }
-      umma_commit(bar0 + 16 * STG);
-      RG_TS(4);
+      __syncwarp();
+      if (++s == STG) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   } else {
     // ---- epilogue: 8 warps, thread = row (TMEM lane); the two warps of a lane quarter take alternate 32-column

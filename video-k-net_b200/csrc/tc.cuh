@@ -43,6 +43,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
+// One lane of a converged warp (deterministic: the same lane for the same mask).  The MMA / TMA issue loops run
+// warp-uniform with only the issuing instructions under elect_one(): the compiler then keeps descriptors, barrier
+// addresses and loop state in uniform registers, which is what makes the tcgen05.mma issue loop a handful of
+// instructions per MMA instead of ~15 (measured: profiles/r1_ncu_summary.md, "issue-bound MMA warp").
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -59,6 +74,46 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// TMA prefetch of a tile into L2 (no shared memory, no barrier): lets a CTA keep more DRAM requests in flight than
+// its shared-memory ring holds -- the ring then only covers the L2 -> SM latency.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// Explicit shared-state-space accesses (32-bit addresses).  Through generic pointers the compiler must assume a
+// shared-memory store may alias the next bias load and serialises load -> convert -> store chains (measured: 54 cycles
+// per element in the mask-conv epilogue); these keep loads batched ahead of the stores.
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("{\n\t.reg .b16 h;\n\tcvt.u16.u32 h, %1;\n\tst.shared.u16 [%0], h;\n\t}" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+// TMA store of a shared-memory box (bulk-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -149,6 +204,21 @@ static int make_tmap_bf16(CUtensorMap *map, const void *base, int rank, const ui
   return VKN_OK;
 }
 
+
+// bf16 tensor, rank 3, contiguous, NO swizzle (TMA stores from a dense shared-memory box); dims/box innermost first.
+static int make_tmap_bf16_plain(CUtensorMap *map, const void *base, const uint64_t *dims, const uint32_t *box) {
+  EncodeTiledFn enc;
+  VKN_TRY(get_encode(&enc));
+  cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+  cuuint64_t gstride[2] = {dims[0] * 2, dims[0] * dims[1] * 2};
+  cuuint32_t bx[3] = {box[0], box[1], box[2]}, estr[3] = {1, 1, 1};
+  if (reinterpret_cast<uintptr_t>(base) & 15) VKN_FAIL(VKN_E_INVALID, "TMA: global base address must be 16-byte aligned");
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim, gstride, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) VKN_FAIL(VKN_E_CUDA, "cuTensorMapEncodeTiled (plain) failed with CUresult %d", (int)r);
+  return VKN_OK;
+}
 
 // bf16 tensor with explicit byte strides (innermost dimension contiguous); dims/box innermost first; 128B swizzle.
 static int make_tmap_bf16_strided(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
