@@ -483,7 +483,9 @@ def test_init_proposals_golden_and_full_size(dev):
 
 # ---- tcgen05 row engine (planes handed between row GEMMs) vs the warp-MMA chain and the oracle -------------------
 @pytest.mark.parametrize('B,N,C,H,W,Fh,S', [(1, 20, 64, 16, 24, 512, 2), (2, 100, 256, 40, 24, 512, 2),
-                                             (5, 100, 256, 24, 40, 2048, 1), (3, 117, 128, 16, 24, 192, 2)])
+                                             (5, 100, 256, 24, 40, 2048, 1), (3, 117, 128, 16, 24, 192, 2),
+                                             # P = 4000 rows: several tiles per persistent CTA (accumulator ring wraps)
+                                             (40, 100, 256, 8, 16, 2048, 1)])
 def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H, W, Fh, S):
     import vknet
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=Fh)
@@ -514,6 +516,25 @@ def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H
     # both engines multiply exact bf16 products with fp32 accumulation: first-stage kernels agree to fp32 round-off
     assert maxabs(outs['tc'][0][2], outs['warp'][0][2].cpu()) < 2e-4
     assert maxabs(outs['tc'][0][0], outs['warp'][0][0].cpu()) < 2e-4
+
+
+@pytest.mark.parametrize('bn', ['32', '64', '128', '256'])
+def test_row_engine_tc_column_tiles(dev, monkeypatch, bn):
+    """Every column-tile width of the persistent row GEMM (VKN_RG_BN) gives the same stage as the default choice."""
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    B, N, C, H, W = 12, 100, 256, 8, 16
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=1024)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=5))
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=6)
+    xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
+    base = [t.clone() for t in h(xb, pfd, mb)]
+    monkeypatch.setenv('VKN_RG_BN', bn)
+    got = h(xb, pfd, mb)
+    for a, b in zip(got, base):
+        assert maxabs(a, b) <= 1e-5 * max(1.0, b.float().abs().max().item()), 'BN=%s' % bn
+    want = ko.kernel_update_head_forward(sd, cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
+    assert maxabs(got[0], want[0]) < TOL_BF16 and maxabs(got[2], want[2]) < TOL_BF16
 
 
 def test_row_engine_tc_variants(dev, monkeypatch):

@@ -519,7 +519,7 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     VKN_TRY(launch_linear_tc(&f1, 1, c.st));
     LinArgs f2 = lin(src_planes(c.L.h, F, (long long)P * F), w.ffn.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
     const int nk = ceil_div(F, 64);
-    int ksp = 148 / (ceil_div(P, 128) * ceil_div(C, 128));
+    int ksp = 148 / (ceil_div(P, 128) * ceil_div(C, 256));      // K slices: fill the SMs with 128 x 256 tiles
     ksp = ksp >= 8 ? 8 : (ksp >= 4 ? 4 : (ksp >= 2 ? 2 : 1));
     while (ksp > 1 && (nk % ksp != 0 || nk / ksp < 4)) ksp /= 2;
     f2.ksplit = ksp;

@@ -23,10 +23,11 @@ struct RgProb {
   __nv_bfloat16 *planes;
   long long out_split_stride, plane_elems;
   int ldres, ldo, M, N, K, epi, split_N, split_Npad, split_C;
+  int mt, nt, tiles;          // row tiles, column tiles, tiles of this problem (mt * nt * ksplit)
 };
 struct RgBatch {
   RgProb p[2];
-  int ksplit, stages, BN;
+  int nprob, ksplit, stages, BN, total_tiles;
   uint32_t idesc;
   unsigned long long *dbg;     // optional per-CTA phase timestamps (vkn_debug_timestamps), null in production
 };
@@ -36,10 +37,9 @@ __device__ __forceinline__ unsigned long long rg_time() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define RG_TS(slot)                                                                                                 \
-  do {                                                                                                              \
-    if (batch.dbg != nullptr)                                                                                       \
-      batch.dbg[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = rg_time(); \
+#define RG_TS(slot)                                                       \
+  do {                                                                    \
+    if (batch.dbg != nullptr) batch.dbg[(size_t)blockIdx.x * 8 + (slot)] = rg_time(); \
   } while (0)
 
 constexpr uint32_t RG_A_PLANE = 128u * 128u;        // 128 rows x 64 k x 2 B
@@ -47,41 +47,64 @@ constexpr uint32_t RG_A_BYTES = 3u * RG_A_PLANE;
 
 constexpr int RG_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
+// tile t of the launch -> problem, K slice, row / column origin
+struct RgTile {
+  int prob, ks, row0, col0;
+};
+__device__ __forceinline__ RgTile rg_decode(const RgBatch &batch, int t) {
+  RgTile r;
+  r.prob = 0;
+  if (t >= batch.p[0].tiles) {
+    t -= batch.p[0].tiles;
+    r.prob = 1;
+  }
+  const RgProb &P = batch.p[r.prob];
+  const int per = P.mt * P.nt;
+  r.ks = t / per;
+  const int rem = t - r.ks * per;
+  const int m = rem / P.nt;
+  r.row0 = m * 128;
+  r.col0 = (rem - m * P.nt) * batch.BN;
+  return r;
+}
+
+// Persistent: a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs on across tiles and the
+// accumulator is double-buffered in TMEM (2 x BN columns), so the tensor core works on tile i+1 while the eight epilogue
+// warps drain tile i.  BN = 256 halves the shared-memory operand traffic per FLOP of the 3-plane product (the limiter
+// of this kernel: every tcgen05.mma re-reads its A and B tiles from shared memory).
 __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __grid_constant__ RgBatch batch) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int BN = batch.BN, STG = batch.stages, ks_total = batch.ksplit;
-  const RgProb &P = batch.p[blockIdx.z / ks_total];
-  const int ks = blockIdx.z % ks_total;
-  const int row0 = blockIdx.y * 128, col0 = blockIdx.x * BN;
-  if (row0 >= P.M || col0 >= P.N) {
-    pdl_trigger();
-    return;
-  }
+  const int BN = batch.BN, STG = batch.stages, total = batch.total_tiles;
   const uint32_t w_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = RG_A_BYTES + w_bytes;
   uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes);
   const uint32_t bar0 = smem_u32(bars);
-  // full[s] = bar0 + 8 s (TMA: A planes + W tile), empty[s] = bar0 + 8 (STG + s) (MMAs retired), tmem_full = bar0 + 16 STG
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 1);
-  float *bias_s = (float *)(tmem_slot + 2);
+  // full[s] = bar0 + 8 s (TMA: A planes + W tile), empty[s] = bar0 + 8 (STG + s) (MMAs retired),
+  // acc_full[a] = bar0 + 8 (2 STG + a), acc_empty[a] = bar0 + 8 (2 STG + 2 + a)
+  const uint32_t acc_full0 = bar0 + 16 * STG, acc_empty0 = acc_full0 + 16;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 4);
   const uint32_t smem0 = smem_u32(smem);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) RG_TS(0);
-  const int nk_total = (P.K + 63) / 64;
-  const int kper = nk_total / ks_total;               // host guarantees divisibility
-  const int kb = ks * kper, nk = kper;
-  const uint32_t ncols = BN < 32 ? 32u : (uint32_t)BN;
+  const uint32_t ncols = BN < 16 ? 32u : 2u * (uint32_t)BN;     // 64 / 128 / 256 / 512
 
   if (warp == 0) {
     if (lane == 0) {
-      prefetch_tmap(&P.tmA);
-      prefetch_tmap(&P.tmW);
+      prefetch_tmap(&batch.p[0].tmA);
+      prefetch_tmap(&batch.p[0].tmW);
+      if (batch.nprob > 1) {
+        prefetch_tmap(&batch.p[1].tmA);
+        prefetch_tmap(&batch.p[1].tmW);
+      }
       for (int s = 0; s < STG; ++s) {
         mbar_init(bar0 + 8 * s, 1);
         mbar_init(bar0 + 8 * (STG + s), 1);
       }
-      mbar_init(bar0 + 16 * STG, 1);
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(acc_full0 + 8 * a, 1);
+        mbar_init(acc_empty0 + 8 * a, 8);                   // one arrive per epilogue warp
+      }
       fence_barrier_init();
     }
   } else if (warp == 1) {
@@ -95,22 +118,38 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
 
   if (warp == 0) {
     if (lane == 0) {
-      const int npre = nk < STG ? nk : STG;
-      for (int i = 0; i < npre; ++i) {                      // weight tiles: nobody in the chain writes them
-        mbar_expect_tx(bar0 + 8 * i, stage_bytes);
-        tma_load_2d(smem0 + i * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * i, (kb + i) * 64, col0);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      int npre = 0;
+      {     // weight tiles of the first ring fill: nobody in the chain writes weights -> before the PDL wait
+        const RgTile T = rg_decode(batch, blockIdx.x);
+        const RgProb &P = batch.p[T.prob];
+        const int nk = ((P.K + 63) / 64) / batch.ksplit;
+        npre = nk < STG ? nk : STG;
+        for (int i = 0; i < npre; ++i) {
+          mbar_expect_tx(bar0 + 8 * i, stage_bytes);
+          tma_load_2d(smem0 + i * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * i, (T.ks * nk + i) * 64, T.col0);
+        }
       }
       pdl_wait();                                           // the A planes come from the previous kernel
       RG_TS(2);
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STG;
-        const uint32_t ph = (uint32_t)(i / STG) & 1u;
-        if (i >= npre) {
-          mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u);
-          mbar_expect_tx(bar0 + 8 * s, stage_bytes);
-          tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, (kb + i) * 64, col0);
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const RgTile T = rg_decode(batch, t);
+        const RgProb &P = batch.p[T.prob];
+        const int nk = ((P.K + 63) / 64) / batch.ksplit;    // host guarantees divisibility
+        const int kb = T.ks * nk;
+        for (int i = 0; i < nk; ++i, ++it) {
+          if (it >= npre) {
+            if (it >= STG) mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u);
+            mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+            tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, (kb + i) * 64, T.col0);
+          }
+          tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, (kb + i) * 64, T.row0, 0);
+          if (++s == STG) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
-        tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, (kb + i) * 64, row0, 0);
       }
     }
   } else if (warp == 1) {
@@ -119,137 +158,172 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
     const uint64_t bdesc0 = adesc0 + (uint64_t)(RG_A_BYTES >> 4);
     const uint32_t idesc = batch.idesc;
     int s = 0;
-    uint32_t ph = 0;
-    for (int i = 0; i < nk; ++i) {
-      mbar_wait(bar0 + 8 * s, ph);
+    uint32_t ph = 0, li = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
+      const RgTile T = rg_decode(batch, t);
+      const int nk = ((batch.p[T.prob].K + 63) / 64) / batch.ksplit;
+      const uint32_t buf = li & 1u;
+      mbar_wait(acc_empty0 + 8 * buf, ((li >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      if (elect_one()) {
-        if (i == 0) RG_TS(3);
-        const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
+      const uint32_t dt = tmem_base + buf * (uint32_t)BN;
+      for (int i = 0; i < nk; ++i) {
+        mbar_wait(bar0 + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          if (li == 0 && i == 0) RG_TS(3);
+          const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
 #pragma unroll
-        for (int pl = 2; pl >= 0; --pl) {                   // lo, mid, hi: small terms first
+          for (int pl = 2; pl >= 0; --pl) {                 // lo, mid, hi: small terms first
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, adesc0 + so + (uint64_t)(pl * (int)(RG_A_PLANE >> 4) + k * 2), bdesc0 + so + (uint64_t)(k * 2), idesc,
-                      (i > 0 || pl < 2 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(dt, adesc0 + so + (uint64_t)(pl * (int)(RG_A_PLANE >> 4) + k * 2), bdesc0 + so + (uint64_t)(k * 2), idesc,
+                        (i > 0 || pl < 2 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar0 + 8 * (STG + s));
+          if (i == nk - 1) {
+            umma_commit(acc_full0 + 8 * buf);
+            if (li == 0) RG_TS(4);
+          }
         }
-        umma_commit(bar0 + 8 * (STG + s));
-        if (i == nk - 1) {
-          umma_commit(bar0 + 16 * STG);
-          RG_TS(4);
+        __syncwarp();
+        if (++s == STG) {
+          s = 0;
+          ph ^= 1u;
         }
-      }
-      __syncwarp();
-      if (++s == STG) {
-        s = 0;
-        ph ^= 1u;
       }
     }
   } else {
     // ---- epilogue: 8 warps, thread = row (TMEM lane); the two warps of a lane quarter take alternate 32-column
     //      blocks.  A thread owns 32 consecutive columns of its row in registers: bias / residual / ReLU / the plane
     //      split run as 32 independent chains and leave as 16-byte stores (no shared-memory round trip).
-    // bias is a weight: staged by the epilogue warps (off the CTA's critical path), before the PDL wait
-    for (int i = threadIdx.x - 64; i < BN; i += RG_THREADS - 64)
-      bias_s[i] = ((P.epi & EPI_BIAS) && col0 + i < P.N) ? __ldg(P.bias + col0 + i) : 0.f;
-    asm volatile("bar.sync 1, %0;" ::"n"(RG_THREADS - 64) : "memory");
     pdl_wait();                                             // residual / rowscale reads, and every global store
-    mbar_wait(bar0 + 16 * STG, 0);
-    tc_fence_after();
-    pdl_trigger();
-    if (threadIdx.x == 64) RG_TS(5);
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                       // 0: even column blocks, 1: odd
-    const int epi = P.epi;
-    const int row = row0 + q * 32 + lane;
-    const bool live = row < P.M;
-    float *outp = P.out + (size_t)ks * P.out_split_stride;
-    const bool out_vec = (P.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
-    const bool res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
-    const bool pl_vec = (P.split_C % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 15) == 0);
-    const float rs = (live && (epi & EPI_ROWSCALE)) ? __ldg(P.rowscale + row) : 1.f;
-    size_t prow = (size_t)row;                              // row of the plane buffer this thread writes
-    if ((epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
-      const int b = row / P.split_N;
-      prow = (size_t)b * P.split_Npad + (row - b * P.split_N);
-    }
-    for (int c0 = half * 32; c0 < BN; c0 += 64) {
-      const int col = col0 + c0;
-      if (col >= P.N) break;
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (!live) continue;
-      const int nc = min(32, P.N - col);
-      float v[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-      if (epi & EPI_BIAS) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c0 + e);
-          v[e] = fmaf(rs, b4.x, v[e]); v[e + 1] = fmaf(rs, b4.y, v[e + 1]);
-          v[e + 2] = fmaf(rs, b4.z, v[e + 2]); v[e + 3] = fmaf(rs, b4.w, v[e + 3]);
+    uint32_t li = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
+      const RgTile T = rg_decode(batch, t);
+      const RgProb &P = batch.p[T.prob];
+      const uint32_t buf = li & 1u;
+      mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u);
+      tc_fence_after();
+      if (t + (int)gridDim.x >= total) pdl_trigger();
+      if (threadIdx.x == 64 && li == 0) RG_TS(5);
+      const int epi = P.epi;
+      const int row = T.row0 + q * 32 + lane;
+      const bool live = row < P.M;
+      float *outp = P.out + (size_t)T.ks * P.out_split_stride;
+      const bool out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(outp) & 31) == 0);
+      const bool res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
+      const bool pl_vec = (P.split_C % 16 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 31) == 0) && (P.plane_elems % 16 == 0);
+      const bool bias_vec = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0;
+      const float rs = (live && (epi & EPI_ROWSCALE)) ? __ldg(P.rowscale + row) : 1.f;
+      size_t prow = (size_t)row;                            // row of the plane buffer this thread writes
+      if ((epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
+        const int b = row / P.split_N;
+        prow = (size_t)b * P.split_Npad + (row - b * P.split_N);
+      }
+      const uint32_t tacc = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      int last_c0 = half * 32;                              // last column block this warp reads from TMEM
+      while (last_c0 + 64 < BN && T.col0 + last_c0 + 64 < P.N) last_c0 += 64;
+      bool released = false;
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        const int col = T.col0 + c0;
+        if (col >= P.N) break;
+        uint32_t r[32];
+        tmem_ld32(tacc + (uint32_t)c0, r);
+        if (c0 == last_c0) {                                // this warp's share of the accumulator is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+          released = true;
         }
-      }
-      if (epi & EPI_RES) {
-        const float *rp = P.res + (size_t)row * P.ldres + col;
-        if (res_vec && nc == 32) {
+        if (!live) continue;
+        const int nc = min(32, P.N - col);
+        float v[32];
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(rp + e));
-            v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
-          }
-        } else {
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        if (epi & EPI_BIAS) {
+          const float *bp = P.bias + col;
+          if (bias_vec && nc == 32 && (col & 3) == 0) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e < nc) v[e] += __ldg(rp + e);
-        }
-      }
-      if (epi & EPI_RELU) {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-      }
-      if (!(epi & EPI_NOOUT)) {
-        float *op = outp + (size_t)row * P.ldo + col;
-        if (out_vec && nc == 32) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4 *>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e < nc) op[e] = v[e];
-        }
-      }
-      if ((epi & EPI_SPLIT3) && col < P.split_C) {
-        const int np = min(32, P.split_C - col);
-        __nv_bfloat16 *pp = P.planes + prow * P.split_C + col;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {                       // v == hi + mid + lo to 24 bits
-          uint32_t w[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
-            v[e] -= __bfloat162float(h0);
-            v[e + 1] -= __bfloat162float(h1);
-            w[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          }
-          __nv_bfloat16 *pt = pp + (size_t)t * P.plane_elems;
-          if (pl_vec && np == 32) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4 *>(pt + 2 * e) = make_uint4(w[e], w[e + 1], w[e + 2], w[e + 3]);
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + e));
+              v[e] = fmaf(rs, b4.x, v[e]); v[e + 1] = fmaf(rs, b4.y, v[e + 1]);
+              v[e + 2] = fmaf(rs, b4.z, v[e + 2]); v[e + 3] = fmaf(rs, b4.w, v[e + 3]);
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
+              if (e < nc) v[e] = fmaf(rs, __ldg(bp + e), v[e]);
           }
         }
+        if (epi & EPI_RES) {
+          const float *rp = P.res + (size_t)row * P.ldres + col;
+          if (res_vec && nc == 32) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4 *>(rp + e));
+              v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nc) v[e] += __ldg(rp + e);
+          }
+        }
+        if (epi & EPI_RELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (!(epi & EPI_NOOUT)) {
+          float *op = outp + (size_t)row * P.ldo + col;
+          if (out_vec && nc == 32) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8)
+              stg_v8(op + e, __float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3]),
+                     __float_as_uint(v[e + 4]), __float_as_uint(v[e + 5]), __float_as_uint(v[e + 6]), __float_as_uint(v[e + 7]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nc) op[e] = v[e];
+          }
+        }
+        if ((epi & EPI_SPLIT3) && col < P.split_C) {
+          const int np = min(32, P.split_C - col);
+          __nv_bfloat16 *pp = P.planes + prow * P.split_C + col;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {                  // v == hi + mid + lo to 24 bits
+            uint32_t w[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
+              v[e] -= __bfloat162float(h0);
+              v[e + 1] -= __bfloat162float(h1);
+              w[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            }
+            __nv_bfloat16 *pt = pp + (size_t)pl * P.plane_elems;
+            if (pl_vec && np == 32) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 8) stg_v8(pt + 2 * e, w[e], w[e + 1], w[e + 2], w[e + 3], w[e + 4], w[e + 5], w[e + 6], w[e + 7]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
+            }
+          }
+        }
+      }
+      if (!released) {                                      // a warp whose column blocks all lie past N
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
       }
     }
     if (threadIdx.x == 64) RG_TS(6);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ncols);
   }
@@ -288,25 +362,34 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
     maxN = max(maxN, a.N);
     nkmax = max(nkmax, nk / ks);
   }
-  // column tile: the widest of {128, 64, 32} that still gives ~one CTA per SM pair (latency-bound launches want
-  // the work spread; wide tiles only pay when the A planes would otherwise be re-read by many column CTAs)
-  const int mt = ceil_div(maxM, 128);
+  // Column tile: the candidate with the lowest estimated launch time = waves x tile time.  Tile time in cycles of the
+  // shared-memory data pipe (the limiter): per 64-deep K chunk the TMA writes 48 KB of A planes + BN x 128 B of W and
+  // the 12 MMAs read 12 x (4 KB + BN x 32 B); plus a fixed prologue/epilogue cost.  Few tiles -> narrow tiles (spread the
+  // work), many tiles -> BN = 256 (A planes read once per 256 output columns).
+  const int sms = 148;
   int BN = 32;
-  for (int cand = 128; cand >= 32; cand >>= 1) {
-    if (cand > 32 && cand / 2 >= maxN) continue;                    // tile wider than the problem
-    if ((long long)mt * ceil_div(maxN, cand) * nprob * ks >= 74 || cand == 32) {
-      BN = cand;
-      break;
+  {
+    double best = 1e30;
+    for (int cand = 32; cand <= 256; cand <<= 1) {
+      if (cand > 32 && cand / 2 >= maxN) break;                     // tile wider than the problem
+      long long tiles = 0;
+      for (int i = 0; i < nprob; ++i) tiles += (long long)ceil_div(probs[i].M, 128) * ceil_div(probs[i].N, cand) * ks;
+      const double tile_cyc = (double)nkmax * (768.0 + 4.0 * cand) + 1200.0 + 6.0 * cand;
+      const double cost = (double)((tiles + sms - 1) / sms) * tile_cyc;
+      if (cost < best) {
+        best = cost;
+        BN = cand;
+      }
     }
   }
   BN = rg_env("VKN_RG_BN", BN);
   if (BN != 32 && BN != 64 && BN != 128 && BN != 256) VKN_FAIL(VKN_E_INVALID, "VKN_RG_BN must be 32, 64, 128 or 256");
   const size_t stage_bytes = (size_t)RG_A_BYTES + (size_t)BN * 128;
-  int stages = rg_env("VKN_RG_STAGES", 2);   // 2 x 56 KB: CTAs of concurrent branches co-reside (measured best)
-  if (stages > nkmax) stages = nkmax;
-  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 1024 + (2 * st + 1) * 8 + 16 + (size_t)BN * 4 + 64; };
+  int stages = rg_env("VKN_RG_STAGES", 4);
+  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 1024 + (2 * st + 4) * 8 + 16 + 64; };
   while (stages > 1 && smem_of(stages) > 227 * 1024) --stages;
   size_t smem = smem_of(stages);
+  b.nprob = nprob;
   b.ksplit = ks;
   b.stages = stages;
   b.BN = BN;
@@ -339,17 +422,24 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
     p.split_N = a.split_N > 0 ? a.split_N : 1;
     p.split_Npad = a.split_Npad;
     p.split_C = a.split_C;
+    p.mt = ceil_div(a.M, 128);
+    p.nt = ceil_div(a.N, BN);
+    p.tiles = p.mt * p.nt * ks;
+    b.total_tiles += p.tiles;
     if ((a.epi & EPI_BIAS) && ks > 1) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: bias with split-K belongs to the consumer");
     if ((a.epi & EPI_SPLIT3) && !a.split_planes) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_SPLIT3 without a plane buffer");
     if (!(a.epi & EPI_NOOUT) && !a.out) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: null output");
   }
-  if (nprob == 1) b.p[1] = b.p[0];
+  if (nprob == 1) {
+    b.p[1] = b.p[0];
+    b.p[1].tiles = 0;
+  }
   static bool attr = false;
   if (!attr) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  dim3 grid(ceil_div(maxN, BN), mt, nprob * ks);
+  dim3 grid(b.total_tiles < sms ? b.total_tiles : sms);
   VKN_LAUNCH_MARK("vkn_rowgemm_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_rowgemm_tc_kernel, grid, dim3(RG_THREADS), smem, stream, b));
   return VKN_OK;

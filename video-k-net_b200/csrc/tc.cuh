@@ -100,6 +100,15 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
+// 256-bit global stores (sm_100): one full 32-byte sector per lane and instruction.  Row-per-thread epilogues write
+// 32 different rows per instruction, so the L2 transaction count -- not bytes -- bounds them: v8 halves it against v4.
+__device__ __forceinline__ void stg_v8(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                       uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 // TMA store of a shared-memory box (bulk-group completion)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
