@@ -537,6 +537,27 @@ def test_row_engine_tc_column_tiles(dev, monkeypatch, bn):
     assert maxabs(got[0], want[0]) < TOL_BF16 and maxabs(got[2], want[2]) < TOL_BF16
 
 
+def test_row_engine_tc_fused_layernorm_epilogue(dev, monkeypatch):
+    """VKN_RG_FUSE_LN=1: fc_norm / attention_norm / the FC-head LayerNorms run in the row-GEMM epilogues (opt-in)."""
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    for (B, N, C, H, W, Fh) in ((3, 100, 256, 8, 16, 512), (2, 37, 128, 8, 16, 128)):
+        cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=Fh)
+        sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=21))
+        h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+        x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=22)
+        xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
+        monkeypatch.setenv('VKN_RG_FUSE_LN', '0')
+        base = [t.clone() for t in h(xb, pfd, mb)]
+        monkeypatch.setenv('VKN_RG_FUSE_LN', '1')
+        got = h(xb, pfd, mb)
+        for i in (0, 2):         # cls_score, obj_feat (fp32): same arithmetic up to the LayerNorm summation order
+            assert maxabs(got[i], base[i]) <= 5e-5 * max(1.0, base[i].float().abs().max().item())
+        # mask logits are rounded to bf16 at the boundary: one-ulp flips at most
+        assert maxabs(got[1], base[1]) <= 2 ** -7 * base[1].float().abs().max().item()
+        want = ko.kernel_update_head_forward(sd, cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
+        assert maxabs(got[0], want[0]) < TOL_BF16 and maxabs(got[2], want[2]) < TOL_BF16
+
+
 def test_row_engine_tc_variants(dev, monkeypatch):
     """with_ffn=False, no feat_transform, deeper FC stacks, non-default threshold, video head (x_feat handed in)."""
     monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')

@@ -39,7 +39,7 @@ def main():
     for _ in range(3):
         loop2.replay()
     torch.cuda.synchronize()
-    ts = buf[: nlaunch * stride].reshape(nlaunch, 4096, 8).cpu()
+    ts = buf[: nlaunch * stride].reshape(nlaunch, 2048, 16).cpu()
     latest = max(int(ts[i][:, 0].max()) for i in range(nlaunch))
     names = ['entry', 'setup', 'dep', 'landed', 'issued', 'acc', 'epi', 'exit']
     t0 = None
@@ -61,7 +61,8 @@ def main():
         # per-CTA durations
         dur = (t[:, 7] - t[:, 0]).float() / 1e3
         gap = '' if prev_end is None else ' | entry-prev_exit %5.1f' % ((int(t[:, 0].min()) - prev_end) / 1e3)
-        print('launch %2d ctas %4d cta-time %4.1f..%4.1f | %s%s' % (i, int(live.sum()), dur.min(), dur.max(), ' | '.join(row), gap))
+        extra = ' | epilogue kcycles/CTA: load %.1f store %.1f wait %.1f, tiles %.1f' % (t[:, 8].float().mean() / 1e3, t[:, 9].float().mean() / 1e3, t[:, 10].float().mean() / 1e3, t[:, 11].float().mean())
+        print('launch %2d ctas %4d cta-time %4.1f..%4.1f | %s%s%s' % (i, int(live.sum()), dur.min(), dur.max(), ' | '.join(row), gap, extra))
         prev_end = int(t[:, 7].max())
 
 

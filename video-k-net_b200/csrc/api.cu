@@ -166,6 +166,7 @@ struct Ctx {
   int P;
   bool use_tc;
   bool rows_tc;     // row operators on the tcgen05 row engine (planes handed between launches)
+  bool fuse_ln;     // row engine: LayerNorms fused into the GEMM epilogues (VKN_RG_FUSE_LN=1; measured slower so far)
 };
 
 static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, Ctx &c) {
@@ -187,6 +188,10 @@ static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, 
   int rows_min = 400;
   if (const char *e = getenv("VKN_ROWS_TC_MIN")) rows_min = atoi(e);
   c.rows_tc = c.use_tc && s->w_dtype == VKN_BF16 && rows_min > 0 && c.P >= rows_min;
+  {
+    const char *e = getenv("VKN_RG_FUSE_LN");
+    c.fuse_ln = e && e[0] == '1';
+  }
   return VKN_OK;
 }
 
@@ -497,23 +502,45 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   gt.a[2] = c.L.igp;       gt.lda[2] = C;      gt.ln_g[2] = u.inorm_in_g;   gt.ln_b[2] = u.inorm_in_b;
   gt.a[3] = c.L.inp + C;   gt.lda[3] = 2 * C;  gt.ln_g[3] = u.inorm_out_g;  gt.ln_b[3] = u.inorm_out_b;
   VKN_TRY(launch_rowprep(gt, nullptr, 0, PLB, C, PS, P, C, c.st));
-  LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.fc, C, P, C, C, 0);                  // :90
-  VKN_TRY(launch_linear_tc(&f, 1, c.st));
-  VKN_TRY(launch_rowprep(src_ln(c.L.fc, C, u.fc_norm_g, u.fc_norm_b, true), c.L.o, C, PLA, C, PS, P, C, c.st));   // :91-92
+  if (c.fuse_ln) {
+    // :90-92  fc_layer -> fc_norm -> ReLU in one launch (LayerNorm fused in the GEMM epilogue): o (fp32) + planes PLA
+    LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.o, C, P, C, C, EPI_LN | EPI_RELU);
+    f.ln_g = u.fc_norm_g;
+    f.ln_b = u.fc_norm_b;
+    out_planes(f, PLA, P, C);
+    VKN_TRY(launch_linear_tc(&f, 1, c.st));
+  } else {
+    LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.fc, C, P, C, C, 0);                  // :90
+    VKN_TRY(launch_linear_tc(&f, 1, c.st));
+    VKN_TRY(launch_rowprep(src_ln(c.L.fc, C, u.fc_norm_g, u.fc_norm_b, true), c.L.o, C, PLA, C, PS, P, C, c.st));   // :91-92
+  }
   // a6 MHSA + LN (kernel_update_head.py:204-208)
   LinArgs qkv = lin(src_planes(PLA, C, PS), w.attn.in_w, C, w.attn.in_b, c.L.qkv, 3 * C, P, 3 * C, C, 0);
   VKN_TRY(launch_linear_tc(&qkv, 1, c.st));
   VKN_TRY(launch_attention(c.L.qkv, 3 * C, c.L.qkv + C, 3 * C, c.L.qkv + 2 * C, 3 * C, nullptr, C, c.s.B, c.s.N, C,
                            c.s.num_heads, c.st, PLB, PS));
-  LinArgs op = lin(src_planes(PLB, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.y, C, P, C, C, EPI_RES);
-  op.res = c.L.o;
-  op.ldres = C;
-  VKN_TRY(launch_linear_tc(&op, 1, c.st));
   float *obj_dst = obj ? obj : c.L.obj_tmp;
-  RowSrc an = src_ln(c.L.y, C, w.attn.norm_g, w.attn.norm_b, false);
+  if (c.fuse_ln) {
+    // out-projection + residual + attention_norm in one launch (:206-208)
+    LinArgs op = lin(src_planes(PLB, C, PS), w.attn.out_w, C, w.attn.out_b, c.s.with_ffn ? c.L.o2 : obj_dst, C, P, C, C,
+                     EPI_RES | EPI_LN);
+    op.res = c.L.o;
+    op.ldres = C;
+    op.ln_g = w.attn.norm_g;
+    op.ln_b = w.attn.norm_b;
+    out_planes(op, c.s.with_ffn ? PLA : obj_planes_out, P, C);
+    VKN_TRY(launch_linear_tc(&op, 1, c.st));
+  } else {
+    LinArgs op = lin(src_planes(PLB, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.y, C, P, C, C, EPI_RES);
+    op.res = c.L.o;
+    op.ldres = C;
+    VKN_TRY(launch_linear_tc(&op, 1, c.st));
+    RowSrc an = src_ln(c.L.y, C, w.attn.norm_g, w.attn.norm_b, false);
+    if (c.s.with_ffn) VKN_TRY(launch_rowprep(an, c.L.o2, C, PLA, C, PS, P, C, c.st));
+    else VKN_TRY(launch_rowprep(an, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
+  }
   if (c.s.with_ffn) {
     // a7 FFN + LN (:214-215)
-    VKN_TRY(launch_rowprep(an, c.L.o2, C, PLA, C, PS, P, C, c.st));
     LinArgs f1 = lin(src_planes(PLA, C, PS), w.ffn.w1, C, w.ffn.b1, nullptr, F, P, F, C, EPI_RELU | EPI_NOOUT);
     out_planes(f1, c.L.h, P, F);
     VKN_TRY(launch_linear_tc(&f1, 1, c.st));
@@ -532,8 +559,6 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     r.pres = c.L.o2;
     r.ldpres = C;
     VKN_TRY(launch_rowprep(r, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
-  } else {
-    VKN_TRY(launch_rowprep(an, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
   }
   // a8 heads (:217-227)
   if (w.num_cls_fcs < 0 || w.num_cls_fcs > VKN_MAX_FCS || w.num_mask_fcs < 0 || w.num_mask_fcs > VKN_MAX_FCS)
@@ -544,17 +569,37 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   const void *cs = obj_planes_out, *ms = obj_planes_out;
   for (int i = 0; i < depth; ++i) {
     int n = 0;
-    if (i < ncls_fcs) two[n++] = lin(src_planes(cs, C, PS), w.cls_fc_w[i], C, nullptr, c.L.pre_c[0], C, P, C, C, 0);
-    if (i < w.num_mask_fcs) two[n++] = lin(src_planes(ms, C, PS), w.mask_fc_w[i], C, nullptr, c.L.pre_m[0], C, P, C, C, 0);
-    VKN_TRY(launch_linear_tc(two, n, c.st));
+    if (!c.fuse_ln) {
+      if (i < ncls_fcs) two[n++] = lin(src_planes(cs, C, PS), w.cls_fc_w[i], C, nullptr, c.L.pre_c[0], C, P, C, C, 0);
+      if (i < w.num_mask_fcs) two[n++] = lin(src_planes(ms, C, PS), w.mask_fc_w[i], C, nullptr, c.L.pre_m[0], C, P, C, C, 0);
+      VKN_TRY(launch_linear_tc(two, n, c.st));
+      if (i < ncls_fcs) {
+        VKN_TRY(launch_rowprep(src_ln(c.L.pre_c[0], C, w.cls_ln_g[i], w.cls_ln_b[i], true), nullptr, 0, PLA, C, PS, P, C, c.st));
+        cs = PLA;
+      }
+      if (i < w.num_mask_fcs) {
+        VKN_TRY(launch_rowprep(src_ln(c.L.pre_m[0], C, w.mask_ln_g[i], w.mask_ln_b[i], true), nullptr, 0, PLB, C, PS, P, C, c.st));
+        ms = PLB;
+      }
+      continue;
+    }
+    // Linear (no bias) -> LN -> ReLU per branch, LayerNorm fused in the epilogue, planes only.  In-place plane buffers
+    // are safe: a tile spans whole rows and its epilogue starts after all of its MMAs have read those rows.
     if (i < ncls_fcs) {
-      VKN_TRY(launch_rowprep(src_ln(c.L.pre_c[0], C, w.cls_ln_g[i], w.cls_ln_b[i], true), nullptr, 0, PLA, C, PS, P, C, c.st));
-      cs = PLA;
+      two[n] = lin(src_planes(cs, C, PS), w.cls_fc_w[i], C, nullptr, nullptr, C, P, C, C, EPI_LN | EPI_RELU | EPI_NOOUT);
+      two[n].ln_g = w.cls_ln_g[i];
+      two[n].ln_b = w.cls_ln_b[i];
+      out_planes(two[n++], PLA, P, C);
     }
     if (i < w.num_mask_fcs) {
-      VKN_TRY(launch_rowprep(src_ln(c.L.pre_m[0], C, w.mask_ln_g[i], w.mask_ln_b[i], true), nullptr, 0, PLB, C, PS, P, C, c.st));
-      ms = PLB;
+      two[n] = lin(src_planes(ms, C, PS), w.mask_fc_w[i], C, nullptr, nullptr, C, P, C, C, EPI_LN | EPI_RELU | EPI_NOOUT);
+      two[n].ln_g = w.mask_ln_g[i];
+      two[n].ln_b = w.mask_ln_b[i];
+      out_planes(two[n++], PLB, P, C);
     }
+    VKN_TRY(launch_linear_tc(two, n, c.st));
+    if (i < ncls_fcs) cs = PLA;
+    if (i < w.num_mask_fcs) ms = PLB;
   }
   two[0] = lin(src_planes(ms, C, PS), w.fc_mask_w, C, w.fc_mask_b, c.L.mk, C, P, C, C, 0);
   out_planes(two[0], PLD, P, C);
@@ -606,7 +651,7 @@ int vkn_version(void) { return VKN_VERSION; }
 const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
-  return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
+  return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
          "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel";
 }
 

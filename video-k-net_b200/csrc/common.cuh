@@ -140,7 +140,10 @@ enum Pro : int {
   PRO_PLANES = 5    // a0 points at bf16 hi/mid/lo planes [3][M][lda] written by a producer's EPI_SPLIT3 epilogue
                     // (plane stride = sum_stride elements): copied with cp.async, no register pass (tensor-core path only)
 };
-enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_SPLIT3 = 16, EPI_NOOUT = 32 };
+enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_SPLIT3 = 16, EPI_NOOUT = 32,
+                 // tcgen05 row GEMM only: y = LayerNorm(acc + bias + res) * ln_g + ln_b (then EPI_RELU) in the epilogue;
+                 // the tile must span the whole row (N <= 256)
+                 EPI_LN = 64 };
 
 struct RowSrc {
   const float *a[4];
@@ -162,6 +165,7 @@ struct LinArgs {
   int ldw;
   const float *bias;        // [N] or null
   const float *rowscale;    // [M] or null: bias is multiplied by rowscale[row] (EPI_ROWSCALE)
+  const float *ln_g, *ln_b; // [N] LayerNorm affine of the fused epilogue (EPI_LN)
   const float *res;         // [M,N] residual added in the epilogue (EPI_RES)
   int ldres;
   float *out;               // [M,N] (slice z of a split-K launch writes out + z * out_split_stride)

@@ -212,10 +212,68 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
   }
 }
 
+// Few slices per set (frame batches: 148 / B pixel chunks per frame): one thread per 4 outputs sums its slices in
+// order -- same fixed order as the kernel above (slice 0, 1, 2, ... -> identical bits), no shared-memory stage, every
+// thread busy.  Requires F == 1.
+__global__ void __launch_bounds__(256) vkn_pool_reduce_flat_kernel(const float *__restrict__ partials,
+                                                                   const float *__restrict__ cnt_partials, int nchunks,
+                                                                   int B, int N, int NC, float *__restrict__ xp0,
+                                                                   float *__restrict__ cnt,
+                                                                   __nv_bfloat16 *__restrict__ planes) {
+  pdl_wait();
+  const size_t total4 = (size_t)B * NC / 4;
+  const size_t i4 = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i4 < total4) {
+    const size_t stride4 = total4;                         // one slice = [B][N][C]
+    const float4 *p = reinterpret_cast<const float4 *>(partials) + i4;
+    float4 t[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < nchunks) t[c] = __ldg(p + (size_t)c * stride4);
+    float4 a = t[0];
+#pragma unroll
+    for (int c = 1; c < 8; ++c)
+      if (c < nchunks) { a.x += t[c].x; a.y += t[c].y; a.z += t[c].z; a.w += t[c].w; }
+    reinterpret_cast<float4 *>(xp0)[i4] = a;
+    if (planes != nullptr) {
+      const float v4[4] = {a.x, a.y, a.z, a.w};
+      uint16_t h[3][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float xr = v4[e];
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const __nv_bfloat16 hb = __float2bfloat16_rn(xr);
+          xr -= __bfloat162float(hb);
+          h[pl][e] = __bfloat16_as_ushort(hb);
+        }
+      }
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+        *reinterpret_cast<uint2 *>(planes + (size_t)pl * B * NC + i4 * 4) =
+            make_uint2((uint32_t)h[pl][0] | ((uint32_t)h[pl][1] << 16), (uint32_t)h[pl][2] | ((uint32_t)h[pl][3] << 16));
+    }
+  }
+  const size_t ic = (size_t)blockIdx.x * 256 + threadIdx.x;   // pixel counts: the first B * N threads
+  if (ic < (size_t)B * N) {
+    float c = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) c += __ldg(cnt_partials + (size_t)ch * B * N + ic);
+    cnt[ic] = c;
+  }
+  pdl_trigger();
+}
+
 int launch_pool_reduce(const VknShape &s, const float *partials, const float *cnt_partials, int nchunks,
                        float *xp0, float *cnt, cudaStream_t stream, void *planes) {
   const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
   const int NC = s.N * s.C;
+  if (F == 1 && nchunks <= 8 && NC % 4 == 0) {
+    const size_t total4 = (size_t)s.B * NC / 4;
+    VKN_LAUNCH_MARK("vkn_pool_reduce_flat_kernel", stream);
+    VKN_CUDA_OK(launch_chain(vkn_pool_reduce_flat_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, partials,
+                             cnt_partials, nchunks, s.B, s.N, NC, xp0, cnt, (__nv_bfloat16 *)planes));
+    return VKN_OK;
+  }
   VKN_LAUNCH_MARK("vkn_pool_reduce_kernel", stream);
   int gx = ceil_div(NC, 128);
   if (gx < ceil_div(s.N, 32)) gx = ceil_div(s.N, 32);

@@ -18,7 +18,10 @@ namespace vkn {
 struct RgProb {
   CUtensorMap tmA;
   CUtensorMap tmW;
-  const float *bias, *rowscale, *res;
+  CUtensorMap tmOut;          // fp32 rows {N, M, K slices}, box {32, 32, 1}, SWIZZLE_128B (valid when tma_out)
+  CUtensorMap tmPl;           // bf16 planes {split_C, M, 3}, box {32, 32, 3}, SWIZZLE_64B (valid when tma_pl)
+  int tma_out, tma_pl;
+  const float *bias, *rowscale, *res, *ln_g, *ln_b;
   float *out;
   __nv_bfloat16 *planes;
   long long out_split_stride, plane_elems;
@@ -39,7 +42,7 @@ __device__ __forceinline__ unsigned long long rg_time() {
 }
 #define RG_TS(slot)                                                       \
   do {                                                                    \
-    if (batch.dbg != nullptr) batch.dbg[(size_t)blockIdx.x * 8 + (slot)] = rg_time(); \
+    if (batch.dbg != nullptr) batch.dbg[(size_t)blockIdx.x * 16 + (slot)] = rg_time(); \
   } while (0)
 
 constexpr uint32_t RG_A_PLANE = 128u * 128u;        // 128 rows x 64 k x 2 B
@@ -68,6 +71,145 @@ __device__ __forceinline__ RgTile rg_decode(const RgBatch &batch, int t) {
   return r;
 }
 
+
+// ---- epilogue pieces (thread = row; 32 consecutive columns in registers) ---------------------------------------
+struct RgRowCtx {
+  int row, epi;
+  int row_base, ks;           // first row of this warp's 32-row block, K slice (TMA store coordinates)
+  uint32_t stg;               // this warp's 6 KB staging buffer (shared-space address, 1024-byte aligned)
+  bool live, out_vec, res_vec, pl_vec, bias_vec;
+  float rs;
+  size_t prow;
+  float *outp;
+};
+
+// v[0..32) = accumulator (+ rowscale x bias) (+ residual) of columns [col, col + 32)
+__device__ __forceinline__ void rg_chunk_load(const RgProb &P, const RgRowCtx &R, uint32_t taddr, int col, int nc, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+#pragma unroll
+  for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+  if (!R.live) return;
+  if (R.epi & EPI_BIAS) {
+    const float *bp = P.bias + col;
+    if (R.bias_vec && nc == 32 && (col & 3) == 0) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + e));
+        v[e] = fmaf(R.rs, b4.x, v[e]); v[e + 1] = fmaf(R.rs, b4.y, v[e + 1]);
+        v[e + 2] = fmaf(R.rs, b4.z, v[e + 2]); v[e + 3] = fmaf(R.rs, b4.w, v[e + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nc) v[e] = fmaf(R.rs, __ldg(bp + e), v[e]);
+    }
+  }
+  if (R.epi & EPI_RES) {
+    const float *rp = P.res + (size_t)R.row * P.ldres + col;
+    if (R.res_vec && nc == 32) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(rp + e));
+        v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nc) v[e] += __ldg(rp + e);
+    }
+  }
+}
+
+// (ReLU) -> fp32 rows and / or bf16 hi/mid/lo planes
+__device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &R, int col, int nc, float (&v)[32]) {
+  if (R.epi & EPI_RELU) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  const int lane = threadIdx.x & 31;
+  if (!(R.epi & EPI_NOOUT) && P.tma_out) {
+    // fp32 rows through a 128B-swizzled [32 rows][128 B] staging box and ONE TMA store: full-line writes instead of 32
+    // rows x 32 B per store instruction (the per-SM store rate of the direct path bounded this kernel)
+    if (lane == 0) bulk_wait_group_read<0>();
+    __syncwarp();
+    const uint32_t rb = R.stg + (uint32_t)lane * 128u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(rb + (uint32_t)((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+             __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&P.tmOut, R.stg, col, R.row_base, R.ks);
+      bulk_commit_group();
+    }
+  } else if (!(R.epi & EPI_NOOUT) && R.live) {
+    float *op = R.outp + (size_t)R.row * P.ldo + col;
+    if (R.out_vec && nc == 32) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 8)
+        stg_v8(op + e, __float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3]),
+               __float_as_uint(v[e + 4]), __float_as_uint(v[e + 5]), __float_as_uint(v[e + 6]), __float_as_uint(v[e + 7]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nc) op[e] = v[e];
+    }
+  }
+  if ((R.epi & EPI_SPLIT3) && col < P.split_C && P.tma_pl) {
+    uint32_t w[3][16];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {                  // v == hi + mid + lo to 24 bits
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
+        v[e] -= __bfloat162float(h0);
+        v[e + 1] -= __bfloat162float(h1);
+        w[pl][e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      }
+    }
+    if (lane == 0) bulk_wait_group_read<0>();           // also covers the fp32 store that used the same buffer
+    __syncwarp();
+    const uint32_t rb = R.stg + (uint32_t)lane * 64u;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts_v4(rb + (uint32_t)pl * 2048u + (uint32_t)((c ^ sw) << 4), w[pl][4 * c], w[pl][4 * c + 1], w[pl][4 * c + 2], w[pl][4 * c + 3]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&P.tmPl, R.stg, col, R.row_base, 0);
+      bulk_commit_group();
+    }
+  } else if ((R.epi & EPI_SPLIT3) && col < P.split_C && R.live) {
+    const int np = min(32, P.split_C - col);
+    __nv_bfloat16 *pp = P.planes + R.prow * P.split_C + col;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {                  // v == hi + mid + lo to 24 bits
+      uint32_t w[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
+        v[e] -= __bfloat162float(h0);
+        v[e + 1] -= __bfloat162float(h1);
+        w[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      }
+      __nv_bfloat16 *pt = pp + (size_t)pl * P.plane_elems;
+      if (R.pl_vec && np == 32) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 8) stg_v8(pt + 2 * e, w[e], w[e + 1], w[e + 2], w[e + 3], w[e + 4], w[e + 5], w[e + 6], w[e + 7]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
+      }
+    }
+  }
+}
+
 // Persistent: a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs on across tiles and the
 // accumulator is double-buffered in TMEM (2 x BN columns), so the tensor core works on tile i+1 while the eight epilogue
 // warps drain tile i.  BN = 256 halves the shared-memory operand traffic per FLOP of the 3-plane product (the limiter
@@ -78,12 +220,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
   const int BN = batch.BN, STG = batch.stages, total = batch.total_tiles;
   const uint32_t w_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = RG_A_BYTES + w_bytes;
-  uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes);
+  const uint32_t stg0 = smem_u32(smem + (size_t)STG * stage_bytes);    // 8 epilogue warps x 6 KB TMA-store staging
+  uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes + 8 * 6144);
   const uint32_t bar0 = smem_u32(bars);
   // full[s] = bar0 + 8 s (TMA: A planes + W tile), empty[s] = bar0 + 8 (STG + s) (MMAs retired),
   // acc_full[a] = bar0 + 8 (2 STG + a), acc_empty[a] = bar0 + 8 (2 STG + 2 + a)
   const uint32_t acc_full0 = bar0 + 16 * STG, acc_empty0 = acc_full0 + 16;
   uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 4);
+  float *ln_stat = (float *)(tmem_slot + 4);                 // [2][128 rows][2 halves][4]: fused-LayerNorm partials (8 KB)
   const uint32_t smem0 = smem_u32(smem);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) RG_TS(0);
@@ -200,126 +344,138 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                       // 0: even column blocks, 1: odd
     uint32_t li = 0;
+    long long dbg_load = 0, dbg_store = 0, dbg_wait = 0;      // vkn_debug_timestamps: cycles in chunk loads / stores / waits
+    const bool dbg_on = batch.dbg != nullptr;
+#define RG_ACC(acc, stmt)               \
+  do {                                  \
+    if (dbg_on) {                       \
+      const long long c0__ = clock64(); \
+      stmt;                             \
+      acc += clock64() - c0__;          \
+    } else {                            \
+      stmt;                             \
+    }                                   \
+  } while (0)
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
       const RgTile T = rg_decode(batch, t);
       const RgProb &P = batch.p[T.prob];
       const uint32_t buf = li & 1u;
-      mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u);
+      RG_ACC(dbg_wait, mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u));
       tc_fence_after();
       if (t + (int)gridDim.x >= total) pdl_trigger();
       if (threadIdx.x == 64 && li == 0) RG_TS(5);
-      const int epi = P.epi;
-      const int row = T.row0 + q * 32 + lane;
-      const bool live = row < P.M;
-      float *outp = P.out + (size_t)T.ks * P.out_split_stride;
-      const bool out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(outp) & 31) == 0);
-      const bool res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
-      const bool pl_vec = (P.split_C % 16 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 31) == 0) && (P.plane_elems % 16 == 0);
-      const bool bias_vec = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0;
-      const float rs = (live && (epi & EPI_ROWSCALE)) ? __ldg(P.rowscale + row) : 1.f;
-      size_t prow = (size_t)row;                            // row of the plane buffer this thread writes
-      if ((epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
-        const int b = row / P.split_N;
-        prow = (size_t)b * P.split_Npad + (row - b * P.split_N);
+      RgRowCtx R;
+      R.epi = P.epi;
+      R.row = T.row0 + q * 32 + lane;
+      R.live = R.row < P.M;
+      R.row_base = T.row0 + q * 32;
+      R.ks = T.ks;
+      R.stg = stg0 + (uint32_t)(warp - 2) * 6144u;
+      R.outp = P.out + (size_t)T.ks * P.out_split_stride;
+      R.out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(R.outp) & 31) == 0);
+      R.res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
+      R.pl_vec = (P.split_C % 16 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 31) == 0) && (P.plane_elems % 16 == 0);
+      R.bias_vec = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0;
+      R.rs = (R.live && (R.epi & EPI_ROWSCALE)) ? __ldg(P.rowscale + R.row) : 1.f;
+      R.prow = (size_t)R.row;                               // row of the plane buffer this thread writes
+      if ((R.epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
+        const int b = R.row / P.split_N;
+        R.prow = (size_t)b * P.split_Npad + (R.row - b * P.split_N);
       }
       const uint32_t tacc = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
       int last_c0 = half * 32;                              // last column block this warp reads from TMEM
       while (last_c0 + 64 < BN && T.col0 + last_c0 + 64 < P.N) last_c0 += 64;
-      bool released = false;
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        const int col = T.col0 + c0;
-        if (col >= P.N) break;
-        uint32_t r[32];
-        tmem_ld32(tacc + (uint32_t)c0, r);
-        if (c0 == last_c0) {                                // this warp's share of the accumulator is in registers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
-          released = true;
-        }
-        if (!live) continue;
-        const int nc = min(32, P.N - col);
-        float v[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-        if (epi & EPI_BIAS) {
-          const float *bp = P.bias + col;
-          if (bias_vec && nc == 32 && (col & 3) == 0) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + e));
-              v[e] = fmaf(rs, b4.x, v[e]); v[e + 1] = fmaf(rs, b4.y, v[e + 1]);
-              v[e + 2] = fmaf(rs, b4.z, v[e + 2]); v[e + 3] = fmaf(rs, b4.w, v[e + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < nc) v[e] = fmaf(rs, __ldg(bp + e), v[e]);
+      const bool any = half * 32 < BN && T.col0 + half * 32 < P.N;   // this warp owns at least one column block
+      if (R.epi & EPI_LN) {
+        // ---- fused LayerNorm: the tile spans the row (host: nt == 1); the two warps of a lane quarter own alternate
+        //      32-column blocks, so each thread reduces its blocks (shifted sums: no cancellation), the pair merges
+        //      (count, mean, M2) through shared memory, then a second pass over TMEM normalises and stores.
+        float K0 = 0.f, S1 = 0.f, S2 = 0.f, cntf = 0.f;
+        bool first = true;
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          const int col = T.col0 + c0;
+          if (col >= P.N) break;
+          const int nc = min(32, P.N - col);
+          float v[32];
+          RG_ACC(dbg_load, rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v));
+          if (first) {
+            K0 = v[0];
+            first = false;
           }
-        }
-        if (epi & EPI_RES) {
-          const float *rp = P.res + (size_t)row * P.ldres + col;
-          if (res_vec && nc == 32) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4 *>(rp + e));
-              v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+          for (int e = 0; e < 32; ++e)
+            if (e < nc) {
+              const float d = v[e] - K0;
+              S1 += d;
+              S2 = fmaf(d, d, S2);
             }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < nc) v[e] += __ldg(rp + e);
-          }
+          cntf += (float)nc;
         }
-        if (epi & EPI_RELU) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        float mean_h = 0.f, m2_h = 0.f;
+        if (cntf > 0.f) {
+          mean_h = K0 + S1 / cntf;
+          m2_h = S2 - S1 * S1 / cntf;
         }
-        if (!(epi & EPI_NOOUT)) {
-          float *op = outp + (size_t)row * P.ldo + col;
-          if (out_vec && nc == 32) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 8)
-              stg_v8(op + e, __float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3]),
-                     __float_as_uint(v[e + 4]), __float_as_uint(v[e + 5]), __float_as_uint(v[e + 6]), __float_as_uint(v[e + 7]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < nc) op[e] = v[e];
+        float *st = ln_stat + ((size_t)(li & 1u) * 128 + q * 32 + lane) * 8;
+        st[half * 4 + 0] = cntf;
+        st[half * 4 + 1] = mean_h;
+        st[half * 4 + 2] = m2_h;
+        RG_ACC(dbg_wait, named_bar_sync(1, RG_THREADS - 64));
+        const float cb = st[(half ^ 1) * 4 + 0], mb = st[(half ^ 1) * 4 + 1], m2b = st[(half ^ 1) * 4 + 2];
+        // merge in a fixed order (half 0 first) so both threads of a row get identical statistics
+        const float n0 = half ? cb : cntf, mu0 = half ? mb : mean_h, q0 = half ? m2b : m2_h;
+        const float n1 = half ? cntf : cb, mu1 = half ? mean_h : mb, q1 = half ? m2_h : m2b;
+        const float nn = n0 + n1, delta = mu1 - mu0;
+        const float mean = mu0 + delta * (n1 / nn);
+        const float var = (q0 + q1 + delta * delta * (n0 * n1 / nn)) / nn;
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          const int col = T.col0 + c0;
+          if (col >= P.N) break;
+          const int nc = min(32, P.N - col);
+          float v[32];
+          RG_ACC(dbg_load, rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v));
+          if (c0 == last_c0) {                              // second read done: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
           }
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nc) v[e] = fmaf((v[e] - mean) * rstd, __ldg(P.ln_g + col + e), __ldg(P.ln_b + col + e));
+          RG_ACC(dbg_store, rg_chunk_store(P, R, col, nc, v));
         }
-        if ((epi & EPI_SPLIT3) && col < P.split_C) {
-          const int np = min(32, P.split_C - col);
-          __nv_bfloat16 *pp = P.planes + prow * P.split_C + col;
-#pragma unroll
-          for (int pl = 0; pl < 3; ++pl) {                  // v == hi + mid + lo to 24 bits
-            uint32_t w[16];
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
-              v[e] -= __bfloat162float(h0);
-              v[e + 1] -= __bfloat162float(h1);
-              w[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            }
-            __nv_bfloat16 *pt = pp + (size_t)pl * P.plane_elems;
-            if (pl_vec && np == 32) {
-#pragma unroll
-              for (int e = 0; e < 16; e += 8) stg_v8(pt + 2 * e, w[e], w[e + 1], w[e + 2], w[e + 3], w[e + 4], w[e + 5], w[e + 6], w[e + 7]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
-            }
+      } else {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          const int col = T.col0 + c0;
+          if (col >= P.N) break;
+          const int nc = min(32, P.N - col);
+          float v[32];
+          RG_ACC(dbg_load, rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v));
+          if (c0 == last_c0) {                              // this warp's share of the accumulator is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
           }
+          RG_ACC(dbg_store, rg_chunk_store(P, R, col, nc, v));
         }
       }
-      if (!released) {                                      // a warp whose column blocks all lie past N
+      if (!any) {                                           // a warp whose column blocks all lie past N
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
       }
     }
-    if (threadIdx.x == 64) RG_TS(6);
+    if (lane == 0) bulk_wait_all();                         // this warp's TMA stores have completed
+    if (threadIdx.x == 64) {
+      RG_TS(6);
+      if (dbg_on) {
+        batch.dbg[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)dbg_load;
+        batch.dbg[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)dbg_store;
+        batch.dbg[(size_t)blockIdx.x * 16 + 10] = (unsigned long long)dbg_wait;
+        batch.dbg[(size_t)blockIdx.x * 16 + 11] = li;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -383,10 +539,16 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
     }
   }
   BN = rg_env("VKN_RG_BN", BN);
+  bool fused_ln = false;
+  for (int i = 0; i < nprob; ++i) fused_ln = fused_ln || (probs[i].epi & EPI_LN);
+  if (fused_ln) {                                                   // the tile must span the whole row
+    if (maxN > 256 || ks != 1) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_LN needs N <= 256 and no split-K (N %d, ksplit %d)", maxN, ks);
+    BN = maxN <= 32 ? 32 : (maxN <= 64 ? 64 : (maxN <= 128 ? 128 : 256));
+  }
   if (BN != 32 && BN != 64 && BN != 128 && BN != 256) VKN_FAIL(VKN_E_INVALID, "VKN_RG_BN must be 32, 64, 128 or 256");
   const size_t stage_bytes = (size_t)RG_A_BYTES + (size_t)BN * 128;
   int stages = rg_env("VKN_RG_STAGES", 4);
-  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 1024 + (2 * st + 4) * 8 + 16 + 64; };
+  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 8 * 6144 + 1024 + (2 * st + 4) * 8 + 16 + 2 * 128 * 8 * 4 + 64; };
   while (stages > 1 && smem_of(stages) > 227 * 1024) --stages;
   size_t smem = smem_of(stages);
   b.nprob = nprob;
@@ -406,9 +568,31 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
     const uint64_t wstr[1] = {(uint64_t)a.ldw * 2};
     const uint32_t wbox[2] = {64u, (uint32_t)BN};
     VKN_TRY(make_tmap_bf16_strided(&p.tmW, a.w, 2, wdims, wstr, wbox));
+    p.tma_out = 0;
+    p.tma_pl = 0;
+    const bool tma_ok = getenv("VKN_RG_TMA_STORE") == nullptr || getenv("VKN_RG_TMA_STORE")[0] != '0';
+    if (tma_ok && !(a.epi & EPI_NOOUT) && a.out && a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+        (ks == 1 || a.out_split_stride % 4 == 0)) {
+      const uint64_t od[3] = {(uint64_t)a.N, (uint64_t)a.M, (uint64_t)ks};
+      const uint64_t os[2] = {(uint64_t)a.ldo * 4, (uint64_t)(ks > 1 ? a.out_split_stride : (long long)a.M * a.ldo) * 4};
+      const uint32_t ob[3] = {32u, 32u, 1u};
+      VKN_TRY(make_tmap_store(&p.tmOut, a.out, true, od, os, ob, true));
+      p.tma_out = 1;
+    }
+    if (tma_ok && (a.epi & EPI_SPLIT3) && a.split_planes && a.split_N == a.split_Npad && a.split_C % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(a.split_planes) & 15) == 0 && ((long long)a.split_B * a.split_Npad * a.split_C) % 8 == 0) {
+      const uint64_t pd[3] = {(uint64_t)a.split_C, (uint64_t)a.M, 3};
+      const uint64_t ps[2] = {(uint64_t)a.split_C * 2, (uint64_t)((long long)a.split_B * a.split_Npad * a.split_C) * 2};
+      const uint32_t pb[3] = {32u, 32u, 3u};
+      VKN_TRY(make_tmap_store(&p.tmPl, a.split_planes, false, pd, ps, pb, false));
+      p.tma_pl = 1;
+    }
     p.bias = a.bias;
     p.rowscale = a.rowscale;
     p.res = a.res;
+    p.ln_g = a.ln_g;
+    p.ln_b = a.ln_b;
+    if ((a.epi & EPI_LN) && (!a.ln_g || !a.ln_b)) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_LN without LayerNorm parameters");
     p.out = a.out;
     p.planes = a.split_planes;
     p.out_split_stride = a.out_split_stride;

@@ -98,6 +98,9 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
 // 256-bit global stores (sm_100): one full 32-byte sector per lane and instruction.  Row-per-thread epilogues write
@@ -226,6 +229,23 @@ static int make_tmap_bf16_plain(CUtensorMap *map, const void *base, const uint64
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) VKN_FAIL(VKN_E_CUDA, "cuTensorMapEncodeTiled (plain) failed with CUresult %d", (int)r);
+  return VKN_OK;
+}
+
+// rank-3 tensor map with explicit byte strides, element size and swizzle mode (TMA stores of the row-GEMM epilogue)
+static int make_tmap_store(CUtensorMap *map, const void *base, bool f32, const uint64_t *dims, const uint64_t *stride_bytes,
+                           const uint32_t *box, bool swizzle128) {
+  EncodeTiledFn enc;
+  VKN_TRY(get_encode(&enc));
+  cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+  cuuint64_t gstride[2] = {stride_bytes[0], stride_bytes[1]};
+  cuuint32_t bx[3] = {box[0], box[1], box[2]}, estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride_bytes[0] & 15) || (stride_bytes[1] & 15))
+    VKN_FAIL(VKN_E_INVALID, "TMA store: base / strides must be 16-byte aligned");
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim,
+                   gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) VKN_FAIL(VKN_E_CUDA, "cuTensorMapEncodeTiled (store) failed with CUresult %d", (int)r);
   return VKN_OK;
 }
 
