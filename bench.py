@@ -105,11 +105,12 @@ class ClockSampler(threading.Thread):
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, source)"""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops', 1650.0)), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1650.0, 'fallback (B200_PROFILING.md)'
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -210,9 +211,10 @@ def run_ours(args):
     # Frames in flight: one CUDA graph = NS concurrent branches x BF frames each (vknet.FramesInFlight).
     # The loop of ONE frame is a chain of small latency-bound kernels that fills a fraction of the 148
     # SMs, so independent frames overlap.  Two such groups alternate; one group's inputs + outputs
-    # (NS*BF frames x 16.2 MB) exceed L2 (126 MB) for the default 4 x 4, so x and the masks stream from HBM.
-    NS = max(1, int(os.environ.get('VKN_STREAMS', '2')))
-    BF = max(1, int(os.environ.get('VKN_BATCH', '8')))
+    # (NS*BF frames x 16.2 MB = 3.1 GB for the default 3 x 64) exceed L2 (126 MB) many times over, so x and the masks
+    # stream from HBM.  Measured sweep (profiles/): 2x8 21k, 2x32 35k, 2x64 40k, 3x64 40.6k frames/s.
+    NS = max(1, int(os.environ.get('VKN_STREAMS', '3')))
+    BF = max(1, int(os.environ.get('VKN_BATCH', '64')))
     quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: small group, no CPU arm
     if quick and 'VKN_STREAMS' not in os.environ and 'VKN_BATCH' not in os.environ:
         NS, BF = 1, 1
@@ -237,10 +239,11 @@ def run_ours(args):
             hf.loops = fif.loops                            # share workspaces
             hf.capture(pinned, host_io=True)
             host_groups.append(hf)
-    before = _lib.launch_count()
     x1, pf1, m1 = dummy_inputs(torch, 7)
-    loop(x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16())
-    launches_per_frame_call = _lib.launch_count() - before      # one vkn_iter_forward (any batch size)
+    st0 = groups[0].static[0]
+    before = _lib.launch_count()
+    loop(st0['x'], st0['pf'], st0['mask'])                      # one vkn_iter_forward at the throughput batch size
+    launches_per_frame_call = _lib.launch_count() - before      # kernels of ONE call = one branch of a graph launch
 
     link_head = heads[-1] if world > 1 else None
 
@@ -359,16 +362,17 @@ def run_ours(args):
     }
 
     def family(name):
-        for key in ('pool_reduce', 'pool', 'maskgemm', 'linear', 'attention'):
+        for key, fam_name in (('pool_reduce', 'pool_reduce'), ('pool', 'pool'), ('maskgemm', 'maskgemm'), ('rowgemm', 'linear'),
+                              ('linear', 'linear'), ('rowop', 'rowop'), ('attention', 'attention')):
             if key in name:
-                return key
+                return fam_name
         return name
     fam = {}
     for k, v in per_kernel.items():
         f_ = fam.setdefault(family(k), dict(total_ms_per_step=0.0, launches_per_step=0))
         f_['total_ms_per_step'] += v['total_ms_per_step']
         f_['launches_per_step'] += v['launches_per_step']
-    peak, peak_src = measured_peaks()
+    peak, peak_tf, peak_src = measured_peaks()
     traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')       # dram bytes per launch from ncu --set full
     if os.path.exists(tpath):
@@ -379,17 +383,35 @@ def run_ours(args):
             f_['achieved_gbs'] = fam_bytes[k] / (f_['total_ms_per_step'] * 1e-3) / 1e9
             f_['frac'] = f_['achieved_gbs'] / peak
             f_['ncu_dram_bytes_per_launch'] = traffic.get(k)
+    # the row GEMMs are tensor-pipe work: algorithmic FLOPs of every nn.Linear of a stage (SURVEY.md 8d row term without
+    # the attention products); the kernel executes 3x that (three exact bf16 planes per fp32 operand)
+    rows_flops = S * P * (28 * C * C + 4 * C * Fh + 2 * C * ncls)
+    if 'linear' in fam:
+        f_ = fam['linear']
+        f_['algorithmic_flops_per_launch'] = rows_flops / max(1, f_['launches_per_step'])
+        f_['achieved_tflops'] = rows_flops / (f_['total_ms_per_step'] * 1e-3) / 1e12
+        f_['frac_tensor'] = f_['achieved_tflops'] / peak_tf
+        f_['executed_mma_flops_factor'] = 3
     dom = max(fam, key=lambda k: fam[k]['total_ms_per_step'])
     d_ = fam[dom]
-    roof = dict(bound='hbm', kernel={'linear': 'vkn_linear_kernel (row operators, %d launches/step)' % d_['launches_per_step'],
-                                     'pool': 'vkn_pool_tc_kernel', 'maskgemm': 'vkn_maskgemm_tc_kernel'}.get(dom, dom),
-                achieved=d_.get('achieved_gbs'), peak=peak, unit='GB/s', frac=d_.get('frac'), traffic=traffic.get(dom),
-                peak_source=peak_src, algorithmic_bytes_per_launch=d_.get('algorithmic_bytes_per_launch'),
-                avg_launch_us=1e3 * d_['total_ms_per_step'] / max(1, d_['launches_per_step']),
-                profiled_batch=BF,
-                note='times are CUDA-event brackets on the launch stream (vkn_profile_begin/end), one call of %d frame(s), eager launches; ' % BF +
-                     'the family with the largest share of the step is reported, all families under "families"',
-                families=fam)
+    note = ('times are CUDA-event brackets on the launch stream (vkn_profile_begin/end), one call of %d frame(s), eager launches; ' % BF +
+            'the family with the largest share of the step is reported, all families under "families"')
+    if dom == 'linear':
+        kname = ('vkn_rowgemm_tc_kernel' if any('rowgemm' in k for k in per_kernel) else 'vkn_linear_kernel') + \
+                ' (row GEMMs, %d launches/step)' % d_['launches_per_step']
+        roof = dict(bound='tensor', kernel=kname, achieved=d_['achieved_tflops'], peak=peak_tf, unit='TFLOP/s',
+                    frac=d_['frac_tensor'], traffic=traffic.get('linear'), peak_source=peak_src + ', dense bf16 burst',
+                    algorithmic_flops_per_launch=d_['algorithmic_flops_per_launch'],
+                    avg_launch_us=1e3 * d_['total_ms_per_step'] / max(1, d_['launches_per_step']), profiled_batch=BF,
+                    note=note + '; algorithmic FLOPs (fp32 Linear math) -- the kernel issues 3x as many bf16 MMA FLOPs (exact '
+                                '3-plane split of the fp32 rows), so tensor-pipe occupancy is about 3x this fraction',
+                    families=fam)
+    else:
+        roof = dict(bound='hbm', kernel={'pool': 'vkn_pool_tc_kernel', 'maskgemm': 'vkn_maskgemm_tc_persist_kernel'}.get(dom, dom),
+                    achieved=d_.get('achieved_gbs'), peak=peak, unit='GB/s', frac=d_.get('frac'), traffic=traffic.get(dom),
+                    peak_source=peak_src, algorithmic_bytes_per_launch=d_.get('algorithmic_bytes_per_launch'),
+                    avg_launch_us=1e3 * d_['total_ms_per_step'] / max(1, d_['launches_per_step']),
+                    profiled_batch=BF, note=note, families=fam)
     # whole-step figure: module-boundary algorithmic bytes per frame: 60.4 MB bf16
     step_bytes = S * ((C * HW + 2 * N * HW) * 2 + (2041856 + 257 * ncls) * 2)
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
@@ -426,8 +448,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=1536)
+    ap.add_argument('--warmup', type=int, default=192)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     args = ap.parse_args()
     if args.impl == 'reference':
