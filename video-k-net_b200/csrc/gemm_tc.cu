@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
                                const __grid_constant__ CUtensorMap tmap_o, const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
                                int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int MP_XS,
-                               unsigned long long *dbg) {
+                               int total_tiles, int pf_dist, unsigned long long *dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
@@ -425,19 +425,22 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 2 x [32 kernels][128 px] bf16
   uint64_t *bars = (uint64_t *)(stg_base + 2 * 32 * MASK_TILE_P * 2);
   const uint32_t bar0 = smem_u32(bars);
-  // barriers: 0 planes_full | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a
-  const int X_FULL = 1, X_EMPTY = 1 + MP_XS, ACC_FULL = 1 + 2 * MP_XS, ACC_EMPTY = 1 + 2 * MP_XS + MP_ACC;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 1 + 2 * MP_XS + 2 * MP_ACC);
-  float *bias_s = (float *)(tmem_slot + 2);
+  // barriers: 0 planes_full | 1 planes_free | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a
+  const int PL_FREE = 1, X_FULL = 2, X_EMPTY = 2 + MP_XS, ACC_FULL = 2 + 2 * MP_XS, ACC_EMPTY = 2 + 2 * MP_XS + MP_ACC;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 + 2 * MP_XS + 2 * MP_ACC);
+  float *bias_s = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [4 epilogue warps][2 segments][128], 16-byte aligned
   const uint32_t smem0 = smem_u32(smem), xring0 = smem_u32(xring);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int b = blockIdx.z, kb = b / F;
   const int ntiles = (HW + MASK_TILE_P - 1) / MASK_TILE_P;
-  const int cpf = gridDim.x;                                            // CTAs per frame
+  // Balanced schedule: the launch's tiles (frame-major) are cut into gridDim.x equal contiguous ranges, so every SM works
+  // whatever the frame count (148 / frames CTAs per frame left 13-35 % of the SMs idle at 64 / 96 frames).  A range that
+  // crosses a frame boundary is a second SEGMENT: the CTA swaps the resident planes (and the folded bias) once.
+  const int g_lo = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int g_hi = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
   const long long t_start = dbg ? clock64() : 0;
   long long w0 = 0, w1 = 0;
   long long w2 = 0, w3 = 0, w4 = 0;
-  if (dbg) dbg += ((size_t)blockIdx.z * gridDim.x + blockIdx.x) * 16;     // <= 148 CTAs x 16 slots
+  if (dbg) dbg += (size_t)blockIdx.x * 16;                              // <= 148 CTAs x 16 slots
 
   if (warp == 0) {
     if (lane == 0) {
@@ -445,6 +448,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       prefetch_tmap(&tmap_a);
       prefetch_tmap(&tmap_o);
       mbar_init(bar0, 1);
+      mbar_init(bar0 + 8 * PL_FREE, 1);
       for (int s = 0; s < MP_XS; ++s) {
         mbar_init(bar0 + 8 * (X_FULL + s), 1);
         mbar_init(bar0 + 8 * (X_EMPTY + s), 1);
@@ -459,8 +463,6 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     tmem_alloc(smem_u32(tmem_slot), 128u * MP_ACC);
   }
   pdl_wait();     // a_ext / the planes come from the previous kernel
-  for (int n = threadIdx.x; n < ((Npad + 31) & ~31); n += TC_THREADS)
-    bias_s[n] = (n < N) ? a_ext[((size_t)kb * N + n) * lda + C] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -468,21 +470,40 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar0, planes_bytes);
-      for (int c = 0; c < nk; ++c)
-        for (int t = 0; t < 3; ++t)
-          tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += cpf) {
-        const int p0 = tile * MASK_TILE_P;
-        for (int c = 0; c < nk; ++c, ++it) {
-          const int s = it % MP_XS;
-          const uint32_t ph = (uint32_t)(it / MP_XS) & 1u;
-          MP_WAIT(w0, mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u));
-          mbar_expect_tx(bar0 + 8 * (X_FULL + s), x_bytes);
-          tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (X_FULL + s), p0, c * CH_BLK, b);
-          tma_load_3d(xring0 + s * x_bytes + x_bytes / 2, &tmap_x, bar0 + 8 * (X_FULL + s), p0 + 64, c * CH_BLK, b);
+      int s = 0;
+      uint32_t ph = 0;
+      int seg = 0;
+      for (int g = g_lo; g < g_hi; ++seg) {
+        const int b = g / ntiles, t0 = g - b * ntiles, kb = b / F;
+        const int t1 = min(ntiles, t0 + (g_hi - g));
+        if (seg > 0) MP_WAIT(w0, mbar_wait(bar0 + 8 * PL_FREE, (uint32_t)(seg - 1) & 1u));   // MMAs of the previous frame retired
+        mbar_expect_tx(bar0, planes_bytes);
+        for (int c = 0; c < nk; ++c)
+          for (int t = 0; t < 3; ++t)
+            tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad);
+        for (int tile = t0; tile < t1; ++tile) {
+          const int p0 = tile * MASK_TILE_P;
+          // The ring holds 48-64 KB per SM -- less than DRAM latency x bandwidth needs: the tile pf_dist ahead is pulled
+          // into L2 by TMA prefetch (no shared memory), so the ring only has to cover the L2 -> SM hop.
+          const int gp = g + (tile - t0) + pf_dist;         // global index of the tile to prefetch
+          const bool pf = pf_dist > 0 && gp < g_hi;
+          const int bp = pf ? gp / ntiles : 0, pp = pf ? (gp - bp * ntiles) * MASK_TILE_P : 0;
+          for (int c = 0; c < nk; ++c) {
+            if (pf) {                                         // interleaved with the loads: one chunk ahead per chunk
+              tma_prefetch_3d(&tmap_x, pp, c * CH_BLK, bp);
+              tma_prefetch_3d(&tmap_x, pp + 64, c * CH_BLK, bp);
+            }
+            MP_WAIT(w0, mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u));
+            mbar_expect_tx(bar0 + 8 * (X_FULL + s), x_bytes);
+            tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (X_FULL + s), p0, c * CH_BLK, b);
+            tma_load_3d(xring0 + s * x_bytes + x_bytes / 2, &tmap_x, bar0 + 8 * (X_FULL + s), p0 + 64, c * CH_BLK, b);
+            if (++s == MP_XS) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
         }
+        g += t1 - t0;
       }
       if (dbg) dbg[1] = (unsigned long long)w0;
     }
@@ -490,13 +511,20 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     // Warp-uniform issue loop (all lanes wait, one elected lane issues): descriptors are 64-bit bases plus small
     // immediates kept in uniform registers -- a single thread walking divergent code needed ~15 dependent
     // instructions per tcgen05.mma (48 MMAs per tile).
-    mbar_wait(bar0, 0);
     const uint64_t adesc0 = umma_desc_sw128(xring0, x_lbo, x_sbo);
     const uint64_t bdesc0 = umma_desc_sw128(smem0, 0, 1024);
     const uint32_t a_plane16 = a_plane >> 4;
     int s = 0;
     uint32_t xph = 0, li = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
+    int seg = 0, seg_end = g_lo;                             // seg_end: first tile (global index) of the next segment
+    for (int g = g_lo; g < g_hi; ++g, ++li) {
+      if (g == seg_end) {                                    // new frame: its planes must have landed
+        const int b = g / ntiles;
+        seg_end = min(g_hi, (b + 1) * ntiles);
+        MP_WAIT(w0, mbar_wait(bar0, (uint32_t)seg & 1u));
+        ++seg;
+      }
+      const bool seg_last = (g + 1 == seg_end);
       const uint32_t buf = li & 1u;
       MP_WAIT(w1, mbar_wait(bar0 + 8 * (ACC_EMPTY + buf), ((li >> 1) & 1u) ^ 1u));
       tc_fence_after();
@@ -515,7 +543,10 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
                         (c > 0 || t > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(bar0 + 8 * (X_EMPTY + s));
-          if (c == nk - 1) umma_commit(bar0 + 8 * (ACC_FULL + buf));
+          if (c == nk - 1) {
+            umma_commit(bar0 + 8 * (ACC_FULL + buf));
+            if (seg_last) umma_commit(bar0 + 8 * PL_FREE);   // the resident planes may be replaced
+          }
         }
         __syncwarp();
         if (++s == MP_XS) {
@@ -537,14 +568,29 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     //      (The earlier per-warp transpose cost 47 % of the shared-memory data pipe the tensor core reads through.)
     const int q = warp & 3;
     const bool leader = threadIdx.x == 64;
-    const uint32_t stg0 = smem_u32(stg_base), bias0 = smem_u32(bias_s);
-    uint32_t jj = 0;
-    int li = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += cpf, ++li) {
+    const uint32_t stg0 = smem_u32(stg_base);
+    uint32_t jj = 0, bias0 = 0;
+    int li = 0, seg = 0, seg_end = g_lo, b = 0, tile = 0;
+    for (int g = g_lo; g < g_hi; ++g, ++li, ++tile) {
+      if (g == seg_end) {                                    // new frame: this warp's private copy of the folded bias
+        b = g / ntiles;
+        tile = g - b * ntiles;
+        seg_end = min(g_hi, (b + 1) * ntiles);
+        const int kb = b / F;
+        bias0 = smem_u32(bias_s) + (uint32_t)(((warp - 2) * 2 + (seg & 1)) * 128) * 4u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = lane + 32 * i;
+          const float v = (n < N) ? a_ext[((size_t)kb * N + n) * lda + C] : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias0 + (uint32_t)n * 4u), "f"(v));
+        }
+        __syncwarp();
+        ++seg;
+      }
       const int buf = li % MP_ACC;
       MP_WAIT(w0, mbar_wait(bar0 + 8 * (ACC_FULL + buf), (uint32_t)(li / MP_ACC) & 1u));
       tc_fence_after();
-      if (tile + cpf >= ntiles) pdl_trigger();
+      if (g + 1 == g_hi) pdl_trigger();
       for (int n0 = 0; n0 < Npad; n0 += 32, ++jj) {
         float4 bq[8];
 #pragma unroll
@@ -628,9 +674,10 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   bool persist = Npad <= 112 && ntiles * frames >= 2 * 148;      // several tiles per SM: keep the planes resident
   if (const char *e = getenv("VKN_MASK_PERSIST")) persist = (e[0] == '1') && Npad <= 112;
   if (persist) {
-    int cpf = 148 / frames;
-    if (cpf < 1) cpf = 1;
-    if (cpf > ntiles) cpf = ntiles;
+    const int total_tiles = ntiles * frames;
+    int pf_dist = 1;                                         // L2 prefetch distance in tiles (VKN_MASK_PF; measured 0/1/2/4: 1 is best)
+    if (const char *e = getenv("VKN_MASK_PF")) pf_dist = atoi(e);
+    const int grid_x = total_tiles < 148 ? total_tiles : 148;
     const int rows8 = (s.N + 7) & ~7;
     {     // resident planes: whole 8-row atoms only (see the kernel comment)
       const uint64_t dims[2] = {(uint64_t)s.C, (uint64_t)3 * s.B * Npad};
@@ -639,8 +686,7 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     }
     auto psmem_of = [&](int xs) {
       return (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + xs * (size_t)CH_BLK * MASK_TILE_P * 2 + 2 * 32 * MASK_TILE_P * 2 +
-             (1 + 2 * xs + 2 * MP_ACC) * 8 + 16 +
-             (size_t)(Npad + 32) * 4 + 1024 + 64;
+             (2 + 2 * xs + 2 * MP_ACC) * 8 + 16 + 4 * 2 * 128 * 4 + 1024 + 64;
     };
     int xs_depth = MP_XS_MAX;
     while (xs_depth > 2 && psmem_of(xs_depth) > 227 * 1024) --xs_depth;
@@ -658,9 +704,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[3] = {(uint32_t)MASK_TILE_P, 32u, 1u};
       VKN_TRY(make_tmap_bf16_plain(&tmo, out, dims, box));
     }
-    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(cpf, 1, frames), dim3(TC_THREADS), psmem, stream, tmx, tma,
+    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x), dim3(TC_THREADS), psmem, stream, tmx, tma,
                              tmo, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
-                             x_lbo, x_sbo, F, xs_depth, debug_ts_slot()));
+                             x_lbo, x_sbo, F, xs_depth, total_tiles, pf_dist, debug_ts_slot()));
     return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);

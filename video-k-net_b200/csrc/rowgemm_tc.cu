@@ -83,42 +83,47 @@ struct RgRowCtx {
   float *outp;
 };
 
-// v[0..32) = accumulator (+ rowscale x bias) (+ residual) of columns [col, col + 32)
+// v[0..32) = accumulator (+ rowscale x bias) (+ residual) of columns [col, col + 32).  The global loads (bias, residual) are
+// issued BEFORE the TMEM load so that their L2 latency overlaps it (and, for the first chunk of a tile, the wait for the
+// accumulator wait of the next chunk).
 __device__ __forceinline__ void rg_chunk_load(const RgProb &P, const RgRowCtx &R, uint32_t taddr, int col, int nc, float (&v)[32]) {
+  float add[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) add[e] = 0.f;
+  if (R.live) {
+    if (R.epi & EPI_BIAS) {
+      const float *bp = P.bias + col;
+      if (R.bias_vec && nc == 32 && (col & 3) == 0) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + e));
+          add[e] = R.rs * b4.x; add[e + 1] = R.rs * b4.y; add[e + 2] = R.rs * b4.z; add[e + 3] = R.rs * b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < nc) add[e] = R.rs * __ldg(bp + e);
+      }
+    }
+    if (R.epi & EPI_RES) {
+      const float *rp = P.res + (size_t)R.row * P.ldres + col;
+      if (R.res_vec && nc == 32) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4 *>(rp + e));
+          add[e] += t4.x; add[e + 1] += t4.y; add[e + 2] += t4.z; add[e + 3] += t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < nc) add[e] += __ldg(rp + e);
+      }
+    }
+  }
   uint32_t r[32];
   tmem_ld32(taddr, r);
 #pragma unroll
-  for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-  if (!R.live) return;
-  if (R.epi & EPI_BIAS) {
-    const float *bp = P.bias + col;
-    if (R.bias_vec && nc == 32 && (col & 3) == 0) {
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bp + e));
-        v[e] = fmaf(R.rs, b4.x, v[e]); v[e + 1] = fmaf(R.rs, b4.y, v[e + 1]);
-        v[e + 2] = fmaf(R.rs, b4.z, v[e + 2]); v[e + 3] = fmaf(R.rs, b4.w, v[e + 3]);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (e < nc) v[e] = fmaf(R.rs, __ldg(bp + e), v[e]);
-    }
-  }
-  if (R.epi & EPI_RES) {
-    const float *rp = P.res + (size_t)R.row * P.ldres + col;
-    if (R.res_vec && nc == 32) {
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(rp + e));
-        v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (e < nc) v[e] += __ldg(rp + e);
-    }
-  }
+  for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + add[e];
 }
 
 // (ReLU) -> fp32 rows and / or bf16 hi/mid/lo planes
