@@ -31,6 +31,7 @@ struct RgProb {
 struct RgBatch {
   RgProb p[2];
   int nprob, ksplit, stages, BN, total_tiles;
+  int stg_bytes, pl_off;       // per-warp TMA-store staging: 10 KB (fp32 box + plane boxes side by side, pl_off = 4096) or 6 KB (shared, pl_off = 0)
   uint32_t idesc;
   unsigned long long *dbg;     // optional per-CTA phase timestamps (vkn_debug_timestamps), null in production
 };
@@ -76,7 +77,8 @@ __device__ __forceinline__ RgTile rg_decode(const RgBatch &batch, int t) {
 struct RgRowCtx {
   int row, epi;
   int row_base, ks;           // first row of this warp's 32-row block, K slice (TMA store coordinates)
-  uint32_t stg;               // this warp's 6 KB staging buffer (shared-space address, 1024-byte aligned)
+  uint32_t stg;               // this warp's staging buffer (shared-space address, 1024-byte aligned)
+  uint32_t pl_off;            // offset of the plane boxes inside it (0: they reuse the fp32 box after its store was read)
   bool live, out_vec, res_vec, pl_vec, bias_vec;
   float rs;
   size_t prow;
@@ -174,9 +176,12 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
         w[pl][e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
       }
     }
-    if (lane == 0) bulk_wait_group_read<0>();           // also covers the fp32 store that used the same buffer
-    __syncwarp();
-    const uint32_t rb = R.stg + (uint32_t)lane * 64u;
+    // staging free?  With side-by-side boxes the wait at the top of the fp32 path already covered the previous chunk.
+    if (R.pl_off == 0 || (R.epi & EPI_NOOUT) || !P.tma_out) {
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+    }
+    const uint32_t rb = R.stg + R.pl_off + (uint32_t)lane * 64u;
     const int sw = (lane >> 1) & 3;
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl)
@@ -186,7 +191,7 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      tma_store_3d(&P.tmPl, R.stg, col, R.row_base, 0);
+      tma_store_3d(&P.tmPl, R.stg + R.pl_off, col, R.row_base, 0);
       bulk_commit_group();
     }
   } else if ((R.epi & EPI_SPLIT3) && col < P.split_C && R.live) {
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
   const uint32_t w_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = RG_A_BYTES + w_bytes;
   const uint32_t stg0 = smem_u32(smem + (size_t)STG * stage_bytes);    // 8 epilogue warps x 6 KB TMA-store staging
-  uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes + 8 * 6144);
+  uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes + 8 * (size_t)batch.stg_bytes);
   const uint32_t bar0 = smem_u32(bars);
   // full[s] = bar0 + 8 s (TMA: A planes + W tile), empty[s] = bar0 + 8 (STG + s) (MMAs retired),
   // acc_full[a] = bar0 + 8 (2 STG + a), acc_empty[a] = bar0 + 8 (2 STG + 2 + a)
@@ -375,7 +380,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
       R.live = R.row < P.M;
       R.row_base = T.row0 + q * 32;
       R.ks = T.ks;
-      R.stg = stg0 + (uint32_t)(warp - 2) * 6144u;
+      R.stg = stg0 + (uint32_t)(warp - 2) * (uint32_t)batch.stg_bytes;
+      R.pl_off = (uint32_t)batch.pl_off;
       R.outp = P.out + (size_t)T.ks * P.out_split_stride;
       R.out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(R.outp) & 31) == 0);
       R.res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
         if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
       }
     }
-    if (lane == 0) bulk_wait_all();                         // this warp's TMA stores have completed
+    if (lane == 0) bulk_wait_group_read<0>();               // staging may be released; the writes drain with the grid
     if (threadIdx.x == 64) {
       RG_TS(6);
       if (dbg_on) {
@@ -553,9 +559,13 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
   if (BN != 32 && BN != 64 && BN != 128 && BN != 256) VKN_FAIL(VKN_E_INVALID, "VKN_RG_BN must be 32, 64, 128 or 256");
   const size_t stage_bytes = (size_t)RG_A_BYTES + (size_t)BN * 128;
   int stages = rg_env("VKN_RG_STAGES", 4);
-  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 8 * 6144 + 1024 + (2 * st + 4) * 8 + 16 + 2 * 128 * 8 * 4 + 64; };
+  int stg_bytes = 10240;                                              // fp32 box + plane boxes side by side when they fit
+  auto smem_of = [&](int st) { return (size_t)st * stage_bytes + 8 * (size_t)stg_bytes + 1024 + (2 * st + 4) * 8 + 16 + 2 * 128 * 8 * 4 + 64; };
+  if (smem_of(2) > 227 * 1024) stg_bytes = 6144;                      // BN = 256: keep two pipeline stages, share the box
   while (stages > 1 && smem_of(stages) > 227 * 1024) --stages;
   size_t smem = smem_of(stages);
+  b.stg_bytes = stg_bytes;
+  b.pl_off = stg_bytes == 10240 ? 4096 : 0;
   b.nprob = nprob;
   b.ksplit = ks;
   b.stages = stages;
