@@ -186,8 +186,10 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the single JSON line
+        # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG >= VERSION
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG', None)
+        os.environ.setdefault('NCCL_DEBUG_FILE', os.devnull)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)

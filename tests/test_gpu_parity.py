@@ -558,6 +558,28 @@ def test_row_engine_tc_fused_layernorm_epilogue(dev, monkeypatch):
         assert maxabs(got[0], want[0]) < TOL_BF16 and maxabs(got[2], want[2]) < TOL_BF16
 
 
+@pytest.mark.parametrize('ptype', ['ffn', 'update'])
+def test_row_engine_tc_link_block(dev, monkeypatch, ptype):
+    """VideoKernelUpdateHead link block (video/kernel_update_head.py:394-444) on the tcgen05 row engine == warp-MMA chain,
+    both within tolerance of the oracle (bf16 storage)."""
+    B, N, C, H, W = 6, 100, 256, 8, 16
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=512, previous='placeholder', previous_type=ptype)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=31))
+    h = build_heads('VideoKernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=32)
+    prev = torch.randn(B, N, C, 1, 1, generator=torch.Generator().manual_seed(33))
+    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
+    want = ko.video_kernel_update_head_forward(sd, cfg, x, pf, mask, previous_obj_feats=prev)
+    outs = {}
+    for mode, rows_min in (('warp', '0'), ('tc', '1')):
+        monkeypatch.setenv('VKN_ROWS_TC_MIN', rows_min)
+        outs[mode] = h(x.to(dev).bfloat16(), pf.to(dev), mask.to(dev).bfloat16(), previous_obj_feats=prev.to(dev))
+    for mode in outs:
+        assert maxabs(outs[mode][4], want[4]) < TOL_BF16, mode
+        assert maxabs(outs[mode][2], want[2]) < TOL_BF16, mode
+    assert maxabs(outs['tc'][4], outs['warp'][4].cpu()) < 5e-4
+
+
 def test_row_engine_tc_variants(dev, monkeypatch):
     """with_ffn=False, no feat_transform, deeper FC stacks, non-default threshold, video head (x_feat handed in)."""
     monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')

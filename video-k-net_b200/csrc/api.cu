@@ -818,6 +818,47 @@ int vkn_init_proposals(const VknShape *s, const float *init_w, const float *init
   return launch_rowop(r, proposal_feats, C, c.P, C, c.st);
 }
 
+// Link block on the tcgen05 row engine (many rows in flight: the sharded clip links all frames of a rank at once):
+// same operators as below, activations handed between the row GEMMs as bf16 planes.
+static int link_planes(Ctx &c, const VknLinkW &w, const float *cur, const RowSrc &kv, float *out) {
+  const int C = c.s.C, P = c.P, F = c.s.ffn_dim;
+  const long long PS = (long long)P * C;
+  void *PLA = c.L.pl[0], *PLB = c.L.pl[1], *PLC = c.L.pl[2];
+  VKN_TRY(launch_rowprep(src_copy(cur, C), nullptr, 0, PLA, C, PS, P, C, c.st));
+  VKN_TRY(launch_rowprep(kv, nullptr, 0, PLB, C, PS, P, C, c.st));
+  // MHA(q = cur, k = v = kv): q rows of in_proj on cur, k/v rows on kv (video/kernel_update_head.py:404-406)
+  LinArgs two[2];
+  two[0] = lin(src_planes(PLA, C, PS), w.attn.in_w, C, w.attn.in_b, c.L.qkv, 3 * C, P, C, C, 0);
+  two[1] = lin(src_planes(PLB, C, PS), wrow(c, w.attn.in_w, C, C), C, w.attn.in_b + C, c.L.qkv + C, 3 * C, P, 2 * C, C, 0);
+  VKN_TRY(launch_linear_tc(two, 2, c.st));
+  VKN_TRY(launch_attention(c.L.qkv, 3 * C, c.L.qkv + C, 3 * C, c.L.qkv + 2 * C, 3 * C, nullptr, C, c.s.B, c.s.N, C,
+                           c.s.num_heads, c.st, PLC, PS));
+  LinArgs op = lin(src_planes(PLC, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.y, C, P, C, C, EPI_RES);
+  op.res = cur;
+  op.ldres = C;
+  VKN_TRY(launch_linear_tc(&op, 1, c.st));
+  VKN_TRY(launch_rowprep(src_ln(c.L.y, C, w.attn.norm_g, w.attn.norm_b, false), c.L.o2, C, PLA, C, PS, P, C, c.st));
+  // link FFN + LN (:407-415)
+  LinArgs f1 = lin(src_planes(PLA, C, PS), w.ffn.w1, C, w.ffn.b1, nullptr, F, P, F, C, EPI_RELU | EPI_NOOUT);
+  out_planes(f1, c.L.h, P, F);
+  VKN_TRY(launch_linear_tc(&f1, 1, c.st));
+  LinArgs f2 = lin(src_planes(c.L.h, F, (long long)P * F), w.ffn.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
+  const int nk = ceil_div(F, 64);
+  int ksp = 148 / (ceil_div(P, 128) * ceil_div(C, 256));
+  ksp = ksp >= 8 ? 8 : (ksp >= 4 ? 4 : (ksp >= 2 ? 2 : 1));
+  while (ksp > 1 && (nk % ksp != 0 || nk / ksp < 4)) ksp /= 2;
+  f2.ksplit = ksp;
+  f2.out_split_stride = PS;
+  VKN_TRY(launch_linear_tc(&f2, 1, c.st));
+  RowSrc r = src_ln(c.L.zpart, C, w.ffn.norm_g, w.ffn.norm_b, false);
+  r.nsum = ksp;
+  r.sum_stride = PS;
+  r.pbias = w.ffn.b2;
+  r.pres = c.L.o2;
+  r.ldpres = C;
+  return launch_rowprep(r, out, C, nullptr, 0, 0, P, C, c.st);
+}
+
 int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, const float *prev, const float *x_feat,
                     float *out, void *workspace, size_t workspace_bytes, void *stream) {
   Ctx c;
@@ -830,6 +871,7 @@ int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, cons
     VKN_TRY(k_update(c, w->upd, x_feat, src_copy(prev, C), c.L.link_fc));
     kv = src_ln(c.L.link_fc, C, w->upd.fc_norm_g, w->upd.fc_norm_b, true);
   }
+  if (c.rows_tc && (reinterpret_cast<uintptr_t>(cur) & 15) == 0) return link_planes(c, *w, cur, kv, out);
   VKN_TRY(k_attn(c, w->attn, src_copy(cur, C), cur, &kv, c.L.y));
   RowSrc pend;
   VKN_TRY(k_ffn(c, w->ffn, src_ln(c.L.y, C, w->attn.norm_g, w->attn.norm_b, false), &pend));
