@@ -353,7 +353,9 @@ def test_error_behaviour(dev):
 
 # ---- tcgen05/TMA engine vs the CUDA-core engine and the oracle (bf16 storage) ---------------------------
 @pytest.mark.parametrize('B,N,C,H,W', [(1, 100, 256, 200, 88), (2, 117, 256, 48, 156), (1, 166, 128, 16, 24),
-                                       (3, 10, 64, 8, 8), (4, 100, 256, 96, 160)])
+                                       (3, 10, 64, 8, 8), (4, 100, 256, 96, 160),
+                                       # cfg4 (VIP-Seg) shape with its real kernel count 100 + 66 stuff: two pooling M tiles, Npad 176
+                                       (4, 166, 256, 120, 216)])
 def test_tc_engine_matches_simt_engine_and_oracle(dev, B, N, C, H, W):
     from vknet import _lib, ops
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
@@ -386,6 +388,28 @@ def test_tc_engine_matches_simt_engine_and_oracle(dev, B, N, C, H, W):
         ref = ko.round_bf16(want[1])
         mism = (nm.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item()
         assert mism < 2e-3, '%s stage: argmax mismatch rate %g' % (name, mism)
+
+
+@pytest.mark.parametrize('B,N,C,H,W', [(300, 20, 64, 8, 16), (160, 100, 128, 16, 16), (37, 100, 256, 24, 40)])
+def test_persistent_mask_conv_balanced_ranges_cross_frames(dev, B, N, C, H, W):
+    """The persistent mask conv cuts the launch's tiles into 148 equal ranges: with 1-2 tiles per frame a CTA's range
+    spans several frames (plane + bias swap per segment).  Must equal the SIMT engine up to 1-ulp bf16 roundings."""
+    from vknet import _lib, ops
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=64)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=4))
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    g = torch.Generator().manual_seed(5)
+    xb = torch.randn(B, C, H, W, generator=g).to(dev).bfloat16()
+    mk = torch.randn(B, N, C, generator=g).to(dev)
+    out = {}
+    for name, eng in (('simt', _lib.ENGINE_SIMT), ('tc', _lib.ENGINE_TC)):
+        h.engine = eng
+        out[name] = ops.mask_gemm(h, xb, mk).float()
+    diff = (out['tc'] - out['simt']).abs()
+    assert diff.max().item() <= 2 ** -7 * out['simt'].abs().max().item()
+    assert (diff > 0).float().mean().item() < 2e-3
+    per_frame = diff.flatten(1).max(1).values           # a wrong plane / bias swap would wreck whole frames
+    assert (per_frame <= 2 ** -7 * out['simt'].abs().max().item()).all()
 
 
 def test_profile_hooks_and_launch_count(dev):
