@@ -225,6 +225,18 @@ int vkn_init_proposals(const VknShape *s, const float *init_w, const float *init
                        const void *x_feats, void *mask_preds, float *proposal_feats, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- next row: the post-loop mask path -------------------------------------------------
+ * One launch for: the last-stage bilinear x`mask_upsample_stride` of _mask_forward (knet/det/kernel_iter_head.py:122-128),
+ * KernelUpdateHead.rescale_masks (knet/det/kernel_update_head.py:443-458: sigmoid -> bilinear to batch_input_shape ->
+ * crop [:img_h,:img_w] -> bilinear to ori_shape) and the `> mask_thr` of get_seg_masks (:460-462).
+ *   masks   [K, H, W] logits of the K selected kernels (dtype = VKN_F32 / VKN_BF16), device memory
+ *   up      mask_upsample_stride (1 = the masks are already the scaled_mask_preds)
+ *   probs   [K, ori_h, ori_w] fp32 or NULL;  bits [K, ori_h, ori_w] uint8 (1 where prob > mask_thr) or NULL
+ * All interpolations are torch's bilinear, align_corners=False.  VKN_E_UNSUPPORTED for resize ratios whose per-tile
+ * dependency cone does not fit shared memory (strong down-scaling). */
+int vkn_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int batch_h, int batch_w, int img_h,
+                      int img_w, int ori_h, int ori_w, float mask_thr, float *probs, unsigned char *bits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

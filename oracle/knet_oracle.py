@@ -448,3 +448,16 @@ def round_bf16(t):
 
 def round_state_dict_bf16(sd):
     return {k: round_bf16(v) for k, v in sd.items()}
+
+
+# ---- post-loop mask path ------------------------------------------------------------------
+def rescale_masks(masks, img_meta, mask_upsample_stride=1):
+    """Last-stage upsample of _mask_forward (knet/det/kernel_iter_head.py:122-128) followed by
+    KernelUpdateHead.rescale_masks (knet/det/kernel_update_head.py:443-458).  masks [K,H,W] logits -> [K,ori_h,ori_w]."""
+    m = masks.float().unsqueeze(0)
+    if mask_upsample_stride > 1:
+        m = F.interpolate(m, scale_factor=mask_upsample_stride, align_corners=False, mode='bilinear')
+    h, w = img_meta['img_shape'][:2]
+    m = F.interpolate(m.sigmoid(), size=tuple(img_meta['batch_input_shape'][:2]), mode='bilinear', align_corners=False)
+    m = m[:, :, :h, :w]
+    return F.interpolate(m, size=tuple(img_meta['ori_shape'][:2]), mode='bilinear', align_corners=False).squeeze(0)

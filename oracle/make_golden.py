@@ -135,6 +135,31 @@ def main_clip():
     case_clip('clip_perframe_b1_f3_n10_c64_8x12', 1, 3, 10, 64, 8, 12, 128, 5, 9, False)
 
 
+def case_rescale(name, K, H, W, up, batch_shape, img_shape, ori_shape, seed):
+    """Post-loop mask path: the x`up` upsample of _mask_forward (knet/det/kernel_iter_head.py:122-128, restated as the same
+    F.interpolate call -- the iter head itself needs the whole detector) followed by the UNMODIFIED reference
+    KernelUpdateHead.rescale_masks (knet/det/kernel_update_head.py:443-458)."""
+    import torch.nn.functional as F
+    ref = ref_shim.load('knet')
+    g = torch.Generator().manual_seed(seed)
+    masks = torch.randn(K, H, W, generator=g) * 3.0
+    img_meta = dict(img_shape=tuple(img_shape) + (3,), batch_input_shape=tuple(batch_shape), ori_shape=tuple(ori_shape) + (3,))
+    with torch.no_grad():
+        scaled = F.interpolate(masks.unsqueeze(0), scale_factor=up, align_corners=False, mode='bilinear').squeeze(0) if up > 1 else masks
+        seg = ref.KernelUpdateHead.rescale_masks(None, scaled, img_meta)
+    blob = dict(masks=masks.numpy(), seg=seg.numpy(),
+                meta=np.array([K, H, W, up, batch_shape[0], batch_shape[1], img_shape[0], img_shape[1], ori_shape[0], ori_shape[1]],
+                              dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **blob)
+    print(name, 'ok', tuple(seg.shape))
+
+
+def main_rescale():
+    os.makedirs(OUT, exist_ok=True)
+    case_rescale('rescale_k5_12x20_up2_96x160_crop90x150_to47x83', 5, 12, 20, 2, (96, 160), (90, 150), (47, 83), 11)
+    case_rescale('rescale_k3_9x13_up1_36x52_crop33x50_to70x101', 3, 9, 13, 1, (36, 52), (33, 50), (70, 101), 12)
+
+
 def main():
     assert ref_shim.available(), '/root/reference is required to (re)generate the fixtures'
     os.makedirs(OUT, exist_ok=True)
@@ -149,11 +174,14 @@ def main():
     case_video('video_link_update_b2_n12_c64_9x11', 2, 12, 64, 9, 11, 128, 5, 5, 'update', 'update_dynamic_cov')
     case_video('video_link_cov_ffn_b1_n12_c64_9x11', 1, 12, 64, 9, 11, 128, 5, 6, 'ffn', 'update_dynamic_cov')
     case_init('init_b2_n20_c64_12x16', 2, 20, 64, 12, 16, 10)
+    main_rescale()
 
 
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'clip':      # knet_vis registers the same keys as knet: own process
         main_clip()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'rescale':
+        main_rescale()
     else:
         main()
         import subprocess

@@ -648,3 +648,58 @@ def test_attention_four_queries_per_warp_kernel(dev, monkeypatch, B, N, C):
     got1 = ops.mhsa_ln(h, rows.to(dev)).clone()
     assert maxabs(got4, want) < 1e-4 and maxabs(got1, want) < 1e-4
     assert maxabs(got4, got1.cpu()) < 2e-5
+
+
+# ---- next row 8f-2: post-loop mask path (upsample + rescale_masks + threshold in one launch) -----------------------
+@pytest.mark.parametrize('path', golden_files('rescale_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_rescale_masks_golden(dev, path):
+    import numpy as np
+    from vknet import ops
+    z = np.load(path)
+    K, H, W, up, Hb, Wb, h, w, Ho, Wo = (int(v) for v in z['meta'])
+    meta = dict(img_shape=(h, w, 3), batch_input_shape=(Hb, Wb), ori_shape=(Ho, Wo, 3))
+    want = torch.from_numpy(z['seg'])
+    probs, bits = ops.rescale_masks(torch.from_numpy(z['masks']).to(dev), meta, up, 0.5)
+    assert probs.shape == (K, Ho, Wo) and bits.dtype == torch.bool
+    assert maxabs(probs, want) < 2e-6
+    near = (want - 0.5).abs() < 2e-6
+    assert torch.equal(bits.cpu() | near, (want > 0.5) | near)
+
+
+@pytest.mark.parametrize('K,H,W,up,batch,img,ori,dt', [
+    (100, 48, 156, 2, (384, 1248), (375, 1242), (375, 1242), 'bf16'),     # KITTI-STEP: stride-8 logits -> full resolution
+    (10, 96, 160, 2, (768, 1280), (720, 1280), (360, 640), 'f32'),        # down-scaling to the original size
+    (7, 25, 44, 1, (200, 352), (200, 350), (480, 840), 'f32'),            # no loop upsample, up-scaling, ragged tiles
+    (3, 50, 88, 4, (200, 352), (190, 333), (97, 171), 'bf16')])
+def test_rescale_masks_vs_oracle(dev, K, H, W, up, batch, img, ori, dt):
+    from vknet import ops
+    g = torch.Generator().manual_seed(K)
+    masks = torch.randn(K, H, W, generator=g) * 4.0
+    if dt == 'bf16':
+        masks = ko.round_bf16(masks)
+    meta = dict(img_shape=img + (3,), batch_input_shape=batch, ori_shape=ori + (3,))
+    want = ko.rescale_masks(masks, meta, up)
+    md = masks.to(dev).bfloat16() if dt == 'bf16' else masks.to(dev)
+    probs, bits = ops.rescale_masks(md, meta, up, 0.5)
+    assert maxabs(probs, want) < 5e-6
+    near = (want - 0.5).abs() < 5e-6
+    assert torch.equal(bits.cpu() | near, (want > 0.5) | near)
+    assert near.float().mean().item() < 1e-3
+    only_bits = ops.rescale_masks(md, meta, up, 0.5, probs=False)
+    assert only_bits[0] is None and torch.equal(only_bits[1], bits)
+    # the module method keeps the reference signature (scaled masks in, probabilities out)
+    import vknet
+    cfg = ko.default_cfg(num_classes=19, in_channels=64, feedforward_channels=64)
+    head = vknet.build_head(dict(type='KernelUpdateHead', **cfg)).to(dev)
+    if up == 1:
+        assert maxabs(head.rescale_masks(md, meta), want) < 5e-6
+
+
+def test_rescale_masks_errors(dev):
+    from vknet import _lib, ops
+    meta = dict(img_shape=(8, 8, 3), batch_input_shape=(8, 8), ori_shape=(8, 8, 3))
+    with pytest.raises(_lib.VknError):
+        ops.rescale_masks(torch.zeros(2, 4, 4), meta)                      # CPU tensor: no fallback
+    with pytest.raises(_lib.VknError):                                     # extreme down-scaling: dependency cone too large
+        ops.rescale_masks(torch.zeros(1, 2000, 2000, device=dev), dict(img_shape=(2000, 2000, 3), batch_input_shape=(2000, 2000),
+                                                                        ori_shape=(20, 20, 3)))

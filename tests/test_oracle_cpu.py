@@ -116,3 +116,15 @@ def test_oracle_matches_reference_fixture_init_proposals():
     prop, mask = ko.init_proposals(t['init_w'], None, t['loc_feats'], t['x_feats'])
     assert maxabs(prop, t['proposal_feats']) < 2e-5 * t['proposal_feats'].abs().max().item()
     assert maxabs(mask, t['mask_preds']) < 2e-5 * t['mask_preds'].abs().max().item()
+
+
+@pytest.mark.parametrize('path', golden_files('rescale_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_oracle_matches_reference_fixtures_rescale_masks(path):
+    """Post-loop mask path: oracle restatement == the reference's rescale_masks output."""
+    import numpy as np
+    z = np.load(path)
+    K, H, W, up, Hb, Wb, h, w, Ho, Wo = (int(v) for v in z['meta'])
+    meta = dict(img_shape=(h, w, 3), batch_input_shape=(Hb, Wb), ori_shape=(Ho, Wo, 3))
+    got = ko.rescale_masks(torch.from_numpy(z['masks']), meta, up)
+    assert got.shape == (K, Ho, Wo)
+    assert (got - torch.from_numpy(z['seg'])).abs().max().item() < 1e-6

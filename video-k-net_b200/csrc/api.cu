@@ -652,7 +652,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -876,6 +876,13 @@ int vkn_link_attend(const VknShape *s, const VknLinkW *w, const float *cur, cons
   RowSrc pend;
   VKN_TRY(k_ffn(c, w->ffn, src_ln(c.L.y, C, w->attn.norm_g, w->attn.norm_b, false), &pend));
   return launch_rowop(pend, out, C, c.P, C, c.st);
+}
+
+int vkn_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int batch_h, int batch_w, int img_h,
+                      int img_w, int ori_h, int ori_w, float mask_thr, float *probs, unsigned char *bits, void *stream) {
+  if (!masks) VKN_FAIL(VKN_E_INVALID, "vkn_rescale_masks: null masks");
+  return launch_rescale_masks(masks, dtype, K, H, W, up, batch_h, batch_w, img_h, img_w, ori_h, ori_w, mask_thr, probs, bits,
+                              (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -215,5 +215,8 @@ int pool_tc_chunks(const VknShape &s);
 int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws,
                        void *out, cudaStream_t stream);
 int maskgemm_tc_npad(const VknShape &s);
+// post-loop mask path (postproc.cu)
+int launch_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int Hb, int Wb, int h, int w, int Ho,
+                         int Wo, float thr, float *probs, uint8_t *bits, cudaStream_t stream);
 
 }  // namespace vkn

@@ -65,7 +65,7 @@ _lib = None
 SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_launch_count', 'vkn_profile_begin',
            'vkn_profile_end', 'vkn_debug_timestamps', 'vkn_workspace_bytes', 'vkn_mask_pool',
            'vkn_kernel_update', 'vkn_mhsa_ln', 'vkn_ffn_ln', 'vkn_heads', 'vkn_mask_gemm',
-           'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend')
+           'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend', 'vkn_rescale_masks')
 
 
 def lib():
@@ -96,6 +96,8 @@ def lib():
     L.vkn_iter_forward.argtypes = [S, C.POINTER(VknHeadW), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, sz, _vp]
     L.vkn_init_proposals.argtypes = [S, _vp, _vp, _vp, _vp, _vp, _vp, _vp, sz, _vp]
     L.vkn_link_attend.argtypes = [S, C.POINTER(VknLinkW), _vp, _vp, _vp, _vp, _vp, sz, _vp]
+    L.vkn_rescale_masks.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]
     L.vkn_debug_timestamps.restype = C.c_int
     L.vkn_debug_timestamps.argtypes = [_vp, C.c_size_t]
     for name in SYMBOLS[7:]:

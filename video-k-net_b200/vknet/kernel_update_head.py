@@ -166,15 +166,35 @@ class _HeadBase(nn.Module):
                                            mode='bilinear').to(new_mask_preds.dtype)
         return new_mask_preds
 
-    # pure-torch helpers the callers of the reference use (kept as pass-throughs) --------------------
+    # helpers the callers of the reference use -----------------------------------------------------------------------
     def rescale_masks(self, masks_per_img, img_meta):
-        """knet/det/kernel_update_head.py:443-458."""
-        h, w, _ = img_meta['img_shape']
-        masks_per_img = F.interpolate(masks_per_img.unsqueeze(0).sigmoid(), size=img_meta['batch_input_shape'],
-                                      mode='bilinear', align_corners=False)
-        masks_per_img = masks_per_img[:, :, :h, :w]
-        ori_shape = img_meta['ori_shape']
-        return F.interpolate(masks_per_img, size=ori_shape[:2], mode='bilinear', align_corners=False).squeeze(0)
+        """knet/det/kernel_update_head.py:443-458 -- one fused launch (vkn_rescale_masks) instead of three full-resolution
+        temporaries.  `masks_per_img` are the (already x mask_upsample_stride) scaled_mask_preds of the selected kernels."""
+        from . import ops
+        return ops.rescale_masks(masks_per_img, img_meta, 1, None)[0]
+
+    def get_seg_masks(self, masks_per_img, labels_per_img, scores_per_img, test_cfg, img_meta):
+        """:460-467: rescale + threshold on the device, then the reference's list packing (segm2result)."""
+        from . import ops
+        thr = test_cfg['mask_thr'] if isinstance(test_cfg, dict) else test_cfg.mask_thr
+        seg_masks = ops.rescale_masks(masks_per_img, img_meta, 1, thr, probs=False)[1]
+        return self.segm2result(seg_masks, labels_per_img, scores_per_img)
+
+    def segm2result(self, mask_preds, det_labels, cls_scores):
+        """:469-483 (host-side result packing, unchanged semantics)."""
+        import numpy as np
+        num_classes = self.num_classes
+        segm_result = [[] for _ in range(num_classes)]
+        mask_preds = mask_preds.cpu().numpy()
+        det_labels = det_labels.cpu().numpy()
+        cls_scores = cls_scores.cpu().numpy()
+        num_ins = mask_preds.shape[0]
+        bboxes = np.zeros((num_ins, 5), dtype=np.float32)       # fake bboxes, score in the last column
+        bboxes[:, -1] = cls_scores
+        bbox_result = [bboxes[det_labels == i, :] for i in range(num_classes)]
+        for idx in range(num_ins):
+            segm_result[det_labels[idx]].append(mask_preds[idx])
+        return bbox_result, segm_result
 
     def loss(self, *args, **kwargs):
         raise NotImplementedError('training (loss/get_targets) is outside this package: inference hot path only')

@@ -117,3 +117,31 @@ def init_proposals(init_kernels, loc_feats, x_feats, engine=_lib.ENGINE_AUTO):
     _lib.check(_lib.lib().vkn_init_proposals(shape, _lib.ptr(wf), _lib.ptr(bf), _lib.ptr(loc_feats), _lib.ptr(x_feats),
                                              _lib.ptr(mask), _lib.ptr(prop), ws, wsb, _lib.stream_ptr()))
     return prop.reshape(B, N, Cc, 1, 1), mask
+
+
+def rescale_masks(masks, img_meta, mask_upsample_stride=1, mask_thr=None, probs=True):
+    """Post-loop mask path in one launch:
+        F.interpolate(masks, scale_factor=mask_upsample_stride)            knet/det/kernel_iter_head.py:122-128
+        KernelUpdateHead.rescale_masks(., img_meta)                        knet/det/kernel_update_head.py:443-458
+        (. > mask_thr)                                                     :460-462 (get_seg_masks)
+    masks [K,H,W] logits (fp32 / bf16, CUDA).  Returns (seg_probs [K,ori_h,ori_w] fp32 or None,
+    seg_masks bool [K,ori_h,ori_w] or None when mask_thr is None)."""
+    if not masks.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    if masks.dim() != 3:
+        raise ValueError('masks must be [K,H,W]')
+    K, H, W = masks.shape
+    h, w = img_meta['img_shape'][:2]
+    Hb, Wb = img_meta['batch_input_shape'][:2]
+    Ho, Wo = img_meta['ori_shape'][:2]
+    masks = masks.contiguous()
+    out_p = torch.empty(K, Ho, Wo, dtype=torch.float32, device=masks.device) if probs else None
+    out_b = torch.empty(K, Ho, Wo, dtype=torch.bool, device=masks.device) if mask_thr is not None else None   # kernel writes 0 / 1 bytes
+    if out_p is None and out_b is None:
+        raise ValueError('nothing to compute: probs=False and mask_thr=None')
+    if K > 0:
+        _lib.check(_lib.lib().vkn_rescale_masks(_lib.ptr(masks), _lib.dtype_code(masks.dtype), K, H, W, int(mask_upsample_stride),
+                                                int(Hb), int(Wb), int(h), int(w), int(Ho), int(Wo),
+                                                float(mask_thr if mask_thr is not None else 0.5), _lib.ptr(out_p), _lib.ptr(out_b),
+                                                _lib.stream_ptr()))
+    return out_p, out_b
