@@ -542,6 +542,32 @@ def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H
     assert maxabs(outs['tc'][0][0], outs['warp'][0][0].cpu()) < 2e-4
 
 
+@pytest.mark.parametrize('thr', [0.5, 0.7])
+def test_loop_bitmask_handoff_equals_stagewise_modules(dev, monkeypatch, thr):
+    """Frame batches: the one-call loop hands the thresholded BIT per (kernel, pixel) from a stage's mask conv to the next
+    stage's pooling instead of bf16 logits.  It thresholds the bf16-rounded logit, so the results must equal the
+    stage-by-stage module calls (which store and re-read the logits) bit for bit -- also for a non-default threshold."""
+    import vknet
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    B, N, C, H, W, S = 6, 100, 256, 96, 80, 3
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256, hard_mask_thr=thr)
+    sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=70 + s)) for s in range(S)]
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=17)
+    xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
+    obj, m = pfd, mb
+    for h in heads:
+        cls, m, obj = h(xb, obj, m)
+    for bits in ('1', '0'):
+        monkeypatch.setenv('VKN_LOOP_BITS', bits)
+        cls_l, m_l, obj_l = vknet.KernelIterLoop(heads)(xb, pfd, mb)
+        assert torch.equal(m_l, m) and torch.equal(obj_l, obj) and torch.equal(cls_l, cls), 'VKN_LOOP_BITS=%s' % bits
+    # first stage against the oracle (later stages are covered by the threshold-aware full-size loop test)
+    want = ko.kernel_update_head_forward(sds[0], cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
+    cls0, _, obj0 = heads[0](xb, pfd, mb)
+    assert maxabs(cls0, want[0]) < TOL_BF16 and maxabs(obj0, want[2]) < TOL_BF16
+
+
 @pytest.mark.parametrize('bn', ['32', '64', '128', '256'])
 def test_row_engine_tc_column_tiles(dev, monkeypatch, bn):
     """Every column-tile width of the persistent row GEMM (VKN_RG_BN) gives the same stage as the default choice."""

@@ -73,6 +73,7 @@ struct Layout {
   void *obj_pl[2];   // planes of a stage's obj_feat (= the next stage's proposal_feat), ping-pong across stages
   // iter loop
   void *mask_pp[2];
+  uint32_t *mask_bits;   // bit-mask hand-off between the stages of the fused loop: [frames][N][words per row]
   float *obj_pp[2], *cls_tmp;
   size_t total;
 };
@@ -136,6 +137,7 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   L.a_split = take((size_t)3 * s.B * npad * C * 2);
   const size_t esz = s.x_dtype == VKN_BF16 ? 2 : 4;
   for (int i = 0; i < 2; ++i) L.mask_pp[i] = take((size_t)s.B * fps * s.N * HW * esz);
+  L.mask_bits = (uint32_t *)take((size_t)s.B * fps * s.N * (size_t)(ceil_div((int)HW, 128) * 4) * 4);
   for (int i = 0; i < 2; ++i) L.obj_pp[i] = (float *)take(P * C * f);
   L.cls_tmp = (float *)take(P * (size_t)s.num_classes * f);
   L.total = align_up(off, 256);
@@ -453,7 +455,7 @@ static void out_planes(LinArgs &a, void *pl, int rows, int ld) {
 
 static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *pf, const void *pf_planes, const void *mask,
                         const float *x_feat_in, float *cls, void *new_mask, float *obj, float *x_feat_out,
-                        void *obj_planes_out) {
+                        void *obj_planes_out, const uint32_t *mask_bits_in = nullptr, uint32_t *mask_bits_out = nullptr) {
   const int C = c.s.C, P = c.P, F = c.s.ffn_dim;
   const long long PS = (long long)P * C;
   void *PLA = c.L.pl[0], *PLB = c.L.pl[1], *PLC = c.L.pl[2], *PLD = c.L.pl[3];
@@ -463,7 +465,7 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     float *xf = x_feat_out ? x_feat_out : c.L.xp;
     int nch = 0;
     const VknShape fs = frames_shape(c.s);
-    VKN_TRY(launch_pool_tc(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+    VKN_TRY(launch_pool_tc(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st, mask_bits_in));
     VKN_TRY(launch_pool_reduce(c.s, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st, PLA));
     LinArgs a = lin(src_planes(PLA, C, PS), w.ft_w, C, w.ft_b, xf, C, P, C, C, EPI_ROWSCALE);
     a.rowscale = c.L.cnt;
@@ -605,7 +607,7 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   out_planes(two[0], PLD, P, C);
   if (with_cls) two[1] = lin(src_planes(cs, C, PS), w.fc_cls_w, C, w.fc_cls_b, cls, c.s.num_classes, P, c.s.num_classes, C, 0);
   VKN_TRY(launch_linear_tc(two, with_cls ? 2 : 1, c.st));
-  if (new_mask == nullptr) return VKN_OK;
+  if (new_mask == nullptr && mask_bits_out == nullptr) return VKN_OK;
   // a9 (+a2 folded): a = mk . ft_w (planes for the mask conv), bias column mk . ft_b
   const int lda = C + A_EXT_PAD;
   LinArgs a = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, c.L.a_ext, lda, P, C + 1, C, EPI_SPLIT3);
@@ -615,13 +617,17 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   a.split_Npad = maskgemm_tc_npad(c.s);
   a.split_C = C;
   VKN_TRY(launch_linear_tc(&a, 1, c.st));
-  return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st);
+  return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st, mask_bits_out);
 }
 
 static int stage(Ctx &c, const VknHeadW &w, const void *x, const float *pf, const void *mask,
                  const float *x_feat_in, float *cls, void *new_mask, float *obj, float *x_feat_out,
-                 const void *pf_planes = nullptr, void *obj_planes_out = nullptr) {
-  if (c.rows_tc) return stage_planes(c, w, x, pf, pf_planes, mask, x_feat_in, cls, new_mask, obj, x_feat_out, obj_planes_out);
+                 const void *pf_planes = nullptr, void *obj_planes_out = nullptr, const uint32_t *mask_bits_in = nullptr,
+                 uint32_t *mask_bits_out = nullptr) {
+  if (c.rows_tc)
+    return stage_planes(c, w, x, pf, pf_planes, mask, x_feat_in, cls, new_mask, obj, x_feat_out, obj_planes_out, mask_bits_in,
+                        mask_bits_out);
+  if (mask_bits_in || mask_bits_out) VKN_FAIL(VKN_E_INVALID, "bit-mask hand-off is a row-engine (frame batch) path");
   const int C = c.s.C;
   const float *xp = x_feat_in;
   if (xp == nullptr) {
@@ -772,15 +778,23 @@ int vkn_iter_forward(const VknShape *s, const VknHeadW *stages, int num_stages, 
     VKN_FAIL(VKN_E_INVALID, "vkn_iter_forward: null argument");
   const float *pf = proposal_feat;
   const void *mk = mask_preds;
+  // Inside the loop the only consumer of an inner stage's masks is the next stage's hard threshold (the reference's
+  // simple_test keeps only the last stage's, knet/det/kernel_iter_head.py:246-253): frame batches hand over the
+  // thresholded BIT per (kernel, pixel) instead of bf16 logits -- 3.5 MB -> 0.22 MB per frame and stage on both sides.
+  bool use_bits = c.rows_tc && maskgemm_tc_persistent(c.s);
+  if (const char *e = getenv("VKN_LOOP_BITS")) use_bits = use_bits && e[0] != '0';
+  const uint32_t *bits_in = nullptr;
   for (int i = 0; i < num_stages; ++i) {
     const bool last = i == num_stages - 1;
     float *obj_o = last ? obj_feat : c.L.obj_pp[i & 1];
-    void *mask_o = last ? new_mask_preds : c.L.mask_pp[i & 1];
+    void *mask_o = last ? new_mask_preds : (use_bits ? nullptr : c.L.mask_pp[i & 1]);
+    uint32_t *bits_o = (!last && use_bits) ? c.L.mask_bits : nullptr;
     float *cls_o = last ? cls_score : c.L.cls_tmp;
     VKN_TRY(stage(c, stages[i], x, pf, mk, nullptr, cls_o, mask_o, obj_o, nullptr,
-                  i > 0 ? c.L.obj_pl[(i - 1) & 1] : nullptr, c.L.obj_pl[i & 1]));
+                  i > 0 ? c.L.obj_pl[(i - 1) & 1] : nullptr, c.L.obj_pl[i & 1], bits_in, bits_o));
     pf = obj_o;
     mk = mask_o;
+    bits_in = bits_o;
   }
   return VKN_OK;
 }

@@ -210,10 +210,13 @@ int launch_maskgemm_simt(const VknShape &s, const void *x, const float *a_ext, i
 // tcgen05 / TMA engines (gemm_tc.cu)
 bool tc_supported(const VknShape &s);
 int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
-                   int *nchunks, cudaStream_t stream);
+                   int *nchunks, cudaStream_t stream, const uint32_t *mask_bits = nullptr);
 int pool_tc_chunks(const VknShape &s);
 int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws,
-                       void *out, cudaStream_t stream);
+                       void *out, cudaStream_t stream, uint32_t *bits_out = nullptr);
+// bit-mask hand-off between the stages of the fused loop (1 bit per kernel and pixel instead of bf16 logits)
+int maskgemm_tc_bits_wpr(const VknShape &s);
+bool maskgemm_tc_persistent(const VknShape &s);
 int maskgemm_tc_npad(const VknShape &s);
 // post-loop mask path (postproc.cu)
 int launch_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int Hb, int Wb, int h, int w, int Ho,

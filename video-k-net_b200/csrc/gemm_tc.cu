@@ -57,7 +57,8 @@ constexpr int POOL_STAGES_MAX = 3;     // (x 32 KB + raw logits 16 KB + A tile 1
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_m,
                    float *__restrict__ partials, float *__restrict__ cnt_partials, int B, int N, int C, int HW,
-                   int nblocks, int bpc, float thr, uint32_t idesc, int POOL_STAGES) {
+                   int nblocks, int bpc, float thr, uint32_t idesc, int POOL_STAGES, const uint32_t *__restrict__ bits_in,
+                   int wpr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t x_bytes = (uint32_t)C * 128u;          // C rows x 64 px x 2 B
@@ -103,9 +104,10 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int s = i % POOL_STAGES;
         const uint32_t ph = (uint32_t)(i / POOL_STAGES) & 1u;
         mbar_wait(bar0 + 8 * (POOL_STAGES + s), ph ^ 1u);
-        mbar_expect_tx(bar0 + 8 * s, x_bytes + m_bytes);
+        mbar_expect_tx(bar0 + 8 * s, bits_in ? x_bytes : x_bytes + m_bytes);
         tma_load_3d(smem0 + s * stage_bytes, &tmap_x, bar0 + 8 * s, (blk_beg + i) * PX_BLK, 0, b);
-        tma_load_3d(smem0 + s * stage_bytes + x_bytes, &tmap_m, bar0 + 8 * s, (blk_beg + i) * PX_BLK, mtile * 128, b);
+        if (!bits_in)
+          tma_load_3d(smem0 + s * stage_bytes + x_bytes, &tmap_m, bar0 + 8 * s, (blk_beg + i) * PX_BLK, mtile * 128, b);
       }
     }
   } else if (warp == 1) {
@@ -140,6 +142,38 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     float cnt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cnt[i] = 0.f;
+    float cnt_row = 0.f;
+    if (bits_in != nullptr) {
+      // Bit-mask input (fused loop, inner stages): the previous stage's mask conv wrote 1 bit per (kernel, pixel) -- the
+      // hard mask itself -- instead of bf16 logits: 16x fewer mask bytes on both sides.  Thread = kernel row: one 8-byte
+      // load per 64-pixel block (prefetched one block ahead), expanded to {0, 1} bf16 in the swizzled A tile.
+      const int r = pt, n = mtile * 128 + r;
+      const uint2 *rowp = reinterpret_cast<const uint2 *>(bits_in + ((size_t)b * N + (n < N ? n : 0)) * wpr) + blk_beg;
+      uint2 cur = make_uint2(0u, 0u);
+      if (n < N) cur = __ldg(rowp);
+      for (int it = 0; it < nk; ++it) {
+        uint2 nxt = make_uint2(0u, 0u);
+        if (n < N && it + 1 < nk) nxt = __ldg(rowp + it + 1);
+        const int s = it % POOL_STAGES;
+        const uint32_t ph = (uint32_t)(it / POOL_STAGES) & 1u;
+        mbar_wait(bar0 + 8 * s, ph);                         // x landed => the MMAs that last read this stage retired
+        const uint32_t mt0 = smem0 + s * stage_bytes + x_bytes + m_bytes + (uint32_t)r * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t byte = ((j < 4 ? cur.x : cur.y) >> ((j & 3) * 8)) & 0xffu;
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = ((byte >> (2 * e)) & 1u ? 0x3f80u : 0u) | ((byte >> (2 * e + 1)) & 1u ? 0x3f800000u : 0u);   // bf16 1.0
+          sts_v4(mt0 + (uint32_t)((j ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+        }
+        cnt_row += (float)(__popc(cur.x) + __popc(cur.y));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (2 * POOL_STAGES + 1 + s));
+        cur = nxt;
+      }
+    } else
     // The raw logits arrive by TMA in the same 128B-swizzled [row][64 px] layout the A tile uses, so a thread
     // reads and writes the SAME offset: no global-load latency on this path, the ring prefetches POOL_STAGES deep.
     for (int it = 0; it < nk; ++it) {
@@ -201,6 +235,10 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       }
       __syncwarp();
     }
+    if (bits_in != nullptr) {                            // thread = row: its count is complete
+      const int nn = mtile * 128 + pt;
+      if (nn < N) cnt_partials[((size_t)chunk * B + b) * N + nn] = cnt_row;
+    } else
     // pixel counts: the 8 chunk-threads of a row are adjacent lanes
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -221,7 +259,7 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 }
 
 int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
-                   int *nchunks, cudaStream_t stream) {
+                   int *nchunks, cudaStream_t stream, const uint32_t *mask_bits) {
   if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 pooling: shape/dtype not supported");
   const int HW = s.H * s.W;
   const PoolPlan p = pool_plan(s);
@@ -238,7 +276,7 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   {
     const uint64_t mdims[3] = {(uint64_t)HW, (uint64_t)s.N, (uint64_t)s.B};
     const uint32_t mbox[3] = {(uint32_t)PX_BLK, 128u, 1u};
-    VKN_TRY(make_tmap_bf16(&tmap_m, mask, 3, mdims, mbox));
+    VKN_TRY(make_tmap_bf16(&tmap_m, mask_bits ? x : mask, 3, mdims, mbox));     // unused in bit-mask mode
   }
   if (smem < 4 * 32 * 36 * 4 + 2048) smem = 4 * 32 * 36 * 4 + 2048;      // epilogue staging
   static bool attr = false;
@@ -250,7 +288,7 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
   VKN_LAUNCH_MARK("vkn_pool_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_pool_tc_kernel, grid, dim3(TC_THREADS), smem, stream, tmap, tmap_m,
                            partials, cnt_partials, s.B, s.N, s.C, HW, p.nblocks, p.bpc, s.mask_thr_logit,
-                           make_idesc_bf16(128, s.C, 0, 0), pool_stages));
+                           make_idesc_bf16(128, s.C, 0, 0), pool_stages, mask_bits, maskgemm_tc_bits_wpr(s)));
   return VKN_OK;
 }
 
@@ -414,7 +452,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
                                const __grid_constant__ CUtensorMap tmap_o, const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
                                int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int MP_XS,
-                               int total_tiles, int pf_dist, unsigned long long *dbg) {
+                               int total_tiles, int pf_dist, uint32_t *__restrict__ bits_out, int wpr, float thr,
+                               unsigned long long *dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
@@ -591,6 +630,34 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       MP_WAIT(w0, mbar_wait(bar0 + 8 * (ACC_FULL + buf), (uint32_t)(li / MP_ACC) & 1u));
       tc_fence_after();
       if (g + 1 == g_hi) pdl_trigger();
+      if (bits_out != nullptr) {
+        // Inner stage of the fused loop: the only consumer is the next stage's hard threshold, so write the thresholded
+        // BIT per (kernel, pixel) -- of the bf16-rounded logit, i.e. exactly what thresholding the stored map would
+        // give -- 32 pixels of a warp per ballot word.  No staging, no TMA store, 16x fewer bytes.
+        const int p = tile * MASK_TILE_P + q * 32 + lane;
+        for (int n0 = 0; n0 < Npad; n0 += 32) {
+          float4 bq[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bq[e] = lds_f4(bias0 + (uint32_t)(n0 + 4 * e) * 4u);
+          const float *bqf = reinterpret_cast<const float *>(bq);
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + n0), r);
+          if (n0 + 32 >= Npad) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
+          }
+          uint32_t mine = 0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float v = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[e]) + bqf[e]));
+            const uint32_t w = __ballot_sync(0xffffffffu, p < HW && v > thr);
+            if (lane == e) mine = w;
+          }
+          if (n0 + lane < N) bits_out[((size_t)b * N + n0 + lane) * wpr + tile * 4 + q] = mine;
+        }
+        continue;
+      }
       for (int n0 = 0; n0 < Npad; n0 += 32, ++jj) {
         float4 bq[8];
 #pragma unroll
@@ -638,8 +705,19 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
 
 int maskgemm_tc_npad(const VknShape &s) { return npad_of(s.N); }
 
+// words of 32 pixel bits per (frame, kernel) row of the bit-mask hand-off: whole 128-pixel tiles
+int maskgemm_tc_bits_wpr(const VknShape &s) { return ceil_div(s.H * s.W, MASK_TILE_P) * (MASK_TILE_P / 32); }
+// true when launch_maskgemm_tc takes the persistent kernel (the one that can emit the bit mask)
+bool maskgemm_tc_persistent(const VknShape &s) {
+  if (!tc_supported(s)) return false;
+  const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
+  bool persist = npad_of(s.N) <= 112 && ceil_div(s.H * s.W, MASK_TILE_P) * s.B * F >= 2 * 148;
+  if (const char *e = getenv("VKN_MASK_PERSIST")) persist = (e[0] == '1') && npad_of(s.N) <= 112;
+  return persist;
+}
+
 int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws, void *out,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, uint32_t *bits_out) {
   if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: shape/dtype not supported");
   const int HW = s.H * s.W, Npad = npad_of(s.N);
   const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
@@ -671,8 +749,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     if (e[0] == '1') { uint32_t t = x_lbo; x_lbo = x_sbo; x_sbo = t; }
   }
   const int ntiles = ceil_div(HW, MASK_TILE_P), frames = s.B * F;
-  bool persist = Npad <= 112 && ntiles * frames >= 2 * 148;      // several tiles per SM: keep the planes resident
-  if (const char *e = getenv("VKN_MASK_PERSIST")) persist = (e[0] == '1') && Npad <= 112;
+  const bool persist = maskgemm_tc_persistent(s);                // several tiles per SM: keep the planes resident
+  if (bits_out && !persist) VKN_FAIL(VKN_E_INVALID, "tcgen05 mask conv: the bit-mask output needs the persistent kernel");
+  if (!bits_out && !out) VKN_FAIL(VKN_E_INVALID, "tcgen05 mask conv: no output");
   if (persist) {
     const int total_tiles = ntiles * frames;
     int pf_dist = 1;                                         // L2 prefetch distance in tiles (VKN_MASK_PF; measured 0/1/2/4: 1 is best)
@@ -702,11 +781,12 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     {
       const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.N, (uint64_t)frames};
       const uint32_t box[3] = {(uint32_t)MASK_TILE_P, 32u, 1u};
-      VKN_TRY(make_tmap_bf16_plain(&tmo, out, dims, box));
+      VKN_TRY(make_tmap_bf16_plain(&tmo, out ? out : x, dims, box));     // unused (never stored through) in bit-mask mode
     }
     VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x), dim3(TC_THREADS), psmem, stream, tmx, tma,
                              tmo, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
-                             x_lbo, x_sbo, F, xs_depth, total_tiles, pf_dist, debug_ts_slot()));
+                             x_lbo, x_sbo, F, xs_depth, total_tiles, pf_dist, bits_out, maskgemm_tc_bits_wpr(s), s.mask_thr_logit,
+                             debug_ts_slot()));
     return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);
