@@ -52,6 +52,7 @@ static PoolPlan pool_plan(const VknShape &s) {
 }
 int pool_tc_chunks(const VknShape &s) { return tc_supported(s) ? pool_plan(s).nchunks : 0; }
 
+constexpr int POOL_BITS_AHEAD = 4;     // bit-mask words loaded this many pixel blocks ahead of their use
 constexpr int POOL_STAGES_MAX = 3;     // (x 32 KB + raw logits 16 KB + A tile 16 KB) x 3 = 192 KB at C = 256
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -149,11 +150,15 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       // load per 64-pixel block (prefetched one block ahead), expanded to {0, 1} bf16 in the swizzled A tile.
       const int r = pt, n = mtile * 128 + r;
       const uint2 *rowp = reinterpret_cast<const uint2 *>(bits_in + ((size_t)b * N + (n < N ? n : 0)) * wpr) + blk_beg;
-      uint2 cur = make_uint2(0u, 0u);
-      if (n < N) cur = __ldg(rowp);
+      // 8-byte loads run POOL_BITS_AHEAD blocks ahead of their use (a block lasts ~0.7 us, an L2/DRAM load ~1 us)
+      uint2 q[POOL_BITS_AHEAD];
+#pragma unroll
+      for (int a = 0; a < POOL_BITS_AHEAD; ++a) q[a] = (n < N && a < nk) ? __ldg(rowp + a) : make_uint2(0u, 0u);
       for (int it = 0; it < nk; ++it) {
-        uint2 nxt = make_uint2(0u, 0u);
-        if (n < N && it + 1 < nk) nxt = __ldg(rowp + it + 1);
+        const uint2 cur = q[0];
+#pragma unroll
+        for (int a = 0; a + 1 < POOL_BITS_AHEAD; ++a) q[a] = q[a + 1];
+        q[POOL_BITS_AHEAD - 1] = (n < N && it + POOL_BITS_AHEAD < nk) ? __ldg(rowp + it + POOL_BITS_AHEAD) : make_uint2(0u, 0u);
         const int s = it % POOL_STAGES;
         const uint32_t ph = (uint32_t)(it / POOL_STAGES) & 1u;
         mbar_wait(bar0 + 8 * s, ph);                         // x landed => the MMAs that last read this stage retired
@@ -171,7 +176,6 @@ vkn_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8 * (2 * POOL_STAGES + 1 + s));
-        cur = nxt;
       }
     } else
     // The raw logits arrive by TMA in the same 128B-swizzled [row][64 px] layout the A tile uses, so a thread

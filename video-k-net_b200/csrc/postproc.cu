@@ -47,10 +47,6 @@ __device__ __forceinline__ RsTap rs_tap(float scale, int dst, int in, int lo) {
   t.l0 = 1.f - t.l1;
   return t;
 }
-__device__ __forceinline__ float rs_lerp2(const float *reg, int pitch, const RsTap &ty, const RsTap &tx) {
-  const float *p = reg + ty.i0 * pitch + tx.i0;
-  return ty.l0 * (tx.l0 * p[0] + tx.l1 * p[tx.step]) + ty.l1 * (tx.l0 * p[ty.step * pitch] + tx.l1 * p[ty.step * pitch + tx.step]);
-}
 
 // y taps of a pass, one float4 per output row: {first-row offset (floats, as bits), second-row step (floats, as bits), l0, l1}
 __device__ __forceinline__ void rs_fill_ytab(float4 *tab, float scale, int dst0, int n, int in, int lo, int pitch) {
@@ -160,14 +156,10 @@ __global__ void __launch_bounds__(RS_NT) vkn_rescale_masks_kernel(const T *__res
   }
 }
 
-// host-side replica of the dependency cone of the worst tile: every staged region must fit RS_MAX_REGION floats
-static float h_src(float scale, int dst) {
-  const float s = scale * ((float)dst + 0.5f) - 0.5f;
-  return s < 0.f ? 0.f : s;
-}
-static int h_extent(float scale, int tile, int in) {      // upper bound of the input extent an output span of `tile` touches
+// host-side bound of the dependency cone: the input extent an output span of `tile` consecutive indices touches
+// (src is affine in dst with slope `scale`; + first tap, second tap, fractional alignment)
+static int h_extent(float scale, int tile, int in) {
   const int e = (int)(scale * (float)tile) + 3;
-  (void)h_src;
   return e < in ? e : in;
 }
 
