@@ -32,6 +32,8 @@ sys.path[:0] = [os.path.join(ROOT, 'video-k-net_b200')]
 
 CFG1 = dict(B=1, N=100, C=256, H=200, W=88, S=3, ncls=19, ffn=2048)
 METRIC = 'frames/sec/GPU (100 kernels, C=256, 200x88, S=3)'
+# the workload both arms are quoted on (BASELINE.json configs[1]); frames are independent, so throughput = frames/s/GPU
+WORKLOAD = 'cfg1 KITTI-STEP R-50 shape per frame: N=100 kernels, C=256, 200x88 feature map, S=3 stages'
 
 
 def head_cfg(link=False):
@@ -165,8 +167,8 @@ def run_reference(args):
     line = dict(impl='reference', metric=METRIC, value=cb['value'], unit='frames/s', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=med * 1e3, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='cfg1: B=1 frame, N=100 kernels, C=256, 200x88, S=3 (KITTI-STEP R-50 shape)',
-                            note='reference CPU PyTorch path (oracle port), one frame per step, all host threads'),
+                config=dict(workload=WORKLOAD,
+                            note='reference CPU PyTorch path (oracle port, fp32), one frame per step, best host thread count'),
                 cpu_baseline=cb,
                 e2e=dict(value=cb['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -434,10 +436,9 @@ def run_ours(args):
         line = dict(metric=METRIC, value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
                     data='synthetic',
-                    config=dict(workload='cfg1 KITTI-STEP R-50 shape: 1 frame/GPU, N=100 kernels, C=256, 200x88, S=3, '
-                                         'bf16 storage of x/masks/weights, fp32 arithmetic' +
-                                         ('; + cfg3 link: every %d frames/rank one all-gather of kernels and the previous_type=ffn '
-                                          'link block' % FPG if world > 1 else ''),
+                    config=dict(workload=WORKLOAD + ('; + cfg3 link: every %d frames/rank one all-gather of kernels and the '
+                                                     'previous_type=ffn link block' % FPG if world > 1 else ''),
+                                storage='bf16 x / masks / weights, fp32 arithmetic (exact 3-plane bf16 products, fp32 accumulation)',
                                 mode='CUDA-graph replay of vkn_iter_forward (S stages); %d frames per graph launch = %d concurrent '
                                      'branches x batch %d' % (FPG, NS, BF),
                                 single_stream_ms_per_frame=latency_ms,

@@ -390,11 +390,13 @@ def test_tc_engine_matches_simt_engine_and_oracle(dev, B, N, C, H, W):
         assert mism < 2e-3, '%s stage: argmax mismatch rate %g' % (name, mism)
 
 
+@pytest.mark.parametrize('wide', ['0', '1'])
 @pytest.mark.parametrize('B,N,C,H,W', [(300, 20, 64, 8, 16), (160, 100, 128, 16, 16), (37, 100, 256, 24, 40)])
-def test_persistent_mask_conv_balanced_ranges_cross_frames(dev, B, N, C, H, W):
+def test_persistent_mask_conv_balanced_ranges_cross_frames(dev, monkeypatch, B, N, C, H, W, wide):
     """The persistent mask conv cuts the launch's tiles into 148 equal ranges: with 1-2 tiles per frame a CTA's range
     spans several frames (plane + bias swap per segment).  Must equal the SIMT engine up to 1-ulp bf16 roundings."""
     from vknet import _lib, ops
+    monkeypatch.setenv('VKN_MASK_WIDE', wide)        # '1': the pixels-as-N (256-pixel tile) form of the persistent kernel
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=64)
     sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=4))
     h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
@@ -542,13 +544,14 @@ def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H
     assert maxabs(outs['tc'][0][0], outs['warp'][0][0].cpu()) < 2e-4
 
 
-@pytest.mark.parametrize('thr', [0.5, 0.7])
-def test_loop_bitmask_handoff_equals_stagewise_modules(dev, monkeypatch, thr):
+@pytest.mark.parametrize('thr,wide', [(0.5, '0'), (0.7, '0'), (0.5, '1'), (0.7, '1')])
+def test_loop_bitmask_handoff_equals_stagewise_modules(dev, monkeypatch, thr, wide):
     """Frame batches: the one-call loop hands the thresholded BIT per (kernel, pixel) from a stage's mask conv to the next
     stage's pooling instead of bf16 logits.  It thresholds the bf16-rounded logit, so the results must equal the
     stage-by-stage module calls (which store and re-read the logits) bit for bit -- also for a non-default threshold."""
     import vknet
     monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    monkeypatch.setenv('VKN_MASK_WIDE', wide)
     B, N, C, H, W, S = 6, 100, 256, 96, 80, 3
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256, hard_mask_thr=thr)
     sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=70 + s)) for s in range(S)]

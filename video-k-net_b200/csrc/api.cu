@@ -137,7 +137,7 @@ static void carve(const VknShape &s, char *base, Layout &L) {
   L.a_split = take((size_t)3 * s.B * npad * C * 2);
   const size_t esz = s.x_dtype == VKN_BF16 ? 2 : 4;
   for (int i = 0; i < 2; ++i) L.mask_pp[i] = take((size_t)s.B * fps * s.N * HW * esz);
-  L.mask_bits = (uint32_t *)take((size_t)s.B * fps * s.N * (size_t)(ceil_div((int)HW, 128) * 4) * 4);
+  L.mask_bits = (uint32_t *)take((size_t)s.B * fps * s.N * (size_t)(ceil_div((int)HW, 256) * 8) * 4);
   for (int i = 0; i < 2; ++i) L.obj_pp[i] = (float *)take(P * C * f);
   L.cls_tmp = (float *)take(P * (size_t)s.num_classes * f);
   L.total = align_up(off, 256);
@@ -658,7 +658,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_rescale_masks_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }

@@ -707,10 +707,210 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   }
 }
 
+
+// ---- mask conv, wide form: pixels are the N operand ---------------------------------------------------------------
+// D[n, p] = sum_c a[n, c] x[c, p]:  A = one plane chunk [128 kernel rows x 64 ch] K-major (resident, as above; rows >= N are
+// whatever follows in shared memory and only produce accumulator ROWS >= N, never read), B = x tile [256 px x 64 ch] MN-major
+// straight from NCHW, accumulators [128 x 256 px] fp32 in TMEM, double-buffered (2 x 256 = all 512 columns).
+// Why: every tcgen05.mma re-reads its A and B tiles from shared memory; at N = 112 the 3-plane product needs
+// 48 x (4 KB + 3.5 KB) = 360 KB of operand reads per 128 pixels and the shared-memory pipe, not HBM, bounds the kernel.
+// With N = 256 the same pixels cost 24 x (4 KB + 8 KB) = 288 KB and the MMAs run at their full 128-column rate.
+// Epilogue: TMEM lane = kernel row, so a thread holds 32 CONSECUTIVE pixels of its row: bias is one register, the bf16
+// row segment leaves as 64 contiguous bytes (no transpose, no staging), the bit mask is packed in-thread (no ballots).
+constexpr int MW_TILE = 256;                 // pixels per tile
+constexpr int MW_XS = 2;                     // x ring depth (32 KB stages)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vkn_maskgemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
+                            const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N, int Npad,
+                            int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int total_tiles, int pf_dist,
+                            uint32_t *__restrict__ bits_out, int wpr, float thr) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nk = C / CH_BLK;
+  const uint32_t x_bytes = (uint32_t)CH_BLK * MW_TILE * 2u;             // 32 KB: four 64-px groups of [64 ch x 128 B]
+  const uint32_t a_plane = (uint32_t)((N + 7) & ~7) * 128u;
+  const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
+  uint8_t *xring = smem + planes_bytes;
+  uint64_t *bars = (uint64_t *)(xring + MW_XS * x_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  constexpr int PL_FREE = 1, X_FULL = 2, X_EMPTY = 2 + MW_XS, ACC_FULL = 2 + 2 * MW_XS, ACC_EMPTY = 2 + 2 * MW_XS + 2;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 + 2 * MW_XS + 4);
+  const uint32_t smem0 = smem_u32(smem), xring0 = smem_u32(xring);
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int ntiles = (HW + MW_TILE - 1) / MW_TILE;
+  const int g_lo = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int g_hi = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_x);
+      prefetch_tmap(&tmap_a);
+      mbar_init(bar0, 1);
+      mbar_init(bar0 + 8 * PL_FREE, 1);
+      for (int s = 0; s < MW_XS; ++s) {
+        mbar_init(bar0 + 8 * (X_FULL + s), 1);
+        mbar_init(bar0 + 8 * (X_EMPTY + s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(bar0 + 8 * (ACC_FULL + a), 1);
+        mbar_init(bar0 + 8 * (ACC_EMPTY + a), 4);                       // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512u);
+  }
+  pdl_wait();     // a_ext / the planes come from the previous kernel
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0, seg = 0;
+      uint32_t ph = 0;
+      for (int g = g_lo; g < g_hi; ++seg) {
+        const int b = g / ntiles, t0 = g - b * ntiles, kb = b / F;
+        const int t1 = min(ntiles, t0 + (g_hi - g));
+        if (seg > 0) mbar_wait(bar0 + 8 * PL_FREE, (uint32_t)(seg - 1) & 1u);     // MMAs of the previous frame retired
+        mbar_expect_tx(bar0, planes_bytes);
+        for (int c = 0; c < nk; ++c)
+          for (int t = 0; t < 3; ++t)
+            tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad);
+        for (int tile = t0; tile < t1; ++tile) {
+          const int p0 = tile * MW_TILE;
+          const int gp = g + (tile - t0) + pf_dist;                      // L2 prefetch of the tile pf_dist ahead
+          const bool pf = pf_dist > 0 && gp < g_hi;
+          const int bp = pf ? gp / ntiles : 0, pp = pf ? (gp - bp * ntiles) * MW_TILE : 0;
+          for (int c = 0; c < nk; ++c) {
+            if (pf) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) tma_prefetch_3d(&tmap_x, pp + 64 * q, c * CH_BLK, bp);
+            }
+            mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u);
+            mbar_expect_tx(bar0 + 8 * (X_FULL + s), x_bytes);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tma_load_3d(xring0 + s * x_bytes + q * (x_bytes / 4), &tmap_x, bar0 + 8 * (X_FULL + s), p0 + 64 * q, c * CH_BLK, b);
+            if (++s == MW_XS) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+        g += t1 - t0;
+      }
+    }
+  } else if (warp == 1) {
+    // warp-uniform issue loop, one elected lane issues (see elect_one() in tc.cuh)
+    const uint64_t adesc0 = umma_desc_sw128(smem0, 0, 1024);              // planes: K-major, 8-row groups 1024 B apart
+    const uint64_t bdesc0 = umma_desc_sw128(xring0, x_lbo, x_sbo);        // x: MN-major, 64-px groups x_lbo apart
+    const uint32_t a_plane16 = a_plane >> 4;
+    int s = 0;
+    uint32_t xph = 0, li = 0;
+    int seg = 0, seg_end = g_lo;
+    for (int g = g_lo; g < g_hi; ++g, ++li) {
+      if (g == seg_end) {                                    // new frame: its planes must have landed
+        const int b = g / ntiles;
+        seg_end = min(g_hi, (b + 1) * ntiles);
+        mbar_wait(bar0, (uint32_t)seg & 1u);
+        ++seg;
+      }
+      const bool seg_last = (g + 1 == seg_end);
+      const uint32_t buf = li & 1u;
+      mbar_wait(bar0 + 8 * (ACC_EMPTY + buf), ((li >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t dt = tmem_base + buf * (uint32_t)MW_TILE;
+      for (int c = 0; c < nk; ++c) {
+        mbar_wait(bar0 + 8 * (X_FULL + s), xph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)(c * 3) * a_plane16);
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)s * (x_bytes >> 4));
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#pragma unroll
+            for (int k = 0; k < CH_BLK / 16; ++k)
+              umma_bf16(dt, ad + (uint64_t)((uint32_t)t * a_plane16 + k * 2), bd + (uint64_t)(k * (2048 >> 4)), idesc,
+                        (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar0 + 8 * (X_EMPTY + s));
+          if (c == nk - 1) {
+            umma_commit(bar0 + 8 * (ACC_FULL + buf));
+            if (seg_last) umma_commit(bar0 + 8 * PL_FREE);
+          }
+        }
+        __syncwarp();
+        if (++s == MW_XS) {
+          s = 0;
+          xph ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int n = q * 32 + lane;                             // this thread's kernel row
+    float bias = 0.f;
+    int li = 0, seg_end = g_lo, b = 0, tile = 0;
+    for (int g = g_lo; g < g_hi; ++g, ++li, ++tile) {
+      if (g == seg_end) {
+        b = g / ntiles;
+        tile = g - b * ntiles;
+        seg_end = min(g_hi, (b + 1) * ntiles);
+        bias = (n < N) ? a_ext[((size_t)(b / F) * N + n) * lda + C] : 0.f;
+      }
+      const int buf = li & 1;
+      mbar_wait(bar0 + 8 * (ACC_FULL + buf), (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+      if (g + 1 == g_hi) pdl_trigger();
+      const size_t rowbase = ((size_t)b * N + (n < N ? n : 0));
+#pragma unroll 1
+      for (int c0 = 0; c0 < MW_TILE; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MW_TILE + c0), r);
+        if (c0 + 32 >= MW_TILE) {          // accumulators of this tile are in registers: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
+        }
+        const int p0 = tile * MW_TILE + c0;
+        if (n >= N) continue;
+        const int np = max(0, min(32, HW - p0));             // HW % 8 == 0: np is a multiple of 8
+        if (bits_out != nullptr) {                           // every word of the row is written (pixels >= HW as 0)
+          uint32_t word = 0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float v = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[e]) + bias));
+            word |= (e < np && v > thr) ? (1u << e) : 0u;
+          }
+          bits_out[rowbase * wpr + (size_t)tile * (MW_TILE / 32) + (c0 >> 5)] = word;
+        } else if (np > 0) {
+          uint32_t w[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2)
+            w[e >> 1] = bf16_bits(__uint_as_float(r[e]) + bias) | (bf16_bits(__uint_as_float(r[e + 1]) + bias) << 16);
+          __nv_bfloat16 *op = out + rowbase * HW + p0;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            if (2 * e < np) *reinterpret_cast<uint4 *>(op + 2 * e) = make_uint4(w[e], w[e + 1], w[e + 2], w[e + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 int maskgemm_tc_npad(const VknShape &s) { return npad_of(s.N); }
 
 // words of 32 pixel bits per (frame, kernel) row of the bit-mask hand-off: whole 128-pixel tiles
-int maskgemm_tc_bits_wpr(const VknShape &s) { return ceil_div(s.H * s.W, MASK_TILE_P) * (MASK_TILE_P / 32); }
+int maskgemm_tc_bits_wpr(const VknShape &s) { return ceil_div(s.H * s.W, MW_TILE) * (MW_TILE / 32); }
 // true when launch_maskgemm_tc takes the persistent kernel (the one that can emit the bit mask)
 bool maskgemm_tc_persistent(const VknShape &s) {
   if (!tc_supported(s)) return false;
@@ -756,6 +956,34 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   const bool persist = maskgemm_tc_persistent(s);                // several tiles per SM: keep the planes resident
   if (bits_out && !persist) VKN_FAIL(VKN_E_INVALID, "tcgen05 mask conv: the bit-mask output needs the persistent kernel");
   if (!bits_out && !out) VKN_FAIL(VKN_E_INVALID, "tcgen05 mask conv: no output");
+  const int rows8w = (s.N + 7) & ~7;
+  const size_t wsmem = (size_t)(s.C / CH_BLK) * 3 * rows8w * 128 + MW_XS * (size_t)CH_BLK * MW_TILE * 2 + (2 + 2 * MW_XS + 4) * 8 + 16 +
+                       1024 + 64;
+  // opt-in (VKN_MASK_WIDE=1): measured equal to the 128-pixel-tile kernel (163 us per 64 frames either way) -- both are
+  // bound by the bytes of x a CTA can keep in flight next to 160 KB of resident planes, not by the operand pipe
+  bool wide = false;
+  if (const char *e = getenv("VKN_MASK_WIDE")) wide = persist && wsmem <= 227 * 1024 && e[0] == '1';
+  if (wide) {
+    const int nt = ceil_div(HW, MW_TILE), total_tiles = nt * frames;
+    int pf_dist = 1;
+    if (const char *e = getenv("VKN_MASK_PF")) pf_dist = atoi(e);
+    const int grid_x = total_tiles < 148 ? total_tiles : 148;
+    {     // resident planes: whole 8-row atoms only
+      const uint64_t dims[2] = {(uint64_t)s.C, (uint64_t)3 * s.B * Npad};
+      const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)rows8w};
+      VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
+    }
+    static bool wattr = false;
+    if (!wattr) {
+      VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      wattr = true;
+    }
+    VKN_LAUNCH_MARK("vkn_maskgemm_tc_wide_kernel", stream);
+    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_wide_kernel, dim3(grid_x), dim3(TC_THREADS), wsmem, stream, tmx, tma, a_ext, lda,
+                             (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, MW_TILE, 0, 1), x_lbo, x_sbo, F,
+                             total_tiles, pf_dist, bits_out, maskgemm_tc_bits_wpr(s), s.mask_thr_logit));
+    return VKN_OK;
+  }
   if (persist) {
     const int total_tiles = ntiles * frames;
     int pf_dist = 1;                                         // L2 prefetch distance in tiles (VKN_MASK_PF; measured 0/1/2/4: 1 is best)
