@@ -454,10 +454,11 @@ constexpr int MP_ACC = 2;     // TMEM accumulator buffers (128 columns each)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
-                               const __grid_constant__ CUtensorMap tmap_o, const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
+                               const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_pf,
+                               const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
                                int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int MP_XS,
                                int total_tiles, int pf_dist, uint32_t *__restrict__ bits_out, int wpr, float thr,
-                               unsigned long long *dbg) {
+                               int stg_bytes, unsigned long long *dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
@@ -466,7 +467,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
   uint8_t *xring = smem + planes_bytes;                                 // (planes_bytes is a multiple of 1024)
   uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 2 x [32 kernels][128 px] bf16
-  uint64_t *bars = (uint64_t *)(stg_base + 2 * 32 * MASK_TILE_P * 2);
+  uint64_t *bars = (uint64_t *)(stg_base + stg_bytes);                  // (no staging in bit-mask mode: one more ring stage)
   const uint32_t bar0 = smem_u32(bars);
   // barriers: 0 planes_full | 1 planes_free | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a
   const int PL_FREE = 1, X_FULL = 2, X_EMPTY = 2 + MP_XS, ACC_FULL = 2 + 2 * MP_XS, ACC_EMPTY = 2 + 2 * MP_XS + MP_ACC;
@@ -490,6 +491,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       prefetch_tmap(&tmap_x);
       prefetch_tmap(&tmap_a);
       prefetch_tmap(&tmap_o);
+      prefetch_tmap(&tmap_pf);
       mbar_init(bar0, 1);
       mbar_init(bar0 + 8 * PL_FREE, 1);
       for (int s = 0; s < MP_XS; ++s) {
@@ -532,10 +534,9 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
           const bool pf = pf_dist > 0 && gp < g_hi;
           const int bp = pf ? gp / ntiles : 0, pp = pf ? (gp - bp * ntiles) * MASK_TILE_P : 0;
           for (int c = 0; c < nk; ++c) {
-            if (pf) {                                         // interleaved with the loads: one chunk ahead per chunk
-              tma_prefetch_3d(&tmap_x, pp, c * CH_BLK, bp);
-              tma_prefetch_3d(&tmap_x, pp + 64, c * CH_BLK, bp);
-            }
+            // interleaved with the loads: one chunk ahead per chunk.  The prefetch map is unswizzled with 256-byte rows
+            // (the whole 128-pixel tile per channel): half the TMA row requests of the two 128-byte-row load boxes
+            if (pf) tma_prefetch_3d(&tmap_pf, pp, c * CH_BLK, bp);
             MP_WAIT(w0, mbar_wait(bar0 + 8 * (X_EMPTY + s), ph ^ 1u));
             mbar_expect_tx(bar0 + 8 * (X_FULL + s), x_bytes);
             tma_load_3d(xring0 + s * x_bytes, &tmap_x, bar0 + 8 * (X_FULL + s), p0, c * CH_BLK, b);
@@ -995,8 +996,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)rows8};
       VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
     }
+    const int stg_bytes = bits_out ? 0 : 2 * 32 * MASK_TILE_P * 2;      // the bit-mask epilogue needs no staging box
     auto psmem_of = [&](int xs) {
-      return (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + xs * (size_t)CH_BLK * MASK_TILE_P * 2 + 2 * 32 * MASK_TILE_P * 2 +
+      return (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + xs * (size_t)CH_BLK * MASK_TILE_P * 2 + (size_t)stg_bytes +
              (2 + 2 * xs + 2 * MP_ACC) * 8 + 16 + 4 * 2 * 128 * 4 + 1024 + 64;
     };
     int xs_depth = MP_XS_MAX;
@@ -1015,10 +1017,16 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[3] = {(uint32_t)MASK_TILE_P, 32u, 1u};
       VKN_TRY(make_tmap_bf16_plain(&tmo, out ? out : x, dims, box));     // unused (never stored through) in bit-mask mode
     }
+    CUtensorMap tmpf;
+    {
+      const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)s.C, (uint64_t)frames};
+      const uint32_t box[3] = {(uint32_t)MASK_TILE_P, (uint32_t)CH_BLK, 1u};
+      VKN_TRY(make_tmap_bf16_plain(&tmpf, x, dims, box));
+    }
     VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x), dim3(TC_THREADS), psmem, stream, tmx, tma,
-                             tmo, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
+                             tmo, tmpf, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
                              x_lbo, x_sbo, F, xs_depth, total_tiles, pf_dist, bits_out, maskgemm_tc_bits_wpr(s), s.mask_thr_logit,
-                             debug_ts_slot()));
+                             stg_bytes, debug_ts_slot()));
     return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);
