@@ -4,17 +4,19 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A "step" = one pass of the hot path over one batch of synthetic input: ONE frame per rank
-(cfg1: N=100 kernels, C=256, 200x88 feature map, S=3 stages, bf16 storage), i.e. a clip of
-`--gpus` frames sharded one frame per GPU.  With more than one GPU the step also performs the one
-exchange frame sharding needs (all-gather of the last-stage kernels over NCCL + the
-`previous_type='ffn'` link block, cfg3).
+(cfg1: N=100 kernels, C=256, 200x88 feature map, S=3 stages, bf16 storage).  Frames are independent, so the
+throughput mode keeps VKN_STREAMS x VKN_BATCH (default 3 x 64) frames in flight per CUDA-graph launch and rank; the
+timed region runs whole launches (K rounded up to a multiple of 192 frames) and is scaled back to exactly K frames.
+With more than one GPU every launch also performs the one exchange frame sharding needs (all-gather of the
+last-stage kernels over NCCL + the `previous_type='ffn'` link block, cfg3).
 
   value     frames/s, whole job, inputs resident in HBM, CUDA-graph replay of the loop, CUDA-event timed,
             max over ranks.  Inputs rotate over R distinct sets whose footprint exceeds L2.
   e2e       same metric through the public API with HOST (pinned) inputs: H2D copies of x / kernels /
             masks and the D2H read of the result tuple are inside the timed region.
-  roofline  dominant kernel of the step, timed live with CUDA events on its launch stream
-            (vkn_profile_begin/end), algorithmic bytes / time vs the measured HBM peak.
+  roofline  the kernel family with the largest share of the step, timed live with CUDA events on its launch stream
+            (vkn_profile_begin/end): row GEMMs -> algorithmic FLOPs vs the measured dense-bf16 peak; pooling / mask conv
+            -> algorithmic bytes vs the measured HBM copy peak (all families under roofline.families).
   cpu_baseline  the CPU oracle port of the reference's PyTorch path (fp32, all host threads) on a bounded
             sample of the same workload.
 --impl reference runs ONLY that CPU arm (rank 0) and prints the same JSON line with "impl": "reference".

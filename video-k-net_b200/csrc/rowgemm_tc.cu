@@ -8,9 +8,12 @@
 //   D = [128 rows x BN] fp32 in TMEM; the three planes accumulate into the same tile (every bf16 x bf16 product is
 //       exact, so the result carries fp32-level accuracy: DESIGN.md section 4)
 //
-// Epilogue: thread = row (TMEM lane); bias (x rowscale), residual, ReLU; fp32 rows and / or bf16 planes for the next
-// GEMM, 32 columns per thread in registers, 16-byte stores.  Split-K over blockIdx.z; two
-// problems per launch.  Weight tiles and bias are prefetched BEFORE griddepcontrol.wait (PDL).
+// Persistent: min(#tiles, 148) CTAs walk tiles of 128 rows x BN columns (BN in {32..256} by a cost model in the launcher);
+// the TMA ring runs across tiles and the accumulator is double-buffered in TMEM.  Epilogue: thread = row (TMEM lane); bias
+// (x rowscale), residual, ReLU, optional fused LayerNorm; fp32 rows and / or bf16 planes for the next GEMM, 32 columns per
+// thread in registers, leaving through swizzled per-warp staging boxes and TMA stores (direct 256-bit stores when a tensor
+// map cannot describe the output).  Split-K and up to two problems per launch are folded into the tile list.  Weight tiles
+// of the first ring fill are issued BEFORE griddepcontrol.wait (PDL).
 #include "tc.cuh"
 
 namespace vkn {
