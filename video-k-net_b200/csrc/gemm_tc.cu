@@ -949,10 +949,7 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     attr = true;
   }
   // x operand (A, MN-major, SWIZZLE_128B): 64-px groups are 8192 B apart (LBO), 8-channel-row groups 1024 B (SBO)
-  uint32_t x_lbo = (uint32_t)CH_BLK * 128u, x_sbo = 1024u;
-  if (const char *e = getenv("VKN_DEBUG_SWAP_LBO_SBO")) {
-    if (e[0] == '1') { uint32_t t = x_lbo; x_lbo = x_sbo; x_sbo = t; }
-  }
+  const uint32_t x_lbo = (uint32_t)CH_BLK * 128u, x_sbo = 1024u;
   const int ntiles = ceil_div(HW, MASK_TILE_P), frames = s.B * F;
   const bool persist = maskgemm_tc_persistent(s);                // several tiles per SM: keep the planes resident
   if (bits_out && !persist) VKN_FAIL(VKN_E_INVALID, "tcgen05 mask conv: the bit-mask output needs the persistent kernel");
