@@ -461,3 +461,35 @@ def rescale_masks(masks, img_meta, mask_upsample_stride=1):
     m = F.interpolate(m.sigmoid(), size=tuple(img_meta['batch_input_shape'][:2]), mode='bilinear', align_corners=False)
     m = m[:, :, :h, :w]
     return F.interpolate(m, size=tuple(img_meta['ori_shape'][:2]), mode='bilinear', align_corners=False).squeeze(0)
+
+
+def panoptic_merge_joint(thing_masks, thing_labels, thing_scores, stuff_masks, stuff_labels, stuff_scores, num_thing_classes,
+                         instance_score_thr, overlap_thr):
+    """Score-weighted argmax merge of thing and stuff probability maps into one id map
+    (VideoKernelIterHead.merge_stuff_thing_stuff_joint, knet/video/kernel_iter_head.py:818-882; the shipped video configs set
+    merge_joint=True).  masks [K,H,W] / [M,H,W] probabilities, labels int, scores float.
+    Returns (panoptic_seg int32 [H,W], segments_info list of dicts, kept thing indices into the concatenated list)."""
+    masks = torch.cat([thing_masks, stuff_masks], 0).float()
+    scores = torch.cat([thing_scores, stuff_scores], 0).float()
+    labels = torch.cat([thing_labels, stuff_labels], 0)
+    owner = (scores.view(-1, 1, 1) * masks).argmax(0)               # the highest score-weighted probability wins a pixel
+    seg = torch.zeros(masks.shape[-2:], dtype=torch.int32)
+    info, kept, next_id = [], [], 0
+    for k in torch.argsort(-scores).tolist():
+        cls = int(labels[k])
+        thing = cls < num_thing_classes
+        if thing and float(scores[k]) < instance_score_thr:
+            continue
+        won = owner == k
+        area = int(won.sum())
+        full = int((masks[k] >= 0.5).sum())
+        if area == 0 or full == 0 or area / full < overlap_thr:
+            continue
+        next_id += 1
+        seg[won] = next_id
+        if thing:
+            info.append(dict(id=next_id, isthing=True, score=float(scores[k]), category_id=cls, instance_id=k))
+            kept.append(k)
+        else:
+            info.append(dict(id=next_id, isthing=False, category_id=cls - num_thing_classes + 1, area=area))
+    return seg, info, kept

@@ -154,6 +154,47 @@ def case_rescale(name, K, H, W, up, batch_shape, img_shape, ori_shape, seed):
     print(name, 'ok', tuple(seg.shape))
 
 
+def case_panoptic(name, K, M, H, W, num_thing, seed):
+    """Joint panoptic merge (merge_joint=True): the UNMODIFIED VideoKernelIterHead.merge_stuff_thing_stuff_joint
+    (knet/video/kernel_iter_head.py:818-882) on smooth random probability maps."""
+    import types
+    import torch.nn.functional as F
+    mod = ref_shim.load_video_iter_head()
+    g = torch.Generator().manual_seed(seed)
+
+    # a random partition of the image into K + M regions (argmax of smooth noise), each mask = a soft indicator of its region;
+    # a few masks are then replaced by near-duplicates of a neighbour so that the overlap rejection (:846-848) triggers
+    noise = F.interpolate(torch.randn(1, K + M, H // 4, W // 4, generator=g), size=(H, W), mode='bilinear', align_corners=False)[0]
+    region = noise.argmax(0)
+    soft = torch.stack([(region == i).float() for i in range(K + M)])
+    soft = F.avg_pool2d(soft.unsqueeze(0), 3, 1, 1)[0]
+    probs = torch.sigmoid(8.0 * (soft - 0.5)) * (0.6 + 0.4 * torch.rand(K + M, 1, 1, generator=g))
+    for dup in range(0, K + M, 5):
+        probs[dup] = 0.9 * probs[(dup + 1) % (K + M)]
+    thing_masks, stuff_masks = probs[:K].contiguous(), probs[K:].contiguous()
+    thing_scores, stuff_scores = torch.rand(K, generator=g), torch.rand(M, generator=g)
+    thing_labels = torch.randint(0, num_thing, (K,), generator=g)
+    stuff_labels = torch.arange(M) + num_thing                      # get_panoptic: stuff_inds + num_thing_classes (:625)
+    cfg = types.SimpleNamespace(instance_score_thr=0.25, overlap_thr=0.6, iou_thr=0.5, stuff_max_area=4096)
+    fake_self = types.SimpleNamespace(num_thing_classes=num_thing)
+    obj_t, obj_s = torch.arange(K).float().view(K, 1), torch.arange(K, K + M).float().view(M, 1)
+    (seg, info), kept_obj = mod.VideoKernelIterHead.merge_stuff_thing_stuff_joint(
+        fake_self, thing_masks, thing_labels, thing_scores, stuff_masks, stuff_labels, stuff_scores, cfg, obj_t, obj_s)
+    rows = np.array([[d['id'], int(d['isthing']), d['category_id'], d.get('instance_id', -1), d.get('area', -1)] for d in info],
+                    dtype=np.int64).reshape(-1, 5)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), thing_masks=thing_masks.numpy(), stuff_masks=stuff_masks.numpy(),
+                        thing_scores=thing_scores.numpy(), stuff_scores=stuff_scores.numpy(), thing_labels=thing_labels.numpy(),
+                        stuff_labels=stuff_labels.numpy(), seg=seg, info=rows, kept=kept_obj.view(-1).long().numpy(),
+                        meta=np.array([K, M, H, W, num_thing], dtype=np.int64), thr=np.array([0.25, 0.6]))
+    print(name, 'ok', seg.shape, len(info), 'segments')
+
+
+def main_panoptic():
+    os.makedirs(OUT, exist_ok=True)
+    case_panoptic('panoptic_joint_k12_m5_40x64', 12, 5, 40, 64, 2, 21)
+    case_panoptic('panoptic_joint_k20_m9_32x48', 20, 9, 32, 48, 2, 22)
+
+
 def main_rescale():
     os.makedirs(OUT, exist_ok=True)
     case_rescale('rescale_k5_12x20_up2_96x160_crop90x150_to47x83', 5, 12, 20, 2, (96, 160), (90, 150), (47, 83), 11)
@@ -175,6 +216,7 @@ def main():
     case_video('video_link_cov_ffn_b1_n12_c64_9x11', 1, 12, 64, 9, 11, 128, 5, 6, 'ffn', 'update_dynamic_cov')
     case_init('init_b2_n20_c64_12x16', 2, 20, 64, 12, 16, 10)
     main_rescale()
+    main_panoptic()
 
 
 if __name__ == '__main__':
@@ -182,6 +224,8 @@ if __name__ == '__main__':
         main_clip()
     elif len(sys.argv) > 1 and sys.argv[1] == 'rescale':
         main_rescale()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'panoptic':
+        main_panoptic()
     else:
         main()
         import subprocess

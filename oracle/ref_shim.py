@@ -241,6 +241,31 @@ def _load_file(modname, relpath):
     return mod
 
 
+def load_video_iter_head():
+    """knet/video/kernel_iter_head.py (VideoKernelIterHead: get_panoptic and the merge_* post-processing) by path.
+    Its two extra imports are stubbed for the duration of the import only: mmdet's BaseRoIHead (an nn.Module base class
+    here) and knet.det.mask_pseudo_sampler (training-side, unused by the post-processing)."""
+    install()
+    saved = {k: sys.modules.get(k) for k in ('mmdet.models.roi_heads', 'knet', 'knet.det', 'knet.det.mask_pseudo_sampler')}
+    rh = types.ModuleType('mmdet.models.roi_heads')
+    rh.BaseRoIHead = nn.Module
+    sys.modules['mmdet.models.roi_heads'] = rh
+    for name in ('knet', 'knet.det', 'knet.det.mask_pseudo_sampler'):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    sys.modules['knet.det.mask_pseudo_sampler'].MaskPseudoSampler = type('MaskPseudoSampler', (), {})
+    try:
+        mod = _load_file('_ref_knet.video.kernel_iter_head', 'knet/video/kernel_iter_head.py')
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
 def load(tree='knet'):
     """Import the reference hot-path modules verbatim.  `tree` is 'knet' or 'knet_vis'
     (they register the same registry keys, so use one per process)."""

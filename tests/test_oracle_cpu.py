@@ -128,3 +128,29 @@ def test_oracle_matches_reference_fixtures_rescale_masks(path):
     got = ko.rescale_masks(torch.from_numpy(z['masks']), meta, up)
     assert got.shape == (K, Ho, Wo)
     assert (got - torch.from_numpy(z['seg'])).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize('path', golden_files('panoptic_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_oracle_matches_reference_fixtures_panoptic_merge(path):
+    """Next part of row 8f-2 (not yet on the GPU): the joint score-weighted argmax merge.  Oracle restatement == the
+    reference's merge_stuff_thing_stuff_joint outputs (id map, segment table, kept thing indices)."""
+    import numpy as np
+    z = np.load(path)
+    K, M, H, W, nthing = (int(v) for v in z['meta'])
+    t = {k: torch.from_numpy(z[k]) for k in ('thing_masks', 'stuff_masks', 'thing_scores', 'stuff_scores', 'thing_labels',
+                                             'stuff_labels')}
+    seg, info, kept = ko.panoptic_merge_joint(t['thing_masks'], t['thing_labels'], t['thing_scores'], t['stuff_masks'],
+                                              t['stuff_labels'], t['stuff_scores'], nthing, float(z['thr'][0]), float(z['thr'][1]))
+    assert np.array_equal(seg.numpy(), z['seg'])
+    rows = np.array([[d['id'], int(d['isthing']), d['category_id'], d.get('instance_id', -1), d.get('area', -1)] for d in info],
+                    dtype=np.int64).reshape(-1, 5)
+    assert np.array_equal(rows, z['info'])
+    assert kept == z['kept'].tolist()
+    assert len(info) >= 10 and any(not d['isthing'] for d in info) and len(info) < K + M      # fixtures exercise every branch
+
+
+def test_no_cpu_path_for_the_post_loop_ops(built_lib):
+    from vknet import _lib, ops
+    meta = dict(img_shape=(8, 8, 3), batch_input_shape=(8, 8), ori_shape=(8, 8, 3))
+    with pytest.raises(_lib.VknError):
+        ops.rescale_masks(torch.zeros(2, 4, 4), meta)
