@@ -181,20 +181,15 @@ class _HeadBase(nn.Module):
         return self.segm2result(seg_masks, labels_per_img, scores_per_img)
 
     def segm2result(self, mask_preds, det_labels, cls_scores):
-        """:469-483 (host-side result packing, unchanged semantics)."""
+        """Result packing of knet/det/kernel_update_head.py:469-483: per class, the score-only pseudo boxes [n_c, 5] and the
+        list of that class's masks (in input order)."""
         import numpy as np
-        num_classes = self.num_classes
-        segm_result = [[] for _ in range(num_classes)]
-        mask_preds = mask_preds.cpu().numpy()
-        det_labels = det_labels.cpu().numpy()
-        cls_scores = cls_scores.cpu().numpy()
-        num_ins = mask_preds.shape[0]
-        bboxes = np.zeros((num_ins, 5), dtype=np.float32)       # fake bboxes, score in the last column
-        bboxes[:, -1] = cls_scores
-        bbox_result = [bboxes[det_labels == i, :] for i in range(num_classes)]
-        for idx in range(num_ins):
-            segm_result[det_labels[idx]].append(mask_preds[idx])
-        return bbox_result, segm_result
+        masks = mask_preds.cpu().numpy()
+        labels = det_labels.cpu().numpy()
+        boxes = np.zeros((labels.shape[0], 5), dtype=np.float32)
+        boxes[:, 4] = cls_scores.cpu().numpy()
+        per_class = [np.flatnonzero(labels == c) for c in range(self.num_classes)]
+        return [boxes[idx] for idx in per_class], [[masks[i] for i in idx] for idx in per_class]
 
     def loss(self, *args, **kwargs):
         raise NotImplementedError('training (loss/get_targets) is outside this package: inference hot path only')
