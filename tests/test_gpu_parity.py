@@ -11,6 +11,7 @@ import torch
 
 import knet_oracle as ko
 from helpers import build_heads, golden_files, load_golden, maxabs, top2_gap
+from vknet import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -607,6 +608,40 @@ def test_row_engine_tc_fused_layernorm_epilogue(dev, monkeypatch):
             assert maxabs(got[i], base[i]) <= 5e-5 * max(1.0, base[i].float().abs().max().item())
         # mask logits are rounded to bf16 at the boundary: one-ulp flips at most
         assert maxabs(got[1], base[1]) <= 2 ** -7 * base[1].float().abs().max().item()
+        want = ko.kernel_update_head_forward(sd, cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
+        assert maxabs(got[0], want[0]) < TOL_BF16 and maxabs(got[2], want[2]) < TOL_BF16
+
+
+@pytest.mark.parametrize('B,N,C,H,W,Fh', [(3, 100, 256, 8, 16, 512), (2, 37, 128, 8, 16, 128), (5, 117, 256, 8, 16, 2048),
+                                         # 20 000 rows = 157 row tiles on 148 CTAs: some CTAs walk the program twice
+                                         (200, 100, 64, 8, 8, 64)])
+def test_row_engine_chain_kernel_equals_separate_launches(dev, monkeypatch, B, N, C, H, W, Fh):
+    """Chain form (default): the row operators between pooling / attention / mask conv run as ONE kernel per segment, a CTA
+    per 128-row tile walking the operator program (vkn_chain_tc_kernel).  Same arithmetic as one launch per operator
+    (VKN_CHAIN=0) up to the summation order of the second FFN Linear (whole K in one pass instead of split-K)."""
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=Fh)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=41))
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=42)
+    xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
+    monkeypatch.setenv('VKN_CHAIN', '0')
+    monkeypatch.setenv('VKN_RG_FUSE_LN', '1')
+    with _lib.profile() as prof0:
+        base = [t.clone() for t in h(xb, pfd, mb)]
+    monkeypatch.setenv('VKN_CHAIN', '1')
+    with _lib.profile() as prof1:
+        got = [t.clone() for t in h(xb, pfd, mb)]
+    again = h(xb, pfd, mb)
+    names0, names1 = [n for n, _ in prof0.records], [n for n, _ in prof1.records]
+    assert names1.count('vkn_chain_tc_kernel') == 2 and 'vkn_rowgemm_tc_kernel' not in names1, names1
+    assert 'vkn_chain_tc_kernel' not in names0 and len(names1) <= 6 < len(names0), (names0, names1)
+    for a, b in zip(got, again):
+        assert torch.equal(a, b), 'chain kernel must be deterministic'
+    for i in (0, 2):
+        assert maxabs(got[i], base[i]) <= 5e-5 * max(1.0, base[i].float().abs().max().item())
+    assert maxabs(got[1], base[1]) <= 2 ** -7 * base[1].float().abs().max().item()
+    if B <= 8:
         want = ko.kernel_update_head_forward(sd, cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
         assert maxabs(got[0], want[0]) < TOL_BF16 and maxabs(got[2], want[2]) < TOL_BF16
 

@@ -168,8 +168,20 @@ struct Ctx {
   int P;
   bool use_tc;
   bool rows_tc;     // row operators on the tcgen05 row engine (planes handed between launches)
-  bool fuse_ln;     // row engine: LayerNorms fused into the GEMM epilogues (VKN_RG_FUSE_LN=1; measured slower so far)
+  bool fuse_ln;     // row engine: LayerNorms fused into the GEMM epilogues (always in chain form; VKN_RG_FUSE_LN=1 forces it for separate launches)
+  bool chain_on;    // row engine: the row operators between two attentions run as ONE chain kernel (VKN_CHAIN=0: one launch per operator)
+  ChainBuild *chain;  // the chain being assembled (null: every operator launches immediately)
 };
+
+// Row-engine operators either launch at once or join the chain under construction; emit_flush launches the chain.
+static int emit_gemm(Ctx &c, const LinArgs *p, int n) {
+  return c.chain ? chain_add_gemm(c.chain, p, n) : launch_linear_tc(p, n, c.st);
+}
+static int emit_rowprep(Ctx &c, const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int M, int K) {
+  return c.chain ? chain_add_rowprep(c.chain, src, out, ldo, planes, ldp, plane_stride, K)
+                 : launch_rowprep(src, out, ldo, planes, ldp, plane_stride, M, K, c.st);
+}
+static int emit_flush(Ctx &c) { return c.chain ? chain_launch(c.chain, c.st) : VKN_OK; }
 
 static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, Ctx &c) {
   VKN_TRY(check_shape(s));
@@ -194,6 +206,11 @@ static int make_ctx(const VknShape *s, void *ws, size_t ws_bytes, void *stream, 
     const char *e = getenv("VKN_RG_FUSE_LN");
     c.fuse_ln = e && e[0] == '1';
   }
+  {
+    const char *e = getenv("VKN_CHAIN");
+    c.chain_on = c.rows_tc && !(e && e[0] == '0');
+  }
+  c.chain = nullptr;
   return VKN_OK;
 }
 
@@ -460,6 +477,10 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   const long long PS = (long long)P * C;
   void *PLA = c.L.pl[0], *PLB = c.L.pl[1], *PLC = c.L.pl[2], *PLD = c.L.pl[3];
   if (obj_planes_out == nullptr) obj_planes_out = c.L.obj_pl[0];
+  // Chain form: everything between the pooled feature and the attention, and between the attention and the mask conv,
+  // is ONE launch each (a CTA per 128-row tile walks the operators by itself); LayerNorms live in the GEMM epilogues.
+  const bool fuse_ln = c.fuse_ln || c.chain_on;
+  if (c.chain_on) c.chain = chain_begin(P);
   // a3+a4 (+a2 folded): pooled feature -> x_feat fp32 + planes (PLB)
   if (x_feat_in == nullptr) {
     float *xf = x_feat_out ? x_feat_out : c.L.xp;
@@ -470,13 +491,13 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     LinArgs a = lin(src_planes(PLA, C, PS), w.ft_w, C, w.ft_b, xf, C, P, C, C, EPI_ROWSCALE);
     a.rowscale = c.L.cnt;
     out_planes(a, PLB, P, C);
-    VKN_TRY(launch_linear_tc(&a, 1, c.st));
+    VKN_TRY(emit_gemm(c, &a, 1));
   } else {
     float *copy_to = (x_feat_out && x_feat_out != x_feat_in) ? x_feat_out : nullptr;
-    VKN_TRY(launch_rowprep(src_copy(x_feat_in, C), copy_to, C, PLB, C, PS, P, C, c.st));
+    VKN_TRY(emit_rowprep(c, src_copy(x_feat_in, C), copy_to, C, PLB, C, PS, P, C));
   }
   if (pf_planes == nullptr) {
-    VKN_TRY(launch_rowprep(src_copy(pf, C), nullptr, 0, PLC, C, PS, P, C, c.st));
+    VKN_TRY(emit_rowprep(c, src_copy(pf, C), nullptr, 0, PLC, C, PS, P, C));
     pf_planes = PLC;
   }
   // a5 KernelUpdator (kernel_updator.py:56-94)
@@ -484,17 +505,17 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   LinArgs two[2];
   two[0] = lin(src_planes(PLB, C, PS), u.dyn_w, C, u.dyn_b, c.L.dyn, 2 * C, P, 2 * C, C, 0);          // :59
   two[1] = lin(src_planes(pf_planes, C, PS), u.inp_w, C, u.inp_b, c.L.inp, 2 * C, P, 2 * C, C, 0);    // :65-66
-  VKN_TRY(launch_linear_tc(two, 2, c.st));
+  VKN_TRY(emit_gemm(c, two, 2));
   RowSrc g;
   memset(&g, 0, sizeof(g));
   g.pro = PRO_MUL;                                                                                     // :70
   g.nsum = 1;
   g.a[0] = c.L.inp;  g.lda[0] = 2 * C;
   g.a[1] = c.L.dyn;  g.lda[1] = 2 * C;
-  VKN_TRY(launch_rowprep(g, nullptr, 0, PLA, C, PS, P, C, c.st));
+  VKN_TRY(emit_rowprep(c, g, nullptr, 0, PLA, C, PS, P, C));
   two[0] = lin(src_planes(PLA, C, PS), u.ig_w, C, u.ig_b, c.L.igp, C, P, C, C, 0);                    // :74
   two[1] = lin(src_planes(PLA, C, PS), u.ug_w, C, u.ug_b, c.L.ugp, C, P, C, C, 0);                    // :75
-  VKN_TRY(launch_linear_tc(two, 2, c.st));
+  VKN_TRY(emit_gemm(c, two, 2));
   RowSrc gt;
   memset(&gt, 0, sizeof(gt));
   gt.pro = PRO_GATE;                                                                                   // :76-88
@@ -503,26 +524,27 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   gt.a[1] = c.L.dyn + C;   gt.lda[1] = 2 * C;  gt.ln_g[1] = u.norm_out_g;   gt.ln_b[1] = u.norm_out_b;
   gt.a[2] = c.L.igp;       gt.lda[2] = C;      gt.ln_g[2] = u.inorm_in_g;   gt.ln_b[2] = u.inorm_in_b;
   gt.a[3] = c.L.inp + C;   gt.lda[3] = 2 * C;  gt.ln_g[3] = u.inorm_out_g;  gt.ln_b[3] = u.inorm_out_b;
-  VKN_TRY(launch_rowprep(gt, nullptr, 0, PLB, C, PS, P, C, c.st));
-  if (c.fuse_ln) {
+  VKN_TRY(emit_rowprep(c, gt, nullptr, 0, PLB, C, PS, P, C));
+  if (fuse_ln) {
     // :90-92  fc_layer -> fc_norm -> ReLU in one launch (LayerNorm fused in the GEMM epilogue): o (fp32) + planes PLA
     LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.o, C, P, C, C, EPI_LN | EPI_RELU);
     f.ln_g = u.fc_norm_g;
     f.ln_b = u.fc_norm_b;
     out_planes(f, PLA, P, C);
-    VKN_TRY(launch_linear_tc(&f, 1, c.st));
+    VKN_TRY(emit_gemm(c, &f, 1));
   } else {
     LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.fc, C, P, C, C, 0);                  // :90
-    VKN_TRY(launch_linear_tc(&f, 1, c.st));
-    VKN_TRY(launch_rowprep(src_ln(c.L.fc, C, u.fc_norm_g, u.fc_norm_b, true), c.L.o, C, PLA, C, PS, P, C, c.st));   // :91-92
+    VKN_TRY(emit_gemm(c, &f, 1));
+    VKN_TRY(emit_rowprep(c, src_ln(c.L.fc, C, u.fc_norm_g, u.fc_norm_b, true), c.L.o, C, PLA, C, PS, P, C));   // :91-92
   }
   // a6 MHSA + LN (kernel_update_head.py:204-208)
   LinArgs qkv = lin(src_planes(PLA, C, PS), w.attn.in_w, C, w.attn.in_b, c.L.qkv, 3 * C, P, 3 * C, C, 0);
-  VKN_TRY(launch_linear_tc(&qkv, 1, c.st));
+  VKN_TRY(emit_gemm(c, &qkv, 1));
+  VKN_TRY(emit_flush(c));
   VKN_TRY(launch_attention(c.L.qkv, 3 * C, c.L.qkv + C, 3 * C, c.L.qkv + 2 * C, 3 * C, nullptr, C, c.s.B, c.s.N, C,
                            c.s.num_heads, c.st, PLB, PS));
   float *obj_dst = obj ? obj : c.L.obj_tmp;
-  if (c.fuse_ln) {
+  if (fuse_ln) {
     // out-projection + residual + attention_norm in one launch (:206-208)
     LinArgs op = lin(src_planes(PLB, C, PS), w.attn.out_w, C, w.attn.out_b, c.s.with_ffn ? c.L.o2 : obj_dst, C, P, C, C,
                      EPI_RES | EPI_LN);
@@ -531,21 +553,31 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     op.ln_g = w.attn.norm_g;
     op.ln_b = w.attn.norm_b;
     out_planes(op, c.s.with_ffn ? PLA : obj_planes_out, P, C);
-    VKN_TRY(launch_linear_tc(&op, 1, c.st));
+    VKN_TRY(emit_gemm(c, &op, 1));
   } else {
     LinArgs op = lin(src_planes(PLB, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.y, C, P, C, C, EPI_RES);
     op.res = c.L.o;
     op.ldres = C;
-    VKN_TRY(launch_linear_tc(&op, 1, c.st));
+    VKN_TRY(emit_gemm(c, &op, 1));
     RowSrc an = src_ln(c.L.y, C, w.attn.norm_g, w.attn.norm_b, false);
-    if (c.s.with_ffn) VKN_TRY(launch_rowprep(an, c.L.o2, C, PLA, C, PS, P, C, c.st));
-    else VKN_TRY(launch_rowprep(an, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
+    if (c.s.with_ffn) VKN_TRY(emit_rowprep(c, an, c.L.o2, C, PLA, C, PS, P, C));
+    else VKN_TRY(emit_rowprep(c, an, obj_dst, C, obj_planes_out, C, PS, P, C));
   }
   if (c.s.with_ffn) {
     // a7 FFN + LN (:214-215)
     LinArgs f1 = lin(src_planes(PLA, C, PS), w.ffn.w1, C, w.ffn.b1, nullptr, F, P, F, C, EPI_RELU | EPI_NOOUT);
     out_planes(f1, c.L.h, P, F);
-    VKN_TRY(launch_linear_tc(&f1, 1, c.st));
+    VKN_TRY(emit_gemm(c, &f1, 1));
+    if (c.chain) {
+      // second Linear over the whole K in one tile pass: + b2 + residual, ffn_norm in the epilogue -> obj_feat + its planes
+      LinArgs f2 = lin(src_planes(c.L.h, F, (long long)P * F), w.ffn.w2, F, w.ffn.b2, obj_dst, C, P, C, F, EPI_RES | EPI_LN);
+      f2.res = c.L.o2;
+      f2.ldres = C;
+      f2.ln_g = w.ffn.norm_g;
+      f2.ln_b = w.ffn.norm_b;
+      out_planes(f2, obj_planes_out, P, C);
+      VKN_TRY(emit_gemm(c, &f2, 1));
+    } else {
     LinArgs f2 = lin(src_planes(c.L.h, F, (long long)P * F), w.ffn.w2, F, nullptr, c.L.zpart, C, P, C, F, 0);
     const int nk = ceil_div(F, 64);
     int ksp = 148 / (ceil_div(P, 128) * ceil_div(C, 256));      // K slices: fill the SMs with 128 x 256 tiles
@@ -553,14 +585,15 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     while (ksp > 1 && (nk % ksp != 0 || nk / ksp < 4)) ksp /= 2;
     f2.ksplit = ksp;
     f2.out_split_stride = PS;
-    VKN_TRY(launch_linear_tc(&f2, 1, c.st));
+    VKN_TRY(emit_gemm(c, &f2, 1));
     RowSrc r = src_ln(c.L.zpart, C, w.ffn.norm_g, w.ffn.norm_b, false);
     r.nsum = ksp;
     r.sum_stride = PS;
     r.pbias = w.ffn.b2;
     r.pres = c.L.o2;
     r.ldpres = C;
-    VKN_TRY(launch_rowprep(r, obj_dst, C, obj_planes_out, C, PS, P, C, c.st));
+    VKN_TRY(emit_rowprep(c, r, obj_dst, C, obj_planes_out, C, PS, P, C));
+    }
   }
   // a8 heads (:217-227)
   if (w.num_cls_fcs < 0 || w.num_cls_fcs > VKN_MAX_FCS || w.num_mask_fcs < 0 || w.num_mask_fcs > VKN_MAX_FCS)
@@ -571,16 +604,16 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   const void *cs = obj_planes_out, *ms = obj_planes_out;
   for (int i = 0; i < depth; ++i) {
     int n = 0;
-    if (!c.fuse_ln) {
+    if (!fuse_ln) {
       if (i < ncls_fcs) two[n++] = lin(src_planes(cs, C, PS), w.cls_fc_w[i], C, nullptr, c.L.pre_c[0], C, P, C, C, 0);
       if (i < w.num_mask_fcs) two[n++] = lin(src_planes(ms, C, PS), w.mask_fc_w[i], C, nullptr, c.L.pre_m[0], C, P, C, C, 0);
-      VKN_TRY(launch_linear_tc(two, n, c.st));
+      VKN_TRY(emit_gemm(c, two, n));
       if (i < ncls_fcs) {
-        VKN_TRY(launch_rowprep(src_ln(c.L.pre_c[0], C, w.cls_ln_g[i], w.cls_ln_b[i], true), nullptr, 0, PLA, C, PS, P, C, c.st));
+        VKN_TRY(emit_rowprep(c, src_ln(c.L.pre_c[0], C, w.cls_ln_g[i], w.cls_ln_b[i], true), nullptr, 0, PLA, C, PS, P, C));
         cs = PLA;
       }
       if (i < w.num_mask_fcs) {
-        VKN_TRY(launch_rowprep(src_ln(c.L.pre_m[0], C, w.mask_ln_g[i], w.mask_ln_b[i], true), nullptr, 0, PLB, C, PS, P, C, c.st));
+        VKN_TRY(emit_rowprep(c, src_ln(c.L.pre_m[0], C, w.mask_ln_g[i], w.mask_ln_b[i], true), nullptr, 0, PLB, C, PS, P, C));
         ms = PLB;
       }
       continue;
@@ -599,15 +632,19 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
       two[n].ln_b = w.mask_ln_b[i];
       out_planes(two[n++], PLB, P, C);
     }
-    VKN_TRY(launch_linear_tc(two, n, c.st));
+    VKN_TRY(emit_gemm(c, two, n));
     if (i < ncls_fcs) cs = PLA;
     if (i < w.num_mask_fcs) ms = PLB;
   }
   two[0] = lin(src_planes(ms, C, PS), w.fc_mask_w, C, w.fc_mask_b, c.L.mk, C, P, C, C, 0);
   out_planes(two[0], PLD, P, C);
   if (with_cls) two[1] = lin(src_planes(cs, C, PS), w.fc_cls_w, C, w.fc_cls_b, cls, c.s.num_classes, P, c.s.num_classes, C, 0);
-  VKN_TRY(launch_linear_tc(two, with_cls ? 2 : 1, c.st));
-  if (new_mask == nullptr && mask_bits_out == nullptr) return VKN_OK;
+  VKN_TRY(emit_gemm(c, two, with_cls ? 2 : 1));
+  if (new_mask == nullptr && mask_bits_out == nullptr) {
+    VKN_TRY(emit_flush(c));
+    c.chain = nullptr;
+    return VKN_OK;
+  }
   // a9 (+a2 folded): a = mk . ft_w (planes for the mask conv), bias column mk . ft_b
   const int lda = C + A_EXT_PAD;
   LinArgs a = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, c.L.a_ext, lda, P, C + 1, C, EPI_SPLIT3);
@@ -616,7 +653,9 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   a.split_N = c.s.N;
   a.split_Npad = maskgemm_tc_npad(c.s);
   a.split_C = C;
-  VKN_TRY(launch_linear_tc(&a, 1, c.st));
+  VKN_TRY(emit_gemm(c, &a, 1));
+  VKN_TRY(emit_flush(c));
+  c.chain = nullptr;
   return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st, mask_bits_out);
 }
 
@@ -658,7 +697,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_rescale_masks_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }

@@ -199,6 +199,13 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
 // tcgen05 row GEMM (rowgemm_tc.cu): same contract as launch_linear for PRO_PLANES inputs and bf16 weights
 bool linear_tc_supported(const LinArgs &a);
 int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream);
+// chain form (rowgemm_tc.cu): a sequence of row GEMMs / row transforms over the same rows in ONE launch, a CTA per 128-row tile
+struct ChainBuild;
+ChainBuild *chain_begin(int M);
+bool chain_empty(const ChainBuild *b);
+int chain_add_gemm(ChainBuild *b, const LinArgs *probs, int nprob);
+int chain_add_rowprep(ChainBuild *b, const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int K);
+int chain_launch(ChainBuild *b, cudaStream_t stream);
 // SIMT fp32 engines for the two big contractions (gemm_simt.cu)
 int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
                      int *nchunks, cudaStream_t stream);

@@ -15,6 +15,7 @@
 // map cannot describe the output).  Split-K and up to two problems per launch are folded into the tile list.  Weight tiles
 // of the first ring fill are issued BEFORE griddepcontrol.wait (PDL).
 #include "tc.cuh"
+#include "rowops.cuh"
 
 namespace vkn {
 
@@ -115,13 +116,13 @@ __device__ __forceinline__ void rg_chunk_load(const RgProb &P, const RgRowCtx &R
       if (R.res_vec && nc == 32) {
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4 *>(rp + e));
+          const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(rp + e));
           add[e] += t4.x; add[e + 1] += t4.y; add[e + 2] += t4.z; add[e + 3] += t4.w;
         }
       } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e)
-          if (e < nc) add[e] += __ldg(rp + e);
+          if (e < nc) add[e] += __ldcg(rp + e);
       }
     }
   }
@@ -220,6 +221,120 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
           if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
       }
     }
+  }
+}
+
+// Epilogue of ONE accumulator tile (rows [row0, row0+128) x columns [col0, col0+BN) of problem P, K slice ks), executed by
+// the 8 epilogue warps: thread = row (TMEM lane), the two warps of a lane quarter take alternate 32-column blocks.
+// `tacc` = TMEM address of the accumulator buffer (column base), `acc_empty` = barrier that hands it back to the MMA warp
+// (one arrive per warp, as soon as its share is in registers), `stg` = this warp's TMA-store staging, `st_base` = fused-
+// LayerNorm scratch of this accumulator buffer ([128 rows][8] floats).
+__device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int col0, int ks, int BN, uint32_t tacc_base,
+                                                 uint32_t acc_empty, uint32_t stg, uint32_t pl_off, float *st_base, int warp,
+                                                 int lane, int nthreads_epi) {
+  const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+  const int half = (warp - 2) >> 2;                       // 0: even column blocks, 1: odd
+  RgRowCtx R;
+  R.epi = P.epi;
+  R.row = row0 + q * 32 + lane;
+  R.live = R.row < P.M;
+  R.row_base = row0 + q * 32;
+  R.ks = ks;
+  R.stg = stg;
+  R.pl_off = pl_off;
+  R.outp = P.out + (size_t)ks * P.out_split_stride;
+  R.out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(R.outp) & 31) == 0);
+  R.res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
+  R.pl_vec = (P.split_C % 16 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 31) == 0) && (P.plane_elems % 16 == 0);
+  R.bias_vec = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0;
+  R.rs = (R.live && (R.epi & EPI_ROWSCALE)) ? __ldcg(P.rowscale + R.row) : 1.f;
+  R.prow = (size_t)R.row;                               // row of the plane buffer this thread writes
+  if ((R.epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
+    const int b = R.row / P.split_N;
+    R.prow = (size_t)b * P.split_Npad + (R.row - b * P.split_N);
+  }
+  const uint32_t tacc = tacc_base + ((uint32_t)(q * 32) << 16);
+  int last_c0 = half * 32;                              // last column block this warp reads from TMEM
+  while (last_c0 + 64 < BN && col0 + last_c0 + 64 < P.N) last_c0 += 64;
+  const bool any = half * 32 < BN && col0 + half * 32 < P.N;   // this warp owns at least one column block
+  if (R.epi & EPI_LN) {
+    // ---- fused LayerNorm: the tile spans the row (host: nt == 1); the two warps of a lane quarter own alternate
+    //      32-column blocks, so each thread reduces its blocks (shifted sums: no cancellation), the pair merges
+    //      (count, mean, M2) through shared memory, then a second pass over TMEM normalises and stores.
+    float K0 = 0.f, S1 = 0.f, S2 = 0.f, cntf = 0.f;
+    bool first = true;
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
+      const int nc = min(32, P.N - col);
+      float v[32];
+      rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v);
+      if (first) {
+        K0 = v[0];
+        first = false;
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nc) {
+          const float d = v[e] - K0;
+          S1 += d;
+          S2 = fmaf(d, d, S2);
+        }
+      cntf += (float)nc;
+    }
+    float mean_h = 0.f, m2_h = 0.f;
+    if (cntf > 0.f) {
+      mean_h = K0 + S1 / cntf;
+      m2_h = S2 - S1 * S1 / cntf;
+    }
+    float *st = st_base + (size_t)(q * 32 + lane) * 8;
+    st[half * 4 + 0] = cntf;
+    st[half * 4 + 1] = mean_h;
+    st[half * 4 + 2] = m2_h;
+    named_bar_sync(1, nthreads_epi);
+    const float cb = st[(half ^ 1) * 4 + 0], mb = st[(half ^ 1) * 4 + 1], m2b = st[(half ^ 1) * 4 + 2];
+    // merge in a fixed order (half 0 first) so both threads of a row get identical statistics
+    const float n0 = half ? cb : cntf, mu0 = half ? mb : mean_h, q0 = half ? m2b : m2_h;
+    const float n1 = half ? cntf : cb, mu1 = half ? mean_h : mb, q1 = half ? m2_h : m2b;
+    const float nn = n0 + n1, delta = mu1 - mu0;
+    const float mean = mu0 + delta * (n1 / nn);
+    const float var = (q0 + q1 + delta * delta * (n0 * n1 / nn)) / nn;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
+      const int nc = min(32, P.N - col);
+      float v[32];
+      rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v);
+      if (c0 == last_c0) {                              // second read done: hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nc) v[e] = fmaf((v[e] - mean) * rstd, __ldg(P.ln_g + col + e), __ldg(P.ln_b + col + e));
+      rg_chunk_store(P, R, col, nc, v);
+    }
+  } else {
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
+      const int nc = min(32, P.N - col);
+      float v[32];
+      rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v);
+      if (c0 == last_c0) {                              // this warp's share of the accumulator is in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+      rg_chunk_store(P, R, col, nc, v);
+    }
+  }
+  if (!any) {                                           // a warp whose column blocks all lie past N
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty);
   }
 }
 
@@ -354,142 +469,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_rowgemm_tc_kernel(const __g
     //      blocks.  A thread owns 32 consecutive columns of its row in registers: bias / residual / ReLU / the plane
     //      split run as 32 independent chains and leave as 16-byte stores (no shared-memory round trip).
     pdl_wait();                                             // residual / rowscale reads, and every global store
-    const int q = warp & 3;                                 // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;                       // 0: even column blocks, 1: odd
     uint32_t li = 0;
-    long long dbg_load = 0, dbg_store = 0, dbg_wait = 0;      // vkn_debug_timestamps: cycles in chunk loads / stores / waits
-    const bool dbg_on = batch.dbg != nullptr;
-#define RG_ACC(acc, stmt)               \
-  do {                                  \
-    if (dbg_on) {                       \
-      const long long c0__ = clock64(); \
-      stmt;                             \
-      acc += clock64() - c0__;          \
-    } else {                            \
-      stmt;                             \
-    }                                   \
-  } while (0)
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
       const RgTile T = rg_decode(batch, t);
       const RgProb &P = batch.p[T.prob];
       const uint32_t buf = li & 1u;
-      RG_ACC(dbg_wait, mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u));
+      mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u);
       tc_fence_after();
       if (t + (int)gridDim.x >= total) pdl_trigger();
       if (threadIdx.x == 64 && li == 0) RG_TS(5);
-      RgRowCtx R;
-      R.epi = P.epi;
-      R.row = T.row0 + q * 32 + lane;
-      R.live = R.row < P.M;
-      R.row_base = T.row0 + q * 32;
-      R.ks = T.ks;
-      R.stg = stg0 + (uint32_t)(warp - 2) * (uint32_t)batch.stg_bytes;
-      R.pl_off = (uint32_t)batch.pl_off;
-      R.outp = P.out + (size_t)T.ks * P.out_split_stride;
-      R.out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(R.outp) & 31) == 0);
-      R.res_vec = (P.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.res) & 15) == 0);
-      R.pl_vec = (P.split_C % 16 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 31) == 0) && (P.plane_elems % 16 == 0);
-      R.bias_vec = (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0;
-      R.rs = (R.live && (R.epi & EPI_ROWSCALE)) ? __ldg(P.rowscale + R.row) : 1.f;
-      R.prow = (size_t)R.row;                               // row of the plane buffer this thread writes
-      if ((R.epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
-        const int b = R.row / P.split_N;
-        R.prow = (size_t)b * P.split_Npad + (R.row - b * P.split_N);
-      }
-      const uint32_t tacc = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
-      int last_c0 = half * 32;                              // last column block this warp reads from TMEM
-      while (last_c0 + 64 < BN && T.col0 + last_c0 + 64 < P.N) last_c0 += 64;
-      const bool any = half * 32 < BN && T.col0 + half * 32 < P.N;   // this warp owns at least one column block
-      if (R.epi & EPI_LN) {
-        // ---- fused LayerNorm: the tile spans the row (host: nt == 1); the two warps of a lane quarter own alternate
-        //      32-column blocks, so each thread reduces its blocks (shifted sums: no cancellation), the pair merges
-        //      (count, mean, M2) through shared memory, then a second pass over TMEM normalises and stores.
-        float K0 = 0.f, S1 = 0.f, S2 = 0.f, cntf = 0.f;
-        bool first = true;
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
-          const int col = T.col0 + c0;
-          if (col >= P.N) break;
-          const int nc = min(32, P.N - col);
-          float v[32];
-          RG_ACC(dbg_load, rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v));
-          if (first) {
-            K0 = v[0];
-            first = false;
-          }
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e < nc) {
-              const float d = v[e] - K0;
-              S1 += d;
-              S2 = fmaf(d, d, S2);
-            }
-          cntf += (float)nc;
-        }
-        float mean_h = 0.f, m2_h = 0.f;
-        if (cntf > 0.f) {
-          mean_h = K0 + S1 / cntf;
-          m2_h = S2 - S1 * S1 / cntf;
-        }
-        float *st = ln_stat + ((size_t)(li & 1u) * 128 + q * 32 + lane) * 8;
-        st[half * 4 + 0] = cntf;
-        st[half * 4 + 1] = mean_h;
-        st[half * 4 + 2] = m2_h;
-        RG_ACC(dbg_wait, named_bar_sync(1, RG_THREADS - 64));
-        const float cb = st[(half ^ 1) * 4 + 0], mb = st[(half ^ 1) * 4 + 1], m2b = st[(half ^ 1) * 4 + 2];
-        // merge in a fixed order (half 0 first) so both threads of a row get identical statistics
-        const float n0 = half ? cb : cntf, mu0 = half ? mb : mean_h, q0 = half ? m2b : m2_h;
-        const float n1 = half ? cntf : cb, mu1 = half ? mean_h : mb, q1 = half ? m2_h : m2b;
-        const float nn = n0 + n1, delta = mu1 - mu0;
-        const float mean = mu0 + delta * (n1 / nn);
-        const float var = (q0 + q1 + delta * delta * (n0 * n1 / nn)) / nn;
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
-          const int col = T.col0 + c0;
-          if (col >= P.N) break;
-          const int nc = min(32, P.N - col);
-          float v[32];
-          RG_ACC(dbg_load, rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v));
-          if (c0 == last_c0) {                              // second read done: hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
-          }
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e < nc) v[e] = fmaf((v[e] - mean) * rstd, __ldg(P.ln_g + col + e), __ldg(P.ln_b + col + e));
-          RG_ACC(dbg_store, rg_chunk_store(P, R, col, nc, v));
-        }
-      } else {
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
-          const int col = T.col0 + c0;
-          if (col >= P.N) break;
-          const int nc = min(32, P.N - col);
-          float v[32];
-          RG_ACC(dbg_load, rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v));
-          if (c0 == last_c0) {                              // this warp's share of the accumulator is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
-          }
-          RG_ACC(dbg_store, rg_chunk_store(P, R, col, nc, v));
-        }
-      }
-      if (!any) {                                           // a warp whose column blocks all lie past N
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
-      }
+      rg_epilogue_tile(P, T.row0, T.col0, T.ks, BN, tmem_base + buf * (uint32_t)BN, acc_empty0 + 8 * buf,
+                       stg0 + (uint32_t)(warp - 2) * (uint32_t)batch.stg_bytes, (uint32_t)batch.pl_off,
+                       ln_stat + (size_t)(li & 1u) * 128 * 8, warp, lane, RG_THREADS - 64);
     }
     if (lane == 0) bulk_wait_group_read<0>();               // staging may be released; the writes drain with the grid
-    if (threadIdx.x == 64) {
-      RG_TS(6);
-      if (dbg_on) {
-        batch.dbg[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)dbg_load;
-        batch.dbg[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)dbg_store;
-        batch.dbg[(size_t)blockIdx.x * 16 + 10] = (unsigned long long)dbg_wait;
-        batch.dbg[(size_t)blockIdx.x * 16 + 11] = li;
-      }
-    }
+    if (threadIdx.x == 64) RG_TS(6);
   }
   tc_fence_before();
   __syncthreads();
@@ -510,6 +504,64 @@ bool linear_tc_supported(const LinArgs &a) {
   if (a.K % 8 != 0 || a.ldw % 8 != 0 || a.src.lda[0] % 8 != 0 || a.src.sum_stride % 8 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(a.w) & 15) || (reinterpret_cast<uintptr_t>(a.src.a[0]) & 15)) return false;
   return true;
+}
+
+// LinArgs (PRO_PLANES input, bf16 weights) -> the device-side problem record: tensor maps of the A planes, the weight
+// matrix and (when describable) the outputs, for column tiles of BN and ks K-slices.
+static int rg_fill_prob(const LinArgs &a, int BN, int ks, RgProb &p) {
+  const uint64_t adims[3] = {(uint64_t)a.K, (uint64_t)a.M, 3};
+  const uint64_t astr[2] = {(uint64_t)a.src.lda[0] * 2, (uint64_t)a.src.sum_stride * 2};
+  const uint32_t abox[3] = {64u, 128u, 3u};
+  VKN_TRY(make_tmap_bf16_strided(&p.tmA, a.src.a[0], 3, adims, astr, abox));
+  const uint64_t wdims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+  const uint64_t wstr[1] = {(uint64_t)a.ldw * 2};
+  const uint32_t wbox[2] = {64u, (uint32_t)BN};
+  VKN_TRY(make_tmap_bf16_strided(&p.tmW, a.w, 2, wdims, wstr, wbox));
+  p.tma_out = 0;
+  p.tma_pl = 0;
+  const bool tma_ok = getenv("VKN_RG_TMA_STORE") == nullptr || getenv("VKN_RG_TMA_STORE")[0] != '0';
+  if (tma_ok && !(a.epi & EPI_NOOUT) && a.out && a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+      (ks == 1 || a.out_split_stride % 4 == 0)) {
+    const uint64_t od[3] = {(uint64_t)a.N, (uint64_t)a.M, (uint64_t)ks};
+    const uint64_t os[2] = {(uint64_t)a.ldo * 4, (uint64_t)(ks > 1 ? a.out_split_stride : (long long)a.M * a.ldo) * 4};
+    const uint32_t ob[3] = {32u, 32u, 1u};
+    VKN_TRY(make_tmap_store(&p.tmOut, a.out, true, od, os, ob, true));
+    p.tma_out = 1;
+  }
+  if (tma_ok && (a.epi & EPI_SPLIT3) && a.split_planes && a.split_N == a.split_Npad && a.split_C % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.split_planes) & 15) == 0 && ((long long)a.split_B * a.split_Npad * a.split_C) % 8 == 0) {
+    const uint64_t pd[3] = {(uint64_t)a.split_C, (uint64_t)a.M, 3};
+    const uint64_t ps[2] = {(uint64_t)a.split_C * 2, (uint64_t)((long long)a.split_B * a.split_Npad * a.split_C) * 2};
+    const uint32_t pb[3] = {32u, 32u, 3u};
+    VKN_TRY(make_tmap_store(&p.tmPl, a.split_planes, false, pd, ps, pb, false));
+    p.tma_pl = 1;
+  }
+  p.bias = a.bias;
+  p.rowscale = a.rowscale;
+  p.res = a.res;
+  p.ln_g = a.ln_g;
+  p.ln_b = a.ln_b;
+  if ((a.epi & EPI_LN) && (!a.ln_g || !a.ln_b)) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_LN without LayerNorm parameters");
+  p.out = a.out;
+  p.planes = a.split_planes;
+  p.out_split_stride = a.out_split_stride;
+  p.plane_elems = (long long)a.split_B * a.split_Npad * a.split_C;
+  p.ldres = a.ldres;
+  p.ldo = a.ldo;
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.epi = a.epi;
+  p.split_N = a.split_N > 0 ? a.split_N : 1;
+  p.split_Npad = a.split_Npad;
+  p.split_C = a.split_C;
+  p.mt = ceil_div(a.M, 128);
+  p.nt = ceil_div(a.N, BN);
+  p.tiles = p.mt * p.nt * ks;
+  if ((a.epi & EPI_BIAS) && ks > 1) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: bias with split-K belongs to the consumer");
+  if ((a.epi & EPI_SPLIT3) && !a.split_planes) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_SPLIT3 without a plane buffer");
+  if (!(a.epi & EPI_NOOUT) && !a.out) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: null output");
+  return VKN_OK;
 }
 
 // Same contract as launch_linear (smallops.cu) for PRO_PLANES inputs and bf16 weights.
@@ -576,61 +628,8 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
   b.idesc = make_idesc_bf16(128, BN, 0, 0);
   b.dbg = debug_ts_slot();
   for (int i = 0; i < nprob; ++i) {
-    const LinArgs &a = probs[i];
-    RgProb &p = b.p[i];
-    const uint64_t adims[3] = {(uint64_t)a.K, (uint64_t)a.M, 3};
-    const uint64_t astr[2] = {(uint64_t)a.src.lda[0] * 2, (uint64_t)a.src.sum_stride * 2};
-    const uint32_t abox[3] = {64u, 128u, 3u};
-    VKN_TRY(make_tmap_bf16_strided(&p.tmA, a.src.a[0], 3, adims, astr, abox));
-    const uint64_t wdims[2] = {(uint64_t)a.K, (uint64_t)a.N};
-    const uint64_t wstr[1] = {(uint64_t)a.ldw * 2};
-    const uint32_t wbox[2] = {64u, (uint32_t)BN};
-    VKN_TRY(make_tmap_bf16_strided(&p.tmW, a.w, 2, wdims, wstr, wbox));
-    p.tma_out = 0;
-    p.tma_pl = 0;
-    const bool tma_ok = getenv("VKN_RG_TMA_STORE") == nullptr || getenv("VKN_RG_TMA_STORE")[0] != '0';
-    if (tma_ok && !(a.epi & EPI_NOOUT) && a.out && a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
-        (ks == 1 || a.out_split_stride % 4 == 0)) {
-      const uint64_t od[3] = {(uint64_t)a.N, (uint64_t)a.M, (uint64_t)ks};
-      const uint64_t os[2] = {(uint64_t)a.ldo * 4, (uint64_t)(ks > 1 ? a.out_split_stride : (long long)a.M * a.ldo) * 4};
-      const uint32_t ob[3] = {32u, 32u, 1u};
-      VKN_TRY(make_tmap_store(&p.tmOut, a.out, true, od, os, ob, true));
-      p.tma_out = 1;
-    }
-    if (tma_ok && (a.epi & EPI_SPLIT3) && a.split_planes && a.split_N == a.split_Npad && a.split_C % 8 == 0 &&
-        (reinterpret_cast<uintptr_t>(a.split_planes) & 15) == 0 && ((long long)a.split_B * a.split_Npad * a.split_C) % 8 == 0) {
-      const uint64_t pd[3] = {(uint64_t)a.split_C, (uint64_t)a.M, 3};
-      const uint64_t ps[2] = {(uint64_t)a.split_C * 2, (uint64_t)((long long)a.split_B * a.split_Npad * a.split_C) * 2};
-      const uint32_t pb[3] = {32u, 32u, 3u};
-      VKN_TRY(make_tmap_store(&p.tmPl, a.split_planes, false, pd, ps, pb, false));
-      p.tma_pl = 1;
-    }
-    p.bias = a.bias;
-    p.rowscale = a.rowscale;
-    p.res = a.res;
-    p.ln_g = a.ln_g;
-    p.ln_b = a.ln_b;
-    if ((a.epi & EPI_LN) && (!a.ln_g || !a.ln_b)) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_LN without LayerNorm parameters");
-    p.out = a.out;
-    p.planes = a.split_planes;
-    p.out_split_stride = a.out_split_stride;
-    p.plane_elems = (long long)a.split_B * a.split_Npad * a.split_C;
-    p.ldres = a.ldres;
-    p.ldo = a.ldo;
-    p.M = a.M;
-    p.N = a.N;
-    p.K = a.K;
-    p.epi = a.epi;
-    p.split_N = a.split_N > 0 ? a.split_N : 1;
-    p.split_Npad = a.split_Npad;
-    p.split_C = a.split_C;
-    p.mt = ceil_div(a.M, 128);
-    p.nt = ceil_div(a.N, BN);
-    p.tiles = p.mt * p.nt * ks;
-    b.total_tiles += p.tiles;
-    if ((a.epi & EPI_BIAS) && ks > 1) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: bias with split-K belongs to the consumer");
-    if ((a.epi & EPI_SPLIT3) && !a.split_planes) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_SPLIT3 without a plane buffer");
-    if (!(a.epi & EPI_NOOUT) && !a.out) VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: null output");
+    VKN_TRY(rg_fill_prob(probs[i], BN, ks, b.p[i]));
+    b.total_tiles += b.p[i].tiles;
   }
   if (nprob == 1) {
     b.p[1] = b.p[0];
@@ -644,6 +643,314 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
   dim3 grid(b.total_tiles < sms ? b.total_tiles : sms);
   VKN_LAUNCH_MARK("vkn_rowgemm_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_rowgemm_tc_kernel, grid, dim3(RG_THREADS), smem, stream, b));
+  return VKN_OK;
+}
+
+
+// =====================================================================================================================
+// Chain kernel: a whole SEQUENCE of row operators of a stage in ONE launch.
+//
+// The row operators of a stage (KernelUpdator -> in-proj | out-proj -> FFN -> FC heads -> fold; knet/kernel_updator.py:56-94,
+// knet/det/kernel_update_head.py:201-227) only ever couple the rows of one kernel set through the attention, so between
+// two attentions a 128-row tile depends on nothing but itself.  Launched as ~14 separate GEMM / row kernels each step ran
+// one TMA -> MMA -> epilogue pass per CTA and then waited for the whole grid (measured: 61 launches, 59 % of the step for
+// 9 % of its FLOPs).  Here a CTA owns a row tile and walks the step program by itself:
+//   GEMM step  = up to two problems x column tiles of 256, the same TMA ring / tcgen05 / double-buffered TMEM pipeline and
+//                the same epilogue as vkn_rowgemm_tc_kernel (fused LayerNorm, planes for the next GEMM, TMA stores);
+//   row step   = a row transform by the epilogue warps (gate arithmetic: 4 LayerNorms + 2 sigmoids, products) -> planes;
+//   step edge  = the epilogue warps drain their TMA stores, fence the proxies, meet on a named barrier and signal
+//                `step_done`; the TMA warp loads the next step's A planes (this tile's rows, just written, L2-resident)
+//                only after that, while its weight tile is already in flight.
+// Nothing but the CTA's own 384 threads ever waits: no grid-wide dependency, no launch gap, weights stream from L2.
+constexpr int CH_MAXP = 16, CH_MAXR = 4, CH_MAXS = 14;
+struct ChRow {
+  RowSrc src;
+  float *out;
+  __nv_bfloat16 *planes;
+  long long plane_stride;
+  int ldo, ldp, K, pad_;
+};
+struct ChStep {
+  int kind, n, first, pad_;      // kind 0: GEMM problems p[first, first + n); kind 1: row op r[first]
+};
+struct ChainProg {
+  RgProb p[CH_MAXP];
+  ChRow r[CH_MAXR];
+  ChStep s[CH_MAXS];
+  int nsteps, M, mtiles, stages, stg_bytes, pl_off;
+  uint32_t idesc;
+  unsigned long long *dbg;       // optional: %globaltimer at every step edge of the CTA's first tile (vkn_debug_timestamps)
+};
+static_assert(sizeof(ChainProg) <= 32000, "chain program must fit the kernel parameter space");
+
+constexpr int CH_BN = 256;
+
+// one row transform of the chain: warp per row, rows of the tile dealt round-robin to the 8 epilogue warps
+__device__ __forceinline__ void ch_row_step(const ChRow &Rw, int row0, int M, int ew, int lane) {
+  for (int rr = ew; rr < 128; rr += 8) {
+    const int row = row0 + rr;
+    if (row >= M) break;
+    RowRaw r;
+    float v[KPL];
+    row_load<4, true>(Rw.src, row, 0, Rw.K, lane, r);
+    row_finish<4>(Rw.src, Rw.K, lane, r, v);
+    if (Rw.out != nullptr) store_pairs(Rw.out + (size_t)row * Rw.ldo, Rw.K, lane, v);
+    if (Rw.planes != nullptr) {
+#pragma unroll
+      for (int p = 0; p < KPL / 2; ++p) {
+        const int k = kidx(lane, 2 * p);
+        float x0 = v[2 * p], x1 = v[2 * p + 1];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {          // hi, then the residuals: v == hi + mid + lo to 24 bits
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+          x0 -= __bfloat162float(h0);
+          x1 -= __bfloat162float(h1);
+          if (k < Rw.K)
+            *reinterpret_cast<uint32_t *>(Rw.planes + (size_t)t * Rw.plane_stride + (size_t)row * Rw.ldp + k) =
+                (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        }
+      }
+    }
+  }
+}
+
+// spin until the CTA's epilogue warps have completed `need` steps (bounded: a protocol bug traps instead of hanging)
+__device__ __forceinline__ void ch_wait_steps(uint32_t ctr, uint32_t need) {
+  for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(ctr) : "memory");
+    if (v >= need) return;
+  }
+  __trap();
+}
+
+__global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __grid_constant__ ChainProg prog) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STG = prog.stages, nsteps = prog.nsteps, mtiles = prog.mtiles;
+  constexpr uint32_t stage_bytes = RG_A_BYTES + (uint32_t)CH_BN * 128u;
+  const uint32_t stg0 = smem_u32(smem + (size_t)STG * stage_bytes);
+  uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes + 8 * (size_t)prog.stg_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (STG + s), acc_full[a], acc_empty[a]; then the step counter
+  const uint32_t acc_full0 = bar0 + 16 * STG, acc_empty0 = acc_full0 + 16;
+  // steps this CTA has completed (monotonic: a parity barrier could be lapped by two back-to-back row steps)
+  const uint32_t step_ctr = acc_empty0 + 16;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 5);
+  float *ln_stat = (float *)(tmem_slot + 4);                 // [2][128 rows][8]: fused-LayerNorm partials (8 KB)
+  const uint32_t smem0 = smem_u32(smem);
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < STG; ++s) {
+        mbar_init(bar0 + 8 * s, 1);
+        mbar_init(bar0 + 8 * (STG + s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(acc_full0 + 8 * a, 1);
+        mbar_init(acc_empty0 + 8 * a, 8);                   // one arrive per epilogue warp
+      }
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(step_ctr), "r"(0u) : "memory");
+      fence_barrier_init();
+    }
+  } else if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 2u * CH_BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                               // the first step reads what the previous kernel wrote
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, it = 0, g = 0;
+      for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+        const int row0 = t * 128;
+        for (int si = 0; si < nsteps; ++si, ++g) {
+          const int kind = prog.s[si].kind, np = prog.s[si].n, first = prog.s[si].first;
+          if (kind != 0) continue;                          // row step: nothing to load
+          for (int pi = 0; pi < np; ++pi) {
+            const RgProb &P = prog.p[first + pi];
+            const int nk = (P.K + 63) / 64;
+            for (int j = 0; j < P.nt; ++j)
+              for (int i = 0; i < nk; ++i, ++it) {
+                if (it >= (uint32_t)STG) mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u);
+                mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+                tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, i * 64, j * CH_BN);
+                ch_wait_steps(step_ctr, g);                 // the A planes were written by the previous steps of this CTA
+                tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, i * 64, row0, 0);
+                if (++s == STG) {
+                  s = 0;
+                  ph ^= 1u;
+                }
+              }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint64_t adesc0 = umma_desc_sw128(smem0, 0, 1024);
+    const uint64_t bdesc0 = adesc0 + (uint64_t)(RG_A_BYTES >> 4);
+    const uint32_t idesc = prog.idesc;
+    int s = 0;
+    uint32_t ph = 0, li = 0;
+    for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+      for (int si = 0; si < nsteps; ++si) {
+        if (prog.s[si].kind != 0) continue;
+        const int np = prog.s[si].n, first = prog.s[si].first;
+        for (int pi = 0; pi < np; ++pi) {
+          const int nk = (prog.p[first + pi].K + 63) / 64, nt = prog.p[first + pi].nt;
+          for (int j = 0; j < nt; ++j, ++li) {
+            const uint32_t buf = li & 1u;
+            mbar_wait(acc_empty0 + 8 * buf, ((li >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t dt = tmem_base + buf * (uint32_t)CH_BN;
+            for (int i = 0; i < nk; ++i) {
+              mbar_wait(bar0 + 8 * s, ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
+#pragma unroll
+                for (int pl = 2; pl >= 0; --pl) {             // lo, mid, hi: small terms first
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(dt, adesc0 + so + (uint64_t)(pl * (int)(RG_A_PLANE >> 4) + k * 2), bdesc0 + so + (uint64_t)(k * 2), idesc,
+                              (i > 0 || pl < 2 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(bar0 + 8 * (STG + s));
+                if (i == nk - 1) umma_commit(acc_full0 + 8 * buf);
+              }
+              __syncwarp();
+              if (++s == STG) {
+                s = 0;
+                ph ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const uint32_t stg = stg0 + (uint32_t)ew * (uint32_t)prog.stg_bytes;
+    uint32_t li = 0, done = 0;
+    bool first_tile = true;
+    for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+      const int row0 = t * 128;
+      for (int si = 0; si < nsteps; ++si) {
+        const int kind = prog.s[si].kind, np = prog.s[si].n, first = prog.s[si].first;
+        if (kind == 0) {
+          for (int pi = 0; pi < np; ++pi) {
+            const RgProb &P = prog.p[first + pi];
+            for (int j = 0; j < P.nt; ++j, ++li) {
+              const uint32_t buf = li & 1u;
+              mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u);
+              tc_fence_after();
+              rg_epilogue_tile(P, row0, j * CH_BN, 0, CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf, stg,
+                               (uint32_t)prog.pl_off, ln_stat + (size_t)buf * 128 * 8, warp, lane, RG_THREADS - 64);
+            }
+          }
+        } else {
+          ch_row_step(prog.r[first], row0, prog.M, ew, lane);
+        }
+        // ---- step edge: everything this tile wrote is complete and visible to the TMA loads / L2 reads of the next step
+        if (lane == 0) bulk_wait_all();
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        named_bar_sync(1, RG_THREADS - 64);
+        ++done;
+        if (threadIdx.x == 64) {
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(step_ctr), "r"(done) : "memory");
+          if (first_tile && prog.dbg != nullptr) prog.dbg[(size_t)blockIdx.x * 16 + (si < 15 ? si : 15)] = rg_time();
+        }
+      }
+      first_tile = false;
+    }
+  }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2u * CH_BN);
+  }
+}
+
+// ---- host: chain builder -------------------------------------------------------------------------------------------
+struct ChainBuild {
+  ChainProg prog;
+  int np, nr;
+};
+static ChainBuild *g_chain_pool = nullptr;     // one reusable host record (the program is copied into the launch)
+
+ChainBuild *chain_begin(int M) {
+  if (!g_chain_pool) g_chain_pool = (ChainBuild *)aligned_alloc(64, (sizeof(ChainBuild) + 63) / 64 * 64);
+  ChainBuild *b = g_chain_pool;
+  memset(b, 0, sizeof(*b));
+  b->prog.M = M;
+  b->prog.mtiles = ceil_div(M, 128);
+  return b;
+}
+bool chain_empty(const ChainBuild *b) { return b->prog.nsteps == 0; }
+
+int chain_add_gemm(ChainBuild *b, const LinArgs *probs, int nprob) {
+  if (b->prog.nsteps >= CH_MAXS || b->np + nprob > CH_MAXP) VKN_FAIL(VKN_E_INVALID, "chain: too many steps / problems");
+  ChStep &st = b->prog.s[b->prog.nsteps++];
+  st.kind = 0;
+  st.n = nprob;
+  st.first = b->np;
+  for (int i = 0; i < nprob; ++i) {
+    const LinArgs &a = probs[i];
+    if (!linear_tc_supported(a)) VKN_FAIL(VKN_E_INVALID, "chain: GEMM steps need bf16 plane inputs with 16-byte aligned rows");
+    if (a.M != b->prog.M) VKN_FAIL(VKN_E_INVALID, "chain: every step must span the same %d rows (got %d)", b->prog.M, a.M);
+    if (a.ksplit > 1 || a.side != nullptr) VKN_FAIL(VKN_E_INVALID, "chain: split-K / side outputs are not part of the chain form");
+    if ((a.epi & EPI_LN) && a.N > CH_BN) VKN_FAIL(VKN_E_INVALID, "chain: EPI_LN needs N <= %d", CH_BN);
+    VKN_TRY(rg_fill_prob(a, CH_BN, 1, b->prog.p[b->np++]));
+  }
+  return VKN_OK;
+}
+
+int chain_add_rowprep(ChainBuild *b, const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int K) {
+  if (b->prog.nsteps >= CH_MAXS || b->nr >= CH_MAXR) VKN_FAIL(VKN_E_INVALID, "chain: too many steps / row operators");
+  if (src.pro == PRO_PLANES || K > KC || (K & 1)) VKN_FAIL(VKN_E_INVALID, "chain: row step needs fp32 sources and an even K <= %d", KC);
+  ChStep &st = b->prog.s[b->prog.nsteps++];
+  st.kind = 1;
+  st.n = 1;
+  st.first = b->nr;
+  ChRow &r = b->prog.r[b->nr++];
+  r.src = src;
+  r.out = out;
+  r.ldo = ldo;
+  r.planes = (__nv_bfloat16 *)planes;
+  r.ldp = ldp;
+  r.plane_stride = plane_stride;
+  r.K = K;
+  return VKN_OK;
+}
+
+int chain_launch(ChainBuild *b, cudaStream_t stream) {
+  if (b->prog.nsteps == 0) return VKN_OK;
+  ChainProg &g = b->prog;
+  constexpr size_t stage_bytes = (size_t)RG_A_BYTES + (size_t)CH_BN * 128;
+  g.stages = 2;
+  g.stg_bytes = 6144;
+  g.pl_off = 0;
+  g.idesc = make_idesc_bf16(128, CH_BN, 0, 0);
+  g.dbg = debug_ts_slot();
+  const size_t smem = (size_t)g.stages * stage_bytes + 8 * (size_t)g.stg_bytes + 1024 + (2 * g.stages + 5) * 8 + 16 + 2 * 128 * 8 * 4 + 64;
+  static bool attr = false;
+  if (!attr) {
+    VKN_CUDA_OK(cudaFuncSetAttribute(vkn_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  if (smem > 227 * 1024) VKN_FAIL(VKN_E_INVALID, "chain: shared memory budget exceeded");
+  dim3 grid(g.mtiles < 148 ? g.mtiles : 148);
+  VKN_LAUNCH_MARK("vkn_chain_tc_kernel", stream);
+  VKN_CUDA_OK(launch_chain(vkn_chain_tc_kernel, grid, dim3(RG_THREADS), smem, stream, g));
+  g.nsteps = 0;
   return VKN_OK;
 }
 
