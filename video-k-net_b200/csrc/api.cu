@@ -488,21 +488,62 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     const VknShape fs = frames_shape(c.s);
     VKN_TRY(launch_pool_tc(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st, mask_bits_in));
     VKN_TRY(launch_pool_reduce(c.s, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st, PLA));
-    LinArgs a = lin(src_planes(PLA, C, PS), w.ft_w, C, w.ft_b, xf, C, P, C, C, EPI_ROWSCALE);
+    // the fp32 copy of x_feat is only written when the caller asked for it (VideoKernelUpdateHead returns it)
+    LinArgs a = lin(src_planes(PLA, C, PS), w.ft_w, C, w.ft_b, x_feat_out ? xf : nullptr, C, P, C, C,
+                    EPI_ROWSCALE | (x_feat_out ? 0 : EPI_NOOUT));
     a.rowscale = c.L.cnt;
     out_planes(a, PLB, P, C);
     VKN_TRY(emit_gemm(c, &a, 1));
   } else {
     float *copy_to = (x_feat_out && x_feat_out != x_feat_in) ? x_feat_out : nullptr;
-    VKN_TRY(emit_rowprep(c, src_copy(x_feat_in, C), copy_to, C, PLB, C, PS, P, C));
+    VKN_TRY(launch_rowprep(src_copy(x_feat_in, C), copy_to, C, PLB, C, PS, P, C, c.st));
   }
   if (pf_planes == nullptr) {
-    VKN_TRY(emit_rowprep(c, src_copy(pf, C), nullptr, 0, PLC, C, PS, P, C));
+    VKN_TRY(launch_rowprep(src_copy(pf, C), nullptr, 0, PLC, C, PS, P, C, c.st));
     pf_planes = PLC;
   }
   // a5 KernelUpdator (kernel_updator.py:56-94)
   const VknUpdatorW &u = w.upd;
   LinArgs two[2];
+  if (c.chain) {
+    // Chain form: the gate arithmetic lives in the GEMM epilogues (no row passes, no fp32 round trips of the gate inputs):
+    //   param_in = dyn_w[:C] xf + b             input_in . param_in -> planes (gate_feats)            :59-70
+    //   param_out, input_out                     -> norm_out / input_norm_out in the epilogue          :86-87
+    //   U = sigmoid(norm_in(update_gate(g))) * param_out;  features = sigmoid(input_norm_in(input_gate(g))) * input_out + U   :74-88
+    LinArgs four[4];
+    four[0] = lin(src_planes(PLB, C, PS), u.dyn_w, C, u.dyn_b, c.L.dyn, 2 * C, P, C, C, 0);                         // param_in
+    four[1] = lin(src_planes(PLB, C, PS), wrow(c, u.dyn_w, C, C), C, u.dyn_b + C, c.L.dyn + C, 2 * C, P, C, C, EPI_LN);   // param_out
+    four[1].ln_g = u.norm_out_g;
+    four[1].ln_b = u.norm_out_b;
+    four[2] = lin(src_planes(pf_planes, C, PS), wrow(c, u.inp_w, C, C), C, u.inp_b + C, c.L.inp + C, 2 * C, P, C, C, EPI_LN);   // input_out
+    four[2].ln_g = u.inorm_out_g;
+    four[2].ln_b = u.inorm_out_b;
+    four[3] = lin(src_planes(pf_planes, C, PS), u.inp_w, C, u.inp_b, nullptr, C, P, C, C, EPI_MUL | EPI_NOOUT);     // input_in . param_in
+    four[3].mul = c.L.dyn;
+    four[3].ldmul = 2 * C;
+    out_planes(four[3], PLA, P, C);
+    VKN_TRY(emit_gemm(c, four, 4));
+    two[0] = lin(src_planes(PLA, C, PS), u.ug_w, C, u.ug_b, c.L.ugp, C, P, C, C, EPI_LN | EPI_SIGMOID | EPI_MUL);    // :75, :77-86
+    two[0].ln_g = u.norm_in_g;
+    two[0].ln_b = u.norm_in_b;
+    two[0].mul = c.L.dyn + C;
+    two[0].ldmul = 2 * C;
+    two[1] = lin(src_planes(PLA, C, PS), u.ig_w, C, u.ig_b, nullptr, C, P, C, C,
+                 EPI_LN | EPI_SIGMOID | EPI_MUL | EPI_ADD2 | EPI_NOOUT);                                                // :74, :76-88
+    two[1].ln_g = u.inorm_in_g;
+    two[1].ln_b = u.inorm_in_b;
+    two[1].mul = c.L.inp + C;
+    two[1].ldmul = 2 * C;
+    two[1].add2 = c.L.ugp;
+    two[1].ldadd2 = C;
+    out_planes(two[1], PLB, P, C);
+    VKN_TRY(emit_gemm(c, two, 2));
+    LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.o, C, P, C, C, EPI_LN | EPI_RELU);              // :90-92
+    f.ln_g = u.fc_norm_g;
+    f.ln_b = u.fc_norm_b;
+    out_planes(f, PLA, P, C);
+    VKN_TRY(emit_gemm(c, &f, 1));
+  } else {
   two[0] = lin(src_planes(PLB, C, PS), u.dyn_w, C, u.dyn_b, c.L.dyn, 2 * C, P, 2 * C, C, 0);          // :59
   two[1] = lin(src_planes(pf_planes, C, PS), u.inp_w, C, u.inp_b, c.L.inp, 2 * C, P, 2 * C, C, 0);    // :65-66
   VKN_TRY(emit_gemm(c, two, 2));
@@ -536,6 +577,7 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     LinArgs f = lin(src_planes(PLB, C, PS), u.fc_w, C, u.fc_b, c.L.fc, C, P, C, C, 0);                  // :90
     VKN_TRY(emit_gemm(c, &f, 1));
     VKN_TRY(emit_rowprep(c, src_ln(c.L.fc, C, u.fc_norm_g, u.fc_norm_b, true), c.L.o, C, PLA, C, PS, P, C));   // :91-92
+  }
   }
   // a6 MHSA + LN (kernel_update_head.py:204-208)
   LinArgs qkv = lin(src_planes(PLA, C, PS), w.attn.in_w, C, w.attn.in_b, c.L.qkv, 3 * C, P, 3 * C, C, 0);
@@ -636,7 +678,7 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
     if (i < ncls_fcs) cs = PLA;
     if (i < w.num_mask_fcs) ms = PLB;
   }
-  two[0] = lin(src_planes(ms, C, PS), w.fc_mask_w, C, w.fc_mask_b, c.L.mk, C, P, C, C, 0);
+  two[0] = lin(src_planes(ms, C, PS), w.fc_mask_w, C, w.fc_mask_b, nullptr, C, P, C, C, EPI_NOOUT);   // only its planes are consumed
   out_planes(two[0], PLD, P, C);
   if (with_cls) two[1] = lin(src_planes(cs, C, PS), w.fc_cls_w, C, w.fc_cls_b, cls, c.s.num_classes, P, c.s.num_classes, C, 0);
   VKN_TRY(emit_gemm(c, two, with_cls ? 2 : 1));
@@ -647,13 +689,15 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   }
   // a9 (+a2 folded): a = mk . ft_w (planes for the mask conv), bias column mk . ft_b
   const int lda = C + A_EXT_PAD;
-  LinArgs a = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, c.L.a_ext, lda, P, C + 1, C, EPI_SPLIT3);
-  a.split_planes = (__nv_bfloat16 *)c.L.a_split;
-  a.split_B = c.s.B;
-  a.split_N = c.s.N;
-  a.split_Npad = maskgemm_tc_npad(c.s);
-  a.split_C = C;
-  VKN_TRY(emit_gemm(c, &a, 1));
+  // the mask conv reads the folded kernels as planes and, of the fp32 rows, only the bias column
+  two[0] = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, nullptr, lda, P, C, C, EPI_SPLIT3 | EPI_NOOUT);
+  two[0].split_planes = (__nv_bfloat16 *)c.L.a_split;
+  two[0].split_B = c.s.B;
+  two[0].split_N = c.s.N;
+  two[0].split_Npad = maskgemm_tc_npad(c.s);
+  two[0].split_C = C;
+  two[1] = lin(src_planes(PLD, C, PS), wrow(c, w.ft_wt_ext, C, C), C, nullptr, c.L.a_ext + C, lda, P, 1, C, 0);
+  VKN_TRY(emit_gemm(c, two, 2));
   VKN_TRY(emit_flush(c));
   c.chain = nullptr;
   return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st, mask_bits_out);

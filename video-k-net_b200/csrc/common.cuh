@@ -143,7 +143,10 @@ enum Pro : int {
 enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_SPLIT3 = 16, EPI_NOOUT = 32,
                  // tcgen05 row GEMM only: y = LayerNorm(acc + bias + res) * ln_g + ln_b (then EPI_RELU) in the epilogue;
                  // the tile must span the whole row (N <= 256)
-                 EPI_LN = 64 };
+                 EPI_LN = 64,
+                 // tcgen05 row GEMM only, applied after bias / residual / LayerNorm and before ReLU, in this order:
+                 // y = sigmoid(y);  y *= mul[row][col];  y += add2[row][col]   (the KernelUpdator gate arithmetic in the epilogue)
+                 EPI_SIGMOID = 128, EPI_MUL = 256, EPI_ADD2 = 512 };
 
 struct RowSrc {
   const float *a[4];
@@ -168,6 +171,10 @@ struct LinArgs {
   const float *ln_g, *ln_b; // [N] LayerNorm affine of the fused epilogue (EPI_LN)
   const float *res;         // [M,N] residual added in the epilogue (EPI_RES)
   int ldres;
+  const float *mul;         // [M,N] elementwise factor (EPI_MUL)
+  int ldmul;
+  const float *add2;        // [M,N] addend applied after the factor (EPI_ADD2)
+  int ldadd2;
   float *out;               // [M,N] (slice z of a split-K launch writes out + z * out_split_stride)
   int ldo;
   long long out_split_stride;

@@ -25,11 +25,11 @@ struct RgProb {
   CUtensorMap tmOut;          // fp32 rows {N, M, K slices}, box {32, 32, 1}, SWIZZLE_128B (valid when tma_out)
   CUtensorMap tmPl;           // bf16 planes {split_C, M, 3}, box {32, 32, 3}, SWIZZLE_64B (valid when tma_pl)
   int tma_out, tma_pl;
-  const float *bias, *rowscale, *res, *ln_g, *ln_b;
+  const float *bias, *rowscale, *res, *ln_g, *ln_b, *mul, *add2;
   float *out;
   __nv_bfloat16 *planes;
   long long out_split_stride, plane_elems;
-  int ldres, ldo, M, N, K, epi, split_N, split_Npad, split_C;
+  int ldres, ldmul, ldadd2, ldo, M, N, K, epi, split_N, split_Npad, split_C;
   int mt, nt, tiles;          // row tiles, column tiles, tiles of this problem (mt * nt * ksplit)
 };
 struct RgBatch {
@@ -130,6 +130,33 @@ __device__ __forceinline__ void rg_chunk_load(const RgProb &P, const RgRowCtx &R
   tmem_ld32(taddr, r);
 #pragma unroll
   for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + add[e];
+}
+
+// sigmoid / elementwise factor / addend after bias, residual and LayerNorm (the KernelUpdator gate, kernel_updator.py:70-88)
+__device__ __forceinline__ void rg_post(const RgProb &P, const RgRowCtx &R, int col, int nc, float (&v)[32]) {
+  if (!(R.epi & (EPI_SIGMOID | EPI_MUL | EPI_ADD2)) || !R.live) return;
+  if (R.epi & EPI_SIGMOID) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = sigmoidf_(v[e]);
+  }
+  if (R.epi & EPI_MUL) {
+    const float *mp = P.mul + (size_t)R.row * P.ldmul + col;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4)
+      if (e < nc) {
+        const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(mp + e));
+        v[e] *= t4.x; v[e + 1] *= t4.y; v[e + 2] *= t4.z; v[e + 3] *= t4.w;
+      }
+  }
+  if (R.epi & EPI_ADD2) {
+    const float *ap = P.add2 + (size_t)R.row * P.ldadd2 + col;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4)
+      if (e < nc) {
+        const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(ap + e));
+        v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+      }
+  }
 }
 
 // (ReLU) -> fp32 rows and / or bf16 hi/mid/lo planes
@@ -253,6 +280,13 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
     const int b = R.row / P.split_N;
     R.prow = (size_t)b * P.split_Npad + (R.row - b * P.split_N);
   }
+  if (R.epi & (EPI_MUL | EPI_ADD2)) {
+    // the factor / addend rows may come from an earlier tile of the SAME step: this very warp stored them (same rows, same
+    // column blocks), possibly through TMA -- drain its bulk stores before reading them back
+    if (lane == 0) bulk_wait_all();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+  }
   const uint32_t tacc = tacc_base + ((uint32_t)(q * 32) << 16);
   int last_c0 = half * 32;                              // last column block this warp reads from TMEM
   while (last_c0 + 64 < BN && col0 + last_c0 + 64 < P.N) last_c0 += 64;
@@ -269,6 +303,12 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
       const int nc = min(32, P.N - col);
       float v[32];
       rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v);
+      {   // keep acc + bias + residual in the accumulator itself: the second pass re-reads TMEM, not global memory
+        uint32_t vr[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) vr[e] = __float_as_uint(v[e]);
+        tmem_st32(tacc + (uint32_t)c0, vr);
+      }
       if (first) {
         K0 = v[0];
         first = false;
@@ -305,15 +345,33 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
       if (col >= P.N) break;
       const int nc = min(32, P.N - col);
       float v[32];
-      rg_chunk_load(P, R, tacc + (uint32_t)c0, col, nc, v);
+      {
+        uint32_t vr[32];
+        tmem_ld32(tacc + (uint32_t)c0, vr);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(vr[e]);
+      }
       if (c0 == last_c0) {                              // second read done: hand the accumulator back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);
       }
+      if (nc == 32 && ((reinterpret_cast<uintptr_t>(P.ln_g) | reinterpret_cast<uintptr_t>(P.ln_b)) & 15) == 0 && (col & 3) == 0) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (e < nc) v[e] = fmaf((v[e] - mean) * rstd, __ldg(P.ln_g + col + e), __ldg(P.ln_b + col + e));
+        for (int e = 0; e < 32; e += 4) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4 *>(P.ln_g + col + e));
+          const float4 b4 = __ldg(reinterpret_cast<const float4 *>(P.ln_b + col + e));
+          v[e] = fmaf((v[e] - mean) * rstd, g4.x, b4.x);
+          v[e + 1] = fmaf((v[e + 1] - mean) * rstd, g4.y, b4.y);
+          v[e + 2] = fmaf((v[e + 2] - mean) * rstd, g4.z, b4.z);
+          v[e + 3] = fmaf((v[e + 3] - mean) * rstd, g4.w, b4.w);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < nc) v[e] = fmaf((v[e] - mean) * rstd, __ldg(P.ln_g + col + e), __ldg(P.ln_b + col + e));
+      }
+      rg_post(P, R, col, nc, v);
       rg_chunk_store(P, R, col, nc, v);
     }
   } else {
@@ -328,6 +386,7 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);
       }
+      rg_post(P, R, col, nc, v);
       rg_chunk_store(P, R, col, nc, v);
     }
   }
@@ -520,7 +579,7 @@ static int rg_fill_prob(const LinArgs &a, int BN, int ks, RgProb &p) {
   p.tma_out = 0;
   p.tma_pl = 0;
   const bool tma_ok = getenv("VKN_RG_TMA_STORE") == nullptr || getenv("VKN_RG_TMA_STORE")[0] != '0';
-  if (tma_ok && !(a.epi & EPI_NOOUT) && a.out && a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+  if (tma_ok && !(a.epi & EPI_NOOUT) && a.out && a.N >= 32 && a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
       (ks == 1 || a.out_split_stride % 4 == 0)) {
     const uint64_t od[3] = {(uint64_t)a.N, (uint64_t)a.M, (uint64_t)ks};
     const uint64_t os[2] = {(uint64_t)a.ldo * 4, (uint64_t)(ks > 1 ? a.out_split_stride : (long long)a.M * a.ldo) * 4};
@@ -547,6 +606,15 @@ static int rg_fill_prob(const LinArgs &a, int BN, int ks, RgProb &p) {
   p.out_split_stride = a.out_split_stride;
   p.plane_elems = (long long)a.split_B * a.split_Npad * a.split_C;
   p.ldres = a.ldres;
+  p.mul = a.mul;
+  p.ldmul = a.ldmul;
+  p.add2 = a.add2;
+  p.ldadd2 = a.ldadd2;
+  if (((a.epi & EPI_MUL) && (!a.mul || a.ldmul % 4 || (reinterpret_cast<uintptr_t>(a.mul) & 15))) ||
+      ((a.epi & EPI_ADD2) && (!a.add2 || a.ldadd2 % 4 || (reinterpret_cast<uintptr_t>(a.add2) & 15))))
+    VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: EPI_MUL / EPI_ADD2 need 16-byte aligned fp32 rows");
+  if ((a.epi & (EPI_MUL | EPI_ADD2 | EPI_SIGMOID)) && a.N % 4 != 0)
+    VKN_FAIL(VKN_E_INVALID, "launch_linear_tc: elementwise epilogue operands need N %% 4 == 0");
   p.ldo = a.ldo;
   p.M = a.M;
   p.N = a.N;
@@ -727,19 +795,33 @@ __device__ __forceinline__ void ch_wait_steps(uint32_t ctr, uint32_t need) {
 __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __grid_constant__ ChainProg prog) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int STG = prog.stages, nsteps = prog.nsteps, mtiles = prog.mtiles;
+  const int STG = prog.stages, nsteps = prog.nsteps, npairs = (prog.mtiles + 1) >> 1;
   constexpr uint32_t stage_bytes = RG_A_BYTES + (uint32_t)CH_BN * 128u;
   const uint32_t stg0 = smem_u32(smem + (size_t)STG * stage_bytes);
   uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes + 8 * (size_t)prog.stg_bytes);
   const uint32_t bar0 = smem_u32(bars);
-  // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (STG + s), acc_full[a], acc_empty[a]; then the step counter
+  // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (STG + s), acc_full[h], acc_empty[h]; then the two step counters
   const uint32_t acc_full0 = bar0 + 16 * STG, acc_empty0 = acc_full0 + 16;
-  // steps this CTA has completed (monotonic: a parity barrier could be lapped by two back-to-back row steps)
+  // steps completed by row tile X / Y of the current pair (monotonic counters: a parity barrier could be lapped by two
+  // back-to-back row steps)
   const uint32_t step_ctr = acc_empty0 + 16;
   uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STG + 5);
   float *ln_stat = (float *)(tmem_slot + 4);                 // [2][128 rows][8]: fused-LayerNorm partials (8 KB)
   const uint32_t smem0 = smem_u32(smem);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  // vkn_debug_timestamps: 64 words per CTA -- [0] start, [1 + 2 si + h] edge of step si / tile h (first pair), [32..] cycle
+  // counters of the three roles (waits and work), see tools/chain_timeline.py
+  unsigned long long *dbg = prog.dbg ? prog.dbg + (size_t)blockIdx.x * 64 : nullptr;
+#define CH_ACC(acc, stmt)               \
+  do {                                  \
+    if (dbg != nullptr) {               \
+      const long long c0__ = clock64(); \
+      stmt;                             \
+      acc += clock64() - c0__;          \
+    } else {                            \
+      stmt;                             \
+    }                                   \
+  } while (0)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -751,7 +833,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
         mbar_init(acc_full0 + 8 * a, 1);
         mbar_init(acc_empty0 + 8 * a, 8);                   // one arrive per epilogue warp
       }
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(step_ctr), "r"(0u) : "memory");
+      asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(step_ctr), "r"(0u) : "memory");
       fence_barrier_init();
     }
   } else if (warp == 1) {
@@ -762,13 +844,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                               // the first step reads what the previous kernel wrote
+  if (dbg != nullptr && threadIdx.x == 0) dbg[0] = rg_time();
 
+  // A CTA owns PAIRS of row tiles (X = 2p, Y = 2p + 1) and interleaves them through every step: while the epilogue warps
+  // drain X's accumulator (TMEM buffer 0) the tensor core multiplies Y's (buffer 1) and vice versa, and a tile's step
+  // edge (stores complete -> the next step's A planes loaded back from L2) hides behind the other tile's work.  An odd
+  // last tile pairs with a phantom (rows >= M: zero-filled loads, no stores).
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0, it = 0, g = 0;
-      for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
-        const int row0 = t * 128;
+      long long c_empty = 0, c_steps = 0;
+      for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
         for (int si = 0; si < nsteps; ++si, ++g) {
           const int kind = prog.s[si].kind, np = prog.s[si].n, first = prog.s[si].first;
           if (kind != 0) continue;                          // row step: nothing to load
@@ -776,19 +863,24 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
             const RgProb &P = prog.p[first + pi];
             const int nk = (P.K + 63) / 64;
             for (int j = 0; j < P.nt; ++j)
-              for (int i = 0; i < nk; ++i, ++it) {
-                if (it >= (uint32_t)STG) mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u);
-                mbar_expect_tx(bar0 + 8 * s, stage_bytes);
-                tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, i * 64, j * CH_BN);
-                ch_wait_steps(step_ctr, g);                 // the A planes were written by the previous steps of this CTA
-                tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, i * 64, row0, 0);
-                if (++s == STG) {
-                  s = 0;
-                  ph ^= 1u;
+              for (int h = 0; h < 2; ++h)
+                for (int i = 0; i < nk; ++i, ++it) {
+                  if (it >= (uint32_t)STG) CH_ACC(c_empty, mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u));
+                  mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+                  tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, i * 64, j * CH_BN);
+                  CH_ACC(c_steps, ch_wait_steps(step_ctr + 4 * h, g));   // this tile's A planes were written by its previous steps
+                  tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, i * 64, (2 * pr + h) * 128, 0);
+                  if (++s == STG) {
+                    s = 0;
+                    ph ^= 1u;
+                  }
                 }
-              }
           }
         }
+      }
+      if (dbg != nullptr) {
+        dbg[48] = (unsigned long long)c_empty;
+        dbg[49] = (unsigned long long)c_steps;
       }
     }
   } else if (warp == 1) {
@@ -796,20 +888,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
     const uint64_t bdesc0 = adesc0 + (uint64_t)(RG_A_BYTES >> 4);
     const uint32_t idesc = prog.idesc;
     int s = 0;
-    uint32_t ph = 0, li = 0;
-    for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+    uint32_t ph = 0, li = 0;                                // li counts accumulator uses: even = tile X, odd = tile Y
+    long long c_full = 0, c_acc = 0;
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
       for (int si = 0; si < nsteps; ++si) {
         if (prog.s[si].kind != 0) continue;
         const int np = prog.s[si].n, first = prog.s[si].first;
         for (int pi = 0; pi < np; ++pi) {
           const int nk = (prog.p[first + pi].K + 63) / 64, nt = prog.p[first + pi].nt;
-          for (int j = 0; j < nt; ++j, ++li) {
+          for (int jh = 0; jh < 2 * nt; ++jh, ++li) {
             const uint32_t buf = li & 1u;
-            mbar_wait(acc_empty0 + 8 * buf, ((li >> 1) & 1u) ^ 1u);
+            CH_ACC(c_acc, mbar_wait(acc_empty0 + 8 * buf, ((li >> 1) & 1u) ^ 1u));
             tc_fence_after();
             const uint32_t dt = tmem_base + buf * (uint32_t)CH_BN;
             for (int i = 0; i < nk; ++i) {
-              mbar_wait(bar0 + 8 * s, ph);
+              CH_ACC(c_full, mbar_wait(bar0 + 8 * s, ph));
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
@@ -833,41 +926,65 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
         }
       }
     }
+    if (dbg != nullptr && lane == 0) {
+      dbg[40] = (unsigned long long)c_full;
+      dbg[41] = (unsigned long long)c_acc;
+    }
   } else {
     const int ew = warp - 2;
     const uint32_t stg = stg0 + (uint32_t)ew * (uint32_t)prog.stg_bytes;
     uint32_t li = 0, done = 0;
-    bool first_tile = true;
-    for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
-      const int row0 = t * 128;
-      for (int si = 0; si < nsteps; ++si) {
+    bool first_pair = true;
+    long long c_wait = 0, c_tile = 0, c_edge = 0, c_row = 0;
+    // step edge of row tile h: everything it wrote is complete and visible to the TMA loads / L2 reads of its next step
+#define CH_EDGE(h, si)                                                                                                  \
+  do {                                                                                                                  \
+    const long long e0 = dbg ? clock64() : 0;                                                                           \
+    if (lane == 0) bulk_wait_all();                                                                                     \
+    __syncwarp();                                                                                                       \
+    asm volatile("fence.proxy.async;" ::: "memory");                                                                    \
+    named_bar_sync(1, RG_THREADS - 64);                                                                                 \
+    if (threadIdx.x == 64) {                                                                                            \
+      asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(step_ctr + 4 * (h)), "r"(done + 1) : "memory");     \
+      if (dbg != nullptr) {                                                                                             \
+        c_edge += clock64() - e0;                                                                                       \
+        if (first_pair && (si) < 15) dbg[1 + 2 * (si) + (h)] = rg_time();                                               \
+      }                                                                                                                 \
+    }                                                                                                                   \
+  } while (0)
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+      for (int si = 0; si < nsteps; ++si, ++done) {
         const int kind = prog.s[si].kind, np = prog.s[si].n, first = prog.s[si].first;
         if (kind == 0) {
           for (int pi = 0; pi < np; ++pi) {
             const RgProb &P = prog.p[first + pi];
-            for (int j = 0; j < P.nt; ++j, ++li) {
-              const uint32_t buf = li & 1u;
-              mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u);
-              tc_fence_after();
-              rg_epilogue_tile(P, row0, j * CH_BN, 0, CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf, stg,
-                               (uint32_t)prog.pl_off, ln_stat + (size_t)buf * 128 * 8, warp, lane, RG_THREADS - 64);
+            for (int j = 0; j < P.nt; ++j) {
+              const bool last = (pi == np - 1) && (j == P.nt - 1);
+              for (int h = 0; h < 2; ++h, ++li) {
+                const uint32_t buf = li & 1u;
+                CH_ACC(c_wait, mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u));
+                tc_fence_after();
+                CH_ACC(c_tile, rg_epilogue_tile(P, (2 * pr + h) * 128, j * CH_BN, 0, CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf,
+                                 stg, (uint32_t)prog.pl_off, ln_stat + (size_t)buf * 128 * 8, warp, lane, RG_THREADS - 64));
+                if (last) CH_EDGE(h, si);
+              }
             }
           }
         } else {
-          ch_row_step(prog.r[first], row0, prog.M, ew, lane);
-        }
-        // ---- step edge: everything this tile wrote is complete and visible to the TMA loads / L2 reads of the next step
-        if (lane == 0) bulk_wait_all();
-        __syncwarp();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        named_bar_sync(1, RG_THREADS - 64);
-        ++done;
-        if (threadIdx.x == 64) {
-          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(step_ctr), "r"(done) : "memory");
-          if (first_tile && prog.dbg != nullptr) prog.dbg[(size_t)blockIdx.x * 16 + (si < 15 ? si : 15)] = rg_time();
+          for (int h = 0; h < 2; ++h) {
+            CH_ACC(c_row, ch_row_step(prog.r[first], (2 * pr + h) * 128, prog.M, ew, lane));
+            CH_EDGE(h, si);
+          }
         }
       }
-      first_tile = false;
+      first_pair = false;
+    }
+    if (dbg != nullptr && threadIdx.x == 64) {
+      dbg[32] = (unsigned long long)c_wait;
+      dbg[33] = (unsigned long long)c_tile;
+      dbg[34] = (unsigned long long)c_edge;
+      dbg[35] = (unsigned long long)c_row;
+      dbg[31] = rg_time();
     }
   }
   pdl_trigger();
@@ -947,10 +1064,13 @@ int chain_launch(ChainBuild *b, cudaStream_t stream) {
     attr = true;
   }
   if (smem > 227 * 1024) VKN_FAIL(VKN_E_INVALID, "chain: shared memory budget exceeded");
-  dim3 grid(g.mtiles < 148 ? g.mtiles : 148);
+  const int npairs = (g.mtiles + 1) / 2;
+  dim3 grid(npairs < 148 ? npairs : 148);
   VKN_LAUNCH_MARK("vkn_chain_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_chain_tc_kernel, grid, dim3(RG_THREADS), smem, stream, g));
   g.nsteps = 0;
+  b->np = 0;
+  b->nr = 0;
   return VKN_OK;
 }
 
