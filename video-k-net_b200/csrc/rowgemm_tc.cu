@@ -78,6 +78,17 @@ __device__ __forceinline__ RgTile rg_decode(const RgBatch &batch, int t) {
 
 
 // ---- epilogue pieces (thread = row; 32 consecutive columns in registers) ---------------------------------------
+#ifdef VKN_EPI_PROF
+__device__ unsigned long long g_epi_prof[16];
+#define EPI_T0 const long long ep0__ = clock64()
+#define EPI_T(slot)                                                              \
+  do {                                                                           \
+    if (threadIdx.x == 64) atomicAdd(&g_epi_prof[slot], (unsigned long long)(clock64() - ep0__)); \
+  } while (0)
+#else
+#define EPI_T0
+#define EPI_T(slot)
+#endif
 struct RgRowCtx {
   int row, epi;
   int row_base, ks;           // first row of this warp's 32-row block, K slice (TMA store coordinates)
@@ -127,28 +138,47 @@ __device__ __forceinline__ void rg_chunk_load(const RgProb &P, const RgRowCtx &R
     }
   }
   uint32_t r[32];
-  tmem_ld32(taddr, r);
+  {
+    EPI_T0;
+    tmem_ld32(taddr, r);
+    EPI_T(0);
+  }
+  {
+    EPI_T0;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + add[e];
+    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + add[e];
+    EPI_T(1);
+  }
 }
 
 // sigmoid / elementwise factor / addend after bias, residual and LayerNorm (the KernelUpdator gate, kernel_updator.py:70-88)
 __device__ __forceinline__ void rg_post(const RgProb &P, const RgRowCtx &R, int col, int nc, float (&v)[32]) {
   if (!(R.epi & (EPI_SIGMOID | EPI_MUL | EPI_ADD2)) || !R.live) return;
-  if (R.epi & EPI_SIGMOID) {
-#pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = sigmoidf_(v[e]);
-  }
-  if (R.epi & EPI_MUL) {
+  float m[32];
+  if (R.epi & EPI_MUL) {                               // in flight while the sigmoids are evaluated
     const float *mp = P.mul + (size_t)R.row * P.ldmul + col;
 #pragma unroll
     for (int e = 0; e < 32; e += 4)
       if (e < nc) {
         const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(mp + e));
-        v[e] *= t4.x; v[e + 1] *= t4.y; v[e + 2] *= t4.z; v[e + 3] *= t4.w;
+        m[e] = t4.x; m[e + 1] = t4.y; m[e + 2] = t4.z; m[e + 3] = t4.w;
       }
   }
+  if (R.epi & EPI_SIGMOID) {
+    EPI_T0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = sigmoid_fast(v[e]);
+    EPI_T(8);
+  }
+  if (R.epi & EPI_MUL) {
+    EPI_T0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e < nc) v[e] *= m[e];
+    EPI_T(9);
+  }
   if (R.epi & EPI_ADD2) {
+    EPI_T0;
     const float *ap = P.add2 + (size_t)R.row * P.ldadd2 + col;
 #pragma unroll
     for (int e = 0; e < 32; e += 4)
@@ -156,6 +186,7 @@ __device__ __forceinline__ void rg_post(const RgProb &P, const RgRowCtx &R, int 
         const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(ap + e));
         v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
       }
+    EPI_T(10);
   }
 }
 
@@ -169,8 +200,13 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
   if (!(R.epi & EPI_NOOUT) && P.tma_out) {
     // fp32 rows through a 128B-swizzled [32 rows][128 B] staging box and ONE TMA store: full-line writes instead of 32
     // rows x 32 B per store instruction (the per-SM store rate of the direct path bounded this kernel)
-    if (lane == 0) bulk_wait_group_read<0>();
-    __syncwarp();
+    {
+      EPI_T0;
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+      EPI_T(2);
+    }
+    EPI_T0;
     const uint32_t rb = R.stg + (uint32_t)lane * 128u;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -182,6 +218,7 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
       tma_store_3d(&P.tmOut, R.stg, col, R.row_base, R.ks);
       bulk_commit_group();
     }
+    EPI_T(11);
   } else if (!(R.epi & EPI_NOOUT) && R.live) {
     float *op = R.outp + (size_t)R.row * P.ldo + col;
     if (R.out_vec && nc == 32) {
@@ -197,20 +234,16 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
   }
   if ((R.epi & EPI_SPLIT3) && col < P.split_C && P.tma_pl) {
     uint32_t w[3][16];
+    EPI_T0;
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {                  // v == hi + mid + lo to 24 bits
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
-        v[e] -= __bfloat162float(h0);
-        v[e + 1] -= __bfloat162float(h1);
-        w[pl][e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      }
-    }
+    for (int e = 0; e < 32; e += 2) split3_pair(v[e], v[e + 1], w[0][e >> 1], w[1][e >> 1], w[2][e >> 1]);
+    EPI_T(12);
     // staging free?  With side-by-side boxes the wait at the top of the fp32 path already covered the previous chunk.
     if (R.pl_off == 0 || (R.epi & EPI_NOOUT) || !P.tma_out) {
+      EPI_T0;
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
+      EPI_T(3);
     }
     const uint32_t rb = R.stg + R.pl_off + (uint32_t)lane * 64u;
     const int sw = (lane >> 1) & 3;
@@ -225,19 +258,16 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
       tma_store_3d(&P.tmPl, R.stg + R.pl_off, col, R.row_base, 0);
       bulk_commit_group();
     }
+    EPI_T(13);
   } else if ((R.epi & EPI_SPLIT3) && col < P.split_C && R.live) {
     const int np = min(32, P.split_C - col);
     __nv_bfloat16 *pp = P.planes + R.prow * P.split_C + col;
+    uint32_t w3[3][16];
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {                  // v == hi + mid + lo to 24 bits
-      uint32_t w[16];
+    for (int e = 0; e < 32; e += 2) split3_pair(v[e], v[e + 1], w3[0][e >> 1], w3[1][e >> 1], w3[2][e >> 1]);
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[e]), h1 = __float2bfloat16_rn(v[e + 1]);
-        v[e] -= __bfloat162float(h0);
-        v[e + 1] -= __bfloat162float(h1);
-        w[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      }
+    for (int pl = 0; pl < 3; ++pl) {
+      const uint32_t (&w)[16] = w3[pl];
       __nv_bfloat16 *pt = pp + (size_t)pl * P.plane_elems;
       if (R.pl_vec && np == 32) {
 #pragma unroll
@@ -331,7 +361,11 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
     st[half * 4 + 0] = cntf;
     st[half * 4 + 1] = mean_h;
     st[half * 4 + 2] = m2_h;
-    named_bar_sync(1, nthreads_epi);
+    {
+      EPI_T0;
+      named_bar_sync(1, nthreads_epi);
+      EPI_T(7);
+    }
     const float cb = st[(half ^ 1) * 4 + 0], mb = st[(half ^ 1) * 4 + 1], m2b = st[(half ^ 1) * 4 + 2];
     // merge in a fixed order (half 0 first) so both threads of a row get identical statistics
     const float n0 = half ? cb : cntf, mu0 = half ? mb : mean_h, q0 = half ? m2b : m2_h;
@@ -371,8 +405,16 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
         for (int e = 0; e < 32; ++e)
           if (e < nc) v[e] = fmaf((v[e] - mean) * rstd, __ldg(P.ln_g + col + e), __ldg(P.ln_b + col + e));
       }
-      rg_post(P, R, col, nc, v);
-      rg_chunk_store(P, R, col, nc, v);
+      {
+        EPI_T0;
+        rg_post(P, R, col, nc, v);
+        EPI_T(4);
+      }
+      {
+        EPI_T0;
+        rg_chunk_store(P, R, col, nc, v);
+        EPI_T(5);
+      }
     }
   } else {
     for (int c0 = half * 32; c0 < BN; c0 += 64) {
@@ -386,8 +428,16 @@ __device__ __forceinline__ void rg_epilogue_tile(const RgProb &P, int row0, int 
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);
       }
-      rg_post(P, R, col, nc, v);
-      rg_chunk_store(P, R, col, nc, v);
+      {
+        EPI_T0;
+        rg_post(P, R, col, nc, v);
+        EPI_T(4);
+      }
+      {
+        EPI_T0;
+        rg_chunk_store(P, R, col, nc, v);
+        EPI_T(5);
+      }
     }
   }
   if (!any) {                                           // a warp whose column blocks all lie past N
@@ -753,6 +803,234 @@ static_assert(sizeof(ChainProg) <= 32000, "chain program must fit the kernel par
 
 constexpr int CH_BN = 256;
 
+// ---- chain-kernel epilogue -----------------------------------------------------------------------------------------
+// Same arithmetic as rg_epilogue_tile, organised around the latency that bounded it (measured, tools/epi_prof.py: every
+// global load an epilogue thread waits for costs ~1.2 us while the TMA ring keeps the L2 path busy, and there were 1-3 per
+// 32-column block):
+//   * bias / LayerNorm gamma / beta of the tile are staged in shared memory ONCE per tile, before the accumulator wait;
+//   * the per-row operand of a block (residual in the first pass, elementwise factor in the second) is prefetched into
+//     registers one block ahead: its latency hides behind the store phase of the previous block (or the accumulator wait).
+// ch_epilogue_pre runs before the wait for the accumulator, ch_epilogue_tile after it.
+struct ChPre {
+  float ra[32];          // prefetched operand block (residual or factor) of the thread's row
+};
+
+__device__ __forceinline__ void ch_load_op(const float *base, int ld, int row, int col, int nc, bool live, float (&ra)[32]) {
+  if (!live) return;
+  const float *p = base + (size_t)row * ld + col;
+  if (nc == 32) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(p + e));
+      ra[e] = t4.x; ra[e + 1] = t4.y; ra[e + 2] = t4.z; ra[e + 3] = t4.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ra[e] = (e < nc) ? __ldcg(p + e) : 0.f;
+  }
+}
+
+// vec_s: [3][256] floats (bias, gamma, beta of columns col0 .. col0+255).  All 256 epilogue threads.
+__device__ __forceinline__ void ch_epilogue_pre(const RgProb &P, int row0, int col0, float *vec_s, int warp, int lane, ChPre &pre) {
+  const int t = (warp - 2) * 32 + lane, col = col0 + t;
+  named_bar_sync(1, RG_THREADS - 64);                    // every warp is done with the previous tile's vectors
+  vec_s[t] = ((P.epi & EPI_BIAS) && col < P.N) ? __ldg(P.bias + col) : 0.f;
+  if (P.epi & EPI_LN) {
+    vec_s[256 + t] = col < P.N ? __ldg(P.ln_g + col) : 0.f;
+    vec_s[512 + t] = col < P.N ? __ldg(P.ln_b + col) : 0.f;
+  }
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  const int row = row0 + q * 32 + lane, c = col0 + half * 32;
+  if (c < P.N) {
+    const int nc = min(32, P.N - c);
+    if (P.epi & EPI_RES) ch_load_op(P.res, P.ldres, row, c, nc, row < P.M, pre.ra);
+    else if ((P.epi & EPI_MUL) && !(P.epi & EPI_LN)) ch_load_op(P.mul, P.ldmul, row, c, nc, row < P.M, pre.ra);
+  }
+}
+
+__device__ __forceinline__ void ch_epilogue_tile(const RgProb &P, int row0, int col0, uint32_t tacc_base, uint32_t acc_empty,
+                                                 uint32_t stg, uint32_t pl_off, float *st_base, const float *vec_s, int warp,
+                                                 int lane, ChPre &pre) {
+  constexpr int BN = CH_BN;
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  RgRowCtx R;
+  R.epi = P.epi;
+  R.row = row0 + q * 32 + lane;
+  R.live = R.row < P.M;
+  R.row_base = row0 + q * 32;
+  R.ks = 0;
+  R.stg = stg;
+  R.pl_off = pl_off;
+  R.outp = P.out;
+  R.out_vec = (P.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(R.outp) & 31) == 0);
+  R.res_vec = true;
+  R.pl_vec = (P.split_C % 16 == 0) && ((reinterpret_cast<uintptr_t>(P.planes) & 31) == 0) && (P.plane_elems % 16 == 0);
+  R.bias_vec = true;
+  R.rs = (R.live && (R.epi & EPI_ROWSCALE)) ? __ldcg(P.rowscale + R.row) : 1.f;
+  R.prow = (size_t)R.row;
+  if ((R.epi & EPI_SPLIT3) && P.split_N != P.split_Npad) {
+    const int b = R.row / P.split_N;
+    R.prow = (size_t)b * P.split_Npad + (R.row - b * P.split_N);
+  }
+  named_bar_sync(1, RG_THREADS - 64);                    // the staged vectors are visible
+  const uint32_t tacc = tacc_base + ((uint32_t)(q * 32) << 16);
+  int last_c0 = half * 32;
+  while (last_c0 + 64 < BN && col0 + last_c0 + 64 < P.N) last_c0 += 64;
+  const bool any = half * 32 < BN && col0 + half * 32 < P.N;
+  const bool has_res = (R.epi & EPI_RES) != 0, has_mul = (R.epi & EPI_MUL) != 0;
+
+  // v = acc + rowscale * bias (+ prefetched residual); then prefetch the next block's operand
+  auto load_block = [&](int c0, float (&v)[32]) {
+    uint32_t r[32];
+    tmem_ld32(tacc + (uint32_t)c0, r);
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float4 b4 = *reinterpret_cast<const float4 *>(vec_s + c0 + e);
+      v[e] = fmaf(R.rs, b4.x, __uint_as_float(r[e]));
+      v[e + 1] = fmaf(R.rs, b4.y, __uint_as_float(r[e + 1]));
+      v[e + 2] = fmaf(R.rs, b4.z, __uint_as_float(r[e + 2]));
+      v[e + 3] = fmaf(R.rs, b4.w, __uint_as_float(r[e + 3]));
+    }
+  };
+  // sigmoid / factor (prefetched) / addend, then ReLU + stores
+  auto finish_block = [&](int c0, int col, int nc, float (&v)[32], bool mul_next_valid, int next_c0) {
+    if (R.live) {
+      if (R.epi & EPI_SIGMOID) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = sigmoid_fast(v[e]);
+      }
+      if (has_mul) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] *= pre.ra[e];
+      }
+    }
+    if (has_mul && mul_next_valid) {
+      const int ncol = col0 + next_c0;
+      ch_load_op(P.mul, P.ldmul, R.row, ncol, min(32, P.N - ncol), R.live, pre.ra);
+    }
+    if ((R.epi & EPI_ADD2) && R.live) {
+      const float *ap = P.add2 + (size_t)R.row * P.ldadd2 + col;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        if (e < nc) {
+          const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(ap + e));
+          v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+        }
+    }
+    rg_chunk_store(P, R, col, nc, v);
+  };
+
+  if (R.epi & EPI_LN) {
+    float K0 = 0.f, S1 = 0.f, S2 = 0.f, cntf = 0.f;
+    bool first = true;
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
+      const int nc = min(32, P.N - col);
+      float v[32];
+      load_block(c0, v);
+      if (has_res) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] += pre.ra[e];
+      }
+      // next operand block: the residual of the next block of this pass, or the factor of the first block of pass 2
+      if (c0 + 64 < BN && col + 64 < P.N) {
+        if (has_res) ch_load_op(P.res, P.ldres, R.row, col + 64, min(32, P.N - col - 64), R.live, pre.ra);
+      } else if (has_mul) {
+        ch_load_op(P.mul, P.ldmul, R.row, col0 + half * 32, min(32, P.N - col0 - half * 32), R.live, pre.ra);
+      }
+      {   // keep acc + bias + residual in the accumulator itself: the second pass re-reads TMEM, not global memory
+        uint32_t vr[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) vr[e] = __float_as_uint(v[e]);
+        tmem_st32(tacc + (uint32_t)c0, vr);
+      }
+      if (first) {
+        K0 = v[0];
+        first = false;
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nc) {
+          const float d = v[e] - K0;
+          S1 += d;
+          S2 = fmaf(d, d, S2);
+        }
+      cntf += (float)nc;
+    }
+    float mean_h = 0.f, m2_h = 0.f;
+    if (cntf > 0.f) {
+      mean_h = K0 + S1 / cntf;
+      m2_h = S2 - S1 * S1 / cntf;
+    }
+    float *st = st_base + (size_t)(q * 32 + lane) * 8;
+    st[half * 4 + 0] = cntf;
+    st[half * 4 + 1] = mean_h;
+    st[half * 4 + 2] = m2_h;
+    named_bar_sync(1, RG_THREADS - 64);
+    const float cb = st[(half ^ 1) * 4 + 0], mb = st[(half ^ 1) * 4 + 1], m2b = st[(half ^ 1) * 4 + 2];
+    const float n0 = half ? cb : cntf, mu0 = half ? mb : mean_h, q0 = half ? m2b : m2_h;
+    const float n1 = half ? cntf : cb, mu1 = half ? mean_h : mb, q1 = half ? m2_h : m2b;
+    const float nn = n0 + n1, delta = mu1 - mu0;
+    const float mean = mu0 + delta * (n1 / nn);
+    const float var = (q0 + q1 + delta * delta * (n0 * n1 / nn)) / nn;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
+      const int nc = min(32, P.N - col);
+      float v[32];
+      {
+        uint32_t vr[32];
+        tmem_ld32(tacc + (uint32_t)c0, vr);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(vr[e]);
+      }
+      if (c0 == last_c0) {                              // second read done: hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 g4 = *reinterpret_cast<const float4 *>(vec_s + 256 + c0 + e);
+        const float4 b4 = *reinterpret_cast<const float4 *>(vec_s + 512 + c0 + e);
+        v[e] = fmaf((v[e] - mean) * rstd, g4.x, b4.x);
+        v[e + 1] = fmaf((v[e + 1] - mean) * rstd, g4.y, b4.y);
+        v[e + 2] = fmaf((v[e + 2] - mean) * rstd, g4.z, b4.z);
+        v[e + 3] = fmaf((v[e + 3] - mean) * rstd, g4.w, b4.w);
+      }
+      finish_block(c0, col, nc, v, c0 + 64 < BN && col + 64 < P.N, c0 + 64);
+    }
+  } else {
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      const int col = col0 + c0;
+      if (col >= P.N) break;
+      const int nc = min(32, P.N - col);
+      float v[32];
+      load_block(c0, v);
+      if (c0 == last_c0) {                              // this warp's share of the accumulator is in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+      const bool more = c0 + 64 < BN && col + 64 < P.N;
+      if (has_res) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] += pre.ra[e];
+        if (more) ch_load_op(P.res, P.ldres, R.row, col + 64, min(32, P.N - col - 64), R.live, pre.ra);
+      }
+      finish_block(c0, col, nc, v, more, c0 + 64);
+    }
+  }
+  if (!any) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty);
+  }
+}
+
+
 // one row transform of the chain: warp per row, rows of the tile dealt round-robin to the 8 epilogue warps
 __device__ __forceinline__ void ch_row_step(const ChRow &Rw, int row0, int M, int ew, int lane) {
   for (int rr = ew; rr < 128; rr += 8) {
@@ -822,6 +1100,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
       stmt;                             \
     }                                   \
   } while (0)
+  // epilogue-side counters live in shared memory (updated by one thread): registers are the scarce resource there
+  long long *epi_ctr = reinterpret_cast<long long *>(ln_stat + 2 * 128 * 8);   // 4 counters behind the LayerNorm scratch
+  // [3][256]: bias / gamma / beta of the current tile (16-byte aligned: read as float4)
+  float *vec_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(epi_ctr + 4) + 15) & ~(uintptr_t)15);
+#define CH_ACC_S(slot, stmt)                                        \
+  do {                                                              \
+    if (dbg != nullptr) {                                           \
+      const long long c0__ = clock64();                             \
+      stmt;                                                         \
+      if (threadIdx.x == 64) epi_ctr[slot] += clock64() - c0__;     \
+    } else {                                                        \
+      stmt;                                                         \
+    }                                                               \
+  } while (0)
+  if (threadIdx.x < 4) epi_ctr[threadIdx.x] = 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -935,7 +1228,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
     const uint32_t stg = stg0 + (uint32_t)ew * (uint32_t)prog.stg_bytes;
     uint32_t li = 0, done = 0;
     bool first_pair = true;
-    long long c_wait = 0, c_tile = 0, c_edge = 0, c_row = 0;
     // step edge of row tile h: everything it wrote is complete and visible to the TMA loads / L2 reads of its next step
 #define CH_EDGE(h, si)                                                                                                  \
   do {                                                                                                                  \
@@ -947,7 +1239,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
     if (threadIdx.x == 64) {                                                                                            \
       asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(step_ctr + 4 * (h)), "r"(done + 1) : "memory");     \
       if (dbg != nullptr) {                                                                                             \
-        c_edge += clock64() - e0;                                                                                       \
+        epi_ctr[2] += clock64() - e0;                                                                                   \
         if (first_pair && (si) < 15) dbg[1 + 2 * (si) + (h)] = rg_time();                                               \
       }                                                                                                                 \
     }                                                                                                                   \
@@ -962,17 +1254,25 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
               const bool last = (pi == np - 1) && (j == P.nt - 1);
               for (int h = 0; h < 2; ++h, ++li) {
                 const uint32_t buf = li & 1u;
-                CH_ACC(c_wait, mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u));
+                ChPre pre;
+                if (P.epi & (EPI_MUL | EPI_ADD2)) {
+                  // the factor / addend rows may come from an earlier tile of the SAME step: this very warp stored them
+                  // (same rows, same column blocks) through TMA -- drain its bulk stores before reading them back
+                  if (lane == 0) bulk_wait_all();
+                  __syncwarp();
+                }
+                ch_epilogue_pre(P, (2 * pr + h) * 128, j * CH_BN, vec_s, warp, lane, pre);
+                CH_ACC_S(0, mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u));
                 tc_fence_after();
-                CH_ACC(c_tile, rg_epilogue_tile(P, (2 * pr + h) * 128, j * CH_BN, 0, CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf,
-                                 stg, (uint32_t)prog.pl_off, ln_stat + (size_t)buf * 128 * 8, warp, lane, RG_THREADS - 64));
+                CH_ACC_S(1, ch_epilogue_tile(P, (2 * pr + h) * 128, j * CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf,
+                                 stg, (uint32_t)prog.pl_off, ln_stat + (size_t)buf * 128 * 8, vec_s, warp, lane, pre));
                 if (last) CH_EDGE(h, si);
               }
             }
           }
         } else {
           for (int h = 0; h < 2; ++h) {
-            CH_ACC(c_row, ch_row_step(prog.r[first], (2 * pr + h) * 128, prog.M, ew, lane));
+            CH_ACC_S(3, ch_row_step(prog.r[first], (2 * pr + h) * 128, prog.M, ew, lane));
             CH_EDGE(h, si);
           }
         }
@@ -980,10 +1280,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
       first_pair = false;
     }
     if (dbg != nullptr && threadIdx.x == 64) {
-      dbg[32] = (unsigned long long)c_wait;
-      dbg[33] = (unsigned long long)c_tile;
-      dbg[34] = (unsigned long long)c_edge;
-      dbg[35] = (unsigned long long)c_row;
+      dbg[32] = (unsigned long long)epi_ctr[0];
+      dbg[33] = (unsigned long long)epi_ctr[1];
+      dbg[34] = (unsigned long long)epi_ctr[2];
+      dbg[35] = (unsigned long long)epi_ctr[3];
       dbg[31] = rg_time();
     }
   }
@@ -995,6 +1295,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
     tmem_dealloc(tmem_base, 2u * CH_BN);
   }
 }
+
+#ifdef VKN_EPI_PROF
+extern "C" int vkn_debug_epi_prof(unsigned long long *out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, g_epi_prof, sizeof(g_epi_prof));
+  if (reset) {
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_epi_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // ---- host: chain builder -------------------------------------------------------------------------------------------
 struct ChainBuild {
@@ -1057,7 +1368,7 @@ int chain_launch(ChainBuild *b, cudaStream_t stream) {
   g.pl_off = 0;
   g.idesc = make_idesc_bf16(128, CH_BN, 0, 0);
   g.dbg = debug_ts_slot();
-  const size_t smem = (size_t)g.stages * stage_bytes + 8 * (size_t)g.stg_bytes + 1024 + (2 * g.stages + 5) * 8 + 16 + 2 * 128 * 8 * 4 + 64;
+  const size_t smem = (size_t)g.stages * stage_bytes + 8 * (size_t)g.stg_bytes + 1024 + (2 * g.stages + 5) * 8 + 16 + 2 * 128 * 8 * 4 + 64 + 32 + 3 * 256 * 4 + 16;
   static bool attr = false;
   if (!attr) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
