@@ -52,3 +52,66 @@ def top2_gap(masks):
     """per-pixel gap between the best and second-best kernel logit ([B,N,H,W] -> [B,H,W])."""
     v = masks.float().topk(2, dim=1).values
     return v[:, 0] - v[:, 1]
+
+
+def bf16_ulp(t):
+    """one bf16 unit in the last place at the magnitude of each element of t (8 significand bits)."""
+    a = t.float().abs().clamp_min(2.0 ** -126)
+    return torch.exp2(torch.floor(torch.log2(a)) - 7)
+
+
+def assert_masks_bf16(got, ref32, what, verbose=True):
+    """bf16-storage mask logits of the CUDA path against the oracle (fp32 math, stored rounded to bf16).
+
+    * every logit within ONE bf16 ulp of the oracle's stored value (plus 2^-16 of the largest logit: the fp32 round-off a whole
+      stage accumulates -- pooling over ~10^4 pixels, LayerNorms, a dozen GEMMs -- which is all that is left of a logit that
+      cancels to ~0; still 2^8 finer than the bf16 resolution the logits are stored at);
+    * argmax over the kernels identical, except at pixels where the oracle's own top-2 stored logits are within that same
+      distance of each other AND the kernel the CUDA path picked is one of those near-ties (the consumer's argmax,
+      knet/video/kernel_iter_head.py:854, cannot distinguish them at bf16 resolution).  Returns the number of such pixels.
+    """
+    got = got.float().cpu()
+    ref = ko.round_bf16(ref32.float())
+    floor_ = 2.0 ** -16 * ref.abs().max().item()
+    err = (got - ref).abs()
+    tol = bf16_ulp(torch.maximum(ref.abs(), got.abs())) * (1 + 1e-6) + floor_
+    worst = (err / tol).max().item()
+    assert worst <= 1.0, '%s: a logit is %.2f x (one bf16 ulp + fp32 noise floor) away from the oracle' % (what, worst)
+    nflip = int((err > floor_).sum())
+    if ref.shape[1] == 1:
+        return 0
+    a, b = got.argmax(1), ref.argmax(1)
+    bad = a != b
+    nbad = int(bad.sum())
+    if nbad:
+        top2 = ref.topk(2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1])[bad]
+        u = bf16_ulp(top2[:, 0])[bad] + floor_
+        assert bool((gap <= u).all()), '%s: %d argmax mismatches at pixels whose oracle top-2 gap exceeds one bf16 ulp ' \
+            '(max gap %.3g ulp)' % (what, int((gap > u).sum()), (gap / u).max().item())
+        picked = ref.gather(1, a.unsqueeze(1)).squeeze(1)[bad]
+        assert bool((top2[:, 0][bad] - picked <= u).all()), '%s: the CUDA path picked a kernel that is not a near-tie' % what
+    if verbose:
+        print('%s: %d of %d logits differ by one bf16 ulp; %d of %d pixels resolve a bf16 near-tie differently' % (
+            what, nflip, got.numel(), nbad, a.numel()))
+    return nbad
+
+
+def stagewise_vs_oracle_bf16(heads, sds, cfg, xb, pfd, mb, what, tol=1e-2):
+    """Every stage of the CUDA path (bf16 storage) against the oracle evaluated on THAT stage's actual inputs -- the
+    CUDA path's own previous outputs -- so no hard-threshold disagreement can cascade between the two and every stage is
+    checked unconditionally: kernel tensors within `tol`, mask logits / argmax by assert_masks_bf16.
+    Returns the per-stage CUDA outputs and the total number of near-tie pixels resolved differently."""
+    obj, m = pfd, mb
+    outs, ties = [], 0
+    B, N = pfd.shape[:2]
+    for s, h in enumerate(heads):
+        cls, m_new, obj_new = h(xb, obj, m)
+        want = ko.kernel_update_head_forward(sds[s], cfg, xb.float().cpu(), obj.float().cpu().reshape(B, N, -1, 1, 1),
+                                             m.float().cpu())
+        e_cls, e_obj = maxabs(cls, want[0]), maxabs(obj_new, want[2])
+        assert e_cls < tol and e_obj < tol, '%s stage %d: cls err %g obj err %g' % (what, s, e_cls, e_obj)
+        ties += assert_masks_bf16(m_new, want[1], '%s stage %d' % (what, s))
+        outs.append((cls, m_new, obj_new))
+        obj, m = obj_new, m_new
+    return outs, ties

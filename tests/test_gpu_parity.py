@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import knet_oracle as ko
-from helpers import build_heads, golden_files, load_golden, maxabs, top2_gap
+from helpers import assert_masks_bf16, build_heads, golden_files, load_golden, maxabs, stagewise_vs_oracle_bf16, top2_gap
 from vknet import _lib
 
 pytestmark = pytest.mark.gpu
@@ -147,12 +147,10 @@ def test_clip_head_vs_oracle(dev, B, Fr, N, C, H, W, with_cls, dt):
     assert maxabs(obj, want[2]) < tol
     if with_cls:
         assert maxabs(cls, want[0]) < tol
-    ref = want[1] if dt == 'f32' else ko.round_bf16(want[1])
     if dt == 'f32':
-        assert_masks(nm.reshape(B * Fr, N, H, W), ref.reshape(B * Fr, N, H, W), 'clip')
+        assert_masks(nm.reshape(B * Fr, N, H, W), want[1].reshape(B * Fr, N, H, W), 'clip')
     else:
-        mism = (nm.float().cpu().argmax(2) != ref.argmax(2)).float().mean().item()
-        assert mism < 2e-3, 'clip bf16: argmax mismatch rate %g' % mism
+        assert_masks_bf16(nm.reshape(B * Fr, N, H, W), want[1].reshape(B * Fr, N, H, W), 'clip bf16')
 
 
 # ---- individual operators against the oracle ------------------------------------------------------
@@ -234,21 +232,9 @@ def test_bf16_storage(dev, B, N, C, H, W, S):
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=512)
     sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=70 + s)) for s in range(S)]
     x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=6)
-    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
-    want = ko.iter_forward(sds, [cfg] * S, x, pf, mask, mask_round=ko.round_bf16)
     heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
-    obj, m = pf.to(dev), mask.to(dev).bfloat16()
-    xb = x.to(dev).bfloat16()
-    for s, h in enumerate(heads):
-        cls, m, obj = h(xb, obj, m)
-        assert m.dtype == torch.bfloat16 and obj.dtype == torch.float32
-        assert maxabs(cls, want[s][0]) < TOL_BF16, 'bf16 stage %d cls' % s
-        assert maxabs(obj, want[s][2]) < TOL_BF16, 'bf16 stage %d obj' % s
-        ref = want[s][1]
-        # bf16 output rounding: 1 ulp = 2^-8 relative
-        assert (m.float().cpu() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
-        mism = (m.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item()
-        assert mism < 2e-3, 'bf16 stage %d: argmax mismatch rate %g' % (s, mism)
+    outs, _ = stagewise_vs_oracle_bf16(heads, sds, cfg, x.to(dev).bfloat16(), pf.to(dev), mask.to(dev).bfloat16(), 'bf16 storage')
+    assert outs[-1][1].dtype == torch.bfloat16 and outs[-1][2].dtype == torch.float32
 
 
 # ---- BASELINE.json cfg1 at full size: N=100, C=256, 200x88, S=3 -------------------------------------
@@ -276,12 +262,46 @@ def test_cfg1_full_size_loop(dev):
         cls_c, m_c, obj_c = h(x.to(dev), obj_c, m_c)
         flips.append(int(((m_c.float().cpu() > 0) != (want[s][1] > 0)).sum()))
     assert torch.equal(m_l, m_c) and torch.equal(obj_l, obj_c) and torch.equal(cls_l, cls_c)
-    # end of the loop vs the oracle: threshold disagreements upstream are counted, not assumed zero
+    # end of the loop vs the oracle: threshold disagreements upstream are counted, not assumed zero ...
     print('cfg1 threshold disagreements per stage vs oracle:', flips)
     assert sum(flips[:-1]) <= 8, 'too many hard-mask disagreements feeding later stages: %s' % flips
-    if sum(flips[:-1]) == 0:
-        assert maxabs(obj_l, want[-1][2]) < TOL_F32 and maxabs(cls_l, want[-1][0]) < TOL_F32
-        assert_masks(m_l, want[-1][1], 'cfg1 loop end')
+    # ... and the end of the loop is checked UNCONDITIONALLY against the oracle chained on the CUDA path's own hard masks
+    # (each oracle stage is fed the previous CUDA stage's outputs, so a flipped pixel upstream cannot cascade)
+    obj_c, m_c = pf.to(dev), mask.to(dev)
+    for s, h in enumerate(heads):
+        ref = ko.kernel_update_head_forward(sds[s], cfg, x, obj_c.cpu().reshape(B, N, C, 1, 1), m_c.cpu())
+        cls_c, m_c, obj_c = h(x.to(dev), obj_c, m_c)
+        assert maxabs(obj_c, ref[2]) < TOL_F32 and maxabs(cls_c, ref[0]) < TOL_F32, 'cfg1 chained stage %d' % s
+        assert_masks(m_c, ref[1], 'cfg1 chained stage %d' % s)
+    assert torch.equal(m_l, m_c) and torch.equal(obj_l, obj_c)
+
+
+def test_bench_operating_point_bf16_cfg1_batch64(dev):
+    """The configuration bench.py quotes its headline on: bf16 storage, cfg1 (N=100, C=256, 200x88), F=2048, S=3, a batch of
+    64 frames through the one-call loop (tcgen05 engines, chain kernel, 1-bit hard-mask hand-off between stages), also as
+    the CUDA graph FramesInFlight replays.  Every stage is checked against the oracle on its actual inputs (kernel tensors
+    1e-2, logits within one bf16 ulp, argmax identical up to bf16 near-ties -- counted and printed), and the one-call loop
+    must reproduce the stage-wise module calls bit for bit."""
+    import vknet
+    B, N, C, H, W, S = 64, 100, 256, 200, 88, 3
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=2048)
+    sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=50 + s)) for s in range(S)]
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(B, C, H, W, generator=g, device=dev)
+    pfd = torch.randn(B, N, C, generator=g, device=dev)
+    mb = pfd.bmm(x.view(B, C, -1)).view(B, N, H, W).bfloat16()
+    xb = x.bfloat16()
+    outs, ties = stagewise_vs_oracle_bf16(heads, sds, cfg, xb, pfd, mb, 'bench point (64 x cfg1)')
+    loop = vknet.KernelIterLoop(heads)
+    cls_l, m_l, obj_l = loop(xb, pfd, mb)
+    assert torch.equal(m_l, outs[-1][1]) and torch.equal(obj_l.reshape(B, N, C), outs[-1][2].reshape(B, N, C)) \
+        and torch.equal(cls_l, outs[-1][0]), 'one-call loop (bit-mask hand-off) != stage-wise modules'
+    fif = vknet.FramesInFlight(heads, branches=1, batch=B).capture([(xb, pfd, mb)])
+    cls_g, m_g, obj_g = fif.replay()[0]
+    torch.cuda.synchronize()
+    assert torch.equal(m_g, m_l) and torch.equal(obj_g.reshape(B, N, C), obj_l.reshape(B, N, C)) and torch.equal(cls_g, cls_l)
+    print('bench operating point: %d bf16 near-tie pixels of %d resolved differently over %d stages' % (ties, S * B * H * W, S))
 
 
 def test_graph_replay_matches_eager_and_is_deterministic(dev):
@@ -386,9 +406,7 @@ def test_tc_engine_matches_simt_engine_and_oracle(dev, B, N, C, H, W):
     for name in ('simt', 'tc'):
         cls, nm, obj = out[name][2]
         assert maxabs(cls, want[0]) < TOL_BF16 and maxabs(obj, want[2]) < TOL_BF16, name
-        ref = ko.round_bf16(want[1])
-        mism = (nm.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item()
-        assert mism < 2e-3, '%s stage: argmax mismatch rate %g' % (name, mism)
+        assert_masks_bf16(nm, want[1], '%s engine stage' % name)
 
 
 @pytest.mark.parametrize('wide', ['0', '1'])
@@ -518,8 +536,6 @@ def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=Fh)
     sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=90 + s)) for s in range(S)]
     x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=16)
-    x, mask = ko.round_bf16(x), ko.round_bf16(mask)
-    want = ko.iter_forward(sds, [cfg] * S, x, pf, mask, mask_round=ko.round_bf16)
     heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
     xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
     outs = {}
@@ -534,12 +550,11 @@ def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H
         loop = vknet.KernelIterLoop(heads)          # one-call loop: obj planes ping-pong between stages
         cls_l, m_l, obj_l = loop(xb, pfd, mb)
         assert torch.equal(m_l, res[-1][1]) and torch.equal(obj_l, res[-1][2]) and torch.equal(cls_l, res[-1][0]), mode
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    tc_outs, _ = stagewise_vs_oracle_bf16(heads, sds, cfg, xb, pfd, mb, 'row engine')
     for s in range(S):
-        cls, m, obj = outs['tc'][s]
-        assert maxabs(cls, want[s][0]) < TOL_BF16 and maxabs(obj, want[s][2]) < TOL_BF16, 'row engine stage %d' % s
-        ref = want[s][1]
-        assert (m.float().cpu() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
-        assert (m.float().cpu().argmax(1) != ref.argmax(1)).float().mean().item() < 2e-3
+        for a, b in zip(tc_outs[s], outs['tc'][s]):
+            assert torch.equal(a, b)
     # both engines multiply exact bf16 products with fp32 accumulation: first-stage kernels agree to fp32 round-off
     assert maxabs(outs['tc'][0][2], outs['warp'][0][2].cpu()) < 2e-4
     assert maxabs(outs['tc'][0][0], outs['warp'][0][0].cpu()) < 2e-4

@@ -796,6 +796,7 @@ struct ChainProg {
   ChRow r[CH_MAXR];
   ChStep s[CH_MAXS];
   int nsteps, M, mtiles, stages, stg_bytes, pl_off;
+  int tpc;                       // row tiles a CTA interleaves per pass of the program: 2 (pairs) or 1
   uint32_t idesc;
   unsigned long long *dbg;       // optional: %globaltimer at every step edge of the CTA's first tile (vkn_debug_timestamps)
 };
@@ -1073,7 +1074,7 @@ __device__ __forceinline__ void ch_wait_steps(uint32_t ctr, uint32_t need) {
 __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __grid_constant__ ChainProg prog) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int STG = prog.stages, nsteps = prog.nsteps, npairs = (prog.mtiles + 1) >> 1;
+  const int STG = prog.stages, nsteps = prog.nsteps, tpc = prog.tpc, npairs = (prog.mtiles + tpc - 1) / tpc;
   constexpr uint32_t stage_bytes = RG_A_BYTES + (uint32_t)CH_BN * 128u;
   const uint32_t stg0 = smem_u32(smem + (size_t)STG * stage_bytes);
   uint64_t *bars = (uint64_t *)(smem + (size_t)STG * stage_bytes + 8 * (size_t)prog.stg_bytes);
@@ -1156,13 +1157,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
             const RgProb &P = prog.p[first + pi];
             const int nk = (P.K + 63) / 64;
             for (int j = 0; j < P.nt; ++j)
-              for (int h = 0; h < 2; ++h)
+              for (int h = 0; h < tpc; ++h)
                 for (int i = 0; i < nk; ++i, ++it) {
                   if (it >= (uint32_t)STG) CH_ACC(c_empty, mbar_wait(bar0 + 8 * (STG + s), ph ^ 1u));
                   mbar_expect_tx(bar0 + 8 * s, stage_bytes);
                   tma_load_2d(smem0 + s * stage_bytes + RG_A_BYTES, &P.tmW, bar0 + 8 * s, i * 64, j * CH_BN);
                   CH_ACC(c_steps, ch_wait_steps(step_ctr + 4 * h, g));   // this tile's A planes were written by its previous steps
-                  tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, i * 64, (2 * pr + h) * 128, 0);
+                  tma_load_3d(smem0 + s * stage_bytes, &P.tmA, bar0 + 8 * s, i * 64, (tpc * pr + h) * 128, 0);
                   if (++s == STG) {
                     s = 0;
                     ph ^= 1u;
@@ -1189,7 +1190,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
         const int np = prog.s[si].n, first = prog.s[si].first;
         for (int pi = 0; pi < np; ++pi) {
           const int nk = (prog.p[first + pi].K + 63) / 64, nt = prog.p[first + pi].nt;
-          for (int jh = 0; jh < 2 * nt; ++jh, ++li) {
+          for (int jh = 0; jh < tpc * nt; ++jh, ++li) {
             const uint32_t buf = li & 1u;
             CH_ACC(c_acc, mbar_wait(acc_empty0 + 8 * buf, ((li >> 1) & 1u) ^ 1u));
             tc_fence_after();
@@ -1252,7 +1253,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
             const RgProb &P = prog.p[first + pi];
             for (int j = 0; j < P.nt; ++j) {
               const bool last = (pi == np - 1) && (j == P.nt - 1);
-              for (int h = 0; h < 2; ++h, ++li) {
+              for (int h = 0; h < tpc; ++h, ++li) {
                 const uint32_t buf = li & 1u;
                 ChPre pre;
                 if (P.epi & (EPI_MUL | EPI_ADD2)) {
@@ -1261,18 +1262,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) vkn_chain_tc_kernel(const __gri
                   if (lane == 0) bulk_wait_all();
                   __syncwarp();
                 }
-                ch_epilogue_pre(P, (2 * pr + h) * 128, j * CH_BN, vec_s, warp, lane, pre);
+                ch_epilogue_pre(P, (tpc * pr + h) * 128, j * CH_BN, vec_s, warp, lane, pre);
                 CH_ACC_S(0, mbar_wait(acc_full0 + 8 * buf, (li >> 1) & 1u));
                 tc_fence_after();
-                CH_ACC_S(1, ch_epilogue_tile(P, (2 * pr + h) * 128, j * CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf,
+                CH_ACC_S(1, ch_epilogue_tile(P, (tpc * pr + h) * 128, j * CH_BN, tmem_base + buf * (uint32_t)CH_BN, acc_empty0 + 8 * buf,
                                  stg, (uint32_t)prog.pl_off, ln_stat + (size_t)buf * 128 * 8, vec_s, warp, lane, pre));
                 if (last) CH_EDGE(h, si);
               }
             }
           }
         } else {
-          for (int h = 0; h < 2; ++h) {
-            CH_ACC_S(3, ch_row_step(prog.r[first], (2 * pr + h) * 128, prog.M, ew, lane));
+          for (int h = 0; h < tpc; ++h) {
+            CH_ACC_S(3, ch_row_step(prog.r[first], (tpc * pr + h) * 128, prog.M, ew, lane));
             CH_EDGE(h, si);
           }
         }
@@ -1375,7 +1376,12 @@ int chain_launch(ChainBuild *b, cudaStream_t stream) {
     attr = true;
   }
   if (smem > 227 * 1024) VKN_FAIL(VKN_E_INVALID, "chain: shared memory budget exceeded");
-  const int npairs = (g.mtiles + 1) / 2;
+  // Pairs of row tiles per CTA (one tile's epilogue and step edge hide behind the other's MMAs) when there are enough
+  // tiles to keep every SM busy that way; otherwise one tile per CTA (twice the CTAs, accumulator double-buffered across
+  // column tiles).  VKN_CHAIN_TPC overrides.
+  g.tpc = g.mtiles > 148 ? 2 : 1;
+  if (const char *e = getenv("VKN_CHAIN_TPC")) g.tpc = atoi(e) == 2 ? 2 : 1;
+  const int npairs = (g.mtiles + g.tpc - 1) / g.tpc;
   dim3 grid(npairs < 148 ? npairs : 148);
   VKN_LAUNCH_MARK("vkn_chain_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_chain_tc_kernel, grid, dim3(RG_THREADS), smem, stream, g));
