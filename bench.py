@@ -5,10 +5,11 @@
 
 A "step" = one pass of the hot path over one batch of synthetic input: ONE frame per rank
 (cfg1: N=100 kernels, C=256, 200x88 feature map, S=3 stages, bf16 storage).  Frames are independent, so the
-throughput mode keeps VKN_STREAMS x VKN_BATCH (default 3 x 64) frames in flight per CUDA-graph launch and rank; the
-timed region runs whole launches (K rounded up to a multiple of 192 frames) and is scaled back to exactly K frames.
-With more than one GPU every launch also performs the one exchange frame sharding needs (all-gather of the
-last-stage kernels over NCCL + the `previous_type='ffn'` link block, cfg3).
+throughput mode keeps VKN_STREAMS x VKN_BATCH (default 3 x 126) frames in flight per CUDA-graph launch and rank; the
+timed region runs whole launches: at least 20 of them and at least K frames, per-launch CUDA events (median / p95 under
+`timing`), and `ms_per_step` = timed device time / frames processed.
+With more than one GPU every launch also performs the one exchange frame sharding needs (all-gather of the ranks'
+shard-boundary kernels over NCCL + the `previous_type='ffn'` link block, cfg3), on a side stream.
 
   value     frames/s, whole job, inputs resident in HBM, CUDA-graph replay of the loop, CUDA-event timed,
             max over ranks.  Inputs rotate over R distinct sets whose footprint exceeds L2.
@@ -36,6 +37,20 @@ CFG1 = dict(B=1, N=100, C=256, H=200, W=88, S=3, ncls=19, ffn=2048)
 METRIC = 'frames/sec/GPU (100 kernels, C=256, 200x88, S=3)'
 # the workload both arms are quoted on (BASELINE.json configs[1]); frames are independent, so throughput = frames/s/GPU
 WORKLOAD = 'cfg1 KITTI-STEP R-50 shape per frame: N=100 kernels, C=256, 200x88 feature map, S=3 stages'
+# --config: the other shapes BASELINE.json / SURVEY.md 8d name (per-frame KernelUpdateHead loop, same kernels); their lines
+# are kept under profiles/.  cfg1 is the one the headline metric is quoted on.
+CONFIGS = {
+    'cfg1': dict(N=100, H=200, W=88, ncls=19, workload=WORKLOAD),
+    'n117': dict(N=117, H=200, W=88, ncls=19, workload='cfg1 feature map with the real KITTI/Cityscapes-STEP kernel count: N=117 '
+                                                       '(100 things + 17 stuff kernels), C=256, 200x88, S=3'),
+    'n166': dict(N=166, H=200, W=88, ncls=124, workload='cfg1 feature map with the VIP-Seg kernel count: N=166 (100 + 66 stuff), '
+                                                        'C=256, 200x88, S=3'),
+    'cfg2': dict(N=100, H=96, W=160, ncls=40, workload='cfg2 YouTube-VIS frame shape: N=100, C=256, 96x160, S=3 (per-frame heads; '
+                                                       'the clip head with frames_per_set=4 is covered by the parity tests)'),
+    'cfg4': dict(N=100, H=120, W=216, ncls=124, workload='cfg4 VIP-Seg frame shape: N=100, C=256, 120x216, S=3'),
+    'cfg4_n166': dict(N=166, H=120, W=216, ncls=124, workload='cfg4 VIP-Seg frame shape with its real kernel count: N=166, C=256, '
+                                                              '120x216, S=3'),
+}
 
 
 def head_cfg(link=False):
@@ -179,6 +194,57 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def parity_check(torch, heads, fif, dev):
+    """`parity` of the JSON line: the CUDA path against the CPU oracle on frames of the TIMED batch (rank 0, outside the
+    timed region; the oracle is the checker here, never the thing measured).
+    * stage-wise: every stage of the batch (module calls at the throughput batch size: tcgen05 engines + chain kernel)
+      against the oracle evaluated on that stage's actual inputs, for `nf` frames: max-abs error of obj_feat / cls_score,
+      logits more than one bf16 ulp (+2^-16 of the largest logit) away, argmax mismatches that are NOT bf16 near-ties of
+      the oracle, near-tie pixels resolved differently, hard-threshold (logit > 0) disagreements handed to the next stage;
+    * loop: the graph-replayed one-call loop (bit-mask hand-off) must equal those stage-wise calls bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import knet_oracle as ko
+    st = fif.static[0]
+    xb, pfd, mb = st['x'], st['pf'], st['mask']
+    B, N, C = pfd.shape
+    nf = min(2, B)
+    cfg = ko.default_cfg(num_classes=CFG1['ncls'], in_channels=C, feedforward_channels=CFG1['ffn'])
+    res = dict(frames_checked=nf, batch=B, obj_max_abs=0.0, cls_max_abs=0.0, logits_beyond_one_bf16_ulp=0,
+               argmax_mismatch_not_near_tie=0, near_tie_pixels_resolved_differently=0, threshold_disagreements=0,
+               pixels=0)
+
+    def ulp(t):
+        return torch.exp2(torch.floor(torch.log2(t.abs().clamp_min(2.0 ** -126))) - 7)
+    obj, m = pfd, mb
+    with torch.no_grad():
+        for h in heads:
+            sd = {k: v.detach().float().cpu() for k, v in h.state_dict().items()}
+            cls, m_new, obj_new = h(xb, obj, m)[:3]
+            want = ko.kernel_update_head_forward(sd, cfg, xb[:nf].float().cpu(), obj[:nf].float().cpu().reshape(nf, N, C, 1, 1),
+                                                 m[:nf].float().cpu())
+            res['obj_max_abs'] = max(res['obj_max_abs'], float((obj_new[:nf].float().cpu().reshape(want[2].shape) - want[2]).abs().max()))
+            res['cls_max_abs'] = max(res['cls_max_abs'], float((cls[:nf].float().cpu() - want[0]).abs().max()))
+            got, ref = m_new[:nf].float().cpu(), ko.round_bf16(want[1])
+            floor_ = 2.0 ** -16 * float(ref.abs().max())
+            res['logits_beyond_one_bf16_ulp'] += int(((got - ref).abs() > ulp(torch.maximum(ref.abs(), got.abs())) * (1 + 1e-6) + floor_).sum())
+            bad = got.argmax(1) != ref.argmax(1)
+            top2 = ref.topk(2, dim=1).values
+            tie = (top2[:, 0] - top2[:, 1]) <= ulp(top2[:, 0]) + floor_
+            res['near_tie_pixels_resolved_differently'] += int((bad & tie).sum())
+            res['argmax_mismatch_not_near_tie'] += int((bad & ~tie).sum())
+            res['threshold_disagreements'] += int(((got > 0) != (want[1] > 0)).sum())
+            res['pixels'] += bad.numel()
+            obj, m = obj_new.reshape(B, N, C), m_new
+        outs = fif.replay()[0]
+        torch.cuda.synchronize()
+        res['loop_equals_stagewise_bitwise'] = bool(torch.equal(outs[1], m) and torch.equal(outs[2].reshape(B, N, C), obj) and
+                                                    torch.equal(outs[0], cls))
+    res['tolerance'] = 'kernel tensors 1e-2 (bf16 storage); logits one bf16 ulp; argmax identical up to oracle near-ties'
+    res['ok'] = bool(res['obj_max_abs'] < 1e-2 and res['cls_max_abs'] < 1e-2 and res['logits_beyond_one_bf16_ulp'] == 0 and
+                     res['argmax_mismatch_not_near_tie'] == 0 and res['loop_equals_stagewise_bitwise'])
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -200,12 +266,13 @@ def run_ours(args):
     S = CFG1['S']
     B, N, C, H, W = (CFG1[k] for k in 'BNCHW')
     HW = H * W
+    with_link = world > 1 or bool(os.environ.get('VKN_BENCH_LINK'))     # cfg3: + the previous_type='ffn' link block
 
     # random-init weights of the KITTI-STEP R-50 head (init_weights semantics), bf16 storage
     torch.manual_seed(0)
     heads = []
     for s in range(S):
-        last_linked = world > 1 and s == S - 1
+        last_linked = with_link and s == S - 1
         h = vknet.build_head(dict(type='VideoKernelUpdateHead' if last_linked else 'KernelUpdateHead',
                                   **head_cfg(link=last_linked)))
         h.init_weights()
@@ -214,13 +281,14 @@ def run_ours(args):
         heads.append(h.to(dev).bfloat16().eval())
     loop = vknet.KernelIterLoop(heads)
 
-    # Frames in flight: one CUDA graph = NS concurrent branches x BF frames each (vknet.FramesInFlight).
-    # The loop of ONE frame is a chain of small latency-bound kernels that fills a fraction of the 148
-    # SMs, so independent frames overlap.  Two such groups alternate; one group's inputs + outputs
-    # (NS*BF frames x 16.2 MB = 3.1 GB for the default 3 x 64) exceed L2 (126 MB) many times over, so x and the masks
-    # stream from HBM.  Measured sweep (profiles/): 2x8 21k, 2x32 35k, 2x64 40k, 3x64 40.6k frames/s.
+    # Frames in flight: one CUDA graph = NS concurrent branches x BF frames each (vknet.FramesInFlight).  Frames are
+    # independent; a branch of 126 frames = 12 600 kernel rows = 99 row tiles keeps the chain kernel, the
+    # pooling and the mask conv on (nearly) every SM, three branches overlap the HBM-bound and the tensor-bound kernels of
+    # different frames.  Two such groups alternate; one group's inputs + outputs exceed L2 (126 MB) many times over, so x and
+    # the masks stream from HBM.  Measured sweep (profiles/r2_inflight_sweep.md): 3x64 42.5k, 2x148 47.0k, 3x126 46.6k,
+    # 2x378 47.4k frames/s; 3x126 has the best end-to-end rate.
     NS = max(1, int(os.environ.get('VKN_STREAMS', '3')))
-    BF = max(1, int(os.environ.get('VKN_BATCH', '64')))
+    BF = max(1, int(os.environ.get('VKN_BATCH', '126')))
     quick = bool(os.environ.get('VKN_BENCH_QUICK'))       # profiler runs: small group, no CPU arm
     if quick and 'VKN_STREAMS' not in os.environ and 'VKN_BATCH' not in os.environ:
         NS, BF = 1, 1
@@ -256,65 +324,94 @@ def run_ours(args):
     loop(st0['x'], st0['pf'], st0['mask'])                      # one vkn_iter_forward at the throughput batch size
     launches_per_frame_call = _lib.launch_count() - before      # kernels of ONE call = one branch of a graph launch
 
-    link_head = heads[-1] if world > 1 else None
+    # ---- cfg3 exchange: the ranks' frames are consecutive blocks of one clip; frame t's tracking kernels attend to frame
+    #      t-1's kernels.  A rank needs ONE frame it does not own (its left neighbour's last): one all-gather of world x
+    #      [N, C] (102 KB each) over NCCL, then the link block on the rank's own FPG frames.  Both run on a side stream so
+    #      that they overlap the next graph launch (the groups alternate, so its inputs / outputs are different buffers).
+    link_head = heads[-1] if with_link else None
+    side = torch.cuda.Stream(device=dev)
+    link_done = [None] * len(groups)
+    track_host = torch.empty(FPG, N, C).pin_memory()
+    link_state = {}
+
+    def link_fn_for(nf):
+        if nf not in link_state:
+            w, links, wd = link_head.packed_weights(dev)
+            shape = link_head._shape(nf, N, H, W, _lib.VKN_BF16, wd)
+            ws = _lib.Workspace()
+            link_state[nf] = (links, shape, ws)
+        links, shape, ws = link_state[nf]
+        wsp, wsb = ws.get(shape, dev)
+        return lambda cur, prev: link_head._link(shape, links['track'], cur.contiguous(), prev.contiguous(), None, wsp, wsb)
 
     def exchange(outs):
-        """cfg3: all-gather of this rank's last-stage kernels [FPG,N,C] + the 'ffn' link block (B = FPG)."""
         obj_local = torch.cat([o[2].reshape(-1, N, C) for o in outs], dim=0)
-        w, links, wd = link_head.packed_weights(dev)
-        nf = obj_local.shape[0]
-        shape = link_head._shape(nf, N, H, W, _lib.VKN_BF16, wd)
-        ws, wsb = link_head._ws.get(shape, dev)
+        return vdist.link_sharded_clip_boundary(link_fn_for(obj_local.shape[0]), obj_local, world * obj_local.shape[0], rank, world)
 
-        def link_fn(cur, prev):
-            return link_head._link(shape, links['track'], cur.contiguous(), prev.contiguous(), None, ws, wsb)
-        return vdist.link_sharded_clip(link_fn, obj_local, world * nf, rank, world)
-
-    track_host = torch.empty(FPG, N, C).pin_memory()
-
-    def run(frames, grp, host=False):
-        """process `frames` frames per rank (rounded up to whole graph launches); returns frames done."""
-        done, i = 0, 0
-        while done < frames:
-            outs = grp[i % len(grp)].replay()
-            if world > 1:
-                track = exchange(outs)
-                if host:
-                    track_host.copy_(track, non_blocking=True)
-            done += FPG
-            i += 1
-        return done
+    def run(launches, grp, host=False, times=None, start=0):
+        """`launches` graph launches (FPG frames each), rotating over the groups; per-launch CUDA events into `times`."""
+        cur = torch.cuda.current_stream(dev)
+        for i in range(start, start + launches):
+            gi = i % len(grp)
+            if with_link and link_done[gi] is not None:
+                cur.wait_event(link_done[gi])                   # the link of this group's previous outputs has read them
+            if times is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(cur)
+                times.append(ev)
+            outs = grp[gi].replay()
+            if with_link:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    track = exchange(outs)
+                    if host:
+                        track_host.copy_(track, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                link_done[gi] = done
+        if with_link:
+            cur.wait_stream(side)
+        return launches * FPG
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    run(max(args.warmup, 3), groups)
+    # Timed region: at least 20 graph launches and at least `--steps` frames, every group visited; per-launch events give
+    # the median / p95 of a launch.  `ms_per_step` = total device time / frames processed (a step = one frame per rank).
+    n_launch = max(20, -(-args.steps // FPG), len(groups))
+    run(max(3, -(-args.warmup // FPG)), groups)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    evs = []
     barrier()
-    e0.record()
-    frames_done = run(args.steps, groups)
+    frames_done = run(n_launch, groups, times=evs, start=1)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
+    total_ms = evs[0].elapsed_time(e1)
+    per_launch = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1))
+    t = torch.tensor([total_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item() * args.steps / frames_done                # time of exactly `steps` frames per rank
+    total_ms = t.item()
+    ms = total_ms / frames_done                             # device time per frame and rank (max over ranks)
 
     # ---- e2e: host buffers in, result tuple out, copies inside the timed region ---------------------
     h2d = (C * HW + N * HW) * 2 + N * C * 4
-    d2h = (N * CFG1['ncls'] + N * C) * 4 + N * HW * 2
-    run(3, host_groups, host=True)
+    d2h = (N * CFG1['ncls'] + N * C) * 4 + N * HW * 2 + (N * C * 4 if with_link else 0)
+    n_e2e = max(6, -(-args.steps // FPG))
+    link_done = [None] * len(groups)
+    run(2, host_groups, host=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    frames_e2e = run(args.steps, host_groups, host=True)
+    frames_e2e = run(n_e2e, host_groups, host=True)
     f1.record()
     barrier()
     sampler.stop()
@@ -322,26 +419,48 @@ def run_ours(args):
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = t.item() * args.steps / frames_e2e
+    e2e_ms = t.item() / frames_e2e
+
+    # ---- sharded link == sequential link (N > 1: every rank checks its shard against the sequential run of the whole clip)
+    shard_parity = None
+    if with_link:
+        outs = groups[0].replay()
+        obj_local = torch.cat([o[2].reshape(-1, N, C) for o in outs], dim=0)
+        track = exchange(outs)
+        obj_all = vdist.all_gather_kernels(obj_local, world * FPG) if world > 1 else obj_local
+        prev_all = torch.cat([obj_all[:1], obj_all[:-1]], dim=0)
+        seq = torch.cat([link_fn_for(FPG)(obj_all[r * FPG:(r + 1) * FPG], prev_all[r * FPG:(r + 1) * FPG]) for r in range(world)])
+        seq[0] = obj_all[0]
+        d = (track - seq[rank * FPG:(rank + 1) * FPG]).abs().max().reshape(1)
+        if world > 1:
+            dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        shard_parity = dict(max_abs_sharded_vs_sequential=float(d.item()), frames_per_rank=FPG, ranks=world,
+                            exchange_bytes_per_rank=N * C * 4)
 
     # ---- single-frame latency (one stream, one frame per graph, no overlap) ----------------------------
-    single = vknet.KernelIterLoop(heads)
+    single = vknet.KernelIterLoop(heads[:S - 1] + [heads[-1]])
     single.capture(x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16())
     for _ in range(5):
         single.replay()
     torch.cuda.synchronize()
-    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0.record()
-    for i in range(50):
+    before = _lib.launch_count()
+    single.forward(x1.to(dev).bfloat16(), pf1.to(dev), m1.to(dev).bfloat16())
+    single_launches = _lib.launch_count() - before
+    lat = []
+    for i in range(60):
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
         single.replay()
-    l1.record()
-    torch.cuda.synchronize()
-    latency_ms = l0.elapsed_time(l1) / 50
+        l1.record()
+        torch.cuda.synchronize()
+        lat.append(l0.elapsed_time(l1))
+    lat.sort()
+    latency_ms = lat[len(lat) // 2]
     launches_per_step = launches_per_frame_call / BF
 
     # ---- roofline of the dominant kernel: live per-kernel device times --------------------------------
     acc = {}
-    reps = 20
+    reps = 10
     # profiled at the batch size of the throughput mode (BF frames per call): the operating point `value` is quoted on
     xb_, pfb_, mb_ = frame_batch()
     xs, pfs, ms_ = xb_.to(dev), pfb_.to(dev), mb_.to(dev)
@@ -360,7 +479,7 @@ def run_ours(args):
     P = BF * N
     Fh, ncls = CFG1['ffn'], CFG1['ncls']
     Npad = (N + 15) // 16 * 16
-    # Algorithmic bytes per STEP (S stages) of each kernel family -- what the math has to move, not what a
+    # Algorithmic bytes per call (BF frames, S stages) of each kernel family -- what the math has to move, not what a
     # particular tiling moves.  Row operators: every weight once (bf16) + fp32 rows in/out.
     w_stage = (2041856 + 257 * ncls) * 2
     rows_stage = 4 * (P * C * (2 + 6 + 6 + 5 + 5 + 3 + 2 + 8 + 9 + 3 + 2) + P * Fh * 2 + P * ncls) + BF * 3 * Npad * C * 2
@@ -380,8 +499,8 @@ def run_ours(args):
     }
 
     def family(name):
-        for key, fam_name in (('pool_reduce', 'pool_reduce'), ('pool', 'pool'), ('maskgemm', 'maskgemm'), ('rowgemm', 'linear'),
-                              ('linear', 'linear'), ('rowop', 'rowop'), ('attention', 'attention')):
+        for key, fam_name in (('pool_reduce', 'pool_reduce'), ('pool', 'pool'), ('maskgemm', 'maskgemm'), ('chain', 'linear'),
+                              ('rowgemm', 'linear'), ('linear', 'linear'), ('rowop', 'rowop'), ('attention', 'attention')):
             if key in name:
                 return fam_name
         return name
@@ -401,8 +520,8 @@ def run_ours(args):
             f_['achieved_gbs'] = fam_bytes[k] / (f_['total_ms_per_step'] * 1e-3) / 1e9
             f_['frac'] = f_['achieved_gbs'] / peak
             f_['ncu_dram_bytes_per_launch'] = traffic.get(k)
-    # the row GEMMs are tensor-pipe work: algorithmic FLOPs of every nn.Linear of a stage (SURVEY.md 8d row term without
-    # the attention products); the kernel executes 3x that (three exact bf16 planes per fp32 operand)
+    # the row operators are tensor-pipe work: algorithmic FLOPs of every nn.Linear of a stage (SURVEY.md 8d row term without
+    # the attention products); the kernels execute 3x that (three exact bf16 planes per fp32 operand)
     rows_flops = S * P * (28 * C * C + 4 * C * Fh + 2 * C * ncls)
     if 'linear' in fam:
         f_ = fam['linear']
@@ -413,10 +532,11 @@ def run_ours(args):
     dom = max(fam, key=lambda k: fam[k]['total_ms_per_step'])
     d_ = fam[dom]
     note = ('times are CUDA-event brackets on the launch stream (vkn_profile_begin/end), one call of %d frame(s), eager launches; ' % BF +
-            'the family with the largest share of the step is reported, all families under "families"')
+            'the family with the largest share of the call is reported, all families under "families" (their *_per_step fields '
+            'are per call of %d frames)' % BF)
     if dom == 'linear':
-        kname = ('vkn_rowgemm_tc_kernel' if any('rowgemm' in k for k in per_kernel) else 'vkn_linear_kernel') + \
-                ' (row GEMMs, %d launches/step)' % d_['launches_per_step']
+        kname = ('vkn_chain_tc_kernel' if any('chain' in k for k in per_kernel) else 'vkn_rowgemm_tc_kernel') + \
+                ' (row operators, %d launches/call)' % d_['launches_per_step']
         roof = dict(bound='tensor', kernel=kname, achieved=d_['achieved_tflops'], peak=peak_tf, unit='TFLOP/s',
                     frac=d_['frac_tensor'], traffic=traffic.get('linear'), peak_source=peak_src + ', dense bf16 burst',
                     algorithmic_flops_per_launch=d_['algorithmic_flops_per_launch'],
@@ -433,31 +553,50 @@ def run_ours(args):
     # whole-step figure: module-boundary algorithmic bytes per frame: 60.4 MB bf16
     # (module-boundary figure: a stage reads x and its masks and writes its masks; the bit-mask hand-off moves fewer bytes)
     step_bytes = S * ((C * HW + 2 * N * HW) * 2 + (2041856 + 257 * ncls) * 2)
-    step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
-    roof['step'] = dict(algorithmic_bytes_per_frame=step_bytes, achieved=step_gbs, frac=step_gbs / peak)
+    step_gbs = step_bytes / (ms * 1e-3) / 1e9
+    step_roof = dict(bound='hbm', kernel='whole step: the S-stage loop of one frame (every kernel)',
+                     algorithmic_bytes_per_frame=step_bytes, achieved=step_gbs, peak=peak, unit='GB/s', frac=step_gbs / peak,
+                     peak_source=peak_src)
+    roof['step'] = step_roof
+    lat_gbs = step_bytes / (latency_ms * 1e-3) / 1e9
 
     if rank == 0:
         cb = dict(value=None, note='skipped (VKN_BENCH_QUICK)') if quick else cpu_arm(steps=8, warmup=2, budget_s=20.0)[0]
-        frames = args.steps * world
-        value = frames / (ms * 1e-3)
+        parity = None if quick else parity_check(torch, heads, groups[0], dev)
+        value = world / (ms * 1e-3)
         line = dict(metric=METRIC, value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
-                    data='synthetic',
-                    config=dict(workload=WORKLOAD + ('; + cfg3 link: every %d frames/rank one all-gather of kernels and the '
-                                                     'previous_type=ffn link block' % FPG if world > 1 else ''),
+                    ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+                    data='synthetic', value_per_gpu=value / world,
+                    config=dict(workload=WORKLOAD + ('; + cfg3 link: per graph launch the ranks exchange their shard-boundary '
+                                                     'kernels (one all-gather of world x [N,C]) and run the previous_type=ffn '
+                                                     'link block on their %d frames, on a side stream' % FPG if with_link else ''),
                                 storage='bf16 x / masks / weights, fp32 arithmetic (exact 3-plane bf16 products, fp32 accumulation)',
                                 mode='CUDA-graph replay of vkn_iter_forward (S stages); %d frames per graph launch = %d concurrent '
                                      'branches x batch %d' % (FPG, NS, BF),
+                                value_is='whole job: frames/s summed over the %d GPU(s); value_per_gpu = value / n_gpus' % world,
                                 single_stream_ms_per_frame=latency_ms,
-                                l2='inputs rotate over %d groups of %d frames (%.0f MB > 126 MB L2); weights stay hot' % (
-                                    G, FPG, G * FPG * set_bytes / 1e6),
+                                l2='inputs rotate over %d groups of %d frames inside the timed region (%.0f MB > 126 MB L2); '
+                                   'weights stay hot' % (G, FPG, G * FPG * set_bytes / 1e6),
                                 engine='tcgen05+TMA' if _lib.lib() and heads[0].engine != _lib.ENGINE_SIMT else 'simt',
                                 parallelism='frame-shard x%d' % world),
-                    e2e=dict(value=frames / (e2e_ms * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d,
-                             d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
-                    gpu_launches=int(round(launches_per_step * args.steps)),
-                    clocks=sampler.summary(), roofline=roof, cpu_baseline=cb,
+                    timing=dict(timed_graph_launches=n_launch, timed_frames_per_rank=frames_done, timed_ms=total_ms,
+                                launch_ms_median=per_launch[len(per_launch) // 2], launch_ms_p95=per_launch[int(0.95 * (len(per_launch) - 1))],
+                                launch_ms_min=per_launch[0], launch_ms_max=per_launch[-1],
+                                note='CUDA events on the launch stream around every graph launch; ms_per_step = timed_ms / '
+                                     'timed_frames_per_rank (max over ranks)'),
+                    e2e=dict(value=world / (e2e_ms * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=d2h, ms_per_step=e2e_ms,
+                             h2d_gbs_per_rank=h2d / (e2e_ms * 1e-3) / 1e9, d2h_gbs_per_rank=d2h / (e2e_ms * 1e-3) / 1e9,
+                             timed_frames_per_rank=frames_e2e),
+                    latency=dict(ms_per_frame=latency_ms, frames_per_s=1e3 / latency_ms, launches=int(single_launches),
+                                 ms_p95=lat[int(0.95 * (len(lat) - 1))], roofline_frac=lat_gbs / peak,
+                                 note='ONE frame per call (the online VPS operating point, knet/video/kernel_iter_head.py:435-468): '
+                                      'CUDA-graph replay of the S-stage loop on one stream, median of 60'),
+                    gpu_launches=int(round(launches_per_step * frames_done)),
+                    clocks=sampler.summary(), roofline=roof, step_roofline=step_roof, cpu_baseline=cb, parity=parity,
                     kernels=per_kernel)
+        if shard_parity is not None:
+            line['shard_parity'] = shard_parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -466,10 +605,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1536)
-    ap.add_argument('--warmup', type=int, default=192)
+    ap.add_argument('--steps', type=int, default=7560)
+    ap.add_argument('--warmup', type=int, default=1134)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg1', choices=sorted(CONFIGS),
+                    help='workload shape (BASELINE.json configs); cfg1 is the one the metric is quoted on')
     args = ap.parse_args()
+    CFG1.update(CONFIGS[args.config])
+    global WORKLOAD
+    WORKLOAD = CONFIGS[args.config]['workload']
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, num_frames, q):
+def _worker(rank, world, port, num_frames, q, boundary=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [os.path.join(root, 'video-k-net_b200'), os.path.join(root, 'oracle')]
@@ -39,7 +39,8 @@ def _worker(rank, world, port, num_frames, q):
                               'attention_previous_norm.', 'link_ffn.', 'link_ffn_norm.', F, N).reshape(F, N, C)
 
     start, end = vd.shard_frames(num_frames, rank, world)
-    track = vd.link_sharded_clip(link, obj_all[start:end].clone(), num_frames)
+    fn = vd.link_sharded_clip_boundary if boundary else vd.link_sharded_clip
+    track = fn(link, obj_all[start:end].clone(), num_frames)
     # sequential reference: frame t links to frame t-1; frame 0 keeps its own kernels
     seq = [obj_all[0]] + [link(obj_all[t:t + 1], obj_all[t - 1:t])[0] for t in range(1, num_frames)]
     want = torch.stack(seq)[start:end]
@@ -48,11 +49,11 @@ def _worker(rank, world, port, num_frames, q):
     dist.destroy_process_group()
 
 
-def _run(num_frames, world=2):
+def _run(num_frames, world=2, boundary=False):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, num_frames, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_frames, q, boundary)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -72,6 +73,14 @@ def test_sharded_link_equals_sequential_uneven_split():
     res = _run(5)
     assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
     assert all(r[3] < 1e-5 for r in res), res
+
+
+def test_boundary_exchange_equals_sequential():
+    """the minimal exchange (one frame per rank: the shard-boundary kernels) gives the same tracking kernels as the
+    sequential run -- even / uneven splits and a clip shorter than the world size (empty shards forward nothing)"""
+    for frames, world in ((8, 2), (5, 2), (2, 3)):
+        res = _run(frames, world, boundary=True)
+        assert all(r[3] < 1e-5 for r in res), (frames, world, res)
 
 
 def test_shard_partition_properties():

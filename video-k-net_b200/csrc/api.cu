@@ -923,13 +923,37 @@ static int link_planes(Ctx &c, const VknLinkW &w, const float *cur, const RowSrc
   void *PLA = c.L.pl[0], *PLB = c.L.pl[1], *PLC = c.L.pl[2];
   VKN_TRY(launch_rowprep(src_copy(cur, C), nullptr, 0, PLA, C, PS, P, C, c.st));
   VKN_TRY(launch_rowprep(kv, nullptr, 0, PLB, C, PS, P, C, c.st));
+  if (c.chain_on) c.chain = chain_begin(P);
   // MHA(q = cur, k = v = kv): q rows of in_proj on cur, k/v rows on kv (video/kernel_update_head.py:404-406)
   LinArgs two[2];
   two[0] = lin(src_planes(PLA, C, PS), w.attn.in_w, C, w.attn.in_b, c.L.qkv, 3 * C, P, C, C, 0);
   two[1] = lin(src_planes(PLB, C, PS), wrow(c, w.attn.in_w, C, C), C, w.attn.in_b + C, c.L.qkv + C, 3 * C, P, 2 * C, C, 0);
-  VKN_TRY(launch_linear_tc(two, 2, c.st));
+  VKN_TRY(emit_gemm(c, two, 2));
+  VKN_TRY(emit_flush(c));
   VKN_TRY(launch_attention(c.L.qkv, 3 * C, c.L.qkv + C, 3 * C, c.L.qkv + 2 * C, 3 * C, nullptr, C, c.s.B, c.s.N, C,
                            c.s.num_heads, c.st, PLC, PS));
+  if (c.chain) {
+    // out-projection + residual + LayerNorm, FFN, + residual + LayerNorm: one chain launch, LayerNorms in the epilogues
+    LinArgs op = lin(src_planes(PLC, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.o2, C, P, C, C, EPI_RES | EPI_LN);
+    op.res = cur;
+    op.ldres = C;
+    op.ln_g = w.attn.norm_g;
+    op.ln_b = w.attn.norm_b;
+    out_planes(op, PLA, P, C);
+    VKN_TRY(emit_gemm(c, &op, 1));
+    LinArgs f1 = lin(src_planes(PLA, C, PS), w.ffn.w1, C, w.ffn.b1, nullptr, F, P, F, C, EPI_RELU | EPI_NOOUT);
+    out_planes(f1, c.L.h, P, F);
+    VKN_TRY(emit_gemm(c, &f1, 1));
+    LinArgs f2 = lin(src_planes(c.L.h, F, (long long)P * F), w.ffn.w2, F, w.ffn.b2, out, C, P, C, F, EPI_RES | EPI_LN);
+    f2.res = c.L.o2;
+    f2.ldres = C;
+    f2.ln_g = w.ffn.norm_g;
+    f2.ln_b = w.ffn.norm_b;
+    VKN_TRY(emit_gemm(c, &f2, 1));
+    VKN_TRY(emit_flush(c));
+    c.chain = nullptr;
+    return VKN_OK;
+  }
   LinArgs op = lin(src_planes(PLC, C, PS), w.attn.out_w, C, w.attn.out_b, c.L.y, C, P, C, C, EPI_RES);
   op.res = cur;
   op.ldres = C;
