@@ -237,6 +237,28 @@ int vkn_init_proposals(const VknShape *s, const float *init_w, const float *init
 int vkn_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int batch_h, int batch_w, int img_h,
                       int img_w, int ori_h, int ori_w, float mask_thr, float *probs, unsigned char *bits, void *stream);
 
+/* Joint panoptic merge (knet/video/kernel_iter_head.py:832-895, merge_stuff_thing_stuff_joint; the shipped video configs
+ * set merge_joint=True): the pixel goes to the kernel with the highest score x probability; kernels are then visited in
+ * descending score order and kept when (thing: score >= instance_score_thr) and won_area > 0, area(prob >= 0.5) > 0 and
+ * won_area / area(prob >= 0.5) >= overlap_thr.  No host synchronisation: three launches on `stream`.
+ *   masks   [T, H, W] fp32 probabilities (things first, then stuff -- the reference's torch.cat order), device memory
+ *   scores  [T] fp32, labels [T] int32 (label < num_thing_classes = thing)
+ *   panoptic_seg  [H, W] int32: segment id per pixel (0 = none)
+ *   segments      [T, 5] int32 rows (id, isthing, category_id, instance_id | -1, area | -1) for the first counts[0] rows
+ *                 (category_id of stuff = label - num_thing_classes + 1, as the reference writes it)
+ *   segment_scores [T] fp32 (score of each segment row), kept_things [T] int32 (indices of kept thing kernels, in order),
+ *   counts [2] int32 = {number of segments, number of kept things}
+ *   workspace: (H*W + 3*T) * 4 bytes. */
+int vkn_panoptic_merge(const float *masks, const float *scores, const int32_t *labels, int num_kernels, int H, int W,
+                       int num_thing_classes, double instance_score_thr, double overlap_thr, int32_t *panoptic_seg,
+                       int32_t *segments, float *segment_scores, int32_t *kept_things, int32_t *counts, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* Mask -> box reduction of VideoKernelUpdateHead.segm2result (knet/video/kernel_update_head.py:734-744; unitrack
+ * tensor_mask2box): boxes[k] = (x_min, y_min, x_max, y_max) of the non-zero pixels of mask k, (-1, -1, 10, 10) when the
+ * mask is empty (the caller clips at 0 like the reference).  masks [K, H, W], elem_bytes 1 (bool / uint8) or 4 (float32). */
+int vkn_mask_boxes(const void *masks, int elem_bytes, int K, int H, int W, float *boxes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,27 @@ def install():
     mods['unitrack.mask'].mask2box = lambda *a, **k: None
     mods['mmtrack.transform'].outs2results = lambda *a, **k: None
     _installed = True
+    # The result-packing helpers of the video / VIS heads call two small pure-python utilities that ship INSIDE the reference
+    # tree (unitrack/utils/mask.py: tensor_mask2box; mmtrack/transform.py: outs2results).  Load the real ones by path when
+    # their own imports can be satisfied (pycocotools is not installed here and is not used by these two functions).
+    try:
+        if 'pycocotools' not in sys.modules:
+            pc = types.ModuleType('pycocotools')
+            pc.mask = types.ModuleType('pycocotools.mask')
+            sys.modules['pycocotools'], sys.modules['pycocotools.mask'] = pc, pc.mask
+        um = _load_file('_ref_unitrack.utils.mask', 'unitrack/utils/mask.py')
+        mods['unitrack.mask'].tensor_mask2box = um.tensor_mask2box
+        mods['unitrack.mask'].mask2box = um.mask2box
+    except Exception:       # noqa: BLE001 -- keep the stand-ins
+        pass
+    try:
+        core.bbox2result = lambda bboxes, labels, num_classes: [
+            (bboxes.cpu().numpy() if hasattr(bboxes, 'cpu') else bboxes)[
+                (labels.cpu().numpy() if hasattr(labels, 'cpu') else labels) == i, :] for i in range(num_classes)]
+        mt = _load_file('_ref_mmtrack.transform', 'mmtrack/transform.py')
+        mods['mmtrack.transform'].outs2results = mt.outs2results
+    except Exception:       # noqa: BLE001
+        pass
 
 
 def available():

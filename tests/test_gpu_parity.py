@@ -782,3 +782,73 @@ def test_rescale_masks_errors(dev):
     with pytest.raises(_lib.VknError):                                     # extreme down-scaling: dependency cone too large
         ops.rescale_masks(torch.zeros(1, 2000, 2000, device=dev), dict(img_shape=(2000, 2000, 3), batch_input_shape=(2000, 2000),
                                                                         ori_shape=(20, 20, 3)))
+
+
+# ---- post-loop result assembly on the device -------------------------------------------------------------------------
+@pytest.mark.parametrize('path', golden_files('panoptic_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_panoptic_merge_golden(dev, path):
+    """vkn_panoptic_merge == the reference's merge_stuff_thing_stuff_joint on the fixtures it wrote
+    (knet/video/kernel_iter_head.py:832-895): id map, segment table and kept thing indices, bit for bit."""
+    import numpy as np
+    from vknet import ops
+    z = np.load(path)
+    K, M, H, W, nthing = (int(v) for v in z['meta'])
+    t = {k: torch.from_numpy(z[k]).to(dev) for k in ('thing_masks', 'stuff_masks', 'thing_scores', 'stuff_scores', 'thing_labels',
+                                                     'stuff_labels')}
+    seg, info, kept = ops.panoptic_merge(t['thing_masks'], t['thing_labels'], t['thing_scores'], t['stuff_masks'], t['stuff_labels'],
+                                         t['stuff_scores'], nthing, float(z['thr'][0]), float(z['thr'][1]))
+    assert np.array_equal(seg.cpu().numpy(), z['seg'])
+    rows = np.array([[d['id'], int(d['isthing']), d['category_id'], d.get('instance_id', -1), d.get('area', -1)] for d in info],
+                    dtype=np.int64).reshape(-1, 5)
+    assert np.array_equal(rows, z['info'])
+    assert kept == z['kept'].tolist()
+
+
+def test_panoptic_merge_full_size_vs_oracle(dev):
+    """KITTI-STEP size: 100 things + 17 stuff kernels at 375 x 1242, probabilities with large overlaps and exact ties"""
+    from vknet import ops
+    g = torch.Generator().manual_seed(4)
+    K, M, H, W, nthing = 100, 17, 375, 1242, 2
+    base = torch.rand(K + M, H // 15 + 1, W // 18 + 1, generator=g) * 0.3
+    masks = torch.nn.functional.interpolate(base[None], size=(H, W), mode='bilinear', align_corners=False)[0]
+    for k in range(K + M):                                           # every kernel: a confident box, boxes overlap their neighbours
+        y0, x0 = int(torch.randint(0, H - 60, (1,), generator=g)), int(torch.randint(0, W - 200, (1,), generator=g))
+        hh, ww = int(torch.randint(20, 60, (1,), generator=g)), int(torch.randint(40, 200, (1,), generator=g))
+        masks[k, y0:y0 + hh, x0:x0 + ww] = 0.55 + 0.45 * torch.rand(hh, ww, generator=g)
+    masks[5] = masks[4]                                              # identical maps: the first index must win the ties
+    scores = 0.2 + 0.8 * torch.rand(K + M, generator=g)
+    scores[5] = scores[4]
+    labels = torch.cat([torch.randint(0, nthing, (K,), generator=g), torch.arange(M) + nthing])
+    want_seg, want_info, want_kept = ko.panoptic_merge_joint(masks[:K], labels[:K], scores[:K], masks[K:], labels[K:], scores[K:],
+                                                             nthing, 0.3, 0.5)
+    seg, info, kept = ops.panoptic_merge(masks[:K].to(dev), labels[:K].to(dev), scores[:K].to(dev), masks[K:].to(dev),
+                                         labels[K:].to(dev), scores[K:].to(dev), nthing, 0.3, 0.5)
+    assert torch.equal(seg.cpu(), want_seg)
+    assert kept == want_kept and len(info) == len(want_info) >= 5 and len(info) < K + M
+    for a, b in zip(info, want_info):
+        assert {k: v for k, v in a.items() if k != 'score'} == {k: v for k, v in b.items() if k != 'score'}
+        if 'score' in a:
+            assert abs(a['score'] - b['score']) < 1e-7
+
+
+def test_mask_boxes_kernel(dev):
+    """mask -> box reduction of VideoKernelUpdateHead.segm2result (knet/video/kernel_update_head.py:734-744) == its torch
+    formulation (which the CPU boundary tests pin to the reference's tensor_mask2box), bool and float masks, empty masks"""
+    import vknet
+    from vknet import ops
+    g = torch.Generator().manual_seed(2)
+    m = torch.rand(37, 90, 160, generator=g) > 0.97
+    m[3] = False
+    m[11, :, :] = False
+    m[11, 89, 159] = True                                            # a single pixel in the far corner
+    want = vknet.VideoKernelUpdateHead.mask_boxes_torch(m)
+    assert torch.equal(ops.mask_boxes(m.to(dev)).cpu(), want)
+    assert torch.equal(ops.mask_boxes(m.float().to(dev) * 0.25).cpu(), want)
+    assert torch.equal(ops.mask_boxes(m.to(torch.uint8).to(dev)).cpu(), want)
+    assert want[3].tolist() == [-1.0, -1.0, 10.0, 10.0] and want[11].tolist() == [159.0, 89.0, 159.0, 89.0]
+    head = vknet.build_head(dict(type='VideoKernelUpdateHead', **ko.default_cfg(num_classes=4, in_channels=64, feedforward_channels=64,
+                                                                                 previous='p', previous_type='ffn')))
+    labels, scores = torch.randint(0, 4, (37,), generator=g), torch.rand(37, generator=g)
+    b_gpu = head.segm2result(m.to(dev), labels.to(dev), scores.to(dev))[0]
+    b_cpu = head.segm2result(m, labels, scores)[0]
+    assert (b_gpu == b_cpu).all() and b_gpu[3, :4].tolist() == [0, 0, 10, 10]

@@ -741,7 +741,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_rescale_masks_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -1004,6 +1004,22 @@ int vkn_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up,
   if (!masks) VKN_FAIL(VKN_E_INVALID, "vkn_rescale_masks: null masks");
   return launch_rescale_masks(masks, dtype, K, H, W, up, batch_h, batch_w, img_h, img_w, ori_h, ori_w, mask_thr, probs, bits,
                               (cudaStream_t)stream);
+}
+
+int vkn_panoptic_merge(const float *masks, const float *scores, const int32_t *labels, int num_kernels, int H, int W,
+                       int num_thing_classes, double instance_score_thr, double overlap_thr, int32_t *panoptic_seg,
+                       int32_t *segments, float *segment_scores, int32_t *kept_things, int32_t *counts, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  if (!masks || !scores || !labels || !panoptic_seg || !segments || !segment_scores || !kept_things || !counts)
+    VKN_FAIL(VKN_E_INVALID, "vkn_panoptic_merge: null argument");
+  return launch_panoptic_merge(masks, scores, labels, num_kernels, H, W, num_thing_classes, instance_score_thr, overlap_thr,
+                               panoptic_seg, segments, segment_scores, kept_things, counts, workspace, workspace_bytes,
+                               (cudaStream_t)stream);
+}
+
+int vkn_mask_boxes(const void *masks, int elem_bytes, int K, int H, int W, float *boxes, void *stream) {
+  if (!masks && K > 0) VKN_FAIL(VKN_E_INVALID, "vkn_mask_boxes: null masks");
+  return launch_mask_boxes(masks, elem_bytes, K, H, W, boxes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -252,4 +252,10 @@ int maskgemm_tc_npad(const VknShape &s);
 int launch_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int Hb, int Wb, int h, int w, int Ho,
                          int Wo, float thr, float *probs, uint8_t *bits, cudaStream_t stream);
 
+// post-loop result assembly (panoptic.cu)
+int launch_panoptic_merge(const float *masks, const float *scores, const int *labels, int T, int H, int W, int num_thing,
+                          double inst_thr, double overlap_thr, int *seg, int *table, float *seg_scores, int *kept, int *counts,
+                          void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_mask_boxes(const void *masks, int elem_bytes, int K, int H, int W, float *boxes, cudaStream_t stream);
+
 }  // namespace vkn

@@ -65,7 +65,8 @@ _lib = None
 SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_launch_count', 'vkn_profile_begin',
            'vkn_profile_end', 'vkn_debug_timestamps', 'vkn_workspace_bytes', 'vkn_mask_pool',
            'vkn_kernel_update', 'vkn_mhsa_ln', 'vkn_ffn_ln', 'vkn_heads', 'vkn_mask_gemm',
-           'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend', 'vkn_rescale_masks')
+           'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend', 'vkn_rescale_masks',
+           'vkn_panoptic_merge', 'vkn_mask_boxes')
 
 
 def lib():
@@ -98,6 +99,9 @@ def lib():
     L.vkn_link_attend.argtypes = [S, C.POINTER(VknLinkW), _vp, _vp, _vp, _vp, _vp, sz, _vp]
     L.vkn_rescale_masks.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]
+    L.vkn_panoptic_merge.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, sz, _vp]
+    L.vkn_mask_boxes.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.vkn_debug_timestamps.restype = C.c_int
     L.vkn_debug_timestamps.argtypes = [_vp, C.c_size_t]
     for name in SYMBOLS[7:]:
@@ -115,8 +119,9 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """the current CUDA stream of `device` (default: the current device) as the void* the C ABI takes"""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def dtype_code(dt):

@@ -37,14 +37,31 @@ class FFNParams(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(0.0))
 
 
+_UNSET = object()
+
+
 class Conv1x1Params(nn.Module):
+    """mmcv ConvModule for the only form the shipped configs build: 1x1, stride 1, conv_cfg Conv2d, bias, NO norm and NO
+    activation.  ConvModule's own default is act_cfg=dict(type='ReLU'): a config that omits act_cfg gets a ReLU in the
+    reference, which the algebraic fold of feat_transform cannot express -- so `act_cfg=None` must be
+    given explicitly (all 29 shipped configs do); anything else raises."""
+
     def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=0, conv_cfg=None,
-                 norm_cfg=None, act_cfg=None, **kwargs):
+                 norm_cfg=None, act_cfg=_UNSET, bias='auto', **kwargs):
         super().__init__()
         if kernel_size != 1 or stride != 1 or padding != 0:
             raise NotImplementedError('feat_transform must be the 1x1 / stride-1 conv of the shipped configs')
+        if act_cfg is _UNSET:
+            raise NotImplementedError("feat_transform_cfg without act_cfg: mmcv's ConvModule would add its default ReLU, which "
+                                      'is not on the shipped path -- pass act_cfg=None as the shipped configs do')
         if norm_cfg is not None or act_cfg is not None:
             raise NotImplementedError('feat_transform with norm/activation is not on the shipped path')
+        if conv_cfg is not None and conv_cfg.get('type', 'Conv2d') not in ('Conv2d', 'Conv'):
+            raise NotImplementedError('feat_transform conv_cfg type %r is not on the shipped path' % conv_cfg.get('type'))
+        if bias not in ('auto', True):
+            raise NotImplementedError('feat_transform without bias is not on the shipped path')
+        if kwargs:
+            raise NotImplementedError('unsupported feat_transform_cfg keys: %s' % sorted(kwargs))
         self.conv = nn.Conv2d(in_channels, out_channels, 1, bias=True)
 
 

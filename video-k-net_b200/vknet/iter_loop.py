@@ -17,6 +17,17 @@ class KernelIterLoop:
         self.heads = list(heads)
         if not self.heads:
             raise ValueError('need at least one stage')
+        # vkn_iter_forward runs every stage with ONE VknShape (built from stage 0): stages with different settings would
+        # silently run with stage 0's values, where stage-by-stage module calls honour each head's own config
+        h0 = self.heads[0]
+        for i, h in enumerate(self.heads[1:], 1):
+            for attr in ('in_channels', 'feedforward_channels', 'with_ffn', 'num_heads', 'hard_mask_thr', 'engine',
+                         'conv_kernel_size'):
+                if getattr(h, attr) != getattr(h0, attr):
+                    raise NotImplementedError('KernelIterLoop: stage %d differs from stage 0 in %s (%r vs %r); run such heads '
+                                              'stage by stage' % (i, attr, getattr(h, attr), getattr(h0, attr)))
+            if h.fc_cls.out_features != h0.fc_cls.out_features:
+                raise NotImplementedError('KernelIterLoop: stage %d has a different number of classes' % i)
         self._ws = _lib.Workspace()
         self._graph = None
         self._static = None

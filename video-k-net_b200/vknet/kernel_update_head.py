@@ -124,8 +124,9 @@ class _HeadBase(nn.Module):
 
     def packed_weights(self, device):
         """(VknHeadW, extra, w_dtype) for `device`; rebuilt when any parameter changed in place."""
-        key = (str(device),) + tuple(p._version for p in self.parameters()) + tuple(
-            p.dtype for p in self.parameters())
+        # _version catches in-place edits through the parameter, data_ptr re-assignment of p.data (EMA / weight surgery);
+        # edits through p.data.copy_() bump neither: call invalidate_weight_cache() after those
+        key = (str(device),) + tuple((p._version, p.data_ptr(), p.dtype) for p in self.parameters())
         if self._packed is None or self._packed_key != key:
             wd = pack.weight_dtype_of(self.parameters())
             pk = pack.Packer(device, wd)
@@ -138,14 +139,26 @@ class _HeadBase(nn.Module):
                                self.num_heads, x_dtype, w_dtype, self.with_ffn, self.engine,
                                thr_logit(self.hard_mask_thr))
 
-    def _prepare(self, x, proposal_feat, mask_preds):
+    def _prepare(self, x, proposal_feat, mask_preds, frames_per_set=1):
         self.check_supported()
         if not x.is_cuda:
             raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+        self._refuse_autograd(x, proposal_feat, mask_preds)
         B, N = proposal_feat.shape[:2]
         Cc, H, W = x.shape[-3:]
         if Cc != self.in_channels:
             raise _lib.VknError('x has %d channels, head expects %d' % (Cc, self.in_channels))
+        # the C ABI receives raw pointers + (B, N, H, W): a mismatched batch / kernel count would be an out-of-bounds device
+        # read where the reference's einsum raises -- check every extent here
+        if x.dim() != 4 or x.shape[0] != B * frames_per_set:
+            raise _lib.VknError('x is %s but proposal_feat describes %d kernel set(s) x %d frame(s)' % (
+                tuple(x.shape), B, frames_per_set))
+        if proposal_feat.numel() != B * N * self.in_channels * self.conv_kernel_size ** 2:
+            raise _lib.VknError('proposal_feat %s does not hold [B=%d, N=%d, C=%d] kernels' % (
+                tuple(proposal_feat.shape), B, N, self.in_channels))
+        if mask_preds is not None and (mask_preds.dim() != 4 or mask_preds.shape[0] != B * frames_per_set or
+                                       mask_preds.shape[1] != N):
+            raise _lib.VknError('mask_preds is %s, expected [%d, %d, h, w]' % (tuple(mask_preds.shape), B * frames_per_set, N))
         x = x.contiguous()
         xd = _lib.dtype_code(x.dtype)
         if mask_preds is not None:
@@ -191,11 +204,64 @@ class _HeadBase(nn.Module):
         per_class = [np.flatnonzero(labels == c) for c in range(self.num_classes)]
         return [boxes[idx] for idx in per_class], [[masks[i] for i in idx] for idx in per_class]
 
+    @staticmethod
+    def _refuse_autograd(*tensors):
+        """The CUDA path is forward only.  The reference's forward is differentiable, so silently detaching would train a
+        frozen head: refuse instead."""
+        if torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+            raise NotImplementedError('vknet heads are inference-only: an input requires grad and autograd is enabled; wrap '
+                                      'the call in torch.no_grad() (or use the reference modules for training)')
+
+    # ---- result packing helpers of the knet_vis heads (knet_vis/det/kernel_update_head.py:484-500,
+    #      knet_vis/tracker/kernel_update_head.py:581-600) -------------------------------------------------------------
+    def get_seg_masks_tracking(self, masks_per_img, labels_per_img, scores_per_img, ids_per_img, test_cfg, img_meta):
+        """rescale + threshold on the device (one launch), then mmtrack's outs2results packing: per class the rows
+        [id, 0, 0, 0, 0, score] of the tracked instances (ids > -1) and the list of their masks."""
+        from . import ops
+        thr = test_cfg['mask_thr'] if isinstance(test_cfg, dict) else test_cfg.mask_thr
+        seg_masks = ops.rescale_masks(masks_per_img, img_meta, 1, thr, probs=False)[1]
+        return self.tracks2result(seg_masks, labels_per_img, scores_per_img, ids_per_img)
+
+    def tracks2result(self, seg_masks, labels, scores, ids):
+        """mmtrack.transform.outs2results (mmtrack/transform.py:6-74) for the call the reference makes: fake boxes
+        [0,0,0,0,score], instances with id > -1 only."""
+        import numpy as np
+        ids = ids.detach().cpu().numpy()
+        valid = ids > -1
+        ids = ids[valid]
+        labels = labels.detach().cpu().numpy()[valid]
+        scores = scores.detach().cpu().numpy().astype(np.float32)[valid]
+        masks = seg_masks.detach().cpu().numpy()[valid]
+        boxes = np.zeros((ids.shape[0], 5), dtype=np.float32)
+        boxes[:, 4] = scores
+        if ids.shape[0] == 0:
+            bbox_results = [np.zeros((0, 6), dtype=np.float32) for _ in range(self.num_classes)]
+        else:
+            bbox_results = [np.concatenate((ids[labels == c, None], boxes[labels == c, :]), axis=1)
+                            for c in range(self.num_classes)]
+        mask_results = [[] for _ in range(self.num_classes)]
+        for i in range(ids.shape[0]):
+            mask_results[labels[i]].append(masks[i])
+        return bbox_results, mask_results
+
+    # ---- training-side methods: pass-throughs to the reference's own pure-torch code (SURVEY.md 8b) -----------------
+    _REF_FILE = 'knet/det/kernel_update_head.py'
+    _REF_CLASS = 'KernelUpdateHead'
+
+    def _reference_method(self, name):
+        from ._refpass import reference_function
+        return reference_function(self._REF_FILE, self._REF_CLASS, name)
+
     def loss(self, *args, **kwargs):
-        raise NotImplementedError('training (loss/get_targets) is outside this package: inference hot path only')
+        """knet/det/kernel_update_head.py:279-... unchanged: the reference's own function, bound to this module (same
+        attribute names).  Needs the reference tree and mmdet importable; raises NotImplementedError otherwise."""
+        return self._reference_method('loss')(self, *args, **kwargs)
 
     def get_targets(self, *args, **kwargs):
-        raise NotImplementedError('training (loss/get_targets) is outside this package: inference hot path only')
+        return self._reference_method('get_targets')(self, *args, **kwargs)
+
+    def _get_target_single(self, *args, **kwargs):
+        return self._reference_method('_get_target_single')(self, *args, **kwargs)
 
 
 @HEADS.register_module(force=True)

@@ -24,6 +24,9 @@ def mask_pool(head, x, mask_preds):
     """x_feat [B,N,C] = sum_p 1[sigmoid(mask) > thr] * feat_transform(x)   (kernel_update_head.py:179-195)."""
     B, Cc, H, W = x.shape
     N = mask_preds.shape[1]
+    if mask_preds.shape != (B, N, H, W) or Cc != head.in_channels:
+        raise _lib.VknError('mask_pool: x %s / mask_preds %s do not describe [B,C=%d,H,W] / [B,N,H,W]' % (
+            tuple(x.shape), tuple(mask_preds.shape), head.in_channels))
     x = x.contiguous()
     mask_preds = mask_preds.to(x.dtype).contiguous()
     w, _, shape, ws, wsb = _ctx(head, x, B, N, H, W)
@@ -82,6 +85,9 @@ def mask_gemm(head, x, mask_kernel):
     """new_mask [B,N,H,W] = mask_kernel . feat_transform(x)   (kernel_update_head.py:179-180, 247-260)."""
     B, Cc, H, W = x.shape
     N = mask_kernel.shape[1]
+    if mask_kernel.shape[0] != B or mask_kernel.numel() != B * N * Cc or Cc != head.in_channels:
+        raise _lib.VknError('mask_gemm: mask_kernel %s does not hold [B=%d, N, C=%d] kernels for x %s' % (
+            tuple(mask_kernel.shape), B, head.in_channels, tuple(x.shape)))
     x = x.contiguous()
     mk = mask_kernel.reshape(B, N, Cc).float().contiguous()
     w, _, shape, ws, wsb = _ctx(head, x, B, N, H, W)
@@ -145,3 +151,58 @@ def rescale_masks(masks, img_meta, mask_upsample_stride=1, mask_thr=None, probs=
                                                 float(mask_thr if mask_thr is not None else 0.5), _lib.ptr(out_p), _lib.ptr(out_b),
                                                 _lib.stream_ptr()))
     return out_p, out_b
+
+
+def mask_boxes(masks):
+    """boxes [K,4] fp32 (x_min, y_min, x_max, y_max) of the non-zero pixels of each mask, (-1,-1,10,10) for an empty one:
+    the mask -> box step of VideoKernelUpdateHead.segm2result (knet/video/kernel_update_head.py:734-744, unitrack
+    tensor_mask2box) as one launch instead of a `.nonzero()` + four `.item()` per mask.  masks [K,H,W] bool / uint8 /
+    float32 CUDA tensor."""
+    if not masks.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    if masks.dim() != 3:
+        raise ValueError('masks must be [K,H,W]')
+    if masks.dtype in (torch.bool, torch.uint8):
+        m, eb = masks.contiguous(), 1
+    else:
+        m, eb = masks.float().contiguous(), 4
+    K, H, W = m.shape
+    out = torch.empty(K, 4, dtype=torch.float32, device=m.device)
+    _lib.check(_lib.lib().vkn_mask_boxes(_lib.ptr(m), eb, K, H, W, _lib.ptr(out), _lib.stream_ptr(m.device)))
+    return out
+
+
+def panoptic_merge(thing_masks, thing_labels, thing_scores, stuff_masks, stuff_labels, stuff_scores, num_thing_classes,
+                   instance_score_thr, overlap_thr):
+    """VideoKernelIterHead.merge_stuff_thing_stuff_joint (knet/video/kernel_iter_head.py:832-895) on the device: three
+    launches and ONE device->host read of the small result tables instead of 2-3 host synchronisations per segment.
+    masks [K,H,W] / [M,H,W] fp32 probabilities, labels integer, scores fp32 (CUDA).
+    Returns (panoptic_seg int32 [H,W] CUDA tensor, segments_info list of dicts as the reference builds it, kept thing
+    indices -- what the reference uses to gather `thing_obj_feat`)."""
+    if not thing_masks.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    dev = thing_masks.device
+    masks = torch.cat([thing_masks, stuff_masks], 0).float().contiguous()
+    scores = torch.cat([thing_scores, stuff_scores], 0).float().contiguous()
+    labels = torch.cat([thing_labels, stuff_labels], 0).to(torch.int32).contiguous()
+    T, H, W = masks.shape
+    seg = torch.empty(H, W, dtype=torch.int32, device=dev)
+    small = torch.zeros(T * 5 + T + 2, dtype=torch.int32, device=dev)          # segment rows | kept | counts
+    seg_scores = torch.empty(T, dtype=torch.float32, device=dev)
+    ws = torch.empty(H * W + 3 * T, dtype=torch.int32, device=dev)
+    table, kept, counts = small[:T * 5], small[T * 5:T * 6], small[T * 6:]
+    _lib.check(_lib.lib().vkn_panoptic_merge(_lib.ptr(masks), _lib.ptr(scores), _lib.ptr(labels), T, H, W, int(num_thing_classes),
+                                             float(instance_score_thr), float(overlap_thr), _lib.ptr(seg), _lib.ptr(table),
+                                             _lib.ptr(seg_scores), _lib.ptr(kept), _lib.ptr(counts), _lib.ptr(ws), ws.numel() * 4,
+                                             _lib.stream_ptr(dev)))
+    host = small.cpu()                                                          # the one synchronising read
+    sc = seg_scores.cpu()
+    nseg, nkept = int(host[T * 6]), int(host[T * 6 + 1])
+    info = []
+    for i in range(nseg):
+        sid, isthing, cat, inst, area = (int(v) for v in host[i * 5:i * 5 + 5])
+        if isthing:
+            info.append(dict(id=sid, isthing=True, score=float(sc[i]), category_id=cat, instance_id=inst))
+        else:
+            info.append(dict(id=sid, isthing=False, category_id=cat, area=area))
+    return seg, info, [int(v) for v in host[T * 5:T * 5 + nkept]]

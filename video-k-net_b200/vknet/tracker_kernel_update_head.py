@@ -49,6 +49,9 @@ class KernelUpdateHeadVideo(_HeadBase):
             self.cls_fcs = torch.nn.ModuleList()
             self.fc_cls = None
 
+    _REF_FILE = 'knet_vis/tracker/kernel_update_head.py'
+    _REF_CLASS = 'KernelUpdateHeadVideo'
+
     def init_weights(self):
         for p in self.parameters():
             if p.dim() > 1:
@@ -93,7 +96,7 @@ class KernelUpdateHeadVideo(_HeadBase):
         mf = mask_preds.reshape(Bc * Fr, N, H, W)
         sets = Bc if gathered else Bc * Fr
         pf = proposal_feat.reshape(sets, N, Cc, -1)
-        xf, pf, mf, _, _, _, _, xd = self._prepare(xf, pf, mf)
+        xf, pf, mf, _, _, _, _, xd = self._prepare(xf, pf, mf, frames_per_set=Fr if gathered else 1)
         w, _, wd = self.packed_weights(x.device)
         shape = self._shape(sets, N, H, W, xd, wd, Fr if gathered else 1)
         dev = x.device

@@ -76,6 +76,52 @@ class VideoKernelUpdateHead(_HeadBase):
                 self.link_ffn_link = link_ffn()
                 self.link_ffn_norm_link = make_ln(dict(type='LN'), in_channels)
 
+    _REF_FILE = 'knet/video/kernel_update_head.py'
+    _REF_CLASS = 'VideoKernelUpdateHead'
+
+    # ---- result helpers with the VIDEO head's contract (knet/video/kernel_update_head.py:725-748): 3-tuples, boxes from
+    #      the masks; called by VideoKernelIterHead.get_panoptic / simple_test (knet/video/kernel_iter_head.py:605-609) ----
+    def get_seg_masks(self, masks_per_img, labels_per_img, scores_per_img, test_cfg, img_meta):
+        from . import ops
+        thr = test_cfg['mask_thr'] if isinstance(test_cfg, dict) else test_cfg.mask_thr
+        seg_masks = ops.rescale_masks(masks_per_img, img_meta, 1, thr, probs=False)[1]
+        return self.segm2result(seg_masks, labels_per_img, scores_per_img)
+
+    def segm2result(self, mask_preds, det_labels, cls_scores):
+        """-> (bboxes [n,5] float32 ndarray: extent of each mask's non-zero pixels clipped at 0 + score,
+               segm_result: per class the list of that class's mask tensors (input order), mask_preds)   (:734-748)"""
+        import numpy as np
+        from . import ops
+        labels = det_labels.detach().cpu().numpy()
+        n = mask_preds.shape[0]
+        bboxes = np.zeros((n, 5), dtype=np.float32)
+        bboxes[:, 4] = cls_scores.detach().cpu().numpy()
+        if n:
+            boxes = ops.mask_boxes(mask_preds) if mask_preds.is_cuda else self.mask_boxes_torch(mask_preds)
+            bboxes[:, :4] = boxes.cpu().numpy().clip(min=0)
+        segm_result = [[] for _ in range(self.num_classes)]
+        for idx in range(n):
+            segm_result[labels[idx]].append(mask_preds[idx])
+        return bboxes, segm_result, mask_preds
+
+    @staticmethod
+    def mask_boxes_torch(masks):
+        """torch formulation of the mask -> box reduction (host-side packing of CPU tensors; the CUDA kernel's checker)"""
+        nz = masks != 0
+        K, H, W = nz.shape
+        rows, cols = nz.any(2), nz.any(1)                                  # [K,H], [K,W]
+        ys = torch.arange(H, device=masks.device).expand(K, H)
+        xs = torch.arange(W, device=masks.device).expand(K, W)
+        big = max(H, W) + 1
+        y0 = torch.where(rows, ys, torch.full_like(ys, big)).min(1).values
+        y1 = torch.where(rows, ys, torch.full_like(ys, -1)).max(1).values
+        x0 = torch.where(cols, xs, torch.full_like(xs, big)).min(1).values
+        x1 = torch.where(cols, xs, torch.full_like(xs, -1)).max(1).values
+        out = torch.stack([x0, y0, x1, y1], 1).float()
+        empty = ~rows.any(1)
+        out[empty] = torch.tensor([-1.0, -1.0, 10.0, 10.0], device=masks.device)
+        return out
+
     def check_supported(self):
         super().check_supported()
         if self.previous is not None:
@@ -124,6 +170,10 @@ class VideoKernelUpdateHead(_HeadBase):
         _lib.check(L.vkn_mask_pool(shape, w, _lib.ptr(x), _lib.ptr(mask_preds), _lib.ptr(x_feat), ws, wsb, st))
         prev = None
         if previous_obj_feats is not None:
+            self._refuse_autograd(previous_obj_feats)
+            if previous_obj_feats.numel() != B * N * Cc:
+                raise _lib.VknError('previous_obj_feats %s does not hold [B=%d, N=%d, C=%d] kernels' % (
+                    tuple(previous_obj_feats.shape), B, N, Cc))
             prev = previous_obj_feats.reshape(B, N, Cc).to(torch.float32).contiguous()
         if prev is not None and 'link' in links:                                    # :324-348
             pf = self._link(shape, links['link'], pf, prev, x_feat, ws, wsb)
