@@ -40,6 +40,9 @@ def main():
 
     start, end = vd.shard_frames(frames, rank, world)
     track = vd.link_sharded_clip(link_fn, obj_all[start:end].to(dev), frames)
+    # the minimal exchange (one frame per rank: the shard-boundary kernels) must give the same tracking kernels
+    track_b = vd.link_sharded_clip_boundary(link_fn, obj_all[start:end].to(dev), frames)
+    same = bool(torch.equal(track, track_b)) if end > start else True
     # sequential oracle: frame t links to frame t-1, frame 0 keeps its own kernels
     want = [obj_all[0]]
     for t in range(1, frames):
@@ -48,8 +51,8 @@ def main():
                                    1, N).reshape(N, C))
     want = torch.stack(want)[start:end]
     err = (track.cpu() - want).abs().max().item() if end > start else 0.0
-    print('rank %d frames [%d,%d) max|diff| %.3e' % (rank, start, end, err), flush=True)
-    ok = torch.tensor([1.0 if err < 1e-3 else 0.0], device=dev)
+    print('rank %d frames [%d,%d) max|diff| %.3e  boundary-exchange == full all-gather: %s' % (rank, start, end, err, same), flush=True)
+    ok = torch.tensor([1.0 if (err < 1e-3 and same) else 0.0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if ok.item() == 1.0 else 1)
