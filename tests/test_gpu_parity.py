@@ -711,6 +711,7 @@ def test_row_engine_tc_variants(dev, monkeypatch):
 
 @pytest.mark.parametrize('B,N,C', [(1, 10, 64), (2, 37, 128), (3, 117, 64), (16, 100, 256), (2, 166, 128)])
 def test_attention_four_queries_per_warp_kernel(dev, monkeypatch, B, N, C):
+    monkeypatch.setenv('VKN_ATT_TC', '0')            # the SIMT kernels are the subject here
     """The batched attention kernel (4 queries per warp, picked when many (head, frame) pairs are in flight) against
     the oracle and against the one-query-per-warp kernel, on ragged N (partial last query group / key sweep)."""
     from vknet import ops
@@ -852,3 +853,29 @@ def test_mask_boxes_kernel(dev):
     b_gpu = head.segm2result(m.to(dev), labels.to(dev), scores.to(dev))[0]
     b_cpu = head.segm2result(m, labels, scores)[0]
     assert (b_gpu == b_cpu).all() and b_gpu[3, :4].tolist() == [0, 0, 10, 10]
+
+
+@pytest.mark.parametrize('B,N,C', [(8, 100, 256), (9, 117, 256), (16, 16, 64), (12, 37, 128), (150, 100, 256), (8, 128, 256)])
+def test_attention_tcgen05_kernel(dev, monkeypatch, B, N, C):
+    """tcgen05 attention (QK^T and PV on tensor cores, two fp16 planes per operand, softmax from TMEM) against the fp32 SIMT
+    kernel and the oracle's MultiheadAttention + LayerNorm block (knet/det/kernel_update_head.py:204-208)."""
+    import vknet
+    from vknet import _lib, ops
+    cfg = ko.default_cfg(num_classes=5, in_channels=C, feedforward_channels=64, num_heads=C // 32)
+    sd = ko.random_state_dict(cfg, seed=12)
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev)[0]
+    g = torch.Generator().manual_seed(13)
+    qin = torch.randn(B, N, C, generator=g) * 1.5
+    want = ko.layer_norm(ko.mha_block(qin.permute(1, 0, 2), qin.permute(1, 0, 2), qin.permute(1, 0, 2), qin.permute(1, 0, 2), sd,
+                                      'attention.', C // 32), sd['attention_norm.weight'], sd['attention_norm.bias']).permute(1, 0, 2)
+    monkeypatch.setenv('VKN_ATT_TC', '0')
+    with _lib.profile() as p0:
+        simt = ops.mhsa_ln(h, qin.to(dev)).clone()
+    monkeypatch.setenv('VKN_ATT_TC', '1')
+    monkeypatch.setenv('VKN_ATT_TC_MIN', '1')
+    with _lib.profile() as p1:
+        tc = ops.mhsa_ln(h, qin.to(dev)).clone()
+    assert any('attention_tc' in n for n, _ in p1.records) and not any('attention_tc' in n for n, _ in p0.records)
+    assert torch.equal(tc, ops.mhsa_ln(h, qin.to(dev))), 'deterministic'
+    assert maxabs(simt, want) < 2e-5 and maxabs(tc, want) < 2e-5, (maxabs(simt, want), maxabs(tc, want))
+    assert maxabs(tc, simt.cpu()) < 1e-5

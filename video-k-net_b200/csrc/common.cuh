@@ -219,6 +219,11 @@ int launch_rowprep(const RowSrc &src, float *out, int ldo, void *planes, int ldp
 int launch_attention(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
                      int ldo, int B, int N, int C, int heads, cudaStream_t stream, void *planes = nullptr,
                      long long plane_stride = 0);
+// tcgen05 attention (attention_tc.cu): head_dim 32, N <= 128; same contract as launch_attention
+bool attention_tc_supported(int N, int C, int heads, const float *q, int ldq, const float *k, int ldk, const float *v, int ldv,
+                            const float *out, int ldo, const void *planes, long long plane_stride);
+int launch_attention_tc(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out, int ldo, int B,
+                        int N, int C, int heads, cudaStream_t stream, void *planes, long long plane_stride);
 // tcgen05 row GEMM (rowgemm_tc.cu): same contract as launch_linear for PRO_PLANES inputs and bf16 weights
 bool linear_tc_supported(const LinArgs &a);
 int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream);

@@ -770,6 +770,15 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   if (heads < 1 || C % heads != 0) VKN_FAIL(VKN_E_INVALID, "attention: C %d not divisible by heads %d", C, heads);
   const int hd = C / heads;
   if (hd > 32) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: head_dim %d > 32", hd);
+  {
+    // frame batches: the tcgen05 kernel (one CTA per frame, both products on tensor cores); a few frames: the SIMT kernels
+    // below spread (query block, head, frame) over many CTAs.  VKN_ATT_TC=0 forces SIMT, VKN_ATT_TC_MIN sets the crossover.
+    int tc_min = 8;
+    if (const char *e = getenv("VKN_ATT_TC_MIN")) tc_min = atoi(e);
+    const char *e = getenv("VKN_ATT_TC");
+    if (!(e && e[0] == '0') && B >= tc_min && attention_tc_supported(N, C, heads, q, ldq, k, ldk, v, ldv, out, ldo, planes, plane_stride))
+      return launch_attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, N, C, heads, stream, planes, plane_stride);
+  }
   const size_t smem = ((size_t)2 * N * (hd + 1) + (NT / 32) * (size_t)N + (NT / 32) * 32) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
