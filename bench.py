@@ -492,7 +492,7 @@ def run_ours(args):
     # frame batches hand 1-bit hard masks between the stages of the loop (vkn_iter_forward): inner-stage mask traffic is
     # N x ceil(HW/128) x 16 bytes per frame instead of N x HW x 2
     ntile = (HW + 127) // 128
-    loop_bits = P >= 400 and Npad <= 112 and ntile * BF >= 296 and os.environ.get('VKN_LOOP_BITS', '1') != '0'
+    loop_bits = P >= 400 and Npad <= 192 and ntile * BF >= 296 and os.environ.get('VKN_LOOP_BITS', '1') != '0'
     m_logits, m_bits = N * HW * 2, N * ntile * 16
     m_in = [m_logits] + [m_bits if loop_bits else m_logits] * (S - 1)          # mask bytes read by pooling, per stage
     m_out = [m_bits if loop_bits else m_logits] * (S - 1) + [m_logits]         # mask bytes written by the mask conv

@@ -473,11 +473,13 @@ def test_frames_in_flight_graph_matches_single_frame_loop(dev):
         assert torch.equal(w[0].cpu(), ho[0]) and torch.equal(w[1].cpu(), ho[1])
 
 
-def test_persistent_mask_conv_equals_tiled_mask_conv(dev, monkeypatch):
+@pytest.mark.parametrize('N', [100, 117, 128, 166, 176])
+def test_persistent_mask_conv_equals_tiled_mask_conv(dev, monkeypatch, N):
     """The persistent (resident-planes) tcgen05 mask conv issues the same MMAs per tile as the one-tile-per-CTA
-    kernel, so their outputs must be bit-identical; both are exercised on a ragged last tile."""
+    kernel, so their outputs must be bit-identical; both are exercised on a ragged last tile.  N > 112 (the real VPS kernel
+    counts 117 / 166) runs as two kernel groups with their own resident planes."""
     from vknet import _lib, ops
-    B, N, C, H, W = 3, 100, 256, 40, 52          # HW = 2080 = 16 tiles + a 32-pixel tail
+    B, C, H, W = 3, 256, 40, 52                  # HW = 2080 = 16 tiles + a 32-pixel tail
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
     sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=4))
     h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
@@ -562,13 +564,24 @@ def test_row_engine_tc_vs_warp_mma_chain_and_oracle(dev, monkeypatch, B, N, C, H
 
 @pytest.mark.parametrize('thr,wide', [(0.5, '0'), (0.7, '0'), (0.5, '1'), (0.7, '1')])
 def test_loop_bitmask_handoff_equals_stagewise_modules(dev, monkeypatch, thr, wide):
+    _loop_bitmask_case(dev, monkeypatch, thr, wide, 100)
+
+
+@pytest.mark.parametrize('N', [117, 166])
+def test_loop_bitmask_handoff_real_kernel_counts(dev, monkeypatch, N):
+    """N = 117 (KITTI / Cityscapes-STEP: 100 things + 17 stuff) and 166 (VIP-Seg): the mask conv runs as two kernel groups,
+    the pooling over two row tiles (N > 128); the loop still hands bit masks between its stages"""
+    _loop_bitmask_case(dev, monkeypatch, 0.5, '0', N)
+
+
+def _loop_bitmask_case(dev, monkeypatch, thr, wide, N):
     """Frame batches: the one-call loop hands the thresholded BIT per (kernel, pixel) from a stage's mask conv to the next
     stage's pooling instead of bf16 logits.  It thresholds the bf16-rounded logit, so the results must equal the
     stage-by-stage module calls (which store and re-read the logits) bit for bit -- also for a non-default threshold."""
     import vknet
     monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
     monkeypatch.setenv('VKN_MASK_WIDE', wide)
-    B, N, C, H, W, S = 6, 100, 256, 96, 80, 3
+    B, C, H, W, S = 6, 256, 96, 80, 3
     cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256, hard_mask_thr=thr)
     sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=70 + s)) for s in range(S)]
     heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)

@@ -458,12 +458,18 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
                                const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
                                int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int MP_XS,
                                int total_tiles, int pf_dist, uint32_t *__restrict__ bits_out, int wpr, float thr,
-                               int stg_bytes, unsigned long long *dbg) {
+                               int stg_bytes, unsigned long long *dbg, int Ng, int rows8) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
+  // Kernel groups (gridDim.y): more kernels than one resident plane set holds (N > 112: the real VPS counts 117 / 166) are
+  // split into groups of Ng (64 or 96, a multiple of the 32-row store box); the CTAs of a group walk ALL pixel tiles with
+  // their group's planes resident, so x is read once per group -- the second read of a tile comes from L2, the groups run
+  // side by side.  Npad stays the row stride of the plane buffer; the MMA N and the epilogue extent are Ng.
+  const int n_off = (int)blockIdx.y * Ng;
+  const int Ncur = min(N - n_off, Ng);                                  // kernels this CTA computes
   const uint32_t x_bytes = (uint32_t)CH_BLK * MASK_TILE_P * 2u;         // 16 KB
-  const uint32_t a_plane = (uint32_t)((N + 7) & ~7) * 128u;             // one plane, one 64-channel chunk (8-row atoms)
+  const uint32_t a_plane = (uint32_t)rows8 * 128u;                      // one plane, one 64-channel chunk (8-row atoms)
   const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
   uint8_t *xring = smem + planes_bytes;                                 // (planes_bytes is a multiple of 1024)
   uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 2 x [32 kernels][128 px] bf16
@@ -525,7 +531,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         mbar_expect_tx(bar0, planes_bytes);
         for (int c = 0; c < nk; ++c)
           for (int t = 0; t < 3; ++t)
-            tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad);
+            tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad + n_off);
         for (int tile = t0; tile < t1; ++tile) {
           const int p0 = tile * MASK_TILE_P;
           // The ring holds 48-64 KB per SM -- less than DRAM latency x bandwidth needs: the tile pf_dist ahead is pulled
@@ -625,7 +631,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int n = lane + 32 * i;
-          const float v = (n < N) ? a_ext[((size_t)kb * N + n) * lda + C] : 0.f;
+          const float v = (n < Ncur) ? a_ext[((size_t)kb * N + n_off + n) * lda + C] : 0.f;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias0 + (uint32_t)n * 4u), "f"(v));
         }
         __syncwarp();
@@ -640,14 +646,14 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         // BIT per (kernel, pixel) -- of the bf16-rounded logit, i.e. exactly what thresholding the stored map would
         // give -- 32 pixels of a warp per ballot word.  No staging, no TMA store, 16x fewer bytes.
         const int p = tile * MASK_TILE_P + q * 32 + lane;
-        for (int n0 = 0; n0 < Npad; n0 += 32) {
+        for (int n0 = 0; n0 < Ng; n0 += 32) {
           float4 bq[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) bq[e] = lds_f4(bias0 + (uint32_t)(n0 + 4 * e) * 4u);
           const float *bqf = reinterpret_cast<const float *>(bq);
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + n0), r);
-          if (n0 + 32 >= Npad) {
+          if (n0 + 32 >= Ng) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
@@ -659,17 +665,17 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
             const uint32_t w = __ballot_sync(0xffffffffu, p < HW && v > thr);
             if (lane == e) mine = w;
           }
-          if (n0 + lane < N) bits_out[((size_t)b * N + n0 + lane) * wpr + tile * 4 + q] = mine;
+          if (n0 + lane < Ncur) bits_out[((size_t)b * N + n_off + n0 + lane) * wpr + tile * 4 + q] = mine;
         }
         continue;
       }
-      for (int n0 = 0; n0 < Npad; n0 += 32, ++jj) {
+      for (int n0 = 0; n0 < Ng; n0 += 32, ++jj) {
         float4 bq[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) bq[e] = lds_f4(bias0 + (uint32_t)(n0 + 4 * e) * 4u);
         uint32_t r[32];
         MP_WAIT(w2, tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + n0), r));
-        if (n0 + 32 >= Npad) {             // accumulators of this tile are in registers: hand the TMEM buffer back
+        if (n0 + 32 >= Ng) {               // accumulators of this tile are in registers: hand the TMEM buffer back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar0 + 8 * (ACC_EMPTY + buf));
@@ -685,7 +691,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         });
         MP_WAIT(w4, fence_proxy_async(); named_bar_sync(1, 128));
         if (leader) {
-          tma_store_3d(&tmap_o, stg0 + (jj & 1u) * (uint32_t)(32 * MASK_TILE_P * 2), tile * MASK_TILE_P, n0, b);
+          tma_store_3d(&tmap_o, stg0 + (jj & 1u) * (uint32_t)(32 * MASK_TILE_P * 2), tile * MASK_TILE_P, n_off + n0, b);
           bulk_commit_group();
         }
       }
@@ -916,8 +922,12 @@ int maskgemm_tc_bits_wpr(const VknShape &s) { return ceil_div(s.H * s.W, MW_TILE
 bool maskgemm_tc_persistent(const VknShape &s) {
   if (!tc_supported(s)) return false;
   const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
-  bool persist = npad_of(s.N) <= 112 && ceil_div(s.H * s.W, MASK_TILE_P) * s.B * F >= 2 * 148;
-  if (const char *e = getenv("VKN_MASK_PERSIST")) persist = (e[0] == '1') && npad_of(s.N) <= 112;
+  // (N > 112 kernels: two kernel groups of 64 / 96, see the kernel; VKN_MASK_GROUPS=0 restricts it to one group)
+  bool groups_ok = true;
+  if (const char *e = getenv("VKN_MASK_GROUPS")) groups_ok = e[0] != '0';
+  const bool fits = npad_of(s.N) <= 112 || (groups_ok && npad_of(s.N) <= 192);
+  bool persist = fits && ceil_div(s.H * s.W, MASK_TILE_P) * s.B * F >= 2 * 148;
+  if (const char *e = getenv("VKN_MASK_PERSIST")) persist = (e[0] == '1') && fits;
   return persist;
 }
 
@@ -986,8 +996,11 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     const int total_tiles = ntiles * frames;
     int pf_dist = 1;                                         // L2 prefetch distance in tiles (VKN_MASK_PF; measured 0/1/2/4: 1 is best)
     if (const char *e = getenv("VKN_MASK_PF")) pf_dist = atoi(e);
-    const int grid_x = total_tiles < 148 ? total_tiles : 148;
-    const int rows8 = (s.N + 7) & ~7;
+    const int ngroups = Npad <= 112 ? 1 : 2;
+    const int Ng = ngroups == 1 ? Npad : (Npad <= 128 ? 64 : 96);      // kernels per group: MMA N, multiple of the 32-row store box
+    const int per_grp = 148 / ngroups;
+    const int grid_x = total_tiles < per_grp ? total_tiles : per_grp;
+    const int rows8 = ngroups == 1 ? ((s.N + 7) & ~7) : Ng;
     {     // resident planes: whole 8-row atoms only (see the kernel comment)
       const uint64_t dims[2] = {(uint64_t)s.C, (uint64_t)3 * s.B * Npad};
       const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)rows8};
@@ -1020,10 +1033,10 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[3] = {(uint32_t)MASK_TILE_P, (uint32_t)CH_BLK, 1u};
       VKN_TRY(make_tmap_bf16_plain(&tmpf, x, dims, box));
     }
-    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x), dim3(TC_THREADS), psmem, stream, tmx, tma,
-                             tmo, tmpf, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Npad, 1, 0),
+    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x, ngroups), dim3(TC_THREADS), psmem, stream, tmx, tma,
+                             tmo, tmpf, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Ng, 1, 0),
                              x_lbo, x_sbo, F, xs_depth, total_tiles, pf_dist, bits_out, maskgemm_tc_bits_wpr(s), s.mask_thr_logit,
-                             stg_bytes, debug_ts_slot()));
+                             stg_bytes, debug_ts_slot(), Ng, rows8));
     return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);
