@@ -254,6 +254,36 @@ int vkn_panoptic_merge(const float *masks, const float *scores, const int32_t *l
                        int32_t *segments, float *segment_scores, int32_t *kept_things, int32_t *counts, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- next row: tracking embeddings + association ----------------------------------------------
+ * A stack of nn.Linear layers over [rows, features] fp32: y = W x + b, then (optional) LayerNorm, then (optional) ReLU.
+ * Covers the tracking-embedding path of the video detectors on the last-stage kernels:
+ *   embed_fcs (Linear(no bias) -> LN -> ReLU) + fc_embed     knet/video/knet_quansi_dense_embed_fc_joint_train.py:113-126, 572-580
+ *   QuasiDenseMaskEmbedHeadGTMask.forward (fcs: Linear -> ReLU, fc_embed)   knet/video/track_heads.py:632-642
+ * One fused launch per Linear (the LayerNorm / ReLU of layer i is the prologue of layer i+1).  w [out_dim, in_dim] in
+ * w_dtype, b / ln_g / ln_b fp32 or NULL.  workspace: 256-byte aligned, 2 * round_up(rows * max(out_dim) * 4, 256) bytes. */
+typedef struct VknMlpLayer {
+  const void *w; const float *b;
+  const float *ln_g, *ln_b;      /* LayerNorm(out_dim) after the Linear, or both NULL */
+  int32_t in_dim, out_dim;
+  int32_t relu;                  /* ReLU after the (normalised) output */
+} VknMlpLayer;
+int vkn_mlp(const VknMlpLayer *layers, int num_layers, int w_dtype, const float *in, float *out, int rows, void *workspace,
+            size_t workspace_bytes, void *stream);
+
+/* QuasiDenseEmbedTracker.match up to the memory update (knet/video/qdtrack/trackers/quasi_dense_embed_tracker.py:137-204,
+ * match_metric='bisoftmax'): sort by score, duplicate removal by box IoU, bi-directional softmax of embeds . memo_embeds^T,
+ * same-category mask, greedy assignment with column knock-out, ids of new tracks.  ONE single-CTA launch.
+ *   bboxes [n,5] fp32 (x1,y1,x2,y2,score), labels [n] int64, embeds [n,D] fp32; memory: memo_labels [m] int64,
+ *   memo_embeds [m,D] fp32, memo_ids [m] int64 (-1 = backdrop); thresholds[6] = {obj_score_thr, match_score_thr,
+ *   init_score_thr, nms_conf_thr, nms_backdrop_iou_thr, nms_class_iou_thr}; num_tracklets = the tracker's id counter.
+ *   selected [n] int32: indices of the kept detections in score order (the rows of the reference's returned bboxes);
+ *   ids [n] int64: track id per kept detection (-1 none, -2 suppressed duplicate); counts[2] = {kept, new tracks}.
+ *   workspace: 2 * n * m * 4 bytes (at least 8). */
+int vkn_track_match(const float *bboxes, const int64_t *labels, const float *embeds, int n, int embed_dim,
+                    const int64_t *memo_labels, const float *memo_embeds, const int64_t *memo_ids, int m,
+                    const float *thresholds, int with_cats, int64_t num_tracklets, int32_t *selected, int64_t *ids,
+                    int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Mask -> box reduction of VideoKernelUpdateHead.segm2result (knet/video/kernel_update_head.py:734-744; unitrack
  * tensor_mask2box): boxes[k] = (x_min, y_min, x_max, y_max) of the non-zero pixels of mask k, (-1, -1, 10, 10) when the
  * mask is empty (the caller clips at 0 like the reference).  masks [K, H, W], elem_bytes 1 (bool / uint8) or 4 (float32). */

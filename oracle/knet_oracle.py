@@ -493,3 +493,68 @@ def panoptic_merge_joint(thing_masks, thing_labels, thing_scores, stuff_masks, s
         else:
             info.append(dict(id=next_id, isthing=False, category_id=cls - num_thing_classes + 1, area=area))
     return seg, info, kept
+
+
+# ----------------------------------------------------------------------------------------
+# tracking embeddings + association
+# ----------------------------------------------------------------------------------------
+def mlp(layers, x):
+    """layers: list of (weight [out,in], bias | None, ln_weight | None, ln_bias | None, relu) -- the embedding stacks
+    knet/video/knet_quansi_dense_embed_fc_joint_train.py:113-126, 572-580 and knet/video/track_heads.py:632-642."""
+    for w, b, g, be, relu in layers:
+        x = linear(x, w, b)
+        if g is not None:
+            x = layer_norm(x, g, be)
+        if relu:
+            x = torch.relu(x)
+    return x
+
+
+def bbox_iou(a, b, eps=1e-6):
+    """mmdet.core.bbox_overlaps(mode='iou', is_aligned=False) (mmdet v2.18: no +1 on the extents, union clamped at eps)."""
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = torch.max(a[:, None, :2], b[None, :, :2])
+    rb = torch.min(a[:, None, 2:], b[None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    ov = wh[..., 0] * wh[..., 1]
+    return ov / (area_a[:, None] + area_b[None, :] - ov).clamp(min=eps)
+
+
+def tracker_match(bboxes, labels, track_feats, memo_labels, memo_embeds, memo_ids, num_tracklets, obj_score_thr=0.5,
+                  match_score_thr=0.5, init_score_thr=0.8, nms_conf_thr=0.5, nms_backdrop_iou_thr=0.3, nms_class_iou_thr=0.7,
+                  with_cats=True):
+    """QuasiDenseEmbedTracker.match up to update_memo (knet/video/qdtrack/trackers/quasi_dense_embed_tracker.py:137-204),
+    match_metric='bisoftmax'.  Returns (selected indices in score order, ids, number of new tracks)."""
+    n = bboxes.shape[0]
+    order = sorted(range(n), key=lambda i: (-float(bboxes[i, 4]), i))                      # :139
+    b = bboxes[order]
+    ious = bbox_iou(b[:, :4], b[:, :4]) if n else b.new_zeros((0, 0))
+    keep = [True] * n
+    for i in range(1, n):                                                                   # :147-151
+        thr = nms_backdrop_iou_thr if float(b[i, 4]) < obj_score_thr else nms_class_iou_thr
+        if bool((ious[i, :i] > thr).any()):
+            keep[i] = False
+    sel = [order[i] for i in range(n) if keep[i]]
+    b, lab, emb = bboxes[sel], labels[sel], track_feats[sel]
+    ids = torch.full((len(sel),), -1, dtype=torch.long)
+    m = 0 if memo_embeds is None else memo_embeds.shape[0]
+    if len(sel) > 0 and m > 0:
+        feats = emb @ memo_embeds.t()                                                        # :166-170
+        scores = (feats.softmax(dim=1) + feats.softmax(dim=0)) / 2
+        if with_cats:
+            scores = scores * (lab.view(-1, 1) == memo_labels.view(1, -1)).float()           # :182-184
+        for i in range(len(sel)):                                                            # :186-198
+            conf, memo_ind = torch.max(scores[i, :], dim=0)
+            tid = int(memo_ids[memo_ind])
+            if float(conf) > match_score_thr and tid > -1:
+                if float(b[i, 4]) > obj_score_thr:
+                    ids[i] = tid
+                    scores[:i, memo_ind] = 0
+                    scores[i + 1:, memo_ind] = 0
+                elif float(conf) > nms_conf_thr:
+                    ids[i] = -2
+    new = (ids == -1) & (b[:, 4] > init_score_thr) if len(sel) else torch.zeros(0, dtype=torch.bool)   # :199-204
+    nnew = int(new.sum())
+    ids[new] = torch.arange(num_tracklets, num_tracklets + nnew, dtype=torch.long)
+    return torch.tensor(sel, dtype=torch.long), ids, nnew

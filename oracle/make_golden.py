@@ -219,8 +219,60 @@ def main():
     main_panoptic()
 
 
+def case_track(name, frames, nmax, D, ncls, seed):
+    """QuasiDenseEmbedTracker.match of the UNMODIFIED reference class over a short sequence (KITTI-STEP tracker settings,
+    configs/det/video_knet_kitti_step/...joint_train_8e.py:61-73): per frame the inputs, the memory it matched against and
+    its outputs.  Instances persist across frames (drifting boxes / embeddings) with births, deaths and duplicates."""
+    mod = ref_shim.load_tracker()
+    cfg = dict(init_score_thr=0.35, obj_score_thr=0.3, match_score_thr=0.5, memo_tracklet_frames=5, memo_backdrop_frames=1,
+               memo_momentum=0.8, nms_conf_thr=0.5, nms_backdrop_iou_thr=0.3, nms_class_iou_thr=0.7, with_cats=True,
+               match_metric='bisoftmax')
+    trk = mod.QuasiDenseEmbedTracker(**cfg)
+    g = torch.Generator().manual_seed(seed)
+    n_obj = nmax
+    base_emb = torch.randn(n_obj, D, generator=g) * 1.2
+    base_box = torch.rand(n_obj, 2, generator=g) * 300
+    size = 20 + torch.rand(n_obj, 2, generator=g) * 80
+    lab = torch.randint(0, ncls, (n_obj,), generator=g)
+    out = dict(meta=np.array([frames, D, ncls], dtype=np.int64),
+               cfg=np.array([cfg['obj_score_thr'], cfg['match_score_thr'], cfg['init_score_thr'], cfg['nms_conf_thr'],
+                             cfg['nms_backdrop_iou_thr'], cfg['nms_class_iou_thr']], dtype=np.float32))
+    for f in range(frames):
+        alive = torch.rand(n_obj, generator=g) > 0.25
+        idx = torch.nonzero(alive).squeeze(1)
+        if f == 2:                                   # a duplicate detection of one object (must be removed by the IoU rule)
+            idx = torch.cat([idx, idx[:1]])
+        xy = base_box[idx] + f * 4.0 + torch.randn(len(idx), 2, generator=g)
+        wh = size[idx]
+        score = 0.15 + 0.85 * torch.rand(len(idx), generator=g)
+        bboxes = torch.cat([xy, xy + wh, score[:, None]], dim=1)
+        feats = base_emb[idx] + 0.15 * torch.randn(len(idx), D, generator=g)
+        labels = lab[idx].clone()
+        if trk.empty:
+            memo = (torch.zeros(0, dtype=torch.long), torch.zeros(0, D), torch.zeros(0, dtype=torch.long))
+        else:
+            mb, ml, me, mi, mv = trk.memo
+            memo = (ml.clone(), me.clone(), mi.clone())
+        ntr = int(trk.num_tracklets)
+        ob, ol, oi = trk.match(bboxes=bboxes.clone(), labels=labels.clone(), track_feats=feats.clone(), frame_id=f)
+        for k, v in (('bboxes', bboxes), ('labels', labels), ('feats', feats), ('memo_labels', memo[0]), ('memo_embeds', memo[1]),
+                     ('memo_ids', memo[2]), ('out_bboxes', ob), ('out_labels', ol), ('out_ids', oi)):
+            out['f%d.%s' % (f, k)] = v.numpy()
+        out['f%d.num_tracklets' % f] = np.array([ntr, int(trk.num_tracklets)], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, {k: v.shape for k, v in out.items() if k.startswith('f1.')})
+
+
+def main_track():
+    ref_shim.install()
+    case_track('track_match_kitti_6f_n24_d256', frames=6, nmax=24, D=256, ncls=2, seed=5)
+    case_track('track_match_4f_n60_d64', frames=4, nmax=60, D=64, ncls=3, seed=9)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'clip':      # knet_vis registers the same keys as knet: own process
+    if len(sys.argv) > 1 and sys.argv[1] == 'track':
+        main_track()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'clip':      # knet_vis registers the same keys as knet: own process
         main_clip()
     elif len(sys.argv) > 1 and sys.argv[1] == 'rescale':
         main_rescale()

@@ -287,6 +287,34 @@ def load_video_iter_head():
     return mod
 
 
+def load_tracker():
+    """knet/video/qdtrack/trackers/quasi_dense_embed_tracker.py by path (QuasiDenseEmbedTracker: match / update_memo).  Its
+    relative import `..builder` is satisfied by a stand-in package holding a TRACKERS registry; mmdet's bbox_overlaps (IoU,
+    mmdet v2.18 semantics: no +1, union clamped at 1e-6) is the oracle's restatement -- third-party arithmetic, see
+    knet_oracle.bbox_iou."""
+    install()
+    import importlib.util
+    import os
+    import knet_oracle as ko
+    sys.modules['mmdet.core'].bbox_overlaps = lambda a, b, mode='iou', is_aligned=False, eps=1e-6: ko.bbox_iou(a, b, eps)
+    for name in ('_ref_qd', '_ref_qd.trackers'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    if '_ref_qd.builder' not in sys.modules:
+        b = types.ModuleType('_ref_qd.builder')
+        b.TRACKERS = Registry('tracker')
+        sys.modules['_ref_qd.builder'] = b
+    path = os.path.join(REFERENCE_ROOT, 'knet/video/qdtrack/trackers/quasi_dense_embed_tracker.py')
+    spec = importlib.util.spec_from_file_location('_ref_qd.trackers.quasi_dense_embed_tracker', path)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = '_ref_qd.trackers'
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load(tree='knet'):
     """Import the reference hot-path modules verbatim.  `tree` is 'knet' or 'knet_vis'
     (they register the same registry keys, so use one per process)."""

@@ -892,3 +892,61 @@ def test_attention_tcgen05_kernel(dev, monkeypatch, B, N, C):
     assert torch.equal(tc, ops.mhsa_ln(h, qin.to(dev))), 'deterministic'
     assert maxabs(simt, want) < 2e-5 and maxabs(tc, want) < 2e-5, (maxabs(simt, want), maxabs(tc, want))
     assert maxabs(tc, simt.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize('path', golden_files('track_match_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_track_match_golden(dev, path):
+    """vkn_track_match == the reference's QuasiDenseEmbedTracker.match (fixtures from the unmodified class): kept detections
+    in score order, track ids (matches, suppressed duplicates, births), frame by frame against the recorded memory."""
+    import numpy as np
+    from vknet import ops
+    z = np.load(path)
+    frames = int(z['meta'][0])
+    thr = [float(v) for v in z['cfg']]
+    for f in range(frames):
+        t = {k: torch.from_numpy(z['f%d.%s' % (f, k)]) for k in ('bboxes', 'labels', 'feats', 'memo_labels', 'memo_embeds', 'memo_ids',
+                                                               'out_bboxes', 'out_labels', 'out_ids')}
+        n0, n1 = (int(v) for v in z['f%d.num_tracklets' % f])
+        memo = (None, None, None) if t['memo_ids'].numel() == 0 else (t['memo_labels'].to(dev), t['memo_embeds'].to(dev), t['memo_ids'].to(dev))
+        sel, ids, nnew = ops.track_match(t['bboxes'].to(dev), t['labels'].to(dev), t['feats'].to(dev), memo[0], memo[1], memo[2], n0, *thr)
+        assert torch.equal(t['bboxes'][sel.cpu()], t['out_bboxes']) and torch.equal(t['labels'][sel.cpu()], t['out_labels']), f
+        assert torch.equal(ids.cpu(), t['out_ids']) and n0 + nnew == n1, f
+    sel, ids, nnew = ops.track_match(torch.zeros(0, 5, device=dev), torch.zeros(0, dtype=torch.long, device=dev),
+                                     torch.zeros(0, 8, device=dev), None, None, None, 3, *thr)
+    assert sel.numel() == 0 and ids.numel() == 0 and nnew == 0
+
+
+@pytest.mark.parametrize('dt', ['f32', 'bf16'])
+def test_tracking_embedding_mlp(dev, dt):
+    """the tracking-embedding stack on the last-stage kernels: embed_fcs (Linear(no bias) -> LN -> ReLU) + fc_embed
+    (knet/video/knet_quansi_dense_embed_fc_joint_train.py:113-126, 572-580) followed by the track head's fcs
+    (Linear -> ReLU) x 2 + fc_embed (knet/video/track_heads.py:632-642), vs the same modules in torch fp32."""
+    from vknet import ops
+    torch.manual_seed(3)
+    C = 256
+    mods = [(torch.nn.Linear(C, C, bias=False), torch.nn.LayerNorm(C), True), (torch.nn.Linear(C, C), None, False),
+            (torch.nn.Linear(C, C), None, True), (torch.nn.Linear(C, C), None, True), (torch.nn.Linear(C, C), None, False)]
+    for lin, norm, _ in mods:
+        torch.nn.init.xavier_uniform_(lin.weight)
+        if norm is not None:
+            torch.nn.init.normal_(norm.weight, 1.0, 0.2)
+            torch.nn.init.normal_(norm.bias, 0.0, 0.2)
+    if dt == 'bf16':
+        for lin, _, _ in mods:
+            lin.weight.data = lin.weight.data.bfloat16().float()
+    x = torch.randn(100, C)
+    want = x
+    with torch.no_grad():
+        for lin, norm, relu in mods:
+            want = lin(want)
+            want = norm(want) if norm is not None else want
+            want = torch.relu(want) if relu else want
+    if dt == 'bf16':
+        for lin, _, _ in mods:
+            lin.weight.data = lin.weight.data.bfloat16()
+    got = ops.mlp([(lin.to(dev), None if norm is None else norm.to(dev), relu) for lin, norm, relu in mods], x.to(dev))
+    assert got.shape == want.shape and maxabs(got, want) < 1e-4 * max(1.0, want.abs().max().item())
+    want_k = ko.mlp([(lin.weight.float().cpu(), None if lin.bias is None else lin.bias.float().cpu(),
+                      None if norm is None else norm.weight.cpu(), None if norm is None else norm.bias.cpu(), relu)
+                     for lin, norm, relu in mods], x)
+    assert maxabs(got, want_k) < 1e-4 * max(1.0, want.abs().max().item())

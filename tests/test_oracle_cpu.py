@@ -154,3 +154,25 @@ def test_no_cpu_path_for_the_post_loop_ops(built_lib):
     meta = dict(img_shape=(8, 8, 3), batch_input_shape=(8, 8), ori_shape=(8, 8, 3))
     with pytest.raises(_lib.VknError):
         ops.rescale_masks(torch.zeros(2, 4, 4), meta)
+
+
+@pytest.mark.parametrize('path', golden_files('track_match_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_oracle_matches_reference_fixtures_tracker_match(path):
+    """Row 8f-3: the association restatement == the reference's QuasiDenseEmbedTracker.match outputs, frame by frame,
+    against the memory the reference held at that frame (fixtures written by oracle/make_golden.py track)."""
+    import numpy as np
+    z = np.load(path)
+    frames = int(z['meta'][0])
+    thr = [float(v) for v in z['cfg']]
+    matched = news = 0
+    for f in range(frames):
+        t = {k: torch.from_numpy(z['f%d.%s' % (f, k)]) for k in ('bboxes', 'labels', 'feats', 'memo_labels', 'memo_embeds', 'memo_ids',
+                                                               'out_bboxes', 'out_labels', 'out_ids')}
+        n0, n1 = (int(v) for v in z['f%d.num_tracklets' % f])
+        sel, ids, nnew = ko.tracker_match(t['bboxes'], t['labels'], t['feats'], t['memo_labels'], t['memo_embeds'], t['memo_ids'], n0,
+                                          *thr, with_cats=True)
+        assert torch.equal(t['bboxes'][sel], t['out_bboxes']) and torch.equal(t['labels'][sel], t['out_labels'])
+        assert torch.equal(ids, t['out_ids']) and n0 + nnew == n1
+        matched += int(((ids > -1) & (ids < n0)).sum())
+        news += nnew
+    assert matched >= 10 and news >= 10          # the fixtures exercise matching, births and the duplicate rule

@@ -741,7 +741,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_attention_tc_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_rescale_masks_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_attention_tc_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_track_match_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -1015,6 +1015,52 @@ int vkn_panoptic_merge(const float *masks, const float *scores, const int32_t *l
   return launch_panoptic_merge(masks, scores, labels, num_kernels, H, W, num_thing_classes, instance_score_thr, overlap_thr,
                                panoptic_seg, segments, segment_scores, kept_things, counts, workspace, workspace_bytes,
                                (cudaStream_t)stream);
+}
+
+int vkn_mlp(const VknMlpLayer *layers, int num_layers, int w_dtype, const float *in, float *out, int rows, void *workspace,
+            size_t workspace_bytes, void *stream) {
+  if (!layers || num_layers < 1 || num_layers > 16 || !in || !out || rows < 1) VKN_FAIL(VKN_E_INVALID, "vkn_mlp: bad argument");
+  if (w_dtype != VKN_F32 && w_dtype != VKN_BF16) VKN_FAIL(VKN_E_INVALID, "vkn_mlp: bad weight dtype");
+  int maxd = 0;
+  for (int i = 0; i < num_layers; ++i) {
+    const VknMlpLayer &l = layers[i];
+    if (!l.w || l.in_dim < 1 || l.out_dim < 1 || (i > 0 && l.in_dim != layers[i - 1].out_dim))
+      VKN_FAIL(VKN_E_INVALID, "vkn_mlp: layer %d is inconsistent", i);
+    if ((l.ln_g == nullptr) != (l.ln_b == nullptr)) VKN_FAIL(VKN_E_INVALID, "vkn_mlp: layer %d has half a LayerNorm", i);
+    if (l.ln_g && l.out_dim > 256) VKN_FAIL(VKN_E_UNSUPPORTED, "vkn_mlp: LayerNorm over %d > 256 features", l.out_dim);
+    if (l.in_dim % 2 != 0) VKN_FAIL(VKN_E_UNSUPPORTED, "vkn_mlp: odd feature count %d", l.in_dim);
+    maxd = l.out_dim > maxd ? l.out_dim : maxd;
+  }
+  const size_t buf = align_up((size_t)rows * maxd * sizeof(float), 256);
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < 2 * buf)
+    VKN_FAIL(VKN_E_WORKSPACE, "vkn_mlp: workspace must be 256-byte aligned and hold %zu bytes", 2 * buf);
+  float *pp[2] = {(float *)workspace, (float *)((char *)workspace + buf)};
+  cudaStream_t st = (cudaStream_t)stream;
+  // layer i: y = W x (+ b); its LayerNorm (+ ReLU) is the PROLOGUE of layer i + 1 (one fused launch per Linear); a ReLU
+  // without LayerNorm is the epilogue of the layer itself
+  RowSrc src = src_copy(in, layers[0].in_dim);
+  for (int i = 0; i < num_layers; ++i) {
+    const VknMlpLayer &l = layers[i];
+    const bool last = i == num_layers - 1;
+    float *dst = (last && !l.ln_g) ? out : pp[i & 1];
+    LinArgs a = lin(src, l.w, l.in_dim, l.b, dst, l.out_dim, rows, l.out_dim, l.in_dim, (l.relu && !l.ln_g) ? EPI_RELU : 0);
+    VKN_TRY(launch_linear(&a, 1, w_dtype, st));
+    src = l.ln_g ? src_ln(dst, l.out_dim, l.ln_g, l.ln_b, l.relu != 0) : src_copy(dst, l.out_dim);
+    if (last && l.ln_g) VKN_TRY(launch_rowop(src, out, l.out_dim, rows, l.out_dim, st));
+  }
+  return VKN_OK;
+}
+
+int vkn_track_match(const float *bboxes, const int64_t *labels, const float *embeds, int n, int embed_dim,
+                    const int64_t *memo_labels, const float *memo_embeds, const int64_t *memo_ids, int m,
+                    const float *thresholds, int with_cats, int64_t num_tracklets, int32_t *selected, int64_t *ids,
+                    int32_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
+  if (!thresholds || !selected || !ids || !counts || (n > 0 && (!bboxes || !labels || !embeds)) ||
+      (m > 0 && (!memo_labels || !memo_embeds || !memo_ids)))
+    VKN_FAIL(VKN_E_INVALID, "vkn_track_match: null argument");
+  return launch_track_match(bboxes, (const long long *)labels, embeds, n, embed_dim, (const long long *)memo_labels, memo_embeds,
+                            (const long long *)memo_ids, m, thresholds, with_cats, (long long)num_tracklets, selected,
+                            (long long *)ids, counts, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int vkn_mask_boxes(const void *masks, int elem_bytes, int K, int H, int W, float *boxes, void *stream) {

@@ -262,5 +262,9 @@ int launch_panoptic_merge(const float *masks, const float *scores, const int *la
                           double inst_thr, double overlap_thr, int *seg, int *table, float *seg_scores, int *kept, int *counts,
                           void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_mask_boxes(const void *masks, int elem_bytes, int K, int H, int W, float *boxes, cudaStream_t stream);
+int launch_track_match(const float *bboxes, const long long *labels, const float *embeds, int n, int D, const long long *memo_labels,
+                       const float *memo_embeds, const long long *memo_ids, int m, const float *thr6, int with_cats,
+                       long long num_tracklets, int *sel, long long *ids, int *counts, void *workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
 
 }  // namespace vkn

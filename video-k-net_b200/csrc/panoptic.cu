@@ -187,4 +187,177 @@ int launch_mask_boxes(const void *masks, int elem_bytes, int K, int H, int W, fl
   return VKN_OK;
 }
 
+
+// ---- tracking association --------------------------------------------------------------------
+// QuasiDenseEmbedTracker.match (knet/video/qdtrack/trackers/quasi_dense_embed_tracker.py:137-207) up to the memory update:
+// sort the detections by score, drop duplicates by box IoU (:145-154), bi-directional softmax of the embedding
+// similarities against the memory (:166-170), same-category mask (:182-184), the greedy assignment with column
+// knock-out (:186-198) and the new-track ids (:199-204).  The reference does this with ~4 host synchronisations per
+// detection; here it is ONE single-CTA launch (tens of detections x a few hundred memory entries).
+constexpr int TM_NT = 256;
+constexpr int TM_MAXN = 256;       // detections per frame
+
+__device__ __forceinline__ float tm_iou(const float *a, const float *b) {      // mmdet bbox_overlaps(mode='iou', eps=1e-6)
+  const float ix = fmaxf(fminf(a[2], b[2]) - fmaxf(a[0], b[0]), 0.f), iy = fmaxf(fminf(a[3], b[3]) - fmaxf(a[1], b[1]), 0.f);
+  const float ov = ix * iy;
+  const float uni = fmaxf((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - ov, 1e-6f);
+  return ov / uni;
+}
+
+__global__ void __launch_bounds__(TM_NT) vkn_track_match_kernel(
+    const float *__restrict__ bboxes, const long long *__restrict__ labels, const float *__restrict__ embeds, int n, int D,
+    const long long *__restrict__ memo_labels, const float *__restrict__ memo_embeds, const long long *__restrict__ memo_ids, int m,
+    float obj_score_thr, float match_score_thr, float init_score_thr, float nms_conf_thr, float nms_backdrop_iou_thr,
+    float nms_class_iou_thr, int with_cats, long long num_tracklets, int *__restrict__ sel, long long *__restrict__ ids,
+    int *__restrict__ counts, float *__restrict__ scores /* workspace [n, m] */) {
+  __shared__ int order[TM_MAXN], keep[TM_MAXN], nkeep_s;
+  __shared__ float red_v[TM_NT / 32];
+  __shared__ int red_i[TM_NT / 32], pick_s;
+  __shared__ float conf_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // 1. order by descending score (stable)
+  for (int i = tid; i < n; i += TM_NT) {
+    const float si = bboxes[i * 5 + 4];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const float sj = bboxes[j * 5 + 4];
+      r += (sj > si) || (sj == si && j < i);
+    }
+    order[r] = i;
+  }
+  __syncthreads();
+  // 2. duplicate removal: detection i (sorted) is dropped when it overlaps ANY better-scored detection too much
+  for (int i = tid; i < n; i += TM_NT) {
+    const float *bi = bboxes + order[i] * 5;
+    const float thr = bi[4] < obj_score_thr ? nms_backdrop_iou_thr : nms_class_iou_thr;
+    int ok = 1;
+    for (int j = 0; j < i; ++j)
+      if (tm_iou(bi, bboxes + order[j] * 5) > thr) {
+        ok = 0;
+        break;
+      }
+    keep[i] = ok;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+      if (keep[i]) sel[k++] = order[i];
+    nkeep_s = k;
+  }
+  __syncthreads();
+  const int nk = nkeep_s;
+  for (int i = tid; i < nk; i += TM_NT) ids[i] = -1;
+  if (nk > 0 && m > 0) {
+    // 3. similarities, bi-directional softmax, category mask
+    for (int e = tid; e < nk * m; e += TM_NT) {
+      const int i = e / m, j = e - i * m;
+      const float *a = embeds + (size_t)sel[i] * D, *b = memo_embeds + (size_t)j * D;
+      float acc = 0.f;
+      for (int d = 0; d < D; ++d) acc = fmaf(a[d], b[d], acc);
+      scores[e] = acc;
+    }
+    __syncthreads();
+    // row softmax -> keep exp and sums in place via two passes; column softmax needs the raw feats: use a second buffer
+    float *feats = scores + (size_t)nk * m;                 // workspace holds 2 x [n, m]
+    for (int e = tid; e < nk * m; e += TM_NT) feats[e] = scores[e];
+    __syncthreads();
+    for (int i = tid; i < nk; i += TM_NT) {                   // d2t: softmax over the memory entries
+      float mx = -3.0e38f, s = 0.f;
+      for (int j = 0; j < m; ++j) mx = fmaxf(mx, feats[i * m + j]);
+      for (int j = 0; j < m; ++j) s += expf(feats[i * m + j] - mx);
+      for (int j = 0; j < m; ++j) scores[i * m + j] = expf(feats[i * m + j] - mx) / s;
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += TM_NT) {                    // t2d: softmax over the detections; average; category mask
+      float mx = -3.0e38f, s = 0.f;
+      for (int i = 0; i < nk; ++i) mx = fmaxf(mx, feats[i * m + j]);
+      for (int i = 0; i < nk; ++i) s += expf(feats[i * m + j] - mx);
+      for (int i = 0; i < nk; ++i) {
+        float v = (scores[i * m + j] + expf(feats[i * m + j] - mx) / s) / 2.f;
+        if (with_cats && labels[sel[i]] != memo_labels[j]) v *= 0.f;
+        scores[i * m + j] = v;
+      }
+    }
+    __syncthreads();
+    // 4. greedy assignment in score order, a matched memory column is knocked out for every other detection
+    for (int i = 0; i < nk; ++i) {
+      float bv = -3.0e38f;
+      int bj = 0x7fffffff;
+      for (int j = tid; j < m; j += TM_NT) {
+        const float v = scores[i * m + j];
+        if (v > bv) {
+          bv = v;
+          bj = j;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov > bv || (ov == bv && oj < bj)) {
+          bv = ov;
+          bj = oj;
+        }
+      }
+      if (lane == 0) {
+        red_v[warp] = bv;
+        red_i[warp] = bj;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < TM_NT / 32; ++w)
+          if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bj)) {
+            bv = red_v[w];
+            bj = red_i[w];
+          }
+        int knock = -1;
+        if (bv > match_score_thr) {
+          const long long id = memo_ids[bj];
+          if (id > -1) {
+            if (bboxes[sel[i] * 5 + 4] > obj_score_thr) {
+              ids[i] = id;
+              knock = bj;
+            } else if (bv > nms_conf_thr) {
+              ids[i] = -2;
+            }
+          }
+        }
+        pick_s = knock;
+        conf_s = bv;
+      }
+      __syncthreads();
+      const int knock = pick_s;
+      if (knock >= 0)
+        for (int r = tid; r < nk; r += TM_NT)
+          if (r != i) scores[r * m + knock] = 0.f;
+      __syncthreads();
+    }
+  }
+  // 5. new tracks: unmatched detections above init_score_thr, numbered in score order
+  if (tid == 0) {
+    long long next = num_tracklets;
+    for (int i = 0; i < nk; ++i)
+      if (ids[i] == -1 && bboxes[sel[i] * 5 + 4] > init_score_thr) ids[i] = next++;
+    counts[0] = nk;
+    counts[1] = (int)(next - num_tracklets);
+  }
+}
+
+int launch_track_match(const float *bboxes, const long long *labels, const float *embeds, int n, int D, const long long *memo_labels,
+                       const float *memo_embeds, const long long *memo_ids, int m, const float *thr6, int with_cats,
+                       long long num_tracklets, int *sel, long long *ids, int *counts, void *workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  if (n < 0 || n > TM_MAXN || m < 0 || D < 1) VKN_FAIL(VKN_E_UNSUPPORTED, "track_match: n = %d detections (supported: 0..%d)", n, TM_MAXN);
+  size_t need = (size_t)2 * n * m * sizeof(float);
+  if (need < 8) need = 8;
+  if (!workspace || workspace_bytes < need) VKN_FAIL(VKN_E_WORKSPACE, "track_match: workspace too small: %zu given, %zu needed", workspace_bytes, need);
+  VKN_LAUNCH_MARK("vkn_track_match_kernel", stream);
+  vkn_track_match_kernel<<<1, TM_NT, 0, stream>>>(bboxes, labels, embeds, n, D, memo_labels, memo_embeds, memo_ids, m, thr6[0], thr6[1],
+                                                  thr6[2], thr6[3], thr6[4], thr6[5], with_cats, num_tracklets, sel, ids, counts,
+                                                  (float *)workspace);
+  VKN_CUDA_OK(cudaGetLastError());
+  return VKN_OK;
+}
+
 }  // namespace vkn

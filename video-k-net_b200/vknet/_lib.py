@@ -51,6 +51,11 @@ class VknHeadW(C.Structure):
                 ('fc_mask_w', _vp), ('fc_mask_b', _vp)]
 
 
+class VknMlpLayer(C.Structure):
+    _fields_ = [('w', _vp), ('b', _vp), ('ln_g', _vp), ('ln_b', _vp), ('in_dim', C.c_int32), ('out_dim', C.c_int32),
+                ('relu', C.c_int32)]
+
+
 class VknLinkW(C.Structure):
     _fields_ = [('has_updator', C.c_int32), ('upd', VknUpdatorW), ('attn', VknAttnW), ('ffn', VknFfnW)]
 
@@ -66,7 +71,7 @@ SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_launch_coun
            'vkn_profile_end', 'vkn_debug_timestamps', 'vkn_workspace_bytes', 'vkn_mask_pool',
            'vkn_kernel_update', 'vkn_mhsa_ln', 'vkn_ffn_ln', 'vkn_heads', 'vkn_mask_gemm',
            'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend', 'vkn_rescale_masks',
-           'vkn_panoptic_merge', 'vkn_mask_boxes')
+           'vkn_panoptic_merge', 'vkn_mask_boxes', 'vkn_mlp', 'vkn_track_match')
 
 
 def lib():
@@ -102,6 +107,9 @@ def lib():
     L.vkn_panoptic_merge.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp,
                                      _vp, _vp, sz, _vp]
     L.vkn_mask_boxes.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.vkn_mlp.argtypes = [C.POINTER(VknMlpLayer), C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, sz, _vp]
+    L.vkn_track_match.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int64, _vp, _vp, _vp,
+                                  _vp, sz, _vp]
     L.vkn_debug_timestamps.restype = C.c_int
     L.vkn_debug_timestamps.argtypes = [_vp, C.c_size_t]
     for name in SYMBOLS[7:]:

@@ -206,3 +206,79 @@ def panoptic_merge(thing_masks, thing_labels, thing_scores, stuff_masks, stuff_l
         else:
             info.append(dict(id=sid, isthing=False, category_id=cat, area=area))
     return seg, info, [int(v) for v in host[T * 5:T * 5 + nkept]]
+
+
+def mlp(layers, x):
+    """A stack of Linear layers on [rows, features] fp32 rows (vkn_mlp).  `layers`: list of
+    (linear: nn.Linear, norm: nn.LayerNorm | None, relu: bool) applied as  y = relu?(norm?(linear(x))).
+    The tracking-embedding path of the video detectors is such a stack:
+        embed_fcs + fc_embed            knet/video/knet_quansi_dense_embed_fc_joint_train.py:113-126, 572-580
+        track_head fcs + fc_embed       knet/video/track_heads.py:632-642"""
+    import ctypes as C
+    if not x.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    dev = x.device
+    rows = x.reshape(-1, x.shape[-1]).float().contiguous()
+    dts = {lin.weight.dtype for lin, _, _ in layers}
+    if len(dts) != 1 or dts.pop() not in (torch.float32, torch.bfloat16):
+        raise _lib.VknError('mlp: weights must be uniformly float32 or bfloat16')
+    wd = _lib.dtype_code(layers[0][0].weight.dtype)
+    arr = (_lib.VknMlpLayer * len(layers))()
+    keep = []
+
+    def vec(t):
+        t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        keep.append(t)
+        return C.c_void_p(t.data_ptr())
+    maxd = 0
+    for i, (lin, norm, relu) in enumerate(layers):
+        w = lin.weight.detach().to(dev).contiguous()
+        keep.append(w)
+        arr[i].w = C.c_void_p(w.data_ptr())
+        arr[i].b = vec(lin.bias) if lin.bias is not None else None
+        arr[i].ln_g = vec(norm.weight) if norm is not None else None
+        arr[i].ln_b = vec(norm.bias) if norm is not None else None
+        arr[i].in_dim, arr[i].out_dim, arr[i].relu = lin.in_features, lin.out_features, int(bool(relu))
+        maxd = max(maxd, lin.out_features)
+    out = torch.empty(rows.shape[0], layers[-1][0].out_features, dtype=torch.float32, device=dev)
+    buf = (rows.shape[0] * maxd * 4 + 255) // 256 * 256
+    ws = torch.empty(2 * buf + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    _lib.check(_lib.lib().vkn_mlp(arr, len(layers), wd, _lib.ptr(rows), _lib.ptr(out), rows.shape[0],
+                                  C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _lib.stream_ptr(dev)))
+    return out.reshape(tuple(x.shape[:-1]) + (out.shape[-1],))
+
+
+def track_match(bboxes, labels, track_feats, memo_labels, memo_embeds, memo_ids, num_tracklets, obj_score_thr=0.5,
+                match_score_thr=0.5, init_score_thr=0.8, nms_conf_thr=0.5, nms_backdrop_iou_thr=0.3, nms_class_iou_thr=0.7,
+                with_cats=True):
+    """QuasiDenseEmbedTracker.match up to the memory update (knet/video/qdtrack/trackers/quasi_dense_embed_tracker.py:
+    137-204, match_metric='bisoftmax') as ONE launch and one device->host read, instead of ~4 host synchronisations per
+    detection.  Returns (selected: indices of the kept detections in score order, ids: their track ids int64, number of new
+    tracks); bboxes[selected], labels[selected], track_feats[selected] are the tensors the reference returns / memorises."""
+    if not bboxes.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    dev = bboxes.device
+    n, m = bboxes.shape[0], (0 if memo_embeds is None else memo_embeds.shape[0])
+    D = track_feats.shape[1] if n else (memo_embeds.shape[1] if m else 1)
+    bb = bboxes.float().contiguous()
+    lab = labels.to(device=dev, dtype=torch.int64).contiguous()
+    emb = track_feats.float().contiguous()
+    if m:
+        ml, me, mi = (memo_labels.to(device=dev, dtype=torch.int64).contiguous(), memo_embeds.to(dev).float().contiguous(),
+                      memo_ids.to(device=dev, dtype=torch.int64).contiguous())
+    else:
+        ml = me = mi = None
+    thr = torch.tensor([obj_score_thr, match_score_thr, init_score_thr, nms_conf_thr, nms_backdrop_iou_thr, nms_class_iou_thr],
+                       dtype=torch.float32)
+    import ctypes as C
+    thr_arr = (C.c_float * 6)(*thr.tolist())
+    sel = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    ids = torch.full((max(n, 1),), -1, dtype=torch.int64, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(2 * n * m, 2), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().vkn_track_match(_lib.ptr(bb), _lib.ptr(lab), _lib.ptr(emb), n, D, _lib.ptr(ml), _lib.ptr(me), _lib.ptr(mi), m,
+                                          thr_arr, int(bool(with_cats)), int(num_tracklets), _lib.ptr(sel), _lib.ptr(ids),
+                                          _lib.ptr(counts), _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr(dev)))
+    nk, nnew = (int(v) for v in counts.cpu())
+    return sel[:nk].long(), ids[:nk], nnew
