@@ -998,7 +998,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     if (const char *e = getenv("VKN_MASK_PF")) pf_dist = atoi(e);
     const int ngroups = Npad <= 112 ? 1 : 2;
     const int Ng = ngroups == 1 ? Npad : (Npad <= 128 ? 64 : 96);      // kernels per group: MMA N, multiple of the 32-row store box
-    const int per_grp = 148 / ngroups;
+    int sms = 148;                                           // VKN_MASK_CTAS: leave SMs to the kernels of other streams
+    if (const char *e = getenv("VKN_MASK_CTAS")) sms = atoi(e) > 0 && atoi(e) <= 148 ? atoi(e) : 148;
+    const int per_grp = sms / ngroups;
     const int grid_x = total_tiles < per_grp ? total_tiles : per_grp;
     const int rows8 = ngroups == 1 ? ((s.N + 7) & ~7) : Ng;
     {     // resident planes: whole 8-row atoms only (see the kernel comment)

@@ -1382,7 +1382,9 @@ int chain_launch(ChainBuild *b, cudaStream_t stream) {
   g.tpc = g.mtiles > 148 ? 2 : 1;
   if (const char *e = getenv("VKN_CHAIN_TPC")) g.tpc = atoi(e) == 2 ? 2 : 1;
   const int npairs = (g.mtiles + g.tpc - 1) / g.tpc;
-  dim3 grid(npairs < 148 ? npairs : 148);
+  int sms = 148;                                             // VKN_CHAIN_CTAS: leave SMs to the kernels of other streams
+  if (const char *e = getenv("VKN_CHAIN_CTAS")) sms = atoi(e) > 0 && atoi(e) <= 148 ? atoi(e) : 148;
+  dim3 grid(npairs < sms ? npairs : sms);
   VKN_LAUNCH_MARK("vkn_chain_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_chain_tc_kernel, grid, dim3(RG_THREADS), smem, stream, g));
   g.nsteps = 0;
