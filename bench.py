@@ -220,8 +220,11 @@ def parity_check(torch, heads, fif, dev):
         for h in heads:
             sd = {k: v.detach().float().cpu() for k, v in h.state_dict().items()}
             cls, m_new, obj_new = h(xb, obj, m)[:3]
-            want = ko.kernel_update_head_forward(sd, cfg, xb[:nf].float().cpu(), obj[:nf].float().cpu().reshape(nf, N, C, 1, 1),
-                                                 m[:nf].float().cpu())
+            m_cpu = m[:nf].float().cpu()
+            sliver = (m_cpu > 0) != (torch.sigmoid(m_cpu) > 0.5)     # fp32 sigmoid rounds 0 < m <~ 1e-7 to 0.5
+            res['threshold_sliver_logits'] = res.get('threshold_sliver_logits', 0) + int(sliver.sum())
+            m_cpu = torch.where(sliver, torch.where(m_cpu > 0, torch.ones_like(m_cpu), -torch.ones_like(m_cpu)), m_cpu)
+            want = ko.kernel_update_head_forward(sd, cfg, xb[:nf].float().cpu(), obj[:nf].float().cpu().reshape(nf, N, C, 1, 1), m_cpu)
             res['obj_max_abs'] = max(res['obj_max_abs'], float((obj_new[:nf].float().cpu().reshape(want[2].shape) - want[2]).abs().max()))
             res['cls_max_abs'] = max(res['cls_max_abs'], float((cls[:nf].float().cpu() - want[0]).abs().max()))
             got, ref = m_new[:nf].float().cpu(), ko.round_bf16(want[1])

@@ -105,10 +105,21 @@ def stagewise_vs_oracle_bf16(heads, sds, cfg, xb, pfd, mb, what, tol=1e-2):
     obj, m = pfd, mb
     outs, ties = [], 0
     B, N = pfd.shape[:2]
+    thr = cfg.get('hard_mask_thr', 0.5)
     for s, h in enumerate(heads):
         cls, m_new, obj_new = h(xb, obj, m)
-        want = ko.kernel_update_head_forward(sds[s], cfg, xb.float().cpu(), obj.float().cpu().reshape(B, N, -1, 1, 1),
-                                             m.float().cpu())
+        # The documented threshold sliver: the CUDA path thresholds the logit (m > logit(thr)), the
+        # reference the fp32 sigmoid, which rounds 0 < m <~ 1e-7 to exactly 0.5.  With 10^8 logits per stage such a value does
+        # occur; those pixels are resolved the CUDA path's way before the oracle runs, and counted.
+        m_cpu = m.float().cpu()
+        logit_thr = float(torch.logit(torch.tensor(thr, dtype=torch.float64)))
+        sliver = (m_cpu > logit_thr) != (torch.sigmoid(m_cpu) > thr)
+        if bool(sliver.any()):
+            print('%s stage %d: %d input logit(s) in the sigmoid rounding sliver (%s)' % (
+                what, s, int(sliver.sum()), m_cpu[sliver][:4].tolist()))
+            m_cpu = torch.where(sliver, torch.where(m_cpu > logit_thr, torch.full_like(m_cpu, logit_thr + 1.0),
+                                                    torch.full_like(m_cpu, logit_thr - 1.0)), m_cpu)
+        want = ko.kernel_update_head_forward(sds[s], cfg, xb.float().cpu(), obj.float().cpu().reshape(B, N, -1, 1, 1), m_cpu)
         e_cls, e_obj = maxabs(cls, want[0]), maxabs(obj_new, want[2])
         assert e_cls < tol and e_obj < tol, '%s stage %d: cls err %g obj err %g' % (what, s, e_cls, e_obj)
         ties += assert_masks_bf16(m_new, want[1], '%s stage %d' % (what, s))

@@ -950,3 +950,31 @@ def test_tracking_embedding_mlp(dev, dt):
                       None if norm is None else norm.weight.cpu(), None if norm is None else norm.bias.cpu(), relu)
                      for lin, norm, relu in mods], x)
     assert maxabs(got, want_k) < 1e-4 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize('N', [100, 166])
+def test_mask_conv_fp16_mode_vs_bf16_planes(dev, monkeypatch, N):
+    """Persistent mask conv, fp16 mode (default for frame batches): the folded kernels as TWO fp16 planes (22 bits) and x
+    converted bf16 -> fp16 in the ring (exact) -- a third fewer MMAs than three bf16 planes.  Same logits up to rare one-ulp
+    roundings of the bf16 store, and both within one bf16 ulp of the oracle."""
+    monkeypatch.setenv('VKN_ROWS_TC_MIN', '1')
+    B, C, H, W = 6, 256, 96, 80
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=256)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=33))
+    h = build_heads('KernelUpdateHead', cfg, [sd], dev, dtype=torch.bfloat16)[0]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=34)
+    xb, mb, pfd = x.to(dev).bfloat16(), mask.to(dev).bfloat16(), pf.to(dev)
+    outs = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('VKN_MASK_F16', mode)
+        with _lib.profile() as p:
+            outs[mode] = [t.clone() for t in h(xb, pfd, mb)]
+        assert any('maskgemm_tc_persist' in n for n, _ in p.records)
+    a, b = outs['0'][1].float(), outs['1'][1].float()
+    assert torch.equal(outs['0'][2], outs['1'][2]) and torch.equal(outs['0'][0], outs['1'][0])     # kernels do not depend on the mode
+    diff = (a - b).abs()
+    assert diff.max().item() <= 2 ** -7 * a.abs().max().item()
+    assert (diff > 0).float().mean().item() < 1e-3, 'fp16 vs bf16-plane mask conv: too many one-ulp differences'
+    want = ko.kernel_update_head_forward(sd, cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
+    for mode in ('0', '1'):
+        assert_masks_bf16(outs[mode][1], want[1], 'mask conv VKN_MASK_F16=%s' % mode)

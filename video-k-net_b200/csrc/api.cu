@@ -690,7 +690,9 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   // a9 (+a2 folded): a = mk . ft_w (planes for the mask conv), bias column mk . ft_b
   const int lda = C + A_EXT_PAD;
   // the mask conv reads the folded kernels as planes and, of the fp32 rows, only the bias column
-  two[0] = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, nullptr, lda, P, C, C, EPI_SPLIT3 | EPI_NOOUT);
+  // (fp16 mode of the persistent mask conv: the folded kernels as two fp16 planes instead of three bf16 planes)
+  const bool f16 = maskgemm_tc_planes_f16(c.s);
+  two[0] = lin(src_planes(PLD, C, PS), w.ft_wt_ext, C, nullptr, nullptr, lda, P, C, C, EPI_SPLIT3 | EPI_NOOUT | (f16 ? EPI_SPLIT2H : 0));
   two[0].split_planes = (__nv_bfloat16 *)c.L.a_split;
   two[0].split_B = c.s.B;
   two[0].split_N = c.s.N;
@@ -700,7 +702,7 @@ static int stage_planes(Ctx &c, const VknHeadW &w, const void *x, const float *p
   VKN_TRY(emit_gemm(c, two, 2));
   VKN_TRY(emit_flush(c));
   c.chain = nullptr;
-  return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st, mask_bits_out);
+  return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st, mask_bits_out, f16);
 }
 
 static int stage(Ctx &c, const VknHeadW &w, const void *x, const float *pf, const void *mask,

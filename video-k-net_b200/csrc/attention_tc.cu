@@ -24,11 +24,6 @@ constexpr uint32_t AT_TILE = 128u * 128u;             // one [128 rows x 64 fp16
 constexpr uint32_t AT_Q = 0, AT_K = 2 * AT_TILE, AT_V = 4 * AT_TILE, AT_P = 6 * AT_TILE;
 constexpr uint32_t AT_SMEM = 14 * AT_TILE;            // 224 KB
 
-static uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
 __device__ __forceinline__ uint32_t at_swz(int row, int chunk16) {       // byte offset inside a [rows x 128 B] K-major SW128 tile
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
 }

@@ -1,6 +1,7 @@
 // Shared device/host helpers for libvknet (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -133,6 +134,14 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __ex
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 // fp32 pair -> three packed bf16x2 words (hi, mid, lo): v == hi + mid + lo to 24 bits.  cvt.rn.bf16x2.f32 converts both
 // halves in ONE instruction (the scalar cvt runs on the quarter-rate conversion pipe and bounded the epilogues)
+// fp32 pair -> two packed fp16x2 words: v == hi + lo to 22 bits (operands well inside the fp16 range)
+__device__ __forceinline__ void split2h_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  __half2 h = __floats2half2_rn(x0, x1);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  const float2 back = __half22float2(h);
+  h = __floats2half2_rn(x0 - back.x, x1 - back.y);
+  lo = *reinterpret_cast<uint32_t *>(&h);
+}
 __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
   hi = *reinterpret_cast<uint32_t *>(&h);
@@ -162,7 +171,10 @@ enum Epi : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_RES = 4, EPI_ROWSCALE = 8, EPI_
                  EPI_LN = 64,
                  // tcgen05 row GEMM only, applied after bias / residual / LayerNorm and before ReLU, in this order:
                  // y = sigmoid(y);  y *= mul[row][col];  y += add2[row][col]   (the KernelUpdator gate arithmetic in the epilogue)
-                 EPI_SIGMOID = 128, EPI_MUL = 256, EPI_ADD2 = 512 };
+                 EPI_SIGMOID = 128, EPI_MUL = 256, EPI_ADD2 = 512,
+                 // with EPI_SPLIT3 and padded rows (the mask conv's kernel operand): two fp16 planes (hi + lo, 22 bits) instead of
+                 // three bf16 planes, for the mask conv's fp16 mode
+                 EPI_SPLIT2H = 1024 };
 
 struct RowSrc {
   const float *a[4];
@@ -248,7 +260,9 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
                    int *nchunks, cudaStream_t stream, const uint32_t *mask_bits = nullptr);
 int pool_tc_chunks(const VknShape &s);
 int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws,
-                       void *out, cudaStream_t stream, uint32_t *bits_out = nullptr);
+                       void *out, cudaStream_t stream, uint32_t *bits_out = nullptr, bool planes_f16 = false);
+// true when the persistent mask conv will take the kernels as two fp16 planes (the producer must then write EPI_SPLIT2H)
+bool maskgemm_tc_planes_f16(const VknShape &s);
 // bit-mask hand-off between the stages of the fused loop (1 bit per kernel and pixel instead of bf16 logits)
 int maskgemm_tc_bits_wpr(const VknShape &s);
 bool maskgemm_tc_persistent(const VknShape &s);

@@ -451,14 +451,15 @@ constexpr int MP_XS_MAX = 4;  // x ring depth (16 KB stages): as many as fit nex
     }                                      \
   } while (0)
 constexpr int MP_ACC = 2;     // TMEM accumulator buffers (128 columns each)
+constexpr int MP_THREADS = 256;   // warps 0-5 as in the one-tile kernel, warps 6-7: x converters of the fp16 mode
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(MP_THREADS, 1)
 vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
                                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_pf,
                                const float *__restrict__ a_ext, int lda, __nv_bfloat16 *__restrict__ out, int B, int N,
                                int Npad, int C, int HW, uint32_t idesc, uint32_t x_lbo, uint32_t x_sbo, int F, int MP_XS,
                                int total_tiles, int pf_dist, uint32_t *__restrict__ bits_out, int wpr, float thr,
-                               int stg_bytes, unsigned long long *dbg, int Ng, int rows8) {
+                               int stg_bytes, unsigned long long *dbg, int Ng, int rows8, int nplanes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nk = C / CH_BLK;
@@ -470,14 +471,18 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   const int Ncur = min(N - n_off, Ng);                                  // kernels this CTA computes
   const uint32_t x_bytes = (uint32_t)CH_BLK * MASK_TILE_P * 2u;         // 16 KB
   const uint32_t a_plane = (uint32_t)rows8 * 128u;                      // one plane, one 64-channel chunk (8-row atoms)
-  const uint32_t planes_bytes = (uint32_t)nk * 3u * a_plane;
+  // nplanes = 3: bf16 hi/mid/lo planes x bf16 x (round 1).  nplanes = 2: fp16 hi/lo planes (22 bits) x fp16 x -- a third fewer
+  // MMAs and resident plane bytes.  kind::f16 does not take fp16 x bf16, so warps 6-7 convert every x stage bf16 -> fp16 in
+  // place (exact: 8 significant bits into 11, |x| far inside the fp16 range) between the TMA ring and the MMA warp.
+  const uint32_t planes_bytes = (uint32_t)nk * (uint32_t)nplanes * a_plane;
   uint8_t *xring = smem + planes_bytes;                                 // (planes_bytes is a multiple of 1024)
   uint8_t *stg_base = xring + MP_XS * x_bytes;                          // epilogue staging: 2 x [32 kernels][128 px] bf16
   uint64_t *bars = (uint64_t *)(stg_base + stg_bytes);                  // (no staging in bit-mask mode: one more ring stage)
   const uint32_t bar0 = smem_u32(bars);
-  // barriers: 0 planes_full | 1 planes_free | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a
+  // barriers: 0 planes_full | 1 planes_free | X_FULL + s | X_EMPTY + s | ACC_FULL + a | ACC_EMPTY + a | X_CONV + s
   const int PL_FREE = 1, X_FULL = 2, X_EMPTY = 2 + MP_XS, ACC_FULL = 2 + 2 * MP_XS, ACC_EMPTY = 2 + 2 * MP_XS + MP_ACC;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 + 2 * MP_XS + 2 * MP_ACC);
+  const int X_CONV = 2 + 2 * MP_XS + 2 * MP_ACC;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 + 3 * MP_XS + 2 * MP_ACC);
   float *bias_s = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [4 epilogue warps][2 segments][128], 16-byte aligned
   const uint32_t smem0 = smem_u32(smem), xring0 = smem_u32(xring);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -503,6 +508,7 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       for (int s = 0; s < MP_XS; ++s) {
         mbar_init(bar0 + 8 * (X_FULL + s), 1);
         mbar_init(bar0 + 8 * (X_EMPTY + s), 1);
+        mbar_init(bar0 + 8 * (X_CONV + s), 2);                                     // one arrive per converter warp
       }
       for (int a = 0; a < MP_ACC; ++a) {
         mbar_init(bar0 + 8 * (ACC_FULL + a), 1);
@@ -530,8 +536,8 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         if (seg > 0) MP_WAIT(w0, mbar_wait(bar0 + 8 * PL_FREE, (uint32_t)(seg - 1) & 1u));   // MMAs of the previous frame retired
         mbar_expect_tx(bar0, planes_bytes);
         for (int c = 0; c < nk; ++c)
-          for (int t = 0; t < 3; ++t)
-            tma_load_2d(smem0 + (uint32_t)(c * 3 + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad + n_off);
+          for (int t = 0; t < nplanes; ++t)
+            tma_load_2d(smem0 + (uint32_t)(c * nplanes + t) * a_plane, &tmap_a, bar0, c * CH_BLK, (t * B + kb) * Npad + n_off);
         for (int tile = t0; tile < t1; ++tile) {
           const int p0 = tile * MASK_TILE_P;
           // The ring holds 48-64 KB per SM -- less than DRAM latency x bandwidth needs: the tile pf_dist ahead is pulled
@@ -580,13 +586,12 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       tc_fence_after();
       const uint32_t dt = tmem_base + buf * 128u;
       for (int c = 0; c < nk; ++c) {
-        MP_WAIT(w0, mbar_wait(bar0 + 8 * (X_FULL + s), xph));
+        MP_WAIT(w0, mbar_wait(bar0 + 8 * ((nplanes == 2 ? X_CONV : X_FULL) + s), xph));
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * (x_bytes >> 4));
-          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(c * 3) * a_plane16);
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(c * nplanes) * a_plane16);
+          for (int t = 0; t < nplanes; ++t) {
 #pragma unroll
             for (int k = 0; k < CH_BLK / 16; ++k)
               umma_bf16(dt, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)((uint32_t)t * a_plane16 + k * 2), idesc,
@@ -610,6 +615,41 @@ vkn_maskgemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       dbg[3] = (unsigned long long)w1;
       dbg[6] = li;
       dbg[7] = 0x6d61736b67656d6dull;
+    }
+  } else if (warp >= 6) {
+    // ---- x converters (fp16 mode): every landed stage bf16 -> fp16 in place, then hand it to the MMA warp ----
+    if (nplanes == 2) {
+      const int ct = (int)threadIdx.x - 192;                 // 0..63
+      int s = 0;
+      uint32_t xph = 0;
+      for (int g = g_lo; g < g_hi; ++g)
+        for (int c = 0; c < nk; ++c) {
+          mbar_wait(bar0 + 8 * (X_FULL + s), xph);
+          const uint32_t base = xring0 + (uint32_t)s * x_bytes + (uint32_t)ct * 16u;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = lds_u4(base + (uint32_t)((half * 8 + i) * 1024));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h = __floats2half2_rn(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+                w[e] = *reinterpret_cast<const uint32_t *>(&h);
+              }
+              sts_v4(base + (uint32_t)((half * 8 + i) * 1024), w[0], w[1], w[2], w[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (X_CONV + s));
+          if (++s == MP_XS) {
+            s = 0;
+            xph ^= 1u;
+          }
+        }
     }
   } else {
     // ---- epilogue: TMEM lane = pixel, column = kernel.  32 kernels x 128 pixels at a time are rounded to bf16 into a
@@ -931,8 +971,19 @@ bool maskgemm_tc_persistent(const VknShape &s) {
   return persist;
 }
 
+// fp16 mode of the persistent kernel (two fp16 planes of the kernels, x converted in the ring): default on; VKN_MASK_F16=0
+// keeps the three bf16 planes of round 1
+bool maskgemm_tc_planes_f16(const VknShape &s) {
+  if (!maskgemm_tc_persistent(s)) return false;
+  if (const char *e = getenv("VKN_MASK_WIDE")) {
+    if (e[0] == '1') return false;                            // the pixels-as-N variant reads three bf16 planes
+  }
+  if (const char *e = getenv("VKN_MASK_F16")) return e[0] != '0';
+  return true;
+}
+
 int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int lda, const void *a_split_ws, void *out,
-                       cudaStream_t stream, uint32_t *bits_out) {
+                       cudaStream_t stream, uint32_t *bits_out, bool planes_f16) {
   if (!tc_supported(s)) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: shape/dtype not supported");
   const int HW = s.H * s.W, Npad = npad_of(s.N);
   const int F = s.frames_per_set > 1 ? s.frames_per_set : 1;
@@ -1009,11 +1060,12 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
     }
     const int stg_bytes = bits_out ? 0 : 2 * 32 * MASK_TILE_P * 2;      // the bit-mask epilogue needs no staging box
+    const int nplanes = planes_f16 ? 2 : 3;
     auto psmem_of = [&](int xs) {
-      return (size_t)(s.C / CH_BLK) * 3 * rows8 * 128 + xs * (size_t)CH_BLK * MASK_TILE_P * 2 + (size_t)stg_bytes +
-             (2 + 2 * xs + 2 * MP_ACC) * 8 + 16 + 4 * 2 * 128 * 4 + 1024 + 64;
+      return (size_t)(s.C / CH_BLK) * nplanes * rows8 * 128 + xs * (size_t)CH_BLK * MASK_TILE_P * 2 + (size_t)stg_bytes +
+             (2 + 3 * xs + 2 * MP_ACC) * 8 + 16 + 4 * 2 * 128 * 4 + 1024 + 64;
     };
-    int xs_depth = MP_XS_MAX;
+    int xs_depth = planes_f16 ? MP_XS_MAX + 2 : MP_XS_MAX;     // the converter adds a hop: a deeper ring where it fits
     while (xs_depth > 2 && psmem_of(xs_depth) > 227 * 1024) --xs_depth;
     const size_t psmem = psmem_of(xs_depth);
     static bool pattr = false;
@@ -1035,10 +1087,11 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[3] = {(uint32_t)MASK_TILE_P, (uint32_t)CH_BLK, 1u};
       VKN_TRY(make_tmap_bf16_plain(&tmpf, x, dims, box));
     }
-    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x, ngroups), dim3(TC_THREADS), psmem, stream, tmx, tma,
-                             tmo, tmpf, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW, make_idesc_bf16(128, Ng, 1, 0),
+    VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_persist_kernel, dim3(grid_x, ngroups), dim3(MP_THREADS), psmem, stream, tmx, tma,
+                             tmo, tmpf, a_ext, lda, (__nv_bfloat16 *)out, s.B, s.N, Npad, s.C, HW,
+                             planes_f16 ? make_idesc_f16(128, Ng, 1, 0) : make_idesc_bf16(128, Ng, 1, 0),
                              x_lbo, x_sbo, F, xs_depth, total_tiles, pf_dist, bits_out, maskgemm_tc_bits_wpr(s), s.mask_thr_logit,
-                             stg_bytes, debug_ts_slot(), Ng, rows8));
+                             stg_bytes, debug_ts_slot(), Ng, rows8, nplanes));
     return VKN_OK;
   }
   dim3 grid(ceil_div(HW, MASK_TILE_P), 1, s.B * F);

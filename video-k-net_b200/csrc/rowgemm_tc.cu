@@ -232,7 +232,7 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
         if (e < nc) op[e] = v[e];
     }
   }
-  if ((R.epi & EPI_SPLIT3) && col < P.split_C && P.tma_pl) {
+  if ((R.epi & EPI_SPLIT3) && !(R.epi & EPI_SPLIT2H) && col < P.split_C && P.tma_pl) {
     uint32_t w[3][16];
     EPI_T0;
 #pragma unroll
@@ -259,6 +259,26 @@ __device__ __forceinline__ void rg_chunk_store(const RgProb &P, const RgRowCtx &
       bulk_commit_group();
     }
     EPI_T(13);
+  } else if ((R.epi & EPI_SPLIT3) && (R.epi & EPI_SPLIT2H) && col < P.split_C && R.live) {
+    // two fp16 planes (the mask conv's fp16 mode): same buffer, same row layout, planes 0 and 1
+    const int np = min(32, P.split_C - col);
+    __nv_bfloat16 *pp = P.planes + R.prow * P.split_C + col;
+    uint32_t w2[2][16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) split2h_pair(v[e], v[e + 1], w2[0][e >> 1], w2[1][e >> 1]);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      const uint32_t (&w)[16] = w2[pl];
+      __nv_bfloat16 *pt = pp + (size_t)pl * P.plane_elems;
+      if (R.pl_vec && np == 32) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 8) stg_v8(pt + 2 * e, w[e], w[e + 1], w[e + 2], w[e + 3], w[e + 4], w[e + 5], w[e + 6], w[e + 7]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < np) pt[e] = __ushort_as_bfloat16((uint16_t)(w[e >> 1] >> ((e & 1) * 16)));
+      }
+    }
   } else if ((R.epi & EPI_SPLIT3) && col < P.split_C && R.live) {
     const int np = min(32, P.split_C - col);
     __nv_bfloat16 *pp = P.planes + R.prow * P.split_C + col;
@@ -637,7 +657,7 @@ static int rg_fill_prob(const LinArgs &a, int BN, int ks, RgProb &p) {
     VKN_TRY(make_tmap_store(&p.tmOut, a.out, true, od, os, ob, true));
     p.tma_out = 1;
   }
-  if (tma_ok && (a.epi & EPI_SPLIT3) && a.split_planes && a.split_N == a.split_Npad && a.split_C % 8 == 0 &&
+  if (tma_ok && (a.epi & EPI_SPLIT3) && !(a.epi & EPI_SPLIT2H) && a.split_planes && a.split_N == a.split_Npad && a.split_C % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(a.split_planes) & 15) == 0 && ((long long)a.split_B * a.split_Npad * a.split_C) % 8 == 0) {
     const uint64_t pd[3] = {(uint64_t)a.split_C, (uint64_t)a.M, 3};
     const uint64_t ps[2] = {(uint64_t)a.split_C * 2, (uint64_t)((long long)a.split_B * a.split_Npad * a.split_C) * 2};

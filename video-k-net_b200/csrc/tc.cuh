@@ -190,6 +190,13 @@ static uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same with fp16 A and B operands (format code 0).  kind::f16 takes fp16 or bf16 operands but NOT one of each (mixed
+// formats raise an illegal-instruction fault on B200: tools/probes/mma_probe.cu)
+static uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- host: tensor maps ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
