@@ -245,10 +245,9 @@ int launch_attention_tc(const float *q, int ldq, const float *k, int ldk, const 
   if (!attention_tc_supported(N, C, heads, q, ldq, k, ldk, v, ldv, out, ldo, planes, plane_stride))
     VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 attention: needs head_dim 32, N <= 128 and 16-byte aligned rows");
   const int Nk = (N + 15) & ~15;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AT_SMEM + 2048)));
-    attr = true;
   }
   VKN_LAUNCH_MARK("vkn_attention_tc_kernel", stream);
   VKN_CUDA_OK(launch_chain(vkn_attention_tc_kernel, dim3(B), dim3(AT_THREADS), (size_t)AT_SMEM + 2048, stream, q, ldq, k, ldk, v, ldv,

@@ -62,6 +62,18 @@ static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// cudaFuncSetAttribute is per DEVICE: a process-wide "done" flag breaks the second GPU of a process.  `mask` is a static
+// bitmask owned by the call site (one bit per device ordinal); returns true when the attribute still has to be set on the
+// current device and marks it.
+static inline bool first_use_on_device(unsigned long long &mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

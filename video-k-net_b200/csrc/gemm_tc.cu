@@ -283,10 +283,9 @@ int launch_pool_tc(const VknShape &s, const void *x, const void *mask, float *pa
     VKN_TRY(make_tmap_bf16(&tmap_m, mask_bits ? x : mask, 3, mdims, mbox));     // unused in bit-mask mode
   }
   if (smem < 4 * 32 * 36 * 4 + 2048) smem = 4 * 32 * 36 * 4 + 2048;      // epilogue staging
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   dim3 grid(p.nchunks, p.mtiles, s.B);
   VKN_LAUNCH_MARK("vkn_pool_tc_kernel", stream);
@@ -1004,10 +1003,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
   if (stages > s.C / CH_BLK) stages = s.C / CH_BLK;
   if (stages < 1) VKN_FAIL(VKN_E_UNSUPPORTED, "tcgen05 mask conv: N %d too large for shared memory", s.N);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 1) * 8 + 16 + (size_t)(Npad + 32) * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   // x operand (A, MN-major, SWIZZLE_128B): 64-px groups are 8192 B apart (LBO), 8-channel-row groups 1024 B (SBO)
   const uint32_t x_lbo = (uint32_t)CH_BLK * 128u, x_sbo = 1024u;
@@ -1032,10 +1030,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
       const uint32_t box[2] = {(uint32_t)CH_BLK, (uint32_t)rows8w};
       VKN_TRY(make_tmap_bf16(&tma, a_split_ws, 2, dims, box));
     }
-    static bool wattr = false;
-    if (!wattr) {
+    static unsigned long long wattr = 0;
+    if (first_use_on_device(wattr)) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      wattr = true;
     }
     VKN_LAUNCH_MARK("vkn_maskgemm_tc_wide_kernel", stream);
     VKN_CUDA_OK(launch_chain(vkn_maskgemm_tc_wide_kernel, dim3(grid_x), dim3(TC_THREADS), wsmem, stream, tmx, tma, a_ext, lda,
@@ -1068,10 +1065,9 @@ int launch_maskgemm_tc(const VknShape &s, const void *x, const float *a_ext, int
     int xs_depth = planes_f16 ? MP_XS_MAX + 2 : MP_XS_MAX;     // the converter adds a hop: a deeper ring where it fits
     while (xs_depth > 2 && psmem_of(xs_depth) > 227 * 1024) --xs_depth;
     const size_t psmem = psmem_of(xs_depth);
-    static bool pattr = false;
-    if (!pattr) {
+    static unsigned long long pattr = 0;
+    if (first_use_on_device(pattr)) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_maskgemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      pattr = true;
     }
     if (psmem > 227 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "persistent mask conv: shared memory %zu exceeds 227 KB", psmem);
     VKN_LAUNCH_MARK("vkn_maskgemm_tc_persist_kernel", stream);

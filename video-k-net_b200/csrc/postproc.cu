@@ -205,18 +205,16 @@ int launch_rescale_masks(const void *masks, int dtype, int K, int H, int W, int 
   if (grid.y > 65535 || grid.z > 65535) VKN_FAIL(VKN_E_UNSUPPORTED, "rescale_masks: too many masks / rows for one launch");
   VKN_LAUNCH_MARK("vkn_rescale_masks_kernel", stream);
   if (dtype == VKN_BF16) {
-    static bool a = false;
-    if (!a) {
+    static unsigned long long a = 0;
+    if (first_use_on_device(a)) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_rescale_masks_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((3 * RS_MAX_REGION + 3 * RS_MAX_ROWS * 4 + 16) * sizeof(float))));
-      a = true;
     }
     VKN_CUDA_OK(launch_chain(vkn_rescale_masks_kernel<__nv_bfloat16>, grid, dim3(RS_NT), smem, stream, (const __nv_bfloat16 *)masks,
                              probs, bits, P, ident3));
   } else if (dtype == VKN_F32) {
-    static bool a = false;
-    if (!a) {
+    static unsigned long long a = 0;
+    if (first_use_on_device(a)) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_rescale_masks_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((3 * RS_MAX_REGION + 3 * RS_MAX_ROWS * 4 + 16) * sizeof(float))));
-      a = true;
     }
     VKN_CUDA_OK(launch_chain(vkn_rescale_masks_kernel<float>, grid, dim3(RS_NT), smem, stream, (const float *)masks, probs, bits, P, ident3));
   } else {

@@ -773,10 +773,9 @@ int launch_linear_tc(const LinArgs *probs, int nprob, cudaStream_t stream) {
     b.p[1] = b.p[0];
     b.p[1].tiles = 0;
   }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   dim3 grid(b.total_tiles < sms ? b.total_tiles : sms);
   VKN_LAUNCH_MARK("vkn_rowgemm_tc_kernel", stream);
@@ -1390,10 +1389,9 @@ int chain_launch(ChainBuild *b, cudaStream_t stream) {
   g.idesc = make_idesc_bf16(128, CH_BN, 0, 0);
   g.dbg = debug_ts_slot();
   const size_t smem = (size_t)g.stages * stage_bytes + 8 * (size_t)g.stg_bytes + 1024 + (2 * g.stages + 5) * 8 + 16 + 2 * 128 * 8 * 4 + 64 + 32 + 3 * 256 * 4 + 16;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   if (smem > 227 * 1024) VKN_FAIL(VKN_E_INVALID, "chain: shared memory budget exceeded");
   // Pairs of row tiles per CTA (one tile's epilogue and step edge hide behind the other's MMAs) when there are enough

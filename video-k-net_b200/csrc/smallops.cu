@@ -445,11 +445,10 @@ template <typename WT, int BM, int BN, int NSRC>
 static int launch_linear_n(const LinBatch &b, dim3 grid, cudaStream_t stream) {
   const size_t smem = b.nwbuf == 2 ? LinSmem<WT, BM, BN>::total : LinSmem<WT, BM, BN>::total_single;
   if (smem > 227 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "linear tile %dx%d needs %zu bytes of shared memory", BM, BN, smem);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_linear_kernel<WT, BM, BN, NSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(LinSmem<WT, BM, BN>::total < 227 * 1024 ? LinSmem<WT, BM, BN>::total : 227 * 1024)));
-    attr = true;
   }
   VKN_CUDA_OK(launch_chain(vkn_linear_kernel<WT, BM, BN, NSRC>, grid, dim3(NT), smem, stream, b));
   return VKN_OK;
@@ -780,10 +779,9 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
       return launch_attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, N, C, heads, stream, planes, plane_stride);
   }
   const size_t smem = ((size_t)2 * N * (hd + 1) + (NT / 32) * (size_t)N + (NT / 32) * 32) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  if (first_use_on_device(attr_set)) {
     VKN_CUDA_OK(cudaFuncSetAttribute(vkn_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
   }
   if (smem > 160 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: N %d too large for shared memory", N);
   // queries per CTA: one per warp for a single frame (latency), more when many (head, frame) pairs are in flight --
@@ -795,10 +793,9 @@ int launch_attention(const float *q, int ldq, const float *k, int ldk, const flo
   if (const char *e = getenv("VKN_ATT4")) four = e[0] == '1';
   if (four) {
     const size_t smem4 = ((size_t)2 * N * (hd + 1) + 4 + (NT / 32) * (size_t)N * 4 + (NT / 32) * 32 * 4) * sizeof(float);
-    static bool attr4 = false;
-    if (!attr4) {
+    static unsigned long long attr4 = 0;
+    if (first_use_on_device(attr4)) {
       VKN_CUDA_OK(cudaFuncSetAttribute(vkn_attention4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr4 = true;
     }
     if (smem4 > 200 * 1024) VKN_FAIL(VKN_E_UNSUPPORTED, "attention: N %d too large for shared memory", N);
     VKN_LAUNCH_MARK("vkn_attention4_kernel", stream);
