@@ -337,7 +337,14 @@ def run_ours(args):
     #      t-1's kernels.  A rank needs ONE frame it does not own (its left neighbour's last): one all-gather of world x
     #      [N, C] (102 KB each) over NCCL, then the link block on the rank's own FPG frames.  Both run on a side stream so
     #      that they overlap the next graph launch (the groups alternate, so its inputs / outputs are different buffers).
-    link_head = heads[-1] if with_link else None
+    if with_link:
+        link_head = heads[-1]
+    else:                                                   # one GPU: a link block of its own for the cfg3 side measurement below
+        torch.manual_seed(1)
+        link_head = vknet.build_head(dict(type='VideoKernelUpdateHead', **head_cfg(link=True)))
+        link_head.init_weights()
+        link_head = link_head.to(dev).bfloat16().eval()
+    do_link = [with_link]                                  # switched on for the cfg3 pass at one GPU
     side = torch.cuda.Stream(device=dev)
     link_done = [None] * len(groups)
     track_host = torch.empty(FPG, N, C).pin_memory()
@@ -362,14 +369,14 @@ def run_ours(args):
         cur = torch.cuda.current_stream(dev)
         for i in range(start, start + launches):
             gi = i % len(grp)
-            if with_link and link_done[gi] is not None:
+            if do_link[0] and link_done[gi] is not None:
                 cur.wait_event(link_done[gi])                   # the link of this group's previous outputs has read them
             if times is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(cur)
                 times.append(ev)
             outs = grp[gi].replay()
-            if with_link:
+            if do_link[0]:
                 ready = torch.cuda.Event()
                 ready.record(cur)
                 side.wait_event(ready)
@@ -380,7 +387,7 @@ def run_ours(args):
                     done = torch.cuda.Event()
                     done.record(side)
                 link_done[gi] = done
-        if with_link:
+        if do_link[0]:
             cur.wait_stream(side)
         return launches * FPG
 
@@ -411,11 +418,32 @@ def run_ours(args):
     total_ms = t.item()
     ms = total_ms / frames_done                             # device time per frame and rank (max over ranks)
 
+    # ---- one GPU: the same timed loop WITH the cfg3 link block on every launch (what each rank of an N-GPU run does besides
+    #      the 102 KB exchange): separates the cost of the link arithmetic from the cost of the collective in the 1 -> N curve
+    cfg3_single = None
+    if not with_link and not quick:
+        do_link[0] = True
+        run(3, groups)
+        barrier()
+        evs3 = []
+        e3 = torch.cuda.Event(enable_timing=True)
+        fr3 = run(n_launch, groups, times=evs3, start=1)
+        e3.record()
+        barrier()
+        ms3 = evs3[0].elapsed_time(e3) / fr3
+        cfg3_single = dict(value=1.0 / (ms3 * 1e-3), ms_per_step=ms3,
+                           note='cfg1 + the previous_type=ffn link block on every frame (side stream), one GPU, no exchange: the '
+                                'per-rank workload of the N-GPU lines; value(N) / (N x this) isolates the collective')
+        do_link[0] = False
+        for i_ in range(len(link_done)):
+            link_done[i_] = None
+
     # ---- e2e: host buffers in, result tuple out, copies inside the timed region ---------------------
     h2d = (C * HW + N * HW) * 2 + N * C * 4
     d2h = (N * CFG1['ncls'] + N * C) * 4 + N * HW * 2 + (N * C * 4 if with_link else 0)
     n_e2e = max(6, -(-args.steps // FPG))
-    link_done = [None] * len(groups)
+    for i_ in range(len(link_done)):
+        link_done[i_] = None
     run(2, host_groups, host=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -606,6 +634,8 @@ def run_ours(args):
                     kernels=per_kernel)
         if shard_parity is not None:
             line['shard_parity'] = shard_parity
+        if cfg3_single is not None:
+            line['cfg3_single_gpu'] = cfg3_single
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
