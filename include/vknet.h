@@ -116,6 +116,9 @@ typedef struct VknHeadW {
   const void *fc_cls_w;  const float *fc_cls_b;     /* [num_classes,C]; NULL = head built with with_cls=False */
   const void *mask_fc_w[VKN_MAX_FCS]; const float *mask_ln_g[VKN_MAX_FCS], *mask_ln_b[VKN_MAX_FCS];
   const void *fc_mask_w; const float *fc_mask_b;    /* [C,C] */
+  const void *fc_pack;     /* optional host-prepared operand of the single-frame row engine (vkn_frame_chain_pack): the weight
+                            * matrices re-laid as the 32-row chunks each CTA of a cluster streams, one bulk copy per chunk.
+                            * NULL: the engine copies the chunks row by row from the matrices above (slower, same results). */
 } VknHeadW;
 
 /* One cross-frame link block of VideoKernelUpdateHead (knet/video/kernel_update_head.py:167-260):
@@ -149,6 +152,13 @@ int vkn_profile_end(const char **names, float *ms, int max_entries, int *count);
  * 8 words per CTA (entry, prefetch issued, dependency resolved, panel built, tile visible, main loop done,
  * stores issued).  Returns the block stride in words.  Pass NULL to switch it off.  tools/linear_timeline.py */
 int vkn_debug_timestamps(unsigned long long *buf, size_t n_u64);
+
+/* Single-frame row engine (csrc/framechain.cu; taken by the stage / iter entry points below ~400 kernel rows when C = 256,
+ * 8 heads, ffn_dim = 2048, bf16 weights, one cls / mask FC): size of, and the one-time fill of, VknHeadW.fc_pack for the weights
+ * `w` points at (only the weight-related fields of `shape` matter).  *bytes = 0 when the engine does not apply to this head.
+ * Re-run after the weights change.  `out` must be 16-byte aligned device memory. */
+int vkn_frame_chain_pack_bytes(const VknShape *shape, const VknHeadW *w, size_t *bytes);
+int vkn_frame_chain_pack(const VknShape *shape, const VknHeadW *w, void *out, size_t bytes, void *stream);
 
 /* Bytes of caller-provided scratch needed by the stage / link / iter entry points for `shape`. */
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes);

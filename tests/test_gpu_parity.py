@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import knet_oracle as ko
-from helpers import assert_masks_bf16, build_heads, golden_files, load_golden, maxabs, stagewise_vs_oracle_bf16, top2_gap
+from helpers import assert_masks_bf16, bf16_ulp, build_heads, golden_files, load_golden, maxabs, stagewise_vs_oracle_bf16, top2_gap
 from vknet import _lib
 
 pytestmark = pytest.mark.gpu
@@ -979,3 +979,86 @@ def test_mask_conv_fp16_mode_vs_bf16_planes(dev, monkeypatch, N):
     want = ko.kernel_update_head_forward(sd, cfg, ko.round_bf16(x), pf, ko.round_bf16(mask))
     for mode in ('0', '1'):
         assert_masks_bf16(outs[mode][1], want[1], 'mask conv VKN_MASK_F16=%s' % mode)
+
+
+# ---- single-frame row engine: the cluster chain kernels (framechain.cu) -------------------------------------------------
+@pytest.mark.parametrize('B,N,H,W,S,ncls', [(1, 100, 200, 88, 3, 19), (2, 117, 48, 156, 2, 19), (1, 166, 24, 40, 2, 124),
+                                           (1, 10, 16, 24, 2, 133), (3, 100, 16, 24, 1, 40), (1, 176, 8, 16, 1, 1)])
+def test_frame_chain_cluster_kernels(dev, monkeypatch, B, N, H, W, S, ncls):
+    """One frame (or a few) per call -- the online VPS operating point: every row operator of a stage runs in the two cluster
+    kernels of framechain.cu (5 launches per stage).  Each stage against the oracle on its actual inputs (bf16 rules), against
+    the warp-MMA chain it replaces, and the one-call loop == the stage-wise modules bit for bit."""
+    import vknet
+    C = 256
+    cfg = ko.default_cfg(num_classes=ncls, in_channels=C, feedforward_channels=2048)
+    sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=90 + s)) for s in range(S)]
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=8)
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
+    xb, pfd, mb = x.to(dev).bfloat16(), pf.to(dev).reshape(B, N, C), mask.to(dev).bfloat16()
+    L = vknet._lib.lib()
+    for h in heads:                       # first use packs the weights (one more launch per head)
+        h.packed_weights(dev)
+    n0 = L.vkn_launch_count()
+    outs, ties = stagewise_vs_oracle_bf16(heads, sds, cfg, xb, pfd, mb, 'frame chain %dx%d' % (B, N))
+    assert L.vkn_launch_count() - n0 == 5 * S, 'expected pool, reduce, chain A, chain B, mask conv per stage'
+    # the engine it replaces: same math on the warp-MMA chain (different summation order -> tolerance, not bits)
+    monkeypatch.setenv('VKN_FRAME_CHAIN', '0')
+    n0 = L.vkn_launch_count()
+    obj, m = pfd, mb
+    for s, h in enumerate(heads):
+        cls, m_new, obj_new = h(xb, obj, m)
+        assert maxabs(cls, outs[s][0]) < 2e-3 and maxabs(obj_new, outs[s][2]) < 2e-3, 'stage %d: chain vs warp-MMA engine' % s
+        # the two engines' logits agree to a bf16 ulp
+        d = (m_new.float() - outs[s][1].float()).abs()
+        assert bool((d <= bf16_ulp(m_new.float()) * 1.001 + 2.0 ** -16 * m_new.float().abs().max()).all())
+        obj, m = outs[s][2].reshape(B, N, C), outs[s][1]
+    assert L.vkn_launch_count() - n0 > 5 * S
+    monkeypatch.delenv('VKN_FRAME_CHAIN')
+    cls_l, m_l, obj_l = vknet.KernelIterLoop(heads)(xb, pfd, mb)
+    assert torch.equal(m_l, outs[-1][1]) and torch.equal(obj_l.reshape(B, N, C), outs[-1][2].reshape(B, N, C)) \
+        and torch.equal(cls_l, outs[-1][0]), 'one-call loop != stage-wise modules'
+    # determinism (fixed-order reductions through distributed shared memory)
+    cls_2, m_2, obj_2 = vknet.KernelIterLoop(heads)(xb, pfd, mb)
+    assert torch.equal(m_l, m_2) and torch.equal(obj_l, obj_2) and torch.equal(cls_l, cls_2)
+
+
+def test_frame_chain_video_head_and_clip_head_without_cls(dev):
+    """The two other entries into the cluster chain: VideoKernelUpdateHead (pooled feature computed first, handed in as
+    x_feat_in; returns x_feat) and KernelUpdateHeadVideo in per-frame mode (with_cls=False: no cls branch)."""
+    import vknet
+    B, N, C, H, W = 1, 100, 256, 24, 40
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=2048)
+    sd = ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=97))
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=9)
+    xr, mr = ko.round_bf16(x), ko.round_bf16(mask)
+    want = ko.kernel_update_head_forward(sd, cfg, xr, pf, mr)
+    h = vknet.build_head(dict(type='VideoKernelUpdateHead', **cfg))
+    h.load_state_dict(sd, strict=True)
+    h = h.to(device=dev, dtype=torch.bfloat16).eval()
+    L = vknet._lib.lib()
+    h.packed_weights(dev)
+    n0 = L.vkn_launch_count()
+    out = h(xr.to(dev).bfloat16(), pf.to(dev), mr.to(dev).bfloat16())
+    assert L.vkn_launch_count() - n0 <= 6, 'video head: pool, reduce, x_feat Linear, chain A, chain B, mask conv'
+    cls, nm, obj, x_feat = out[0], out[1], out[2], out[3]
+    assert maxabs(cls, want[0]) < TOL_BF16 and maxabs(obj, want[2]) < TOL_BF16
+    assert_masks_bf16(nm, want[1], 'video head via frame chain')
+    want_xf = ko._pool(sd, cfg, xr, pf, mr)[1]
+    assert maxabs(x_feat, want_xf) < 1e-3 * max(1.0, want_xf.abs().max().item())
+    # clip head, per-frame mode
+    Fr = 2
+    sd2 = {k: v for k, v in sd.items() if not (k.startswith('cls_fcs') or k.startswith('fc_cls'))}
+    gen = torch.Generator().manual_seed(5)
+    x2 = ko.round_bf16(torch.randn(B, Fr, C, H, W, generator=gen))
+    pf2 = torch.randn(B, Fr, N, C, 1, 1, generator=gen)
+    mask2 = ko.round_bf16(torch.einsum('bfnc,bfchw->bfnhw', pf2.view(B, Fr, N, C), x2))
+    want2 = ko.kernel_update_head_video_forward(sd2, cfg, x2, pf2, mask2)
+    h2 = vknet.build_head(dict(type='KernelUpdateHeadVideo', with_cls=False, num_proposals=N, **cfg))
+    h2.load_state_dict(sd2, strict=True)
+    h2 = h2.to(device=dev, dtype=torch.bfloat16).eval()
+    h2.packed_weights(dev)
+    n0 = L.vkn_launch_count()
+    cls2, nm2, obj2 = h2(x2.to(dev).bfloat16(), pf2.to(dev), mask2.to(dev).bfloat16())
+    assert L.vkn_launch_count() - n0 == 5
+    assert maxabs(obj2, want2[2]) < TOL_BF16
+    assert_masks_bf16(nm2.reshape(B * Fr, N, H, W), want2[1].reshape(B * Fr, N, H, W), 'clip head (per-frame) via frame chain')

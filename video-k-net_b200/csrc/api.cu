@@ -714,6 +714,25 @@ static int stage(Ctx &c, const VknHeadW &w, const void *x, const float *pf, cons
                         mask_bits_out);
   if (mask_bits_in || mask_bits_out) VKN_FAIL(VKN_E_INVALID, "bit-mask hand-off is a row-engine (frame batch) path");
   const int C = c.s.C;
+  if (frame_chain_supported(c.s, w)) {
+    // a frame or two (the online VPS operating point): pooling, then the cluster chain (framechain.cu: every row operator of
+    // the stage in two launches, activations handed between the Linears through distributed shared memory), then the mask conv
+    if (x_feat_in == nullptr) {
+      int nch = 0;
+      const VknShape fs = frames_shape(c.s);
+      if (c.use_tc) VKN_TRY(launch_pool_tc(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+      else VKN_TRY(launch_pool_simt(fs, x, mask, c.L.pool_part, c.L.cnt_part, &nch, c.st));
+      VKN_TRY(launch_pool_reduce(c.s, c.L.pool_part, c.L.cnt_part, nch, c.L.xp0, c.L.cnt, c.st));
+    } else if (x_feat_out && x_feat_out != x_feat_in) {
+      VKN_CUDA_OK(cudaMemcpyAsync(x_feat_out, x_feat_in, (size_t)c.P * C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+    }
+    const int lda = C + A_EXT_PAD;
+    VKN_TRY(launch_frame_chain(c.s, w, c.L.xp0, c.L.cnt, x_feat_in, pf, x_feat_in ? nullptr : x_feat_out, c.L.o, c.L.qkv, obj, cls, c.L.a_ext, lda, c.L.a_split,
+                               maskgemm_tc_npad(c.s), c.st));
+    if (!new_mask) return VKN_OK;
+    if (c.use_tc) return launch_maskgemm_tc(c.s, x, c.L.a_ext, lda, c.L.a_split, new_mask, c.st);
+    return launch_maskgemm_simt(c.s, x, c.L.a_ext, lda, new_mask, c.st);
+  }
   const float *xp = x_feat_in;
   if (xp == nullptr) {
     float *dst = x_feat_out ? x_feat_out : c.L.xp;
@@ -743,7 +762,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_attention_tc_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_track_match_kernel\nvkn_rescale_masks_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_attention_tc_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_frame_chain_a_kernel\nvkn_frame_chain_b_kernel\nvkn_frame_chain_pack_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_track_match_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -780,6 +799,19 @@ int vkn_profile_end(const char **names, float *ms, int max_entries, int *count) 
     VKN_CUDA_OK(cudaEventElapsedTime(&ms[i], g_prof.ev[i], g_prof.ev[i + 1]));
   }
   return VKN_OK;
+}
+
+int vkn_frame_chain_pack_bytes(const VknShape *shape, const VknHeadW *w, size_t *bytes) {
+  VKN_TRY(check_shape(shape));
+  if (!w || !bytes) VKN_FAIL(VKN_E_INVALID, "vkn_frame_chain_pack_bytes: null argument");
+  *bytes = frame_chain_pack_bytes(*shape, *w);
+  return VKN_OK;
+}
+
+int vkn_frame_chain_pack(const VknShape *shape, const VknHeadW *w, void *out, size_t bytes, void *stream) {
+  VKN_TRY(check_shape(shape));
+  if (!w) VKN_FAIL(VKN_E_INVALID, "vkn_frame_chain_pack: null argument");
+  return launch_frame_chain_pack(*shape, *w, out, bytes, (cudaStream_t)stream);
 }
 
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes) {

@@ -258,6 +258,13 @@ bool chain_empty(const ChainBuild *b);
 int chain_add_gemm(ChainBuild *b, const LinArgs *probs, int nprob);
 int chain_add_rowprep(ChainBuild *b, const RowSrc &src, float *out, int ldo, void *planes, int ldp, long long plane_stride, int K);
 int chain_launch(ChainBuild *b, cudaStream_t stream);
+// single-frame row engine (framechain.cu): the row operators of a stage as two cluster launches
+bool frame_chain_supported(const VknShape &s, const VknHeadW &w);
+size_t frame_chain_pack_bytes(const VknShape &s, const VknHeadW &w);
+int launch_frame_chain_pack(const VknShape &s, const VknHeadW &w, void *out, size_t bytes, cudaStream_t stream);
+int launch_frame_chain(const VknShape &s, const VknHeadW &w, const float *xp0, const float *cnt, const float *x_feat_in,
+                       const float *pf, float *x_feat_out, float *obj0_ws, float *qkv_ws, float *obj_out, float *cls_out, float *a_ext, int lda, void *a_split, int Npad,
+                       cudaStream_t stream);
 // SIMT fp32 engines for the two big contractions (gemm_simt.cu)
 int launch_pool_simt(const VknShape &s, const void *x, const void *mask, float *partials, float *cnt_partials,
                      int *nchunks, cudaStream_t stream);

@@ -48,7 +48,7 @@ class VknHeadW(C.Structure):
                 ('cls_fc_w', _vp * VKN_MAX_FCS), ('cls_ln_g', _vp * VKN_MAX_FCS), ('cls_ln_b', _vp * VKN_MAX_FCS),
                 ('fc_cls_w', _vp), ('fc_cls_b', _vp),
                 ('mask_fc_w', _vp * VKN_MAX_FCS), ('mask_ln_g', _vp * VKN_MAX_FCS), ('mask_ln_b', _vp * VKN_MAX_FCS),
-                ('fc_mask_w', _vp), ('fc_mask_b', _vp)]
+                ('fc_mask_w', _vp), ('fc_mask_b', _vp), ('fc_pack', _vp)]
 
 
 class VknMlpLayer(C.Structure):
@@ -71,7 +71,8 @@ SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_launch_coun
            'vkn_profile_end', 'vkn_debug_timestamps', 'vkn_workspace_bytes', 'vkn_mask_pool',
            'vkn_kernel_update', 'vkn_mhsa_ln', 'vkn_ffn_ln', 'vkn_heads', 'vkn_mask_gemm',
            'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend', 'vkn_rescale_masks',
-           'vkn_panoptic_merge', 'vkn_mask_boxes', 'vkn_mlp', 'vkn_track_match')
+           'vkn_panoptic_merge', 'vkn_mask_boxes', 'vkn_mlp', 'vkn_track_match', 'vkn_frame_chain_pack_bytes',
+           'vkn_frame_chain_pack')
 
 
 def lib():
@@ -110,6 +111,8 @@ def lib():
     L.vkn_mlp.argtypes = [C.POINTER(VknMlpLayer), C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, sz, _vp]
     L.vkn_track_match.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int64, _vp, _vp, _vp,
                                   _vp, sz, _vp]
+    L.vkn_frame_chain_pack_bytes.argtypes = [S, C.POINTER(VknHeadW), C.POINTER(sz)]
+    L.vkn_frame_chain_pack.argtypes = [S, C.POINTER(VknHeadW), _vp, sz, _vp]
     L.vkn_debug_timestamps.restype = C.c_int
     L.vkn_debug_timestamps.argtypes = [_vp, C.c_size_t]
     for name in SYMBOLS[7:]:

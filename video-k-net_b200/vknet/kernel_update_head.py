@@ -130,7 +130,9 @@ class _HeadBase(nn.Module):
         if self._packed is None or self._packed_key != key:
             wd = pack.weight_dtype_of(self.parameters())
             pk = pack.Packer(device, wd)
-            self._packed = (pack.pack_head(pk, self), self._pack_extra(pk), wd, pk)
+            w = pack.pack_head(pk, self)
+            pack.attach_frame_chain_pack(pk, w, self._shape(1, 1, 1, 1, _lib.VKN_BF16, wd))
+            self._packed = (w, self._pack_extra(pk), wd, pk)
             self._packed_key = key
         return self._packed[0], self._packed[1], self._packed[2]
 

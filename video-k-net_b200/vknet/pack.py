@@ -103,6 +103,23 @@ def pack_head(pk, head):
     return w
 
 
+def attach_frame_chain_pack(pk, w, shape):
+    """VknHeadW.fc_pack: the weights re-laid for the single-frame row engine (csrc/framechain.cu), built once per weight
+    version by the library itself (vkn_frame_chain_pack); heads the engine does not apply to keep fc_pack = NULL."""
+    if torch.device(pk.device).type != 'cuda':
+        return
+    L = _lib.lib()
+    n = C.c_size_t(0)
+    _lib.check(L.vkn_frame_chain_pack_bytes(C.byref(shape), C.byref(w), C.byref(n)))
+    if n.value == 0:
+        return
+    buf = torch.empty(n.value, dtype=torch.uint8, device=pk.device)
+    with torch.cuda.device(pk.device):
+        _lib.check(L.vkn_frame_chain_pack(C.byref(shape), C.byref(w), _lib.ptr(buf), n.value, _lib.stream_ptr(pk.device)))
+    pk.keep.append(buf)
+    w.fc_pack = buf.data_ptr()
+
+
 def pack_link(pk, updator, att, att_norm, ffn, ffn_norm):
     w = _lib.VknLinkW()
     w.has_updator = int(updator is not None)
