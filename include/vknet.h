@@ -160,6 +160,18 @@ int vkn_debug_timestamps(unsigned long long *buf, size_t n_u64);
 int vkn_frame_chain_pack_bytes(const VknShape *shape, const VknHeadW *w, size_t *bytes);
 int vkn_frame_chain_pack(const VknShape *shape, const VknHeadW *w, void *out, size_t bytes, void *stream);
 
+/* Row f4 (training side): the cost matrix of MaskHungarianAssigner.assign for one image
+ * (knet/det/mask_hungarian_assigner.py:228-247 with DiceCost :43-75, MaskCost :93-110, mmdet FocalLossCost; pred_act=True,
+ * act_mode='sigmoid'):  cost [N,M] fp32 = w_cls * focal + w_mask * mask + w_dice * dice  (a zero weight skips the term).
+ *   mask_logits [N,HW] fp32, cls_logits [N,ncls] fp32 or NULL, gt_masks [M,HW] fp32, gt_labels [M] int64.
+ *   params [7] (host): w_cls, w_mask, w_dice, dice_eps (1e-3), focal_alpha (0.25), focal_gamma (2), focal_eps (1e-12).
+ * One pass over the masks (the reference materialises two activations and runs three einsums); deterministic.  The Hungarian
+ * solve on the cost matrix stays the caller's (scipy.optimize.linear_sum_assignment in the reference, :246-251). */
+int vkn_match_cost_workspace_bytes(int N, int M, int HW, size_t *bytes);
+int vkn_match_cost(const float *mask_logits, const float *cls_logits, const float *gt_masks, const int64_t *gt_labels, int N,
+                   int M, int HW, int ncls, const float *params, float *cost, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
 /* Bytes of caller-provided scratch needed by the stage / link / iter entry points for `shape`. */
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes);
 

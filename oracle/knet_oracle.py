@@ -558,3 +558,45 @@ def tracker_match(bboxes, labels, track_feats, memo_labels, memo_embeds, memo_id
     nnew = int(new.sum())
     ids[new] = torch.arange(num_tracklets, num_tracklets + nnew, dtype=torch.long)
     return torch.tensor(sel, dtype=torch.long), ids, nnew
+
+
+# ---- row f4: cost matrix of MaskHungarianAssigner (training side) ------------------------------------------------------------
+def focal_loss_cost(cls_pred, gt_labels, weight=1.0, alpha=0.25, gamma=2, eps=1e-12):
+    """mmdet.core.bbox.match_costs.FocalLossCost.__call__ (mmdet v2.18, the version the reference README pins) -- third-party
+    arithmetic restated: sigmoid, then pos_cost[:, labels] - neg_cost[:, labels]."""
+    p = cls_pred.sigmoid()
+    neg = -(1 - p + eps).log() * (1 - alpha) * p.pow(gamma)
+    pos = -(p + eps).log() * alpha * (1 - p).pow(gamma)
+    return (pos[:, gt_labels] - neg[:, gt_labels]) * weight
+
+
+def dice_cost(mask_preds, gt_masks, weight=1.0, eps=1e-3):
+    """DiceCost.__call__ with pred_act=True, act_mode='sigmoid' (knet/det/mask_hungarian_assigner.py:43-75)."""
+    p = mask_preds.sigmoid().clamp(min=0.001, max=1.0)                         # :69
+    inp = p.reshape(p.size(0), -1)                                            # :44-45
+    tgt = gt_masks.reshape(gt_masks.size(0), -1).float()
+    a = torch.einsum('nh,mh->nm', inp, tgt)                                   # :48
+    b = torch.sum(inp * inp, 1) + eps                                         # :49
+    c = torch.sum(tgt * tgt, 1) + eps                                         # :50
+    return -((2 * a) / (b[:, None] + c[None, ...])) * weight                  # :51-53, :75
+
+
+def mask_cost(mask_preds, gt_masks, weight=1.0):
+    """MaskCost.__call__ with pred_act=True, act_mode='sigmoid' (knet/det/mask_hungarian_assigner.py:93-110)."""
+    p = mask_preds.sigmoid().clamp(min=0.01, max=1.0)                          # :97
+    _, H, W = gt_masks.shape                                                  # :101
+    pos = torch.einsum('nhw,mhw->nm', p, gt_masks)                            # :104
+    neg = torch.einsum('nhw,mhw->nm', 1 - p, 1 - gt_masks)                    # :105
+    return (-(pos + neg) / (H * W)) * weight                                  # :109-110
+
+
+def match_cost(mask_preds, cls_pred, gt_masks, gt_labels, w_cls=2.0, w_mask=1.0, w_dice=4.0):
+    """The weighted cost MaskHungarianAssigner.assign hands to linear_sum_assignment (:228-247): cls + mask + dice."""
+    cost = 0
+    if w_cls != 0 and cls_pred is not None:
+        cost = focal_loss_cost(cls_pred, gt_labels, w_cls)
+    if w_mask != 0:
+        cost = cost + mask_cost(mask_preds, gt_masks, w_mask)
+    if w_dice != 0:
+        cost = cost + dice_cost(mask_preds, gt_masks, w_dice)
+    return cost

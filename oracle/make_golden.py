@@ -269,8 +269,42 @@ def main_track():
     case_track('track_match_4f_n60_d64', frames=4, nmax=60, D=64, ncls=3, seed=9)
 
 
+def case_assign(name, N, M, H, W, ncls, seed):
+    """MaskHungarianAssigner of the UNMODIFIED reference (shipped weights: FocalLossCost 2, MaskCost 1, DiceCost 4, pred_act=True;
+    configs/det/_base_/models/knet_s3_r50_fpn.py:114-118): the three cost terms of its own cost objects, their sum, and the
+    assignment `assign` returns.  Targets are bilinearly down-sampled blobs (values in [0, 1], as in training)."""
+    mod = ref_shim.load_assigner()
+    asg = mod.MaskHungarianAssigner(cls_cost=dict(type='FocalLossCost', weight=2.0), dice_cost=dict(type='DiceCost', weight=4.0, pred_act=True),
+                                    mask_cost=dict(type='MaskCost', weight=1.0, pred_act=True))
+    g = torch.Generator().manual_seed(seed)
+    big = (torch.rand(M, 1, 4 * H // 8 + 2, 4 * W // 8 + 2, generator=g) > 0.6).float()
+    gt = torch.nn.functional.interpolate(big, (H, W), mode='bilinear', align_corners=False)[:, 0]
+    pred = 3.0 * torch.randn(N, H, W, generator=g)
+    for m in range(min(M, N)):                       # some predictions resemble a target (a meaningful matching)
+        pred[(m * 7) % N] = (gt[m] - 0.5) * 12 + torch.randn(H, W, generator=g)
+    cls = 2.0 * torch.randn(N, ncls, generator=g) - 2.0
+    labels = torch.randint(0, ncls, (M,), generator=g)
+    with torch.no_grad():
+        c_cls, c_mask, c_dice = asg.cls_cost(cls, labels), asg.mask_cost(pred, gt), asg.dice_cost(pred, gt)
+        res = asg.assign(pred, cls, gt, labels)
+    out = dict(meta=np.array([N, M, H, W, ncls], dtype=np.int64), mask_logits=pred.numpy(), cls_logits=cls.numpy(), gt_masks=gt.numpy(),
+               gt_labels=labels.numpy(), cost_cls=c_cls.numpy(), cost_mask=c_mask.numpy(), cost_dice=c_dice.numpy(),
+               cost=(c_cls + c_mask + c_dice).numpy(), gt_inds=res.gt_inds.numpy(), labels=res.labels.numpy())
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, 'matched', int((res.gt_inds > 0).sum()))
+
+
+def main_assign():
+    ref_shim.install()
+    case_assign('assign_n100_m17_40x56_c19', 100, 17, 40, 56, 19, seed=3)
+    case_assign('assign_n20_m3_13x17_c5', 20, 3, 13, 17, 5, seed=4)
+    case_assign('assign_n150_m40_24x32_c124', 150, 40, 24, 32, 124, seed=6)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'track':
+    if len(sys.argv) > 1 and sys.argv[1] == 'assign':
+        main_assign()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'track':
         main_track()
     elif len(sys.argv) > 1 and sys.argv[1] == 'clip':      # knet_vis registers the same keys as knet: own process
         main_clip()

@@ -315,6 +315,48 @@ def load_tracker():
     return mod
 
 
+def load_assigner():
+    """knet/det/mask_hungarian_assigner.py by path (DiceCost, MaskCost, MaskHungarianAssigner).  mmdet's side of it is stubbed:
+    AssignResult (a record), BaseAssigner (an empty base), the two registries, and FocalLossCost -- third-party arithmetic,
+    restated in knet_oracle.focal_loss_cost (mmdet v2.18)."""
+    install()
+    import knet_oracle as ko
+    core = sys.modules['mmdet.core']
+
+    class AssignResult:
+        def __init__(self, num_gts, gt_inds, max_overlaps, labels=None):
+            self.num_gts, self.gt_inds, self.max_overlaps, self.labels = num_gts, gt_inds, max_overlaps, labels
+
+    core.AssignResult = AssignResult
+    core.BaseAssigner = type('BaseAssigner', (), {})
+    core.reduce_mean = lambda t: t
+    for name in ('mmdet.core.bbox', 'mmdet.core.bbox.builder', 'mmdet.core.bbox.match_costs', 'mmdet.core.bbox.match_costs.builder'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    b = sys.modules['mmdet.core.bbox.builder']
+    if not hasattr(b, 'BBOX_ASSIGNERS'):
+        b.BBOX_ASSIGNERS = Registry('bbox_assigner')
+    mc = sys.modules['mmdet.core.bbox.match_costs.builder']
+    if not hasattr(mc, 'MATCH_COST'):
+        mc.MATCH_COST = Registry('match_cost')
+
+        class FocalLossCost:
+            def __init__(self, weight=1., alpha=0.25, gamma=2, eps=1e-12):
+                self.weight, self.alpha, self.gamma, self.eps = weight, alpha, gamma, eps
+
+            def __call__(self, cls_pred, gt_labels):
+                return ko.focal_loss_cost(cls_pred, gt_labels, self.weight, self.alpha, self.gamma, self.eps)
+
+        mc.MATCH_COST.register_module()(FocalLossCost)
+
+        def build_match_cost(cfg, default_args=None):
+            return mc.MATCH_COST.build(cfg)
+        mc.build_match_cost = build_match_cost
+    return _load_file('_ref_knet.det.mask_hungarian_assigner', 'knet/det/mask_hungarian_assigner.py')
+
+
 def load(tree='knet'):
     """Import the reference hot-path modules verbatim.  `tree` is 'knet' or 'knet_vis'
     (they register the same registry keys, so use one per process)."""

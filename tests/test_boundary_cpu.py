@@ -64,7 +64,7 @@ def test_struct_sizes_match_header_layout(built_lib):
     assert ctypes.sizeof(L.VknShape) == 14 * 4
     assert ctypes.sizeof(L.VknUpdatorW) == 20 * p
     assert ctypes.sizeof(L.VknAttnW) == 6 * p and ctypes.sizeof(L.VknFfnW) == 6 * p
-    assert ctypes.sizeof(L.VknHeadW) == (3 + 20 + 6 + 6 + 1 + 3 * 4 + 2 + 3 * 4 + 2) * p
+    assert ctypes.sizeof(L.VknHeadW) == (3 + 20 + 6 + 6 + 1 + 3 * 4 + 2 + 3 * 4 + 2 + 1) * p      # + fc_pack
     assert ctypes.sizeof(L.VknLinkW) == (1 + 20 + 6 + 6) * p
 
 

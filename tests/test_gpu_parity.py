@@ -6,6 +6,7 @@ within 1e-3 in fp32 / 1e-2 in bf16 storage; mask argmax over the N kernels ident
 oracle's.  Logit maps are additionally checked to 1e-3 * max|logit| (they feed the next stage's
 hard threshold).
 """
+import numpy as np
 import pytest
 import torch
 
@@ -1062,3 +1063,46 @@ def test_frame_chain_video_head_and_clip_head_without_cls(dev):
     assert L.vkn_launch_count() - n0 == 5
     assert maxabs(obj2, want2[2]) < TOL_BF16
     assert_masks_bf16(nm2.reshape(B * Fr, N, H, W), want2[1].reshape(B * Fr, N, H, W), 'clip head (per-frame) via frame chain')
+
+
+# ---- row f4: MaskHungarianAssigner cost matrix (vkn_match_cost) -----------------------------------------------------------
+@pytest.mark.parametrize('path', golden_files('assign_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_match_cost_golden(dev, path):
+    """The fused cost kernel against the reference's own cost objects (fixtures), each term and the sum, and the drop-in
+    MaskHungarianAssigner.assign against the reference's assignment."""
+    from vknet import assigner, ops
+    z = np.load(path)
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    pred, cls, gt, lab = (t[k].to(dev) for k in ('mask_logits', 'cls_logits', 'gt_masks', 'gt_labels'))
+    tol = 2e-5
+    assert maxabs(ops.match_cost(pred, cls, gt, lab), t['cost']) < tol
+    assert maxabs(ops.match_cost(pred, cls, gt, lab, w_mask=0.0, w_dice=0.0), t['cost_cls']) < tol
+    assert maxabs(assigner.MaskCost(weight=1.0, pred_act=True)(pred, gt), t['cost_mask']) < tol
+    assert maxabs(assigner.DiceCost(weight=4.0, pred_act=True)(pred, gt), t['cost_dice']) < tol
+    asg = assigner.MaskHungarianAssigner(cls_cost=dict(type='FocalLossCost', weight=2.0),
+                                         dice_cost=dict(type='DiceCost', weight=4.0, pred_act=True),
+                                         mask_cost=dict(type='MaskCost', weight=1.0, pred_act=True))
+    res = asg.assign(pred, cls, gt, lab)
+    assert res.num_gts == gt.shape[0] and torch.equal(res.gt_inds.cpu(), t['gt_inds']) and torch.equal(res.labels.cpu(), t['labels'])
+    # twice the same bits (fixed-order reduction of the pixel chunks)
+    assert torch.equal(ops.match_cost(pred, cls, gt, lab), ops.match_cost(pred, cls, gt, lab))
+
+
+@pytest.mark.parametrize('N,M,H,W,ncls', [(100, 30, 200, 304, 19), (166, 70, 97, 131, 124), (1, 1, 5, 3, 1), (130, 33, 64, 64, 8)])
+def test_match_cost_vs_oracle(dev, N, M, H, W, ncls):
+    """Training-size masks (1/4-resolution KITTI crop), ragged sizes (HW not a multiple of the 64-pixel block), more than one
+    target / prediction block, single elements; plus the empty-set behaviour of assign (reference :218-224)."""
+    from vknet import assigner, ops
+    g = torch.Generator().manual_seed(N + M)
+    pred, gt = 3 * torch.randn(N, H, W, generator=g), torch.rand(M, H, W, generator=g).round()
+    cls, lab = torch.randn(N, ncls, generator=g), torch.randint(0, ncls, (M,), generator=g)
+    want = ko.match_cost(pred, cls, gt, lab)
+    got = ops.match_cost(pred.to(dev), cls.to(dev), gt.to(dev), lab.to(dev))
+    assert maxabs(got, want) < 2e-5 * max(1.0, want.abs().max().item())
+    asg = assigner.MaskHungarianAssigner(cls_cost=dict(type='FocalLossCost', weight=2.0),
+                                         dice_cost=dict(type='DiceCost', weight=4.0, pred_act=True),
+                                         mask_cost=dict(type='MaskCost', weight=1.0, pred_act=True))
+    res = asg.assign(pred.to(dev), cls.to(dev), gt[:0].to(dev), lab[:0].to(dev))
+    assert res.num_gts == 0 and bool((res.gt_inds == 0).all()) and bool((res.labels == -1).all())
+    with pytest.raises(NotImplementedError):
+        assigner.DiceCost(weight=1.0, pred_act=False)(pred.to(dev), gt.to(dev))

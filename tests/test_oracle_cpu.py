@@ -3,6 +3,7 @@
  (2) when /root/reference is present (build container only), the live reference on fresh seeds."""
 import copy
 
+import numpy as np
 import pytest
 import torch
 
@@ -176,3 +177,34 @@ def test_oracle_matches_reference_fixtures_tracker_match(path):
         matched += int(((ids > -1) & (ids < n0)).sum())
         news += nnew
     assert matched >= 10 and news >= 10          # the fixtures exercise matching, births and the duplicate rule
+
+
+# ---- row f4: MaskHungarianAssigner cost matrix ---------------------------------------------------------------------------
+@pytest.mark.parametrize('path', golden_files('assign_'), ids=lambda p: p.split('/')[-1][:-4])
+def test_match_cost_oracle_matches_reference_fixtures(path):
+    """The restated DiceCost / MaskCost / FocalLossCost against the outputs of the reference's own cost objects, and the
+    Hungarian assignment on the restated cost against the reference's `assign`."""
+    from scipy.optimize import linear_sum_assignment
+    z = np.load(path)
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    pred, cls, gt, lab = t['mask_logits'], t['cls_logits'], t['gt_masks'], t['gt_labels']
+    assert (ko.focal_loss_cost(cls, lab, 2.0) - t['cost_cls']).abs().max() < 1e-6
+    assert (ko.mask_cost(pred, gt, 1.0) - t['cost_mask']).abs().max() < 1e-6
+    assert (ko.dice_cost(pred, gt, 4.0) - t['cost_dice']).abs().max() < 1e-6
+    cost = ko.match_cost(pred, cls, gt, lab)
+    assert (cost - t['cost']).abs().max() < 2e-6
+    rows, cols = linear_sum_assignment(cost)
+    inds = torch.zeros(pred.shape[0], dtype=torch.long)
+    inds[torch.from_numpy(rows)] = torch.from_numpy(cols) + 1
+    assert torch.equal(inds, t['gt_inds'])
+
+
+def test_match_cost_oracle_matches_live_reference():
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip('needs /root/reference')
+    mod = ref_shim.load_assigner()
+    g = torch.Generator().manual_seed(12)
+    pred, gt = 2 * torch.randn(9, 7, 11, generator=g), torch.rand(4, 7, 11, generator=g)
+    assert (mod.DiceCost(weight=4.0, pred_act=True)(pred, gt) - ko.dice_cost(pred, gt, 4.0)).abs().max() < 1e-6
+    assert (mod.MaskCost(weight=1.0, pred_act=True)(pred, gt) - ko.mask_cost(pred, gt, 1.0)).abs().max() < 1e-6

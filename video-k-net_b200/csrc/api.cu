@@ -762,7 +762,7 @@ const char *vkn_last_error(void) { return g_err; }
 
 const char *vkn_kernel_names(void) {
   return "vkn_pool_simt_kernel\nvkn_pool_reduce_kernel\nvkn_pool_reduce_flat_kernel\nvkn_maskgemm_simt_kernel\nvkn_linear_kernel\n"
-         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_attention_tc_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_frame_chain_a_kernel\nvkn_frame_chain_b_kernel\nvkn_frame_chain_pack_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_track_match_kernel\nvkn_rescale_masks_kernel";
+         "vkn_rowop_kernel\nvkn_attention_kernel\nvkn_attention4_kernel\nvkn_attention_tc_kernel\nvkn_pool_tc_kernel\nvkn_maskgemm_tc_kernel\nvkn_maskgemm_tc_persist_kernel\nvkn_maskgemm_tc_wide_kernel\nvkn_pack_kernels_kernel\nvkn_rowgemm_tc_kernel\nvkn_chain_tc_kernel\nvkn_frame_chain_a_kernel\nvkn_frame_chain_b_kernel\nvkn_frame_chain_pack_kernel\nvkn_match_cost_partial_kernel\nvkn_match_cost_final_kernel\nvkn_panoptic_owner_kernel\nvkn_panoptic_segments_kernel\nvkn_panoptic_paint_kernel\nvkn_mask_boxes_kernel\nvkn_track_match_kernel\nvkn_rescale_masks_kernel";
 }
 
 unsigned long long vkn_launch_count(void) { return g_launches; }
@@ -812,6 +812,19 @@ int vkn_frame_chain_pack(const VknShape *shape, const VknHeadW *w, void *out, si
   VKN_TRY(check_shape(shape));
   if (!w) VKN_FAIL(VKN_E_INVALID, "vkn_frame_chain_pack: null argument");
   return launch_frame_chain_pack(*shape, *w, out, bytes, (cudaStream_t)stream);
+}
+
+int vkn_match_cost_workspace_bytes(int N, int M, int HW, size_t *bytes) {
+  if (!bytes || N < 1 || M < 1 || HW < 1) VKN_FAIL(VKN_E_INVALID, "vkn_match_cost_workspace_bytes: bad argument");
+  *bytes = match_cost_workspace_bytes(N, M, HW);
+  return VKN_OK;
+}
+
+int vkn_match_cost(const float *mask_logits, const float *cls_logits, const float *gt_masks, const int64_t *gt_labels, int N,
+                   int M, int HW, int ncls, const float *params, float *cost, void *workspace, size_t workspace_bytes,
+                   void *stream) {
+  return launch_match_cost(mask_logits, cls_logits, gt_masks, (const long long *)gt_labels, N, M, HW, ncls, params, cost, workspace,
+                           workspace_bytes, (cudaStream_t)stream);
 }
 
 int vkn_workspace_bytes(const VknShape *shape, size_t *bytes) {

@@ -290,6 +290,12 @@ int maskgemm_tc_npad(const VknShape &s);
 int launch_rescale_masks(const void *masks, int dtype, int K, int H, int W, int up, int Hb, int Wb, int h, int w, int Ho,
                          int Wo, float thr, float *probs, uint8_t *bits, cudaStream_t stream);
 
+// training-side cost matrix (matchcost.cu)
+size_t match_cost_workspace_bytes(int N, int M, int HW);
+int launch_match_cost(const float *mask_logits, const float *cls_logits, const float *gt_masks, const long long *gt_labels, int N,
+                      int M, int HW, int ncls, const float *params7, float *cost, void *workspace, size_t workspace_bytes,
+                      cudaStream_t stream);
+
 // post-loop result assembly (panoptic.cu)
 int launch_panoptic_merge(const float *masks, const float *scores, const int *labels, int T, int H, int W, int num_thing,
                           double inst_thr, double overlap_thr, int *seg, int *table, float *seg_scores, int *kept, int *counts,

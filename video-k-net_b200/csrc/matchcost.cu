@@ -21,7 +21,7 @@ constexpr int MC_LD = MC_PX + 4;     // row stride (floats): 16-byte aligned row
 constexpr int MC_NB = 128;           // predictions per CTA (4 per thread: n = tn + 32 i)
 constexpr int MC_MB = 32;            // targets per CTA     (4 per thread: m = tm + 8 j)
 
-__global__ void __launch_bounds__(MC_NT) vkn_match_cost_partial_kernel(const float *__restrict__ logits, const float *__restrict__ gt,
+__global__ void __launch_bounds__(MC_NT, 2) vkn_match_cost_partial_kernel(const float *__restrict__ logits, const float *__restrict__ gt,
                                                                       int N, int M, int HW, int blocks_per_chunk,
                                                                       float *__restrict__ p_dm, float *__restrict__ p_row,
                                                                       float *__restrict__ p_col) {
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(MC_NT) vkn_match_cost_partial_kernel(const flo
       const int r = idx >> 6, px = idx & 63, n = n0 + r, p = p0 + px;
       float d = 0.f, m = 0.f;
       if (n < N && p < HW) {
-        const float s = 1.0f / (1.0f + expf(-__ldg(logits + (size_t)n * HW + p)));
+        const float s = sigmoid_fast(__ldg(logits + (size_t)n * HW + p));      // ex2.approx + rcp.approx: ~1e-7 relative
         d = fminf(fmaxf(s, 0.001f), 1.0f);
         m = fminf(fmaxf(s, 0.01f), 1.0f);
       }
@@ -131,11 +131,12 @@ __global__ void __launch_bounds__(256) vkn_match_cost_final_kernel(const float *
                                                                    const float *__restrict__ cls_logits,
                                                                    const long long *__restrict__ gt_labels, int N, int M, int HW,
                                                                    int ncls, McParams P, float *__restrict__ cost) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;
+  // one warp per output: lane l sums the chunks l, l + 32, ... (fixed order), then a fixed shuffle tree -> deterministic
+  const int idx = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (idx >= N * M) return;
   const int n = idx / M, m = idx - n * M;
   float a = 0.f, pt = 0.f, b = 0.f, spm = 0.f, c = 0.f, st = 0.f;
-  for (int ch = 0; ch < nchunks; ++ch) {       // fixed order
+  for (int ch = lane; ch < nchunks; ch += 32) {
     const float2 dm = __ldg(reinterpret_cast<const float2 *>(p_dm + (((size_t)ch * N + n) * M + m) * 2));
     const float2 r = __ldg(reinterpret_cast<const float2 *>(p_row + ((size_t)ch * N + n) * 2));
     const float2 cc = __ldg(reinterpret_cast<const float2 *>(p_col + ((size_t)ch * M + m) * 2));
@@ -146,6 +147,13 @@ __global__ void __launch_bounds__(256) vkn_match_cost_final_kernel(const float *
     c += cc.x;
     st += cc.y;
   }
+  a = warp_sum(a);
+  pt = warp_sum(pt);
+  b = warp_sum(b);
+  spm = warp_sum(spm);
+  c = warp_sum(c);
+  st = warp_sum(st);
+  if (lane != 0) return;
   float total = 0.f;
   if (P.w_cls != 0.f && cls_logits != nullptr) {       // mmdet FocalLossCost: pos_cost[:, label] - neg_cost[:, label]
     const long long lab = gt_labels[m];
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(256) vkn_match_cost_final_kernel(const float *
 static int mc_chunks(int N, int M, int HW, int *bpc) {
   const int nblk = ceil_div(HW, MC_PX);
   const int tiles = ceil_div(M, MC_MB) * ceil_div(N, MC_NB);
-  int chunks = 296 / tiles;                 // two CTAs per SM
+  int chunks = 296 / tiles;                 // two CTAs (78 KB of shared memory each) per SM
   if (chunks < 1) chunks = 1;
   if (chunks > nblk) chunks = nblk;
   *bpc = ceil_div(nblk, chunks);
@@ -203,7 +211,7 @@ int launch_match_cost(const float *mask_logits, const float *cls_logits, const f
   vkn_match_cost_partial_kernel<<<dim3(ch, ceil_div(M, MC_MB), ceil_div(N, MC_NB)), MC_NT, smem, stream>>>(mask_logits, gt_masks, N, M, HW,
                                                                                                          bpc, p_dm, p_row, p_col);
   VKN_LAUNCH_MARK("vkn_match_cost_final_kernel", stream);
-  vkn_match_cost_final_kernel<<<ceil_div(N * M, 256), 256, 0, stream>>>(p_dm, p_row, p_col, ch, cls_logits, gt_labels, N, M, HW, ncls, P,
+  vkn_match_cost_final_kernel<<<ceil_div(N * M, 8), 256, 0, stream>>>(p_dm, p_row, p_col, ch, cls_logits, gt_labels, N, M, HW, ncls, P,
                                                                        cost);
   VKN_CUDA_OK(cudaGetLastError());
   return VKN_OK;

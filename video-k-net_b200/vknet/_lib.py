@@ -72,7 +72,7 @@ SYMBOLS = ('vkn_version', 'vkn_last_error', 'vkn_kernel_names', 'vkn_launch_coun
            'vkn_kernel_update', 'vkn_mhsa_ln', 'vkn_ffn_ln', 'vkn_heads', 'vkn_mask_gemm',
            'vkn_stage_forward', 'vkn_iter_forward', 'vkn_init_proposals', 'vkn_link_attend', 'vkn_rescale_masks',
            'vkn_panoptic_merge', 'vkn_mask_boxes', 'vkn_mlp', 'vkn_track_match', 'vkn_frame_chain_pack_bytes',
-           'vkn_frame_chain_pack')
+           'vkn_frame_chain_pack', 'vkn_match_cost_workspace_bytes', 'vkn_match_cost')
 
 
 def lib():
@@ -113,6 +113,8 @@ def lib():
                                   _vp, sz, _vp]
     L.vkn_frame_chain_pack_bytes.argtypes = [S, C.POINTER(VknHeadW), C.POINTER(sz)]
     L.vkn_frame_chain_pack.argtypes = [S, C.POINTER(VknHeadW), _vp, sz, _vp]
+    L.vkn_match_cost_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(sz)]
+    L.vkn_match_cost.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _vp, _vp, sz, _vp]
     L.vkn_debug_timestamps.restype = C.c_int
     L.vkn_debug_timestamps.argtypes = [_vp, C.c_size_t]
     for name in SYMBOLS[7:]:

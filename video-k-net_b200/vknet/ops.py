@@ -282,3 +282,39 @@ def track_match(bboxes, labels, track_feats, memo_labels, memo_embeds, memo_ids,
                                           _lib.ptr(counts), _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr(dev)))
     nk, nnew = (int(v) for v in counts.cpu())
     return sel[:nk].long(), ids[:nk], nnew
+
+
+def match_cost(mask_logits, cls_logits, gt_masks, gt_labels, w_cls=2.0, w_mask=1.0, w_dice=4.0, dice_eps=1e-3, focal_alpha=0.25,
+               focal_gamma=2.0, focal_eps=1e-12):
+    """Cost matrix [N, M] of MaskHungarianAssigner.assign for one image (knet/det/mask_hungarian_assigner.py:228-247; DiceCost
+    :43-75, MaskCost :93-110 with pred_act=True / act_mode='sigmoid', mmdet FocalLossCost) in one pass over the masks
+    (vkn_match_cost).  mask_logits [N, H, W], cls_logits [N, ncls] or None, gt_masks [M, H, W] (float), gt_labels [M].
+    The default weights are the shipped configs' (cls 2, mask 1, dice 4); a zero weight skips the term."""
+    import ctypes as C
+    if not mask_logits.is_cuda:
+        raise _lib.VknError('vknet has no CPU path: inputs must live on a CUDA device')
+    dev = mask_logits.device
+    N, M = mask_logits.shape[0], gt_masks.shape[0]
+    if N == 0 or M == 0:
+        return torch.zeros(N, M, dtype=torch.float32, device=dev)
+    if tuple(mask_logits.shape[1:]) != tuple(gt_masks.shape[1:]):
+        raise _lib.VknError('mask_logits %s and gt_masks %s differ in size' % (tuple(mask_logits.shape), tuple(gt_masks.shape)))
+    HW = int(mask_logits[0].numel())
+    ml = mask_logits.reshape(N, HW).float().contiguous()
+    gm = gt_masks.to(dev).reshape(M, HW).float().contiguous()
+    use_cls = cls_logits is not None and w_cls != 0
+    cl = cls_logits.float().contiguous() if use_cls else None
+    ncls = cl.shape[1] if use_cls else 0
+    gl = gt_labels.to(device=dev, dtype=torch.int64).contiguous() if use_cls else None
+    if use_cls and (cl.shape[0] != N or gl.numel() != M):
+        raise _lib.VknError('cls_logits / gt_labels do not match the mask counts')
+    L = _lib.lib()
+    nb = C.c_size_t(0)
+    _lib.check(L.vkn_match_cost_workspace_bytes(N, M, HW, C.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    cost = torch.empty(N, M, dtype=torch.float32, device=dev)
+    params = (C.c_float * 7)(w_cls if use_cls else 0.0, w_mask, w_dice, dice_eps, focal_alpha, focal_gamma, focal_eps)
+    with torch.cuda.device(dev):
+        _lib.check(L.vkn_match_cost(_lib.ptr(ml), _lib.ptr(cl), _lib.ptr(gm), _lib.ptr(gl), N, M, HW, ncls, params, _lib.ptr(cost),
+                                    _lib.ptr(ws), nb.value, _lib.stream_ptr(dev)))
+    return cost
