@@ -1063,6 +1063,21 @@ def test_frame_chain_video_head_and_clip_head_without_cls(dev):
     assert L.vkn_launch_count() - n0 == 5
     assert maxabs(obj2, want2[2]) < TOL_BF16
     assert_masks_bf16(nm2.reshape(B * Fr, N, H, W), want2[1].reshape(B * Fr, N, H, W), 'clip head (per-frame) via frame chain')
+    # clip head, gathered mode (BASELINE cfg2: one kernel set pools the mean over its 4 frames and convolves all of them)
+    Fr = 4
+    x3 = ko.round_bf16(torch.randn(B, Fr, C, H, W, generator=gen))
+    pf3 = torch.randn(B, N, C, 1, 1, generator=gen)
+    mask3 = ko.round_bf16(torch.einsum('bnc,bfchw->bfnhw', pf3.view(B, N, C), x3))
+    want3 = ko.kernel_update_head_video_forward(sd, cfg, x3, pf3, mask3)
+    h3 = vknet.build_head(dict(type='KernelUpdateHeadVideo', with_cls=True, num_proposals=N, **cfg))
+    h3.load_state_dict(sd, strict=True)
+    h3 = h3.to(device=dev, dtype=torch.bfloat16).eval()
+    h3.packed_weights(dev)
+    n0 = L.vkn_launch_count()
+    cls3, nm3, obj3 = h3(x3.to(dev).bfloat16(), pf3.to(dev), mask3.to(dev).bfloat16())
+    assert L.vkn_launch_count() - n0 == 5
+    assert maxabs(obj3, want3[2]) < TOL_BF16 and maxabs(cls3, want3[0]) < TOL_BF16
+    assert_masks_bf16(nm3.reshape(B * Fr, N, H, W), want3[1].reshape(B * Fr, N, H, W), 'clip head (gathered) via frame chain')
 
 
 # ---- row f4: MaskHungarianAssigner cost matrix (vkn_match_cost) -----------------------------------------------------------

@@ -146,6 +146,23 @@ __device__ __forceinline__ void fc_mma(float (&d)[4], const uint32_t (&a)[4], ui
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// bounded mbarrier wait as ONE shared body (tc.cuh's inlined spin loop is unrolled by the compiler: ~40 instructions per site,
+// ~60 sites per kernel)
+__device__ __noinline__ void fc_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
 __device__ __forceinline__ float fc_lds(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -206,35 +223,40 @@ __device__ __forceinline__ void fc_setup(FcCtx &x, const FcCommon &c, uint8_t *s
 
 // weight ring: chunk k lives in slot k % nslot; warp 0 issues (one 512-byte bulk copy per row and lane), everybody waits on the
 // slot's mbarrier.  fc_ring_fill(consumed) may only be called after a __syncthreads that follows the last read of chunk consumed-1.
+__device__ __forceinline__ void fc_ring_issue(const FcCommon *cp, int first, int upto, uint32_t rank, int nslot, int nchunks,
+                                           uint32_t ring, uint32_t bars, int lane) {      // warp 0 only
+  const FcCommon &c = *cp;
+#pragma unroll 1
+  for (int k = first; k < upto; ++k) {
+    const FcChunk &ch = c.chunk[k];
+    int rows = ch.rows_total - (int)rank * ch.rows_per_rank;
+    rows = max(0, min(rows, min(ch.rows_per_rank, 32)));
+    const uint32_t slot = (uint32_t)(k % nslot);
+    const uint32_t bar = bars + 8u * slot;
+    if (c.pack != nullptr) {        // host-prepared chunk image: ONE bulk copy
+      if (lane == 0) {
+        mbar_expect_tx(bar, rows > 0 ? (uint32_t)FC_CHUNK_B : 0u);
+        if (rows > 0) fc_bulk_g2s(ring + slot * FC_CHUNK_B, c.pack + ((size_t)rank * nchunks + k) * (FC_CHUNK_B / 2), FC_CHUNK_B, bar);
+      }
+    } else {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)rows * (FC_K * 2));
+      __syncwarp();
+      if (lane < rows)
+        fc_bulk_g2s(ring + slot * FC_CHUNK_B + (uint32_t)lane * (FC_LD * 2),
+                    ch.base + (long long)rank * ch.rank_stride + (long long)lane * ch.ld, FC_K * 2, bar);
+    }
+  }
+}
 __device__ __forceinline__ void fc_ring_fill(FcCtx &x, const FcCommon &c, int consumed) {
   const int upto = min(x.nchunks, consumed + x.nslot);
-  while (x.issued < upto) {
-    if (x.warp == 0) {
-      const FcChunk &ch = c.chunk[x.issued];
-      int rows = ch.rows_total - (int)x.rank * ch.rows_per_rank;
-      rows = max(0, min(rows, min(ch.rows_per_rank, 32)));
-      const uint32_t slot = (uint32_t)(x.issued % x.nslot);
-      const uint32_t bar = x.bars + 8u * slot;
-      if (c.pack != nullptr) {        // host-prepared chunk image: ONE bulk copy
-        if (x.lane == 0) {
-          mbar_expect_tx(bar, rows > 0 ? (uint32_t)FC_CHUNK_B : 0u);
-          if (rows > 0)
-            fc_bulk_g2s(x.ring + slot * FC_CHUNK_B, c.pack + ((size_t)x.rank * x.nchunks + x.issued) * (FC_CHUNK_B / 2), FC_CHUNK_B, bar);
-        }
-      } else {
-        if (x.lane == 0) mbar_expect_tx(bar, (uint32_t)rows * (FC_K * 2));
-        __syncwarp();
-        if (x.lane < rows)
-          fc_bulk_g2s(x.ring + slot * FC_CHUNK_B + (uint32_t)x.lane * (FC_LD * 2),
-                      ch.base + (long long)x.rank * ch.rank_stride + (long long)x.lane * ch.ld, FC_K * 2, bar);
-      }
-    }
-    ++x.issued;
+  if (x.issued < upto) {
+    if (x.warp == 0) fc_ring_issue(&c, x.issued, upto, x.rank, x.nslot, x.nchunks, x.ring, x.bars, x.lane);
+    x.issued = upto;
   }
 }
 __device__ __forceinline__ uint32_t fc_chunk(const FcCtx &x, int k) {
   const int slot = k % x.nslot;
-  mbar_wait(x.bars + 8u * (uint32_t)slot, (uint32_t)(k / x.nslot) & 1u);
+  fc_mbar_wait(x.bars + 8u * (uint32_t)slot, (uint32_t)(k / x.nslot) & 1u);
   return x.ring + (uint32_t)slot * FC_CHUNK_B;
 }
 
@@ -249,7 +271,12 @@ __device__ __forceinline__ void fc_load_vecs(const FcCtx &x, const FcCommon &c) 
 __device__ __forceinline__ float2 fc_vec2(const FcCtx &x, int v, int col) { return fc_lds2(x.vecs + (uint32_t)(v * 32 + col) * 4u); }
 
 // D[16 x 8] = sum over the three planes of A_pl[16 x 256] . W[8 rows][256]^T    (one independent accumulation chain per plane)
-__device__ __forceinline__ void fc_mma_tile(uint32_t a_buf, uint32_t w_rows, int lane, float (&d)[4]) {
+// (__noinline__: the two kernels are straight-line programs of ~10^4 instructions that every warp executes once -- shared
+// bodies keep the hot loops in the instruction cache; ncu showed "no instruction" as the top stall with everything inlined)
+struct FcFrag { float d[4]; };
+struct FcFrag2 { float d0[4], d1[4]; };
+__device__ __noinline__ FcFrag fc_mma_tile(uint32_t a_buf, uint32_t w_rows, int lane) {
+  FcFrag out;
   float acc[3][4];
 #pragma unroll
   for (int pl = 0; pl < 3; ++pl)
@@ -271,13 +298,14 @@ __device__ __forceinline__ void fc_mma_tile(uint32_t a_buf, uint32_t w_rows, int
       }
   }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) d[e] = (acc[2][e] + acc[1][e]) + acc[0][e];      // small terms first
+  for (int e = 0; e < 4; ++e) out.d[e] = (acc[2][e] + acc[1][e]) + acc[0][e];      // small terms first
+  return out;
 }
 
 // two n8 tiles that share the A fragments (the FFN phases: 16 tiles per phase -> every warp owns a pair; the A operand is
 // what the shared-memory pipe is busy with)
-__device__ __forceinline__ void fc_mma_tile2(uint32_t a_buf, uint32_t w_rows0, uint32_t w_rows1, int lane, float (&d0)[4],
-                                             float (&d1)[4]) {
+__device__ __noinline__ FcFrag2 fc_mma_tile2(uint32_t a_buf, uint32_t w_rows0, uint32_t w_rows1, int lane) {
+  FcFrag2 out;
   float acc[2][3][4];
 #pragma unroll
   for (int t = 0; t < 2; ++t)
@@ -304,19 +332,19 @@ __device__ __forceinline__ void fc_mma_tile2(uint32_t a_buf, uint32_t w_rows0, u
   }
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    d0[e] = (acc[0][2][e] + acc[0][1][e]) + acc[0][0][e];
-    d1[e] = (acc[1][2][e] + acc[1][1][e]) + acc[1][0][e];
+    out.d0[e] = (acc[0][2][e] + acc[0][1][e]) + acc[0][0][e];
+    out.d1[e] = (acc[1][2][e] + acc[1][1][e]) + acc[1][0][e];
   }
+  return out;
 }
 // GEMM phase over FOUR full chunks [k0, k0 + 4) with one A operand: warp w owns tile (w & 3) of chunks k0 + (w >> 2) and + 2
 template <typename Epi>
 __device__ __forceinline__ void fc_gemm2(const FcCtx &x, const FcCommon &, int k0, uint32_t a_buf, Epi epi) {
   const int kc0 = k0 + (x.warp >> 2), kc1 = kc0 + 2, j = x.warp & 3;
   const uint32_t w0 = fc_chunk(x, kc0), w1 = fc_chunk(x, kc1);
-  float d0[4], d1[4];
-  fc_mma_tile2(a_buf, w0 + (uint32_t)(j * 8 * FC_LD) * 2u, w1 + (uint32_t)(j * 8 * FC_LD) * 2u, x.lane, d0, d1);
-  epi(kc0, j, d0);
-  epi(kc1, j, d1);
+  const FcFrag2 f = fc_mma_tile2(a_buf, w0 + (uint32_t)(j * 8 * FC_LD) * 2u, w1 + (uint32_t)(j * 8 * FC_LD) * 2u, x.lane);
+  epi(kc0, j, f.d0);
+  epi(kc1, j, f.d1);
 }
 
 // GEMM phase over the ring chunks [k0, k0 + nk): n8-tile items round-robin over the 8 warps.
@@ -331,9 +359,8 @@ __device__ __forceinline__ void fc_gemm(const FcCtx &x, const FcCommon &c, int k
     rows = min(rows, min(ch.rows_per_rank, 32));
     if (j * 8 >= rows) continue;                       // no live weight row in this tile (warp-uniform)
     const uint32_t w = fc_chunk(x, kc);
-    float d[4];
-    fc_mma_tile(a_of(kc), w + (uint32_t)(j * 8 * FC_LD) * 2u, x.lane, d);
-    epi(kc, j, d);
+    const FcFrag f = fc_mma_tile(a_of(kc), w + (uint32_t)(j * 8 * FC_LD) * 2u, x.lane);
+    epi(kc, j, f.d);
   }
 }
 // fragment -> fp32 slice buffer [16][33]
@@ -355,6 +382,19 @@ __device__ __forceinline__ void fc_slice2_store(const FcCtx &x, uint32_t sl, flo
   fc_sts(sl + (uint32_t)(x.row * 33 + 2 * x.cp + 1) * 4u, b);
 }
 
+// staged slice planes -> CTA `to` (one warp per destination); every 16-byte store reports to the destination's barrier
+__device__ __forceinline__ void fc_bcast_send(uint32_t st, uint32_t dst_col0, uint32_t bar_local, uint32_t to, int lane) {
+  __syncthreads();
+  const uint32_t bar = fc_mapa(bar_local, to);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int p = lane + 32 * i;
+    const int pl = p >> 6, r = (p >> 2) & 15, q = p & 3;
+    const uint4 v = lds_u4(st + (uint32_t)((pl * FC_TM + r) * 16 + q * 4) * 4u);
+    const uint32_t d = dst_col0 + (uint32_t)(pl * FC_PLANE + r * FC_LD + 8 * q) * 2u;
+    fc_st_remote_v4(fc_mapa(d, to), v, bar);
+  }
+}
 // the owner's transformed slice -> bf16 planes in the A buffer `dst` of ALL 8 CTAs (warp w serves CTA w)
 __device__ __forceinline__ void fc_bcast_planes(const FcCtx &x, int stg, uint32_t dst, int xch, float v0, float v1) {
   uint32_t w3[3];
@@ -362,18 +402,9 @@ __device__ __forceinline__ void fc_bcast_planes(const FcCtx &x, int stg, uint32_
   const uint32_t st = x.stage[stg];
 #pragma unroll
   for (int pl = 0; pl < 3; ++pl) sts_u32(st + (uint32_t)((pl * FC_TM + x.row) * 16 + x.cp) * 4u, w3[pl]);
-  __syncthreads();
-  const uint32_t bar = fc_mapa(x.xbar + 8u * (uint32_t)xch, (uint32_t)x.warp);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int p = x.lane + 32 * i;
-    const int pl = p >> 6, r = (p >> 2) & 15, q = p & 3;
-    const uint4 v = lds_u4(st + (uint32_t)((pl * FC_TM + r) * 16 + q * 4) * 4u);
-    const uint32_t d = dst + (uint32_t)(pl * FC_PLANE + r * FC_LD + FC_SW * (int)x.rank + 8 * q) * 2u;
-    fc_st_remote_v4(fc_mapa(d, (uint32_t)x.warp), v, bar);
-  }
+  fc_bcast_send(st, dst + (uint32_t)(FC_SW * (int)x.rank) * 2u, x.xbar + 8u * (uint32_t)xch, (uint32_t)x.warp, x.lane);
 }
-__device__ __forceinline__ void fc_xwait(const FcCtx &x, int xch) { mbar_wait(x.xbar + 8u * (uint32_t)xch, 0u); }
+__device__ __forceinline__ void fc_xwait(const FcCtx &x, int xch) { fc_mbar_wait(x.xbar + 8u * (uint32_t)xch, 0u); }
 
 // LayerNorm statistics of NLN row vectors whose 256 columns are spread over the 8 CTAs: per-slice (mean, M2) of the own 32
 // columns -> every CTA's table -> (after the caller's cluster barrier) merged mean / rstd.
@@ -406,16 +437,16 @@ __device__ __forceinline__ void fc_stats_send(const FcCtx &x, int xch, const flo
   }
   fc_xwait(x, xch);
 }
-__device__ __forceinline__ void fc_stats_merge(const FcCtx &x, int t, float &mean, float &rstd) {
+__device__ __forceinline__ float2 fc_stats_merge_(uint32_t stats_row /* &stats[t][0][row] */) {
   float m[FC_CL], s = 0.f, q = 0.f;
 #pragma unroll
   for (int i = 0; i < FC_CL; ++i) {
-    const float2 e = fc_lds2(x.stats + (uint32_t)((t * FC_CL + i) * FC_TM + x.row) * 8u);
+    const float2 e = fc_lds2(stats_row + (uint32_t)(i * FC_TM) * 8u);
     m[i] = e.x;
     s += e.x;
     q += e.y;
   }
-  mean = s * (1.0f / FC_CL);
+  const float mean = s * (1.0f / FC_CL);
   float dd = 0.f;
 #pragma unroll
   for (int i = 0; i < FC_CL; ++i) {
@@ -423,7 +454,12 @@ __device__ __forceinline__ void fc_stats_merge(const FcCtx &x, int t, float &mea
     dd = fmaf(d, d, dd);
   }
   q = fmaf((float)FC_SW, dd, q);
-  rstd = 1.0f / sqrtf(q * (1.0f / (FC_SW * FC_CL)) + 1e-5f);
+  return make_float2(mean, 1.0f / sqrtf(q * (1.0f / (FC_SW * FC_CL)) + 1e-5f));
+}
+__device__ __forceinline__ void fc_stats_merge(const FcCtx &x, int t, float &mean, float &rstd) {
+  const float2 r = fc_stats_merge_(x.stats + (uint32_t)(t * FC_CL * FC_TM + x.row) * 8u);
+  mean = r.x;
+  rstd = r.y;
 }
 __device__ __forceinline__ float2 fc_ln_apply(const FcCtx &x, float2 v, float mean, float rstd, int vg, int vb) {
   const float2 g = fc_vec2(x, vg, 2 * x.cp), b = fc_vec2(x, vb, 2 * x.cp);
@@ -642,6 +678,10 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     float *Ks = reinterpret_cast<float *>(fc_smem + (BUF_B - x.ring));        // [N][33]
     float *Vs = Ks + (size_t)N * 33;                                           // [N][33]
     float *Qs = reinterpret_cast<float *>(fc_smem + (S1 - x.ring));            // [16][32] (slice buffers 1-2 are idle here)
+    // probabilities [8 warps][N][2]: the rest of slice buffers 1-2, both staging buffers and the LayerNorm statistics table are
+    // contiguous and idle until this CTA's attention output has been handed on (12.4 KB: N <= 192)
+    float *Ps = Qs + FC_TM * 32;
+    static_assert(2 * FC_SL * 4 - FC_TM * 32 * 4 + 2 * FC_STAGE_B + FC_STATS_B >= (FC_NT / 32) * 2 * 192 * 4, "probability rows do not fit");
     const float *kbase = P.qkv + (size_t)frame_row0 * (3 * FC_K) + FC_K + FC_SW * (int)x.rank;
     for (int idx = x.tid; idx < N * 8; idx += FC_NT) {
       const int j = idx >> 3, d = (idx & 7) * 4;
@@ -658,77 +698,63 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     __syncthreads();
     FC_TS(4);
     // a warp carries its TWO query rows through every pass: each K / V element fetched from shared memory feeds both.
-    // Scores / probabilities never leave registers (lane l holds keys l, l + 32, ...: at most 6 for N <= 192); the PV pass
-    // fetches them by shuffle.
+    // Compact loops on purpose: this kernel is a straight-line program every warp runs once, instruction fetch is its top stall.
     const int r0 = 2 * x.warp;
     float ov0 = 0.f, ov1 = 0.f;
     if (r0 < x.nvalid) {                   // warp-uniform (a row beyond nvalid has q = 0: harmless, not stored)
+      float *ps = Ps + (size_t)x.warp * ((2 * N + 3) & ~3);    // [N][2]: scores, then probabilities, of the two rows (16-byte aligned)
       const float4 *q0 = reinterpret_cast<const float4 *>(Qs + r0 * 32), *q1 = reinterpret_cast<const float4 *>(Qs + (r0 + 1) * 32);
-      constexpr int KPLANE = 6;            // keys per lane
-      float p0[KPLANE], p1[KPLANE];
-      const float *kp[KPLANE];
-#pragma unroll
-      for (int u = 0; u < KPLANE; ++u) {
-        kp[u] = Ks + (size_t)min(x.lane + 32 * u, N - 1) * 33;
-        p0[u] = 0.f;
-        p1[u] = 0.f;
-      }
-      const int nu = (N + 31) >> 5;        // live key slots (warp-uniform)
-#pragma unroll
-      for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 a = q0[d4], b = q1[d4];
-#pragma unroll
-        for (int u = 0; u < KPLANE; ++u) {
-          if (u < nu) {
-            const float k0 = kp[u][4 * d4], k1 = kp[u][4 * d4 + 1], k2 = kp[u][4 * d4 + 2], k3 = kp[u][4 * d4 + 3];
-            p0[u] = fmaf(a.x, k0, p0[u]);  p1[u] = fmaf(b.x, k0, p1[u]);
-            p0[u] = fmaf(a.y, k1, p0[u]);  p1[u] = fmaf(b.y, k1, p1[u]);
-            p0[u] = fmaf(a.z, k2, p0[u]);  p1[u] = fmaf(b.z, k2, p1[u]);
-            p0[u] = fmaf(a.w, k3, p0[u]);  p1[u] = fmaf(b.w, k3, p1[u]);
-          }
-        }
-      }
       float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll 1
+      for (int j = x.lane; j < N; j += 32) {
+        const float *kp = Ks + (size_t)j * 33;
+        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
 #pragma unroll
-      for (int u = 0; u < KPLANE; ++u)
-        if (x.lane + 32 * u < N) {
-          mx0 = fmaxf(mx0, p0[u]);
-          mx1 = fmaxf(mx1, p1[u]);
+        for (int d4 = 0; d4 < 8; ++d4) {
+          const float4 a = q0[d4], b = q1[d4];
+          const float k0 = kp[4 * d4], k1 = kp[4 * d4 + 1], k2 = kp[4 * d4 + 2], k3 = kp[4 * d4 + 3];
+          s0 = fmaf(a.x, k0, s0);  s1 = fmaf(b.x, k0, s1);
+          t0 = fmaf(a.y, k1, t0);  t1 = fmaf(b.y, k1, t1);
+          s0 = fmaf(a.z, k2, s0);  s1 = fmaf(b.z, k2, s1);
+          t0 = fmaf(a.w, k3, t0);  t1 = fmaf(b.w, k3, t1);
         }
+        s0 += t0;
+        s1 += t1;
+        *reinterpret_cast<float2 *>(ps + 2 * j) = make_float2(s0, s1);
+        mx0 = fmaxf(mx0, s0);
+        mx1 = fmaxf(mx1, s1);
+      }
       mx0 = warp_max(mx0);
       mx1 = warp_max(mx1);
       float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-      for (int u = 0; u < KPLANE; ++u) {
-        const bool in = x.lane + 32 * u < N;
-        p0[u] = in ? expf(p0[u] - mx0) : 0.f;
-        p1[u] = in ? expf(p1[u] - mx1) : 0.f;
-        sum0 += p0[u];
-        sum1 += p1[u];
+#pragma unroll 1
+      for (int j = x.lane; j < N; j += 32) {
+        float2 e = *reinterpret_cast<float2 *>(ps + 2 * j);
+        e.x = expf(e.x - mx0);
+        e.y = expf(e.y - mx1);
+        *reinterpret_cast<float2 *>(ps + 2 * j) = e;
+        sum0 += e.x;
+        sum1 += e.y;
       }
       sum0 = warp_sum(sum0);
       sum1 = warp_sum(sum1);
+      __syncwarp();
       float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-      for (int u = 0; u < KPLANE; ++u) {
-        if (u < nu) {
-          const int jn = min(32, N - 32 * u);         // keys of this slot (warp-uniform)
-          const float *vp = Vs + (size_t)(32 * u) * 33 + x.lane;
-          int l = 0;
-#pragma unroll 4
-          for (; l + 2 <= jn; l += 2) {
-            const float v0 = vp[l * 33], v1 = vp[(l + 1) * 33];
-            a0 = fmaf(__shfl_sync(0xffffffffu, p0[u], l), v0, a0);
-            b0 = fmaf(__shfl_sync(0xffffffffu, p1[u], l), v0, b0);
-            a1 = fmaf(__shfl_sync(0xffffffffu, p0[u], l + 1), v1, a1);
-            b1 = fmaf(__shfl_sync(0xffffffffu, p1[u], l + 1), v1, b1);
-          }
-          if (l < jn) {
-            const float v0 = vp[l * 33];
-            a0 = fmaf(__shfl_sync(0xffffffffu, p0[u], l), v0, a0);
-            b0 = fmaf(__shfl_sync(0xffffffffu, p1[u], l), v0, b0);
-          }
-        }
+      int j = 0;
+#pragma unroll 2
+      for (; j + 2 <= N; j += 2) {
+        const float4 pp = *reinterpret_cast<const float4 *>(ps + 2 * j);      // (p0[j], p1[j], p0[j+1], p1[j+1])
+        const float v0 = Vs[j * 33 + x.lane], v1 = Vs[(j + 1) * 33 + x.lane];
+        a0 = fmaf(pp.x, v0, a0);
+        b0 = fmaf(pp.y, v0, b0);
+        a1 = fmaf(pp.z, v1, a1);
+        b1 = fmaf(pp.w, v1, b1);
+      }
+      if (j < N) {
+        const float2 pp = *reinterpret_cast<const float2 *>(ps + 2 * j);
+        const float v0 = Vs[j * 33 + x.lane];
+        a0 = fmaf(pp.x, v0, a0);
+        b0 = fmaf(pp.y, v0, b0);
       }
       ov0 = (a0 + a1) / sum0;
       ov1 = (b0 + b1) / sum1;
@@ -1095,7 +1121,7 @@ static bool fc_weights_supported(const VknShape &s, const VknHeadW &w) {
 bool frame_chain_supported(const VknShape &s, const VknHeadW &w) {
   if (const char *e = getenv("VKN_FRAME_CHAIN"))
     if (e[0] == '0') return false;
-  if (!fc_weights_supported(s, w) || s.frames_per_set > 1) return false;
+  if (!fc_weights_supported(s, w)) return false;      // frames_per_set > 1 (clip head) only changes pooling / mask conv: rows are kernel sets
   // K / V of one head must fit the two A buffers they overlay, a lane holds at most 6 keys' probabilities
   if ((size_t)(2 * s.N * 33) * 4 > (size_t)2 * FC_ABUF || s.N > 192) return false;
   return true;
