@@ -1021,6 +1021,14 @@ def test_frame_chain_cluster_kernels(dev, monkeypatch, B, N, H, W, S, ncls):
     # determinism (fixed-order reductions through distributed shared memory)
     cls_2, m_2, obj_2 = vknet.KernelIterLoop(heads)(xb, pfd, mb)
     assert torch.equal(m_l, m_2) and torch.equal(obj_l, obj_2) and torch.equal(cls_l, cls_2)
+    # a C-ABI caller that does not provide the pre-laid weight image (VknHeadW.fc_pack = NULL): the ring is fed row by row,
+    # same bits
+    for h in heads:
+        h.packed_weights(dev)[0].fc_pack = None
+    cls_3, m_3, obj_3 = vknet.KernelIterLoop(heads)(xb, pfd, mb)
+    assert torch.equal(m_l, m_3) and torch.equal(obj_l, obj_3) and torch.equal(cls_l, cls_3)
+    for h in heads:
+        h.invalidate_weight_cache()
 
 
 def test_frame_chain_video_head_and_clip_head_without_cls(dev):

@@ -15,13 +15,13 @@ import bench  # noqa: E402
 import vknet  # noqa: E402
 from vknet import _lib  # noqa: E402
 
-NAMES_A = {0: 'entry', 1: 'ring+vec issued', 2: 'cluster sync 0', 3: 'dependency ok', 4: 'planes built', 5: 'gemm1 (x_feat, input_layer)',
-           6: 'x_feat handed', 7: 'gemm2 (dynamic_layer)', 8: 'gate_feats handed', 9: 'gemm3 (gates)', 10: 'LN stats', 11: 'features handed',
+NAMES_A = {0: 'entry', 1: 'ring+vec issued', 2: 'cluster sync 0', 3: 'dependency ok', 4: 'planes built', 5: 'x_feat GEMM, hand-off issued',
+           6: 'input_layer GEMM, x_feat in', 7: 'gemm2 (dynamic_layer)', 8: 'gate_feats handed', 9: 'gemm3 (gates)', 10: 'LN stats', 11: 'features handed',
            12: 'gemm4 (fc_layer)', 13: 'LN stats', 14: 'obj0 handed', 30: 'end (in_proj stored)'}
 NAMES_B = {0: 'entry', 1: 'ring+vec issued', 2: 'cluster sync 0', 3: 'dependency ok', 4: 'k/v loaded', 5: 'attention', 6: 'att handed',
            7: 'gemm out_proj', 8: 'LN stats', 9: 'o1 handed', 10: 'ffn1 a', 11: 'ffn1 b', 12: 'ffn2 a', 13: 'ffn2 b', 14: 'partials scattered',
-           15: 'LN stats', 16: 'obj handed', 17: 'gemm cls/mask fc', 18: 'LN stats', 19: 'planes handed', 20: 'gemm fc_mask/fc_cls',
-           21: 'mk handed', 30: 'end (fold stored)'}
+           15: 'LN stats', 16: 'obj handed', 17: 'gemm cls/mask fc', 18: 'LN stats', 19: 'planes handed', 20: 'fc_mask GEMM, hand-off issued',
+           21: 'fc_cls GEMM, mk in', 30: 'end (fold stored)'}
 
 
 def main():

@@ -550,20 +550,23 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_a_kernel(const __gri
   fc_rows_to_planes(x, P.pf, FC_K, x.buf[2]);
   __syncthreads();
   FC_TS(4);
-  fc_gemm(x, c, 0, 3, [&](int kc) { return kc == 0 ? x.buf[0] : x.buf[2]; },
-          [&](int kc, int j, const float (&d)[4]) { fc_frag_to_slice(kc == 0 ? S_XF : (kc == 1 ? S_II : S_IO), j, x.lane, d); });
-  __syncthreads();
-  FC_TS(5);
-  fc_ring_fill(x, c, 3);
+  // x_feat first: its hand-off travels while input_layer (which does not need it) is multiplied
   if (!have_xf) {
+    fc_gemm(x, c, 0, 1, [&](int) { return x.buf[0]; }, [&](int, int j, const float (&d)[4]) { fc_frag_to_slice(S_XF, j, x.lane, d); });
+    __syncthreads();
     float2 v = fc_slice2(x, S_XF);
     const float2 b = fc_vec2(x, AV_FT_B, 2 * x.cp);
     v.x = fmaf(cnt, b.x, v.x);
     v.y = fmaf(cnt, b.y, v.y);
     if (P.x_feat_out != nullptr && live) *reinterpret_cast<float2 *>(P.x_feat_out + grow * FC_K + gcol) = v;
     fc_bcast_planes(x, 0, x.buf[1], XA_XF, v.x, v.y);
-    fc_xwait(x, XA_XF);
   }
+  FC_TS(5);
+  fc_gemm(x, c, 1, 2, [&](int) { return x.buf[2]; },
+          [&](int kc, int j, const float (&d)[4]) { fc_frag_to_slice(kc == 1 ? S_II : S_IO, j, x.lane, d); });
+  __syncthreads();
+  fc_ring_fill(x, c, 3);
+  if (!have_xf) fc_xwait(x, XA_XF);
   FC_TS(6);
 
   // ---- phase 2: dynamic_layer (A = x_feat) -> param_in, param_out;  gate_feats = input_in * param_in
@@ -879,11 +882,16 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
   FC_TS(19);
 
   // ---- phase 5: fc_mask (A = mask branch) -> mask kernels; fc_cls (A = cls branch) -> global
-  fc_gemm(x, c, 19, 2, [&](int kc) { return kc == 19 ? BUF_H : BUF_A; }, [&](int kc, int j, const float (&d)[4]) {
-    if (kc == 19) {
-      fc_frag_to_slice(S0, j, x.lane, d);
-      return;
-    }
+  // fc_mask first: the hand-off of the mask kernels travels while fc_cls is multiplied
+  fc_gemm(x, c, 19, 1, [&](int) { return BUF_H; }, [&](int, int j, const float (&d)[4]) { fc_frag_to_slice(S0, j, x.lane, d); });
+  __syncthreads();
+  {
+    const float2 m = fc_slice2(x, S0), b = fc_vec2(x, BV_FCM_B, 2 * x.cp);
+    fc_bcast_planes(x, 0, BUF_B, XB_MK, m.x + b.x, m.y + b.y);
+    fc_cluster_arrive();            // last remote store of this CTA issued
+  }
+  FC_TS(20);
+  fc_gemm(x, c, 20, 1, [&](int) { return BUF_A; }, [&](int, int j, const float (&d)[4]) {
     const int g = x.lane >> 2, cc = j * 8 + 2 * (x.lane & 3), col = FC_SW * (int)x.rank + cc;
     const float2 b = fc_vec2(x, BV_FCC_B, cc);
     float *dst = P.cls_out + (size_t)x.row0 * P.ncls + col;
@@ -897,14 +905,8 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     }
   });
   __syncthreads();
-  FC_TS(20);
   fc_ring_fill(x, c, 21);
-  {
-    const float2 m = fc_slice2(x, S0), b = fc_vec2(x, BV_FCM_B, 2 * x.cp);
-    fc_bcast_planes(x, 0, BUF_B, XB_MK, m.x + b.x, m.y + b.y);
-    fc_cluster_arrive();            // last remote store of this CTA issued
-    fc_xwait(x, XB_MK);
-  }
+  fc_xwait(x, XB_MK);
   FC_TS(21);
 
   // ---- phase 6: fold  a = mk . ft_w (+ the bias column mk . ft_b on CTA 0) -> a_ext rows and the mask conv's bf16 planes
