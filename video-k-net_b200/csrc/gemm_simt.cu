@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
   const int idx = blockIdx.x * 128 + lane * 4;
   const int nsl = nchunks * F;
   pdl_wait();
+  pdl_trigger();      // the consumer's prologue (weight ring of the cluster chain, ~3 us) overlaps this kernel; it waits for our
+                      // completion at its own dependency wait
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   auto slice = [&](int sl) -> size_t {       // slice (chunk, f) of set b -> frame-slice index in the partials
     if (F == 1) return (size_t)sl * B + b;
@@ -143,6 +145,13 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
 #pragma unroll
     for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     int sl = warp;
+    for (; sl + 56 < nsl; sl += 64) {        // eight independent 16-byte loads in flight per thread, same association order
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(reinterpret_cast<const float4 *>(partials + slice(sl + 8 * u) * NC + idx));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a[u & 3].x += t[u].x; a[u & 3].y += t[u].y; a[u & 3].z += t[u].z; a[u & 3].w += t[u].w; }
+    }
     for (; sl + 24 < nsl; sl += 32) {
       float4 t[4];
 #pragma unroll
@@ -159,7 +168,6 @@ __global__ void __launch_bounds__(256) vkn_pool_reduce_kernel(const float *__res
   }
   red[warp][lane] = acc;
   __syncthreads();
-  pdl_trigger();
   if (warp == 0 && idx < NC) {
     float4 t = red[0][lane];
 #pragma unroll
