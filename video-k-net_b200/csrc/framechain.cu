@@ -12,8 +12,11 @@
 //   * the row transforms between the Linears (LayerNorm, the KernelUpdator gate, ReLU, residuals) run once per element on
 //     the slice owner; LayerNorm statistics are merged across the 8 slices (Chan's formula on per-slice mean / M2) through
 //     distributed shared memory;
-//   * the owner broadcasts its transformed slice as bf16 planes into the A-operand buffer of all 8 CTAs (st.shared::cluster),
-//     one cluster barrier per hand-off: activations never touch global memory between two Linears;
+//   * the owner hands its transformed slice, as bf16 planes, to the A-operand buffer of all 8 CTAs: the buffer is K-blocked (one
+//     XOR-swizzled 3 KB block per 32-column slice), so a hand-off is ONE bulk copy shared -> distributed shared memory per
+//     destination, reporting its bytes to a single-use mbarrier of the receiver -- no cluster-wide barrier, no per-thread remote
+//     stores (those were 1.5-2.0 us per hand-off, the bulk copies 0.8-1.3 us); activations never touch global memory between two
+//     Linears;
 //   * the 8 heads of the attention map onto the 8 CTAs (head r = columns [32 r, 32 r + 32) of q / k / v / the attention
 //     output), the FFN's hidden columns too: CTA r keeps its 256 hidden channels local (they are the K slice of its partial
 //     second Linear) and the partial outputs are reduce-scattered to the column owners in a fixed order (deterministic).
@@ -36,8 +39,15 @@ constexpr int FC_TM = 16;                       // rows per tile (one m16 MMA ti
 constexpr int FC_SW = 32;                       // columns per slice
 constexpr int FC_K = 256;                       // K of every GEMM step (= C; the FFN's second Linear: a 256-wide K slice per CTA)
 constexpr int FC_LD = FC_K + 8;                 // bf16 row stride of planes and weight chunks (528 B: conflict-free ldmatrix)
-constexpr int FC_PLANE = FC_TM * FC_LD;         // bf16 elements of one plane of a row tile
-constexpr int FC_ABUF = 3 * FC_PLANE * 2;       // bytes of an A-operand buffer (hi / mid / lo)
+// A-operand buffer: K-BLOCKED, one 3072-byte block per 32-column slice = [plane 3][row 16][32 bf16], the four 16-byte pieces of a
+// 64-byte row XOR-swizzled with (row >> 1) & 3 (conflict-free ldmatrix without padding).  A block is exactly what one CTA of the
+// cluster hands to the others: ONE bulk copy (shared -> distributed shared memory) per destination.
+constexpr int FC_BLK = 3 * FC_TM * FC_SW * 2;   // bytes of a slice block
+constexpr int FC_ABUF = FC_CL * FC_BLK;         // bytes of an A-operand buffer (K = 256)
+__device__ __forceinline__ uint32_t fc_a_off(int pl, int row, int k) {       // byte offset of element (plane, row, k), k even-aligned use
+  return (uint32_t)((k >> 5) * FC_BLK + pl * (FC_TM * FC_SW * 2) + row * (FC_SW * 2) + ((((k & 31) >> 3) ^ ((row >> 1) & 3)) << 4) +
+                    (k & 7) * 2);
+}
 constexpr int FC_CHUNK_B = 32 * FC_LD * 2;      // bytes of a weight chunk (32 rows x K)
 constexpr int FC_MAXSLOT = 8;
 constexpr int FC_MAXCHUNK = 24;
@@ -93,11 +103,11 @@ static_assert(AV_COUNT <= FC_MAXVEC && BV_COUNT <= FC_MAXVEC, "vector table too 
 // ---- shared-memory maps (bytes) ----------------------------------------------------------------------------------------
 // both kernels: [ring | buf0 | buf1 | buf2 | slices | staging x2 | LN stats | vectors | mbarriers]
 constexpr int FC_NSL_A = 5, FC_NSL_B = 3;
-constexpr int FC_STAGE_B = 3 * FC_TM * FC_SW * 2;                  // planes of one slice [3][16][32] bf16
+constexpr int FC_STAGE_B = FC_BLK;                                 // staging of one slice block (three of them: see fc_bcast_planes)
 constexpr int FC_STATS_B = 4 * FC_CL * FC_TM * 8;                  // [4 LNs][8 ranks][16 rows] float2
 constexpr int FC_VEC_B = FC_MAXVEC * 32 * 4;
 constexpr size_t fc_smem_bytes(int nslot, int nslices) {
-  return (size_t)nslot * FC_CHUNK_B + 3 * FC_ABUF + (size_t)nslices * FC_SL * 4 + 2 * FC_STAGE_B + FC_STATS_B + FC_VEC_B + 8 * (FC_MAXSLOT + FC_MAXXCH);
+  return (size_t)nslot * FC_CHUNK_B + 3 * FC_ABUF + (size_t)nslices * FC_SL * 4 + 3 * FC_STAGE_B + FC_STATS_B + FC_VEC_B + 8 * (FC_MAXSLOT + FC_MAXXCH);
 }
 constexpr int FC_NSLOT_A = 7, FC_NSLOT_B = 8;
 static_assert(fc_smem_bytes(FC_NSLOT_A, FC_NSL_A) <= 232448 && fc_smem_bytes(FC_NSLOT_B, FC_NSL_B) <= 232448, "over the 227 KB limit");
@@ -191,7 +201,7 @@ struct FcCtx {
   int tid, warp, lane;
   int row, cp;             // transform mapping: thread -> (row = tid / 16, column pair cp = tid % 16) of the CTA's [16 x 32] slice
   uint32_t rank;
-  uint32_t ring, buf[3], sl, stage[2], stats, vecs, bars, xbar;    // shared-memory addresses
+  uint32_t ring, buf[3], sl, stage[3], stats, vecs, bars, xbar;    // shared-memory addresses
   int nslot, nchunks, issued;
   int row0, nvalid;        // first global row of the tile, valid rows in it
 };
@@ -212,6 +222,7 @@ __device__ __forceinline__ void fc_setup(FcCtx &x, const FcCommon &c, uint8_t *s
   x.sl = a;                   a += (uint32_t)nslices * FC_SL * 4;
   x.stage[0] = a;             a += FC_STAGE_B;
   x.stage[1] = a;             a += FC_STAGE_B;
+  x.stage[2] = a;             a += FC_STAGE_B;
   x.stats = a;                a += FC_STATS_B;
   x.vecs = a;                 a += FC_VEC_B;
   x.bars = a;                 a += 8 * FC_MAXSLOT;
@@ -282,7 +293,10 @@ __device__ __noinline__ FcFrag fc_mma_tile(uint32_t a_buf, uint32_t w_rows, int 
   for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[pl][e] = 0.f;
-  const uint32_t a_addr = a_buf + (uint32_t)((lane & 15) * FC_LD + (lane >> 4) * 8) * 2u;
+  // lane's ldmatrix row address inside a slice block, for the two 16-wide k-steps of a 32-column block
+  const int arow = lane & 15, aswz = (arow >> 1) & 3;
+  const uint32_t a_row = a_buf + (uint32_t)(arow * (FC_SW * 2));
+  const uint32_t a_h0 = a_row + (uint32_t)((((lane >> 4)) ^ aswz) << 4), a_h1 = a_row + (uint32_t)(((2 + (lane >> 4)) ^ aswz) << 4);
   const uint32_t b_addr = w_rows + (uint32_t)((lane & 7) * FC_LD + (lane >> 3) * 8) * 2u;
 #pragma unroll 2
   for (int k0 = 0; k0 < FC_K; k0 += 32) {
@@ -293,7 +307,7 @@ __device__ __noinline__ FcFrag fc_mma_tile(uint32_t a_buf, uint32_t w_rows, int 
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl) {
         uint32_t a[4];
-        fc_ldsm_x4(a, a_addr + (uint32_t)(pl * FC_PLANE + k0 + 16 * h) * 2u);
+        fc_ldsm_x4(a, (h ? a_h1 : a_h0) + (uint32_t)((k0 >> 5) * FC_BLK + pl * (FC_TM * FC_SW * 2)));
         fc_mma(acc[pl], a, b[2 * h], b[2 * h + 1]);
       }
   }
@@ -313,7 +327,10 @@ __device__ __noinline__ FcFrag2 fc_mma_tile2(uint32_t a_buf, uint32_t w_rows0, u
     for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[t][pl][e] = 0.f;
-  const uint32_t a_addr = a_buf + (uint32_t)((lane & 15) * FC_LD + (lane >> 4) * 8) * 2u;
+  // lane's ldmatrix row address inside a slice block, for the two 16-wide k-steps of a 32-column block
+  const int arow = lane & 15, aswz = (arow >> 1) & 3;
+  const uint32_t a_row = a_buf + (uint32_t)(arow * (FC_SW * 2));
+  const uint32_t a_h0 = a_row + (uint32_t)((((lane >> 4)) ^ aswz) << 4), a_h1 = a_row + (uint32_t)(((2 + (lane >> 4)) ^ aswz) << 4);
   const uint32_t b_off = (uint32_t)((lane & 7) * FC_LD + (lane >> 3) * 8) * 2u;
 #pragma unroll 2
   for (int k0 = 0; k0 < FC_K; k0 += 32) {
@@ -325,7 +342,7 @@ __device__ __noinline__ FcFrag2 fc_mma_tile2(uint32_t a_buf, uint32_t w_rows0, u
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl) {
         uint32_t a[4];
-        fc_ldsm_x4(a, a_addr + (uint32_t)(pl * FC_PLANE + k0 + 16 * h) * 2u);
+        fc_ldsm_x4(a, (h ? a_h1 : a_h0) + (uint32_t)((k0 >> 5) * FC_BLK + pl * (FC_TM * FC_SW * 2)));
         fc_mma(acc[0][pl], a, b0[2 * h], b0[2 * h + 1]);
         fc_mma(acc[1][pl], a, b1[2 * h], b1[2 * h + 1]);
       }
@@ -382,27 +399,30 @@ __device__ __forceinline__ void fc_slice2_store(const FcCtx &x, uint32_t sl, flo
   fc_sts(sl + (uint32_t)(x.row * 33 + 2 * x.cp + 1) * 4u, b);
 }
 
-// staged slice planes -> CTA `to` (one warp per destination); every 16-byte store reports to the destination's barrier
-__device__ __forceinline__ void fc_bcast_send(uint32_t st, uint32_t dst_col0, uint32_t bar_local, uint32_t to, int lane) {
+// staged slice block -> the same block of the A buffer of CTA `to` (one warp, one lane, per destination): a single bulk copy
+// shared::cta -> shared::cluster that reports its 3072 bytes to the destination's barrier
+__device__ __forceinline__ void fc_bulk_s2d(uint32_t dst_remote, uint32_t src, uint32_t bytes, uint32_t bar_remote) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_remote),
+               "r"(src), "r"(bytes), "r"(bar_remote)
+               : "memory");
+}
+__device__ __forceinline__ void fc_bcast_send(uint32_t st, uint32_t dst_block, uint32_t bar_local, uint32_t to, int lane) {
+  fence_proxy_async();            // the staging writes (generic proxy) are read by the copy engine (async proxy)
   __syncthreads();
-  const uint32_t bar = fc_mapa(bar_local, to);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int p = lane + 32 * i;
-    const int pl = p >> 6, r = (p >> 2) & 15, q = p & 3;
-    const uint4 v = lds_u4(st + (uint32_t)((pl * FC_TM + r) * 16 + q * 4) * 4u);
-    const uint32_t d = dst_col0 + (uint32_t)(pl * FC_PLANE + r * FC_LD + 8 * q) * 2u;
-    fc_st_remote_v4(fc_mapa(d, to), v, bar);
-  }
+  if (lane == 0) fc_bulk_s2d(fc_mapa(dst_block, to), st, FC_BLK, fc_mapa(bar_local, to));
 }
 // the owner's transformed slice -> bf16 planes in the A buffer `dst` of ALL 8 CTAs (warp w serves CTA w)
+// Staging buffers: a buffer may be rewritten only when every destination has received the block last sent from it.  With the
+// assignment used by the kernels (A: 0 1 0 1; B: 0 1 0 1 2 0) a CTA has, between two uses of a buffer, waited for data that each
+// peer sent only after receiving that earlier block.
 __device__ __forceinline__ void fc_bcast_planes(const FcCtx &x, int stg, uint32_t dst, int xch, float v0, float v1) {
   uint32_t w3[3];
   split3_pair(v0, v1, w3[0], w3[1], w3[2]);
   const uint32_t st = x.stage[stg];
+  const uint32_t o = (uint32_t)(x.row * (FC_SW * 2) + ((((x.cp >> 2)) ^ ((x.row >> 1) & 3)) << 4) + (x.cp & 3) * 4);
 #pragma unroll
-  for (int pl = 0; pl < 3; ++pl) sts_u32(st + (uint32_t)((pl * FC_TM + x.row) * 16 + x.cp) * 4u, w3[pl]);
-  fc_bcast_send(st, dst + (uint32_t)(FC_SW * (int)x.rank) * 2u, x.xbar + 8u * (uint32_t)xch, (uint32_t)x.warp, x.lane);
+  for (int pl = 0; pl < 3; ++pl) sts_u32(st + (uint32_t)(pl * (FC_TM * FC_SW * 2)) + o, w3[pl]);
+  fc_bcast_send(st, dst + (uint32_t)((int)x.rank * FC_BLK), x.xbar + 8u * (uint32_t)xch, (uint32_t)x.warp, x.lane);
 }
 __device__ __forceinline__ void fc_xwait(const FcCtx &x, int xch) { fc_mbar_wait(x.xbar + 8u * (uint32_t)xch, 0u); }
 
@@ -485,7 +505,7 @@ __device__ __forceinline__ void fc_rows_to_planes(const FcCtx &x, const float *s
       uint32_t w3[3];
       split3_pair(t[q][p].x, t[q][p].y, w3[0], w3[1], w3[2]);
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) sts_u32(dst + (uint32_t)(pl * FC_PLANE + r * FC_LD + 64 * p + 2 * x.lane) * 2u, w3[pl]);
+      for (int pl = 0; pl < 3; ++pl) sts_u32(dst + fc_a_off(pl, r, 64 * p + 2 * x.lane), w3[pl]);
     }
   }
 }
@@ -578,7 +598,7 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_a_kernel(const __gri
   {
     const float2 a = fc_slice2(x, S_II), b = fc_slice2(x, S_PI);
     const float2 ba = fc_vec2(x, AV_INP_B0, 2 * x.cp), bb = fc_vec2(x, AV_DYN_B0, 2 * x.cp);
-    fc_bcast_planes(x, 0, x.buf[0], XA_GF, (a.x + ba.x) * (b.x + bb.x), (a.y + ba.y) * (b.y + bb.y));      // kernel_updator.py:70
+    fc_bcast_planes(x, 1, x.buf[0], XA_GF, (a.x + ba.x) * (b.x + bb.x), (a.y + ba.y) * (b.y + bb.y));      // kernel_updator.py:70
     fc_xwait(x, XA_GF);
   }
   FC_TS(8);
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_a_kernel(const __gri
     o.x = fmaxf(o.x, 0.f);
     o.y = fmaxf(o.y, 0.f);
     if (live) *reinterpret_cast<float2 *>(P.obj0 + grow * FC_K + gcol) = o;
-    fc_bcast_planes(x, 0, x.buf[0], XA_OBJ, o.x, o.y);
+    fc_bcast_planes(x, 1, x.buf[0], XA_OBJ, o.x, o.y);
     fc_cluster_arrive();            // last remote store of this CTA issued
     fc_xwait(x, XA_OBJ);
   }
@@ -684,7 +704,7 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     // probabilities [8 warps][N][2]: the rest of slice buffers 1-2, both staging buffers and the LayerNorm statistics table are
     // contiguous and idle until this CTA's attention output has been handed on (12.4 KB: N <= 192)
     float *Ps = Qs + FC_TM * 32;
-    static_assert(2 * FC_SL * 4 - FC_TM * 32 * 4 + 2 * FC_STAGE_B + FC_STATS_B >= (FC_NT / 32) * 2 * 192 * 4, "probability rows do not fit");
+    static_assert(2 * FC_SL * 4 - FC_TM * 32 * 4 + 3 * FC_STAGE_B + FC_STATS_B >= (FC_NT / 32) * 2 * 192 * 4, "probability rows do not fit");
     const float *kbase = P.qkv + (size_t)frame_row0 * (3 * FC_K) + FC_K + FC_SW * (int)x.rank;
     for (int idx = x.tid; idx < N * 8; idx += FC_NT) {
       const int j = idx >> 3, d = (idx & 7) * 4;
@@ -789,7 +809,7 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     float mean, rstd;
     fc_stats_merge(x, 0, mean, rstd);
     o1 = fc_ln_apply(x, v[0], mean, rstd, BV_AN_G, BV_AN_B);
-    fc_bcast_planes(x, 0, BUF_B, XB_O1, o1.x, o1.y);
+    fc_bcast_planes(x, 1, BUF_B, XB_O1, o1.x, o1.y);
     fc_xwait(x, XB_O1);
   }
   FC_TS(9);
@@ -801,10 +821,10 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     uint32_t w3[3];
     split3_pair(fmaxf(d[0] + b.x, 0.f), fmaxf(d[1] + b.y, 0.f), w3[0], w3[1], w3[2]);
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) sts_u32(BUF_H + (uint32_t)(pl * FC_PLANE + g * FC_LD + 32 * i + cc) * 2u, w3[pl]);
+    for (int pl = 0; pl < 3; ++pl) sts_u32(BUF_H + fc_a_off(pl, g, 32 * i + cc), w3[pl]);
     split3_pair(fmaxf(d[2] + b.x, 0.f), fmaxf(d[3] + b.y, 0.f), w3[0], w3[1], w3[2]);
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) sts_u32(BUF_H + (uint32_t)(pl * FC_PLANE + (g + 8) * FC_LD + 32 * i + cc) * 2u, w3[pl]);
+    for (int pl = 0; pl < 3; ++pl) sts_u32(BUF_H + fc_a_off(pl, g + 8, 32 * i + cc), w3[pl]);
   };
   fc_gemm2(x, c, 1, BUF_B, ffn1_epi);
   __syncthreads();
@@ -874,8 +894,8 @@ __global__ void __launch_bounds__(FC_NT, 1) vkn_frame_chain_b_kernel(const __gri
     float2 cf = fc_ln_apply(x, v[0], mean, rstd, BV_CLN_G, BV_CLN_B);
     fc_stats_merge(x, 1, mean, rstd);
     float2 mf = fc_ln_apply(x, v[1], mean, rstd, BV_MLN_G, BV_MLN_B);
-    if (with_cls) fc_bcast_planes(x, 0, BUF_A, XB_CLS, fmaxf(cf.x, 0.f), fmaxf(cf.y, 0.f));
-    fc_bcast_planes(x, 1, BUF_H, XB_MASK, fmaxf(mf.x, 0.f), fmaxf(mf.y, 0.f));
+    if (with_cls) fc_bcast_planes(x, 1, BUF_A, XB_CLS, fmaxf(cf.x, 0.f), fmaxf(cf.y, 0.f));
+    fc_bcast_planes(x, 2, BUF_H, XB_MASK, fmaxf(mf.x, 0.f), fmaxf(mf.y, 0.f));
     if (with_cls) fc_xwait(x, XB_CLS);
     fc_xwait(x, XB_MASK);
   }
