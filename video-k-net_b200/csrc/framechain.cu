@@ -130,11 +130,6 @@ __device__ __forceinline__ uint32_t fc_mapa(uint32_t addr, uint32_t rank) {
 }
 // remote stores that report their bytes to an mbarrier of the DESTINATION CTA: the receiver waits for "all bytes of this
 // exchange have landed" on its own barrier -- no cluster-wide barrier per hand-off
-__device__ __forceinline__ void fc_st_remote_v4(uint32_t addr, const uint4 &v, uint32_t bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
-               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ void fc_st_remote_f2(uint32_t addr, float a, float b, uint32_t bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr),
                "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(bar)
@@ -427,7 +422,7 @@ __device__ __forceinline__ void fc_bcast_planes(const FcCtx &x, int stg, uint32_
 __device__ __forceinline__ void fc_xwait(const FcCtx &x, int xch) { fc_mbar_wait(x.xbar + 8u * (uint32_t)xch, 0u); }
 
 // LayerNorm statistics of NLN row vectors whose 256 columns are spread over the 8 CTAs: per-slice (mean, M2) of the own 32
-// columns -> every CTA's table -> (after the caller's cluster barrier) merged mean / rstd.
+// columns -> every CTA's table (st.async, completion on the receiver's barrier `xch`) -> merged mean / rstd.
 template <int NLN>
 __device__ __forceinline__ void fc_stats_send(const FcCtx &x, int xch, const float2 (&v)[NLN]) {
   float m[NLN], q[NLN];
