@@ -862,6 +862,16 @@ def test_mask_boxes_kernel(dev):
     assert torch.equal(ops.mask_boxes(m.float().to(dev) * 0.25).cpu(), want)
     assert torch.equal(ops.mask_boxes(m.to(torch.uint8).to(dev)).cpu(), want)
     assert want[3].tolist() == [-1.0, -1.0, 10.0, 10.0] and want[11].tolist() == [159.0, 89.0, 159.0, 89.0]
+    # odd sizes: every mask starts at a different alignment (H*W = 7 * 13), head / tail elements, groups spanning rows
+    m2 = torch.rand(23, 7, 13, generator=g) > 0.8
+    m2[5] = False
+    m2[5, 0, 0] = True
+    m2[6] = False
+    m2[6, 6, 12] = True
+    want2 = vknet.VideoKernelUpdateHead.mask_boxes_torch(m2)
+    assert torch.equal(ops.mask_boxes(m2.to(dev)).cpu(), want2) and torch.equal(ops.mask_boxes(m2.float().to(dev)).cpu(), want2)
+    m3 = torch.rand(5, 375, 1242, generator=g) > 0.999                 # KITTI size, row length not a multiple of 16
+    assert torch.equal(ops.mask_boxes(m3.to(dev)).cpu(), vknet.VideoKernelUpdateHead.mask_boxes_torch(m3))
     head = vknet.build_head(dict(type='VideoKernelUpdateHead', **ko.default_cfg(num_classes=4, in_channels=64, feedforward_channels=64,
                                                                                  previous='p', previous_type='ffn')))
     labels, scores = torch.randint(0, 4, (37,), generator=g), torch.rand(37, generator=g)
