@@ -57,6 +57,32 @@ def test_workspace_and_shape_validation(built_lib):
     assert b'C = 100' in L.lib().vkn_last_error() or True
 
 
+def test_frame_chain_pack_size_and_match_cost_workspace_queries(built_lib):
+    """The two size queries of the round-2 entry points need no device: the single-frame row engine applies to the shipped head
+    shape only (fc_pack = 34 chunk images per cluster rank), and the match-cost workspace grows with N x M."""
+    import vknet
+    L = vknet._lib
+    lib = L.lib()
+    w = L.VknHeadW()
+    w.num_cls_fcs, w.num_mask_fcs = 1, 1
+    w.fc_cls_w = 1                                                     # any non-null pointer: only its presence is inspected
+    n = ctypes.c_size_t(123)
+    s = L.make_shape(1, 100, 256, 8, 8, 2048, 19, 8, L.VKN_BF16, L.VKN_BF16)
+    assert lib.vkn_frame_chain_pack_bytes(ctypes.byref(s), ctypes.byref(w), ctypes.byref(n)) == 0
+    assert n.value == 8 * (11 + 23) * 32 * 264 * 2
+    for kw in (dict(Cc=64, ffn_dim=2048), dict(Cc=256, ffn_dim=512), dict(Cc=256, ffn_dim=2048, w_dtype=L.VKN_F32)):
+        args = dict(B=1, N=100, Cc=256, H=8, W=8, ffn_dim=2048, num_classes=19, num_heads=8, x_dtype=L.VKN_BF16, w_dtype=L.VKN_BF16)
+        args.update(kw)
+        assert lib.vkn_frame_chain_pack_bytes(ctypes.byref(L.make_shape(**args)), ctypes.byref(w), ctypes.byref(n)) == 0 and n.value == 0
+    w.num_mask_fcs = 2
+    assert lib.vkn_frame_chain_pack_bytes(ctypes.byref(s), ctypes.byref(w), ctypes.byref(n)) == 0 and n.value == 0
+    assert lib.vkn_frame_chain_pack(ctypes.byref(s), ctypes.byref(w), None, 0, None) != 0      # refused before any launch
+    a, b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert lib.vkn_match_cost_workspace_bytes(100, 30, 200 * 304, ctypes.byref(a)) == 0
+    assert lib.vkn_match_cost_workspace_bytes(100, 60, 200 * 304, ctypes.byref(b)) == 0 and b.value > a.value > 100 * 30 * 8
+    assert lib.vkn_match_cost_workspace_bytes(0, 30, 10, ctypes.byref(a)) != 0
+
+
 def test_struct_sizes_match_header_layout(built_lib):
     import vknet
     L = vknet._lib
