@@ -25,20 +25,29 @@ __global__ void __launch_bounds__(PM_NT) vkn_panoptic_owner_kernel(const float *
   for (int i = threadIdx.x; i < 2 * T; i += PM_NT) sm_cnt[i] = 0;
   __syncthreads();
   const int p = blockIdx.x * PM_NT + threadIdx.x;
-  if (p < HW) {
-    float best = 0.f;
-    int bk = 0;
-    for (int k = 0; k < T; ++k) {
-      const float m = __ldg(masks + (size_t)k * HW + p);
-      const float v = __fmul_rn(__ldg(scores + k), m);   // the reference multiplies in fp32, then compares
-      if (k == 0 || v > best) {
-        best = v;
-        bk = k;
-      }
-      if (m >= 0.5f) atomicAdd(&sm_cnt[T + k], 1);
+  const bool valid = p < HW;                              // whole warps walk the maps: the counters are warp-aggregated
+  const size_t pp = valid ? (size_t)p : 0;
+  const int lane = threadIdx.x & 31;
+  float best = 0.f;
+  int bk = 0;
+#pragma unroll 4
+  for (int k = 0; k < T; ++k) {
+    const float m = valid ? __ldg(masks + (size_t)k * HW + pp) : 0.f;
+    const float v = __fmul_rn(__ldg(scores + k), m);     // the reference multiplies in fp32, then compares
+    if (k == 0 || v > best) {
+      best = v;
+      bk = k;
     }
-    owner[p] = bk;
-    atomicAdd(&sm_cnt[bk], 1);
+    const unsigned hot = __ballot_sync(0xffffffffu, valid && m >= 0.5f);     // one shared-memory atomic per warp and map
+    if (lane == 0 && hot) atomicAdd(&sm_cnt[T + k], __popc(hot));
+  }
+  if (valid) owner[p] = bk;
+  {
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned same = __match_any_sync(act, bk);   // neighbouring pixels mostly share their owner
+      if (lane == __ffs(same) - 1) atomicAdd(&sm_cnt[bk], __popc(same));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T; i += PM_NT) {
