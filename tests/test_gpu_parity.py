@@ -1041,6 +1041,23 @@ def test_frame_chain_cluster_kernels(dev, monkeypatch, B, N, H, W, S, ncls):
         h.invalidate_weight_cache()
 
 
+def test_frame_chain_handoff_transports_agree(dev, monkeypatch):
+    """The plane hand-off of the cluster chain has two transports into the same K-blocked buffers: one bulk copy shared ->
+    distributed shared memory per destination (default) and 16-byte st.async stores (VKN_FC_BULK=0, the form compute-sanitizer can
+    follow).  Same bits."""
+    import vknet
+    B, N, C, H, W, S = 2, 100, 256, 16, 24, 2
+    cfg = ko.default_cfg(num_classes=19, in_channels=C, feedforward_channels=2048)
+    sds = [ko.round_state_dict_bf16(ko.random_state_dict(cfg, seed=60 + s)) for s in range(S)]
+    heads = build_heads('KernelUpdateHead', cfg, sds, dev, dtype=torch.bfloat16)
+    x, pf, mask = ko.dummy_inputs(B, N, C, H, W, seed=4)
+    xb, pfd, mb = x.to(dev).bfloat16(), pf.to(dev).reshape(B, N, C), mask.to(dev).bfloat16()
+    a = vknet.KernelIterLoop(heads)(xb, pfd, mb)
+    monkeypatch.setenv('VKN_FC_BULK', '0')
+    b = vknet.KernelIterLoop(heads)(xb, pfd, mb)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+
+
 def test_frame_chain_video_head_and_clip_head_without_cls(dev):
     """The two other entries into the cluster chain: VideoKernelUpdateHead (pooled feature computed first, handed in as
     x_feat_in; returns x_feat) and KernelUpdateHeadVideo in per-frame mode (with_cls=False: no cls branch)."""

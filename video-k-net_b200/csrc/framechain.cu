@@ -72,6 +72,7 @@ struct FcCommon {
   int nchunks, nslot, nvec;
   int N, B;                // kernels per frame, frames
   const __nv_bfloat16 *pack;   // optional (VknHeadW.fc_pack): this kernel's chunks re-laid [rank][chunk][32][FC_LD], zero padded
+  int handoff_stores;      // 1: plane hand-offs as 16-byte st.async stores instead of one bulk copy per destination (VKN_FC_BULK=0)
   unsigned long long *dbg; // optional: 32 phase timestamps per CTA (vkn_debug_timestamps, tools/frame_chain_timeline.py); null in production
 };
 struct FcParamsA {
@@ -130,6 +131,11 @@ __device__ __forceinline__ uint32_t fc_mapa(uint32_t addr, uint32_t rank) {
 }
 // remote stores that report their bytes to an mbarrier of the DESTINATION CTA: the receiver waits for "all bytes of this
 // exchange have landed" on its own barrier -- no cluster-wide barrier per hand-off
+__device__ __forceinline__ void fc_st_remote_v4(uint32_t addr, const uint4 &v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void fc_st_remote_f2(uint32_t addr, float a, float b, uint32_t bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr),
                "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(bar)
@@ -198,6 +204,7 @@ struct FcCtx {
   uint32_t rank;
   uint32_t ring, buf[3], sl, stage[3], stats, vecs, bars, xbar;    // shared-memory addresses
   int nslot, nchunks, issued;
+  bool stores;             // plane hand-offs as st.async stores (see fc_bcast_send)
   int row0, nvalid;        // first global row of the tile, valid rows in it
 };
 
@@ -211,6 +218,7 @@ __device__ __forceinline__ void fc_setup(FcCtx &x, const FcCommon &c, uint8_t *s
   x.nslot = c.nslot;
   x.nchunks = c.nchunks;
   x.issued = 0;
+  x.stores = c.handoff_stores != 0;
   uint32_t a = smem_u32(smem);
   x.ring = a;                 a += (uint32_t)c.nslot * FC_CHUNK_B;
   for (int i = 0; i < 3; ++i) { x.buf[i] = a; a += FC_ABUF; }
@@ -401,10 +409,23 @@ __device__ __forceinline__ void fc_bulk_s2d(uint32_t dst_remote, uint32_t src, u
                "r"(src), "r"(bytes), "r"(bar_remote)
                : "memory");
 }
-__device__ __forceinline__ void fc_bcast_send(uint32_t st, uint32_t dst_block, uint32_t bar_local, uint32_t to, int lane) {
-  fence_proxy_async();            // the staging writes (generic proxy) are read by the copy engine (async proxy)
+// `stores`: the same block as 192 16-byte st.async stores (6 per lane) -- the transport of the first version, 13 us per frame
+// slower; kept selectable (VKN_FC_BULK=0) because compute-sanitizer's memcheck, clean on these stores, reports every bulk copy
+// shared::cta -> shared::cluster as "not located in remote CTA" although both transports use the same mapa addresses and
+// produce bit-identical results (tests/test_gpu_parity.py::test_frame_chain_handoff_transports_agree)
+__device__ __forceinline__ void fc_bcast_send(uint32_t st, uint32_t dst_block, uint32_t bar_local, uint32_t to, int lane, bool stores) {
+  if (!stores) fence_proxy_async();   // the staging writes (generic proxy) are read by the copy engine (async proxy)
   __syncthreads();
-  if (lane == 0) fc_bulk_s2d(fc_mapa(dst_block, to), st, FC_BLK, fc_mapa(bar_local, to));
+  const uint32_t dst = fc_mapa(dst_block, to), bar = fc_mapa(bar_local, to);
+  if (stores) {
+#pragma unroll
+    for (int i = 0; i < FC_BLK / 16 / 32; ++i) {
+      const uint32_t o = (uint32_t)(lane + 32 * i) * 16u;
+      fc_st_remote_v4(dst + o, lds_u4(st + o), bar);
+    }
+  } else if (lane == 0) {
+    fc_bulk_s2d(dst, st, FC_BLK, bar);
+  }
 }
 // the owner's transformed slice -> bf16 planes in the A buffer `dst` of ALL 8 CTAs (warp w serves CTA w)
 // Staging buffers: a buffer may be rewritten only when every destination has received the block last sent from it.  With the
@@ -417,7 +438,7 @@ __device__ __forceinline__ void fc_bcast_planes(const FcCtx &x, int stg, uint32_
   const uint32_t o = (uint32_t)(x.row * (FC_SW * 2) + ((((x.cp >> 2)) ^ ((x.row >> 1) & 3)) << 4) + (x.cp & 3) * 4);
 #pragma unroll
   for (int pl = 0; pl < 3; ++pl) sts_u32(st + (uint32_t)(pl * (FC_TM * FC_SW * 2)) + o, w3[pl]);
-  fc_bcast_send(st, dst + (uint32_t)((int)x.rank * FC_BLK), x.xbar + 8u * (uint32_t)xch, (uint32_t)x.warp, x.lane);
+  fc_bcast_send(st, dst + (uint32_t)((int)x.rank * FC_BLK), x.xbar + 8u * (uint32_t)xch, (uint32_t)x.warp, x.lane, x.stores);
 }
 __device__ __forceinline__ void fc_xwait(const FcCtx &x, int xch) { fc_mbar_wait(x.xbar + 8u * (uint32_t)xch, 0u); }
 
@@ -1175,11 +1196,14 @@ int launch_frame_chain(const VknShape &s, const VknHeadW &w, const float *xp0, c
   }
   const bool with_cls = w.fc_cls_w != nullptr && cls_out != nullptr;
   const bool pack_ok = w.fc_pack != nullptr;
+  int handoff_stores = 0;
+  if (const char *e = getenv("VKN_FC_BULK")) handoff_stores = e[0] == '0';
   {
     FcParamsA a;
     fc_tables_a(s, w, x_feat_in != nullptr, a);
     a.c.pack = pack_ok ? (const __nv_bfloat16 *)w.fc_pack : nullptr;
     a.c.dbg = debug_ts_slot();
+    a.c.handoff_stores = handoff_stores;
     a.xp0 = xp0;
     a.cnt = cnt;
     a.pf = pf;
@@ -1194,6 +1218,7 @@ int launch_frame_chain(const VknShape &s, const VknHeadW &w, const float *xp0, c
     fc_tables_b(s, w, with_cls, b);
     b.c.pack = pack_ok ? (const __nv_bfloat16 *)((const char *)w.fc_pack + FC_PACK_A) : nullptr;
     b.c.dbg = debug_ts_slot();
+    b.c.handoff_stores = handoff_stores;
     b.qkv = qkv_ws;
     b.obj0 = obj0_ws;
     b.obj_out = obj_out;
