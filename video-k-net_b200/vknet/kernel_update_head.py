@@ -118,6 +118,21 @@ class _HeadBase(nn.Module):
 
     def invalidate_weight_cache(self):
         self._packed = None
+        self.__dict__['_param_list'] = None
+
+    def _apply(self, fn, *args, **kwargs):          # .to() / .bfloat16() / .cuda(): parameters may be re-created
+        self.__dict__['_param_list'] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _weights(self):
+        """The module's parameters as a list, walked once: `self.parameters()` traverses the module tree on every call (86 us
+        for the 44 tensors of a stage -- more than the stage's device time at one frame per call).  Re-derived after `_apply`
+        and `invalidate_weight_cache()`; code that swaps Parameter OBJECTS of a built head must call the latter."""
+        pl = self.__dict__.get('_param_list')
+        if pl is None:
+            pl = list(self.parameters())
+            self.__dict__['_param_list'] = pl
+        return pl
 
     def _pack_extra(self, pk):
         return None
@@ -126,9 +141,9 @@ class _HeadBase(nn.Module):
         """(VknHeadW, extra, w_dtype) for `device`; rebuilt when any parameter changed in place."""
         # _version catches in-place edits through the parameter, data_ptr re-assignment of p.data (EMA / weight surgery);
         # edits through p.data.copy_() bump neither: call invalidate_weight_cache() after those
-        key = (str(device),) + tuple((p._version, p.data_ptr(), p.dtype) for p in self.parameters())
+        key = (str(device),) + tuple((p._version, p.data_ptr(), p.dtype) for p in self._weights())
         if self._packed is None or self._packed_key != key:
-            wd = pack.weight_dtype_of(self.parameters())
+            wd = pack.weight_dtype_of(self._weights())
             pk = pack.Packer(device, wd)
             w = pack.pack_head(pk, self)
             pack.attach_frame_chain_pack(pk, w, self._shape(1, 1, 1, 1, _lib.VKN_BF16, wd))
