@@ -129,6 +129,8 @@ class _HeadBase(nn.Module):
         for the 44 tensors of a stage -- more than the stage's device time at one frame per call).  Re-derived after `_apply`
         and `invalidate_weight_cache()`; code that swaps Parameter OBJECTS of a built head must call the latter."""
         pl = self.__dict__.get('_param_list')
+        if pl is not None and next(self.parameters(), None) is not pl[0]:
+            pl = None                              # a replica / re-built module: its first parameter is another object
         if pl is None:
             pl = list(self.parameters())
             self.__dict__['_param_list'] = pl
