@@ -1,5 +1,5 @@
 import sys, os
-ROOT='/root/repo'
+ROOT=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0]=[os.path.join(ROOT,'video-k-net_b200'), os.path.join(ROOT,'oracle'), ROOT]
 import torch
 from vknet import ops, _lib
