@@ -301,8 +301,8 @@ __device__ __noinline__ FcFrag fc_mma_tile(uint32_t a_buf, uint32_t w_rows, int 
   const uint32_t a_row = a_buf + (uint32_t)(arow * (FC_SW * 2));
   const uint32_t a_h0 = a_row + (uint32_t)((((lane >> 4)) ^ aswz) << 4), a_h1 = a_row + (uint32_t)(((2 + (lane >> 4)) ^ aswz) << 4);
   const uint32_t b_addr = w_rows + (uint32_t)((lane & 7) * FC_LD + (lane >> 3) * 8) * 2u;
-#pragma unroll 2
-  for (int k0 = 0; k0 < FC_K; k0 += 32) {
+#pragma unroll
+  for (int k0 = 0; k0 < FC_K; k0 += 32) {      // fully unrolled: all ldmatrix of a tile can be in flight (A/B: 213.8 -> 209.8 us per frame)
     uint32_t b[4];
     fc_ldsm_x4(b, b_addr + (uint32_t)k0 * 2u);
 #pragma unroll
@@ -335,8 +335,8 @@ __device__ __noinline__ FcFrag2 fc_mma_tile2(uint32_t a_buf, uint32_t w_rows0, u
   const uint32_t a_row = a_buf + (uint32_t)(arow * (FC_SW * 2));
   const uint32_t a_h0 = a_row + (uint32_t)((((lane >> 4)) ^ aswz) << 4), a_h1 = a_row + (uint32_t)(((2 + (lane >> 4)) ^ aswz) << 4);
   const uint32_t b_off = (uint32_t)((lane & 7) * FC_LD + (lane >> 3) * 8) * 2u;
-#pragma unroll 2
-  for (int k0 = 0; k0 < FC_K; k0 += 32) {
+#pragma unroll
+  for (int k0 = 0; k0 < FC_K; k0 += 32) {      // fully unrolled: all ldmatrix of a tile can be in flight (A/B: 213.8 -> 209.8 us per frame)
     uint32_t b0[4], b1[4];
     fc_ldsm_x4(b0, w_rows0 + b_off + (uint32_t)k0 * 2u);
     fc_ldsm_x4(b1, w_rows1 + b_off + (uint32_t)k0 * 2u);
