@@ -365,3 +365,27 @@ def test_inputs_are_validated_before_the_c_call(built_lib):
     b = vknet.build_head(dict(type='KernelUpdateHead', **_small_cfg(hard_mask_thr=0.7)))
     with pytest.raises(NotImplementedError, match='hard_mask_thr'):
         vknet.KernelIterLoop([a, b])
+
+
+def test_assigner_drop_in_contract_without_a_device(built_lib):
+    """vknet.assigner mirrors knet/det/mask_hungarian_assigner.py: constructor kwargs of the shipped config block, the empty-set
+    behaviour of assign (:218-224, no cost matrix needed), unsupported cost settings refused, no CPU path for the cost itself."""
+    import vknet
+    from vknet import assigner
+    asg = assigner.MaskHungarianAssigner(cls_cost=dict(type='FocalLossCost', weight=2.0),
+                                         dice_cost=dict(type='DiceCost', weight=4.0, pred_act=True),
+                                         mask_cost=dict(type='MaskCost', weight=1.0, pred_act=True))
+    assert (asg.cls_cost.weight, asg.mask_cost.weight, asg.dice_cost.weight, asg.dice_cost.eps, asg.topk) == (2.0, 1.0, 4.0, 1e-3, 1)
+    pred, cls = torch.randn(7, 5, 6), torch.randn(7, 3)
+    res = asg.assign(pred, cls, torch.zeros(0, 5, 6), torch.zeros(0, dtype=torch.long))
+    assert res.num_gts == 0 and res.gt_inds.tolist() == [0] * 7 and res.labels.tolist() == [-1] * 7
+    res = asg.assign(pred[:0], cls[:0], torch.ones(2, 5, 6), torch.zeros(2, dtype=torch.long))
+    assert res.num_gts == 2 and res.gt_inds.numel() == 0
+    with pytest.raises(vknet.VknError, match='no CPU path'):
+        asg.assign(pred, cls, torch.ones(2, 5, 6), torch.zeros(2, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        assigner.MaskHungarianAssigner(cls_cost=dict(type='ClassificationCost', weight=1.0))
+    with pytest.raises(NotImplementedError):
+        assigner.MaskCost(weight=1.0, pred_act=False)(pred, torch.ones(2, 5, 6))
+    with pytest.raises(NotImplementedError):
+        assigner.MaskHungarianAssigner(boundary_cost=dict(type='DiceCost'))
