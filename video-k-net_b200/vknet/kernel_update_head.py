@@ -151,6 +151,10 @@ class _HeadBase(nn.Module):
             pack.attach_frame_chain_pack(pk, w, self._shape(1, 1, 1, 1, _lib.VKN_BF16, wd))
             self._packed = (w, self._pack_extra(pk), wd, pk)
             self._packed_key = key
+            # the derived operands (ft_wt_ext, fc_pack, dtype copies) were produced on the CURRENT stream; a caller that drives
+            # several streams may use them from another one next: finish them once, here (weights change rarely)
+            if torch.device(device).type == 'cuda' and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(device).synchronize()
         return self._packed[0], self._packed[1], self._packed[2]
 
     def _shape(self, B, N, H, W, x_dtype, w_dtype):
